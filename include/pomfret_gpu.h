@@ -1,0 +1,190 @@
+/* pomfret_gpu.h — C ABI of libpomfret_gpu, the B200 (sm_100a) engine behind
+ * `pomfret methphase` / `pomfret report`.
+ *
+ * The reference (nanoporetech/pomfret v0.1-r14) has no plugin / FFI layer; the
+ * two internal seams this library replaces are:
+ *
+ *   window engine    dataset_t *haplotag_region_given_bam(storage_t*, char *fn_bam,
+ *                        char *chrom, uint32_t ref_start, uint32_t ref_end, mmr_config_t,
+ *                        int n_candidates_per_iter, int do_n_permuations, int *decision)
+ *                    reference blockjoin.c:4217-4335, called from :4400 and :5058
+ *   read haplotagger void pre_haplotagging_read_in_one_ref(char *fn_bam, char *ref_itvl,
+ *                        vvar_t *known_vars, htstri_t *qname2haptag_raw)
+ *                    reference blockjoin.c:1841-1898, called from :2075 and :2152
+ *
+ * BAM iteration and the record filters stay on the host (htslib side of the
+ * seam); everything from "a record passed the filters" to "decision + one
+ * haplotag per read" runs on the device.
+ *
+ * Conventions
+ *   - every entry point returns 0 (POMFRET_GPU_OK) or a negative error code;
+ *     the library never calls exit()/abort(): the reference's fatal cases
+ *     (e.g. unknown CIGAR op, blockjoin.c:776-778) surface as error codes /
+ *     per-read status bits that the host front end turns into the same message;
+ *   - the caller owns every buffer it passes in and every output buffer;
+ *     add_read() copies, so inputs may be reused as soon as it returns;
+ *   - the library owns device memory and pinned staging arenas;
+ *   - a ctx is thread-safe; a batch is used by one thread at a time and is bound
+ *     to one device and one stream; results are valid when collect() returns;
+ *   - there is no CPU fallback: init fails if no CUDA device is usable.
+ */
+#ifndef POMFRET_GPU_H
+#define POMFRET_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POMFRET_GPU_OK 0
+#define POMFRET_GPU_ERR_NO_DEVICE -1
+#define POMFRET_GPU_ERR_CUDA -2
+#define POMFRET_GPU_ERR_NOMEM -3
+#define POMFRET_GPU_ERR_ARG -4
+#define POMFRET_GPU_ERR_STATE -5
+#define POMFRET_GPU_ERR_FATAL_CIGAR -6  /* reference: "fatal: unknown cigar operation" blockjoin.c:777 */
+#define POMFRET_GPU_ERR_DUP_QNAME -7    /* reserved for the host loader, blockjoin.c:1149 */
+#define POMFRET_GPU_ERR_UNSUPPORTED -8  /* input outside the engine's compiled limits (e.g. k > 6) */
+#define POMFRET_GPU_ERR_MISSING_MD -9   /* reference: assert(tagd) blockjoin.c:1596 */
+#define POMFRET_GPU_ERR_BAD_MD -10      /* reference: "invalid MD" blockjoin.c:1622 */
+
+typedef struct pomfret_gpu_ctx pomfret_gpu_ctx;
+typedef struct pomfret_gpu_batch pomfret_gpu_batch;
+
+/* Mirrors mmr_config_t (reference blockjoin.h:7-16) plus the per-call scalars of
+ * haplotag_region_given_bam. */
+typedef struct pomfret_gpu_config {
+    int32_t k;
+    int32_t k_span;
+    int32_t lo, hi;
+    int32_t cov_known;
+    int32_t cov_for_selection;
+    int32_t cov_for_runtime;
+    int32_t readlen_threshold;
+    int32_t min_mapq;
+    int32_t n_candidates_per_iter;
+} pomfret_gpu_config;
+
+/* One alignment record that passed the host-side filters of
+ * load_reads_given_interval (blockjoin.c:1081-1084).  Pointers address the
+ * caller's copy of the BAM record. */
+typedef struct pomfret_gpu_read_desc {
+    uint32_t pos;         /* core.pos */
+    uint32_t l_qseq;      /* core.l_qseq */
+    uint32_t n_cigar;     /* core.n_cigar */
+    uint16_t flag;        /* core.flag */
+    uint8_t mapq;         /* core.qual */
+    uint8_t tags_malformed; /* 1: MM not 'Z' / ML not 'B,C' / MN mismatch handled by caller => record has no mods */
+    int32_t hp;           /* get_hp_from_aln (blockjoin.c:910-923) or the qname2haptag_raw override (:1114-1122) */
+    int32_t mn;           /* value of the MN tag, -1 if absent */
+    const uint32_t *cigar;
+    const uint8_t *seq;   /* 4-bit packed, (l_qseq+1)/2 bytes */
+    const char *mm;       /* MM/Mm string without the type byte, not necessarily NUL terminated; NULL if absent */
+    uint32_t mm_len;
+    int32_t ml_len;       /* number of ML bytes, -1 if the tag is absent */
+    const uint8_t *ml;
+    const char *md;       /* MD string (only the haplotagger needs it); NULL if absent */
+    uint32_t md_len;
+    uint32_t reserved;
+} pomfret_gpu_read_desc;
+
+/* Phased variant of the known set, as produced by insert_variant_from_vcf_line
+ * (blockjoin.c:1432-1543): pos is 0-based (deletions: +1), op 1=X 2=I 3=D,
+ * bases in seq_nt4 code (A0 C1 G2 T3 other 4), haptag = haplotype of the REF allele. */
+typedef struct pomfret_gpu_variant {
+    uint32_t pos;
+    uint32_t len;
+    uint8_t op;
+    uint8_t haptag;
+    uint16_t reserved;
+    uint32_t bases_off;   /* offset of the first base in the `bases` array given to haptag() */
+} pomfret_gpu_variant;
+
+typedef struct pomfret_gpu_window_result {
+    int32_t decision;      /* 0 cis, 1 trans, -1 no join (blockjoin.c:4313-4320) */
+    int32_t join_fwd;      /* join1, haplotag_region2 direction 0 */
+    int32_t join_bwd;      /* join2, direction 1 */
+    int32_t n_reads;       /* rs->n after the left-coverage gate (0 if abandoned, blockjoin.c:1161-1163) */
+    int32_t n_reads_loaded;/* reads that produced a record before the gate */
+    int32_t n_sites_fwd, n_sites_bwd;
+    int32_t n_left, n_left_strict, n_right, n_right_strict;
+    int32_t table_fwd[4];  /* evaluate_separation1 2x2 table buf[ref][query], direction 0 (right strict reads) */
+    int32_t table_bwd[4];  /* same for direction 1 (left strict reads) */
+    float score_fwd, score_bwd;
+    int32_t which_way_fwd, which_way_bwd;
+    int32_t status;        /* 0, or a negative error code raised inside this window */
+} pomfret_gpu_window_result;
+
+/* per-read status bits written by decode() */
+#define POMFRET_GPU_READ_KEPT 1u          /* add_read_record_from_bam_line returned 1 */
+#define POMFRET_GPU_READ_HAS_IMPLICIT 2u  /* has_implicit, blockjoin.c:856 */
+#define POMFRET_GPU_READ_FATAL_CIGAR 4u
+#define POMFRET_GPU_READ_MM_ERROR 8u      /* malformed MM/ML: record has no modifications */
+#define POMFRET_GPU_READ_SLOWPATH 16u     /* decoded by the single-lane general path */
+
+/* ---- context ---- */
+int pomfret_gpu_init(pomfret_gpu_ctx **out, const int *devices, int n_devices, int n_workers);
+void pomfret_gpu_destroy(pomfret_gpu_ctx *ctx);
+const char *pomfret_gpu_strerror(int rc);
+int pomfret_gpu_device_count(void);
+const char *pomfret_gpu_version(void);
+
+/* ---- (a) staging ---- */
+int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfret_gpu_batch **out);
+int pomfret_gpu_batch_reset(pomfret_gpu_batch *b);
+int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r);
+/* reads [first_read, first_read+n_reads) are the records of the region query
+ * chrom:(ref_start-50000)-(ref_end+50000) in BAM order */
+int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
+                                 uint32_t n_reads);
+int pomfret_gpu_batch_submit(pomfret_gpu_batch *b); /* async H2D of the staged records */
+
+/* ---- (b) MM/ML + CIGAR decode: fill_read_meth_record_from_bam_line + get_mod_poss_on_ref ---- */
+int pomfret_gpu_decode(pomfret_gpu_batch *b, uint8_t qual_lo, uint8_t qual_hi);
+/* ---- (c) read haplotagging: parse_variants_for_one_read + haptag_one_read_with_variants.
+ * known_first[i] is the i_left cursor of read i (blockjoin.c:1716-1720), computed by the caller. */
+int pomfret_gpu_haptag(pomfret_gpu_batch *b, const pomfret_gpu_variant *known, uint32_t n_known,
+                       const uint8_t *bases, uint32_t n_bases, const uint32_t *known_first);
+/* ---- (d) read set, CpG site pileup, methmer layout + extraction ---- */
+int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg);
+/* ---- (e) greedy propagation in both directions + join evaluation ---- */
+int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg);
+
+/* Synchronise and fetch: one result per window; read_tags[i] = final hp of batch read i in its
+ * window (rs->a[j].hp after haplotag_region_given_bam; 255 for records that were not kept);
+ * read_ids[i] = index j of the read inside its window's read set, -1 if not kept.  Either
+ * output pointer may be NULL. */
+int pomfret_gpu_batch_collect(pomfret_gpu_batch *b, pomfret_gpu_window_result *win, uint8_t *read_tags,
+                              int32_t *read_ids);
+/* haplotagger output: tags[i] in {0,1,254}; status[i] 0 or a negative code */
+int pomfret_gpu_batch_collect_haptags(pomfret_gpu_batch *b, uint8_t *tags, int32_t *status);
+void pomfret_gpu_batch_end(pomfret_gpu_batch *b);
+
+/* ---- timing of the last run of each stage on this batch (CUDA events, ms) ---- */
+typedef struct pomfret_gpu_timing {
+    float h2d_ms, decode_ms, haptag_ms, readset_ms, pileup_ms, methmer_ms, join_ms, d2h_ms;
+    uint64_t bytes_h2d, bytes_d2h;
+    uint64_t decode_bytes, pileup_bytes, methmer_bytes, haptag_bytes; /* algorithmic bytes, SURVEY.md §8(d) */
+    uint32_t launches;
+} pomfret_gpu_timing;
+int pomfret_gpu_batch_timing(pomfret_gpu_batch *b, pomfret_gpu_timing *out);
+
+/* ---- parity / debug getters (valid after the stage that produces them; they synchronise) ---- */
+int pomfret_gpu_debug_read_info(pomfret_gpu_batch *b, uint32_t read, uint32_t *status, uint32_t *n_calls,
+                                uint32_t *end_pos);
+int pomfret_gpu_debug_get_calls(pomfret_gpu_batch *b, uint32_t read, uint32_t *pos, uint8_t *cat, uint32_t cap,
+                                uint32_t *n);
+int pomfret_gpu_debug_get_sites(pomfret_gpu_batch *b, uint32_t window, int direction, uint32_t *real_pos,
+                                uint32_t *starts, uint8_t *lens, uint32_t cap, uint32_t *n);
+int pomfret_gpu_debug_get_mmrs(pomfret_gpu_batch *b, uint32_t read, int direction, uint32_t *mmr, uint32_t cap,
+                               uint32_t *n, uint32_t *start_i);
+int pomfret_gpu_debug_get_tags(pomfret_gpu_batch *b, int direction, uint8_t *tags /* one per batch read */);
+/* tagging order of the greedy loop: read ids (within window) in the order they were tagged */
+int pomfret_gpu_debug_get_tag_order(pomfret_gpu_batch *b, uint32_t window, int direction, uint32_t *ids,
+                                    uint32_t cap, uint32_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

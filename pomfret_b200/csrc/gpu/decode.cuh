@@ -1,0 +1,919 @@
+// (b) Per-read decode kernel: MM/ML base-modification tags + CIGAR -> reference-coordinate 5mC
+// calls at CpG sites.  One warp per alignment record.
+//
+// Replaces, for records that passed the host filters:
+//   bam_parse_basemod / bam_mods_at_next_pos as used at reference blockjoin.c:807,832-882
+//     (htslib semantics restated from the SAMtags spec),
+//   fill_read_meth_record_from_bam_line  blockjoin.c:794-908  (C+m only, CpG check on SEQ, ML -> category),
+//   get_mod_poss_on_ref                  blockjoin.c:605-792  (CIGAR walk with its quirks, App. A.3),
+//   bam_endpos                           (blockjoin.c:1125).
+//
+// Data flow per warp (all global accesses are 128-bit or lane-consecutive):
+//   1. CIGAR pre-scan: reference span, first stopping op, fatal-op test.
+//   2. MM structure scan: ';' positions -> segment table; headers parsed by lane 0.
+//   3. Delta lists: one lane per comma parses its number out of a shared-memory staged chunk;
+//      warp prefix sums turn deltas into "index among canonical bases" targets.
+//   4. SEQ scan, 512 B per warp step: nibble match flags, popcount prefix scan, targets selected with
+//      a lane binary search + find-nth-set-bit; CpG context checked on SEQ; ML byte -> category.
+//      Reverse-strand records scan SEQ from its end so targets count from the read's own 5' end.
+//   5. CIGAR walk: M/I ops compacted (read-end, offset) into shared memory in chunks; each kept mod
+//      binary-searches the op that the reference's inclusive trigger loop would handle it under;
+//      positions de-duplicated with the reference's overwrite rule and written out.
+// Records that need the general sequential semantics (several C+m segments, >10 mod streams,
+// implicit canonical calls, more segments than the table holds) take decode_generic() on lane 0.
+#ifndef POMFRET_GPU_DECODE_CUH
+#define POMFRET_GPU_DECODE_CUH
+#include "gpu_rt.h"
+#include "types.h"
+
+namespace pomfret_gpu {
+
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_MAXSEG = 16;
+constexpr int DEC_MI_CAP = 768;       // M/I ops staged per chunk
+constexpr int DEC_MM_CHUNK = 512;     // MM bytes staged per step
+constexpr int N_MODS_LIMIT = 10;      // reference N_MODS, blockjoin.c:34
+
+struct DecodeParams {
+    const ReadRec *reads;
+    uint32_t n_reads;
+    const uint8_t *blob;
+    uint32_t *calls_pos;
+    uint8_t *calls_cat;
+    uint32_t *tmp_rank;   // scratch, same slot layout as the call arrays
+    uint32_t *tmp_mpos;
+    uint8_t *tmp_mcat;
+    uint32_t *r_ncalls, *r_status, *r_end;
+    uint32_t lo, hi;
+};
+
+struct SegInfo {
+    uint32_t list_begin;  // offset of the first ',' (or of ';' for an empty list)
+    uint32_t list_end;    // offset of the terminating ';'
+    uint32_t n_delta;
+    uint32_t total;       // sum of (delta+1)
+    uint32_t ml_base;
+    uint16_t n_codes;
+    int16_t m_idx;        // index of code 'm' or -1
+    uint8_t canon;        // 4-bit code of the canonical base (A1 C2 G4 T8 N15)
+    uint8_t m_count;      // how many times 'm' occurs in the code list
+    uint8_t pad[2];
+};
+
+struct DecodeWarpSmem {
+    __align__(16) uint8_t mmbuf[DEC_MM_CHUNK + 16];
+    uint32_t s_first[32];
+    uint32_t s_cnt[32];
+    uint32_t s_m[32][4];
+    uint32_t mi_end[DEC_MI_CAP];
+    int32_t mi_off[DEC_MI_CAP];
+    SegInfo seg[DEC_MAXSEG];
+};
+
+constexpr int32_t MI_DROP = (int32_t)0x80000000;
+
+__device__ __forceinline__ uint32_t seq_nib(const uint8_t *seq, uint32_t i) {
+    return (seq[i >> 1] >> ((~i & 1u) << 2)) & 0xfu;
+}
+
+// flags word: bit 4*i set iff base i (0..7) of the 32-bit SEQ word equals nibble value `want`
+__device__ __forceinline__ uint32_t nib_match_flags(uint32_t w, uint32_t want) {
+    // put base i into bits [4i,4i+3]: swap the nibbles of every byte (BAM packs the first base high)
+    uint32_t x = ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu);
+    x ^= want * 0x11111111u;
+    x |= x >> 1;
+    x |= x >> 2;
+    return ~x & 0x11111111u;
+}
+
+__device__ __forceinline__ int base_code_of(int ch) {
+    switch (ch) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8; case 'N': return 15;
+    default: return -1;
+    }
+}
+__device__ __forceinline__ bool is_digit(int c) { return c >= '0' && c <= '9'; }
+__device__ __forceinline__ bool is_alpha(int c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+__device__ __forceinline__ uint32_t comp_code(uint32_t c) {
+    // complement of a 4-bit base code: reverse the 4 bits (A1<->T8, C2<->G4, N15 fixed)
+    return ((c & 1u) << 3) | ((c & 2u) << 1) | ((c & 4u) >> 1) | ((c & 8u) >> 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MM structure scan.  Returns (uniform across the warp) the number of segments, or -1 malformed,
+// or -2 "take the generic path".  Segment table in sm.seg.
+// ---------------------------------------------------------------------------------------------
+__device__ int mm_scan_segments(const uint8_t *mm, uint32_t mm_len, DecodeWarpSmem &sm) {
+    const unsigned lane = lane_id();
+    if (mm_len == 0) return 0;
+    // pass 1: positions of ';'
+    int n_seg = 0;
+    bool too_many = false;
+    for (uint32_t base = 0; base < mm_len; base += 32 * 16) {
+        uint32_t off = base + lane * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (off < mm_len) v = *reinterpret_cast<const uint4 *>(mm + off);  // blob segments are padded to 16 B
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t semi = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+            if (off + i < mm_len && c == ';') semi |= 1u << i;
+        }
+        uint32_t cnt = __popc(semi);
+        uint32_t incl = warp_inclusive_sum(cnt);
+        uint32_t excl = incl - cnt;
+        uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+        uint32_t idx = n_seg + excl;
+        while (semi) {
+            int b = __ffs(semi) - 1;
+            semi &= semi - 1;
+            if (idx < DEC_MAXSEG) sm.seg[idx].list_end = off + b;
+            idx++;
+        }
+        n_seg += (int)tot;
+        if (n_seg > DEC_MAXSEG) too_many = true;
+    }
+    __syncwarp();
+    if (too_many) return -2;
+    // the string must end with ';' (htslib: "Missing semicolon")
+    if (n_seg == 0 || sm.seg[n_seg - 1].list_end != mm_len - 1) return -1;
+    // pass 2: headers, lane 0
+    int err = 0;
+    if (lane == 0) {
+        uint32_t p = 0;
+        int n_streams = 0;
+        for (int s = 0; s < n_seg && !err; s++) {
+            SegInfo &g = sm.seg[s];
+            const uint32_t e = g.list_end;
+            int canon = base_code_of(mm[p]);
+            if (canon < 0) { err = -1; break; }
+            p++;
+            if (p > e || (mm[p] != '+' && mm[p] != '-')) { err = -1; break; }
+            p++;
+            int n_codes = 0, m_idx = -1, m_count = 0;
+            if (p <= e && is_digit(mm[p])) {
+                while (p <= e && is_digit(mm[p])) p++;
+                n_codes = 1;
+            } else {
+                while (p <= e && is_alpha(mm[p])) {
+                    if (mm[p] == 'm') { if (m_idx < 0) m_idx = n_codes; m_count++; }
+                    n_codes++;
+                    p++;
+                }
+            }
+            if (p <= e && (mm[p] == '.' || mm[p] == '?')) p++;
+            else if (p > e || (mm[p] != ',' && mm[p] != ';')) { err = -1; break; }
+            if (p > e || (mm[p] != ',' && mm[p] != ';')) { err = -1; break; }
+            if (mm[p] == ';' && p != e) { err = -1; break; }  // cannot happen: e is the first ';' after the start
+            if (n_codes > 0 && n_streams + n_codes >= 256) { err = -1; break; }
+            n_streams += n_codes;
+            g.list_begin = p;
+            g.canon = (uint8_t)canon;
+            g.n_codes = (uint16_t)n_codes;
+            g.m_idx = (int16_t)m_idx;
+            g.m_count = (uint8_t)m_count;
+            g.n_delta = 0;
+            g.total = 0;
+            p = e + 1;
+        }
+        if (!err && n_streams > N_MODS_LIMIT) err = -2;  // a position could carry more than N_MODS entries
+    }
+    err = __shfl_sync(FULL_MASK, err, 0);
+    __syncwarp();
+    if (err) return err;
+    return n_seg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Parse the delta list of one segment: count the deltas, sum (delta+1) and, if rank_out != nullptr,
+// write the cumulative target index c_k = sum_{j<=k}(delta_j+1) - 1 of every delta.
+// Returns false (uniform) if the list is malformed.
+// ---------------------------------------------------------------------------------------------
+__device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm, uint32_t *rank_out, uint32_t rank_cap) {
+    const unsigned lane = lane_id();
+    const uint32_t lb = g.list_begin, le = g.list_end;  // list chars are [lb, le), le is ';'
+    uint32_t n_delta = 0, total = 0;
+    bool bad = false;
+    for (uint32_t base = lb & ~15u; base < le; base += DEC_MM_CHUNK) {
+        // stage [base, base+512+16) — bytes past the MM string are blob padding / later fields, never used
+        uint32_t off = base + lane * 16;
+        uint4 v = *reinterpret_cast<const uint4 *>(mm + off);
+        *reinterpret_cast<uint4 *>(sm.mmbuf + lane * 16) = v;
+        if (lane == 0) *reinterpret_cast<uint4 *>(sm.mmbuf + DEC_MM_CHUNK) = *reinterpret_cast<const uint4 *>(mm + base + DEC_MM_CHUNK);
+        __syncwarp();
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // commas owned by this lane, parsed values
+        uint32_t vals[8];
+        int nv = 0;
+        uint32_t lsum = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            uint32_t pos = off + i;
+            uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+            if (pos >= lb && pos < le) {
+                if (c == ',') {
+                    // digits follow at pos+1.. (stop at le)
+                    uint32_t q = lane * 16 + i + 1;  // index into mmbuf
+                    uint32_t val = 0;
+                    int nd = 0;
+                    while (base + q < le && nd < 10) {
+                        uint32_t d = sm.mmbuf[q];
+                        if (d < '0' || d > '9') break;
+                        val = val * 10 + (d - '0');
+                        q++; nd++;
+                    }
+                    if (nd == 0) bad = true;
+                    if (nv < 8) vals[nv] = val;
+                    nv++;
+                    lsum += val + 1;
+                } else if (c < '0' || c > '9') bad = true;
+            }
+        }
+        uint32_t cnt = (uint32_t)nv;
+        uint32_t incl_c = warp_inclusive_sum(cnt);
+        uint32_t incl_s = warp_inclusive_sum(lsum);
+        if (rank_out) {
+            uint32_t k = n_delta + incl_c - cnt;
+            uint32_t run = total + incl_s - lsum;
+            for (int j = 0; j < nv && j < 8; j++) {
+                run += vals[j] + 1;
+                if (k < rank_cap) rank_out[k] = run - 1;
+                k++;
+            }
+        }
+        n_delta += __shfl_sync(FULL_MASK, incl_c, 31);
+        total += __shfl_sync(FULL_MASK, incl_s, 31);
+        __syncwarp();
+    }
+    bad = __any_sync(FULL_MASK, bad);
+    g.n_delta = n_delta;
+    g.total = total;
+    __syncwarp();
+    return !bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The warp-parallel fast path.  Returns status bits; n_calls_out receives the number of calls.
+// ---------------------------------------------------------------------------------------------
+__device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeWarpSmem &sm, uint32_t *n_calls_out,
+                                bool *need_generic) {
+    const unsigned lane = lane_id();
+    const uint8_t *blob = P.blob;
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(blob + (size_t)R.cigar_off * 16);
+    const uint8_t *seq = blob + (size_t)R.seq_off * 16;
+    const uint8_t *mm = blob + (size_t)R.mm_off * 16;
+    const uint8_t *ml = blob + (size_t)R.ml_off * 16;
+    const uint32_t len = R.l_qseq;
+    const bool rev = (R.flags & 16u) != 0;
+    const bool has_ml = (R.flags & RF_HAS_ML) != 0;
+    uint32_t *rank = P.tmp_rank + R.calls_off;
+    uint32_t *mpos = P.tmp_mpos + R.calls_off;
+    uint8_t *mcat = P.tmp_mcat + R.calls_off;
+    uint32_t *opos = P.calls_pos + R.calls_off;
+    uint8_t *ocat = P.calls_cat + R.calls_off;
+    const uint32_t cap = R.calls_cap;
+    uint32_t status = 0;
+    *n_calls_out = 0;
+    *need_generic = false;
+
+    // ---- MM structure ----
+    int n_seg = 0;
+    bool mm_error = false;
+    if (!(R.flags & RF_HAS_MM)) n_seg = 0;
+    else if (R.flags & RF_MALFORMED) mm_error = true;
+    else {
+        n_seg = mm_scan_segments(mm, R.mm_len, sm);
+        if (n_seg == -2) { *need_generic = true; return 0; }
+        if (n_seg < 0) { mm_error = true; n_seg = 0; }
+    }
+    int rel = -1;
+    if (!mm_error) {
+        int n_rel = 0;
+        for (int s = 0; s < n_seg; s++) {
+            const SegInfo &g = sm.seg[s];
+            if (g.canon == 2 && g.m_idx >= 0) { n_rel += g.m_count; rel = s; }
+        }
+        if (n_rel > 1) { *need_generic = true; return 0; }
+    }
+    // ---- delta lists ----
+    uint32_t ml_need = 0;
+    if (!mm_error) {
+        for (int s = 0; s < n_seg; s++) {
+            SegInfo &g = sm.seg[s];
+            const bool want_ranks = (s == rel);
+            // forward strand: other segments only need their comma count (for ML offsets); counting and
+            // parsing share one pass either way
+            bool ok = mm_parse_list(mm, g, sm, want_ranks ? rank : nullptr, cap);
+            if (!ok) { mm_error = true; break; }
+            if (lane == 0) sm.seg[s].ml_base = ml_need;
+            ml_need += g.n_delta * g.n_codes;
+            if (has_ml && ml_need > R.ml_len) { mm_error = true; break; }
+            if (want_ranks && g.n_delta > cap) { *need_generic = true; return 0; }  // cannot happen: cap >= ML length
+        }
+        if (!mm_error && has_ml && ml_need != R.ml_len) mm_error = true;
+        __syncwarp();
+    }
+
+    // ---- SEQ scan: select the listed canonical bases of the relevant segment ----
+    uint32_t n_mods = 0;
+    bool has_implicit = false;
+    uint32_t freq_a = 0, freq_c = 0, freq_g = 0, freq_t = 0, freq_n = 0;  // reverse strand only
+    const bool do_select = !mm_error && rel >= 0 && sm.seg[rel].n_delta > 0;
+    if ((do_select || (rev && !mm_error && n_seg > 0)) && len > 0) {
+        const uint32_t want = rev ? 4u : 2u;  // C on the read strand is G in SEQ for reverse alignments
+        const uint32_t n_targets = do_select ? sm.seg[rel].n_delta : 0;
+        const uint32_t ml_base = do_select ? sm.seg[rel].ml_base : 0;
+        const uint32_t stride = do_select ? sm.seg[rel].n_codes : 0;
+        const uint32_t m_idx = do_select ? (uint32_t)sm.seg[rel].m_idx : 0;
+        const uint32_t n_bytes = (len + 1) >> 1;
+        const uint32_t n_tiles = (n_bytes + 511) / 512;
+        uint32_t run = 0;   // matches seen so far in scan order
+        uint32_t tcur = 0;  // next target (targets are in scan order for both strands)
+        for (uint32_t ti = 0; ti < n_tiles; ti++) {
+            if (!rev && tcur >= n_targets) break;  // forward: nothing left to find
+            const uint32_t tile = rev ? n_tiles - 1 - ti : ti;
+            const uint32_t byte_off = tile * 512 + lane * 16;
+            const uint32_t base0 = byte_off * 2;  // first base of this lane's chunk
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (byte_off < n_bytes) v = *reinterpret_cast<const uint4 *>(seq + byte_off);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t m[4];
+            uint32_t C = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t b0 = base0 + j * 8;
+                uint32_t valid = b0 >= len ? 0u : (len - b0 >= 8 ? 0x11111111u : ((1u << ((len - b0) * 4)) - 1u) & 0x11111111u);
+                m[j] = nib_match_flags(w[j], want) & valid;
+                C += __popc(m[j]);
+                if (rev) {
+                    freq_a += __popc(nib_match_flags(w[j], 1u) & valid);
+                    freq_c += __popc(nib_match_flags(w[j], 2u) & valid);
+                    freq_t += __popc(nib_match_flags(w[j], 8u) & valid);
+                    freq_n += __popc(nib_match_flags(w[j], 15u) & valid);
+                }
+            }
+            if (rev) freq_g += C;
+            uint32_t incl = warp_inclusive_sum(C);
+            uint32_t tile_total = __shfl_sync(FULL_MASK, incl, 31);
+            // rank (in scan order) of this lane's first match
+            uint32_t first = rev ? run + (tile_total - incl) : run + (incl - C);
+            sm.s_first[lane] = first;
+            sm.s_cnt[lane] = C;
+#pragma unroll
+            for (int j = 0; j < 4; j++) sm.s_m[lane][j] = m[j];
+            __syncwarp();
+            // hand out the targets that fall into this tile
+            while (tcur < n_targets) {
+                uint32_t k = tcur + lane;
+                uint32_t r = 0xffffffffu;
+                if (k < n_targets) r = rank[k];
+                bool mine = k < n_targets && r < run + tile_total && r >= run;
+                // a malformed list could repeat a rank (delta = -1 is impossible: digits only), so ranks
+                // strictly increase; `mine` lanes are a prefix
+                unsigned act = __ballot_sync(FULL_MASK, mine);
+                if (act == 0) break;
+                uint32_t p = 0;
+                bool keep = false, implicit = false;
+                uint8_t cat = 0;
+                if (mine) {
+                    // owner lane L: first[L] <= r < first[L] + cnt[L]
+                    int lo_l = 0, hi_l = 31;
+                    if (!rev) {  // first[] ascending with lane
+                        while (lo_l < hi_l) {
+                            int mid = (lo_l + hi_l + 1) >> 1;
+                            if (sm.s_first[mid] <= r) lo_l = mid; else hi_l = mid - 1;
+                        }
+                        // skip empty lanes that share the same first rank: take the last lane with first<=r that has matches
+                        while (sm.s_cnt[lo_l] == 0 && lo_l > 0) lo_l--;
+                    } else {     // first[] descending with lane
+                        while (lo_l < hi_l) {
+                            int mid = (lo_l + hi_l) >> 1;
+                            if (sm.s_first[mid] <= r) hi_l = mid; else lo_l = mid + 1;
+                        }
+                        while (sm.s_cnt[lo_l] == 0 && lo_l < 31) lo_l++;
+                    }
+                    const int L = lo_l;
+                    uint32_t local = r - sm.s_first[L];
+                    int bitpos = -1, wj = 0;
+                    if (!rev) {
+                        for (wj = 0; wj < 4; wj++) {
+                            uint32_t c = __popc(sm.s_m[L][wj]);
+                            if (local < c) { bitpos = (int)__fns(sm.s_m[L][wj], 0, (int)local + 1); break; }
+                            local -= c;
+                        }
+                    } else {
+                        for (wj = 3; wj >= 0; wj--) {
+                            uint32_t c = __popc(sm.s_m[L][wj]);
+                            if (local < c) { bitpos = (int)__fns(sm.s_m[L][wj], 31, -((int)local + 1)); break; }
+                            local -= c;
+                        }
+                    }
+                    p = tile * 1024 + (uint32_t)L * 32 + (uint32_t)wj * 8 + (uint32_t)(bitpos >> 2);
+                    // blockjoin.c:846-858
+                    if (p < len - 1 && p > 0) {
+                        bool ok = seq_nib(seq, p) == 2u ? seq_nib(seq, p + 1) == 4u : seq_nib(seq, p - 1) == 2u;
+                        if (ok) {
+                            keep = true;
+                            // targets are in scan order on both strands: reverse records are scanned from the
+                            // right end of SEQ, i.e. from the read's own 5' end, so target k is delta k
+                            uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
+                            cat = q < P.lo ? 1 : (q >= P.hi ? 0 : 2);
+                        } else implicit = true;
+                    }
+                }
+                unsigned km = __ballot_sync(FULL_MASK, keep);
+                if (__any_sync(FULL_MASK, implicit)) has_implicit = true;
+                if (keep) {
+                    uint32_t j = n_mods + __popc(km & ((1u << lane) - 1u));
+                    uint32_t slot = rev ? cap - 1 - j : j;
+                    mpos[slot] = p;
+                    mcat[slot] = cat;
+                }
+                n_mods += __popc(km);
+                tcur += __popc(act);
+                if (__popc(act) < 32) break;
+            }
+            run += tile_total;
+            __syncwarp();
+        }
+        if (rev) {
+            freq_a = warp_sum(freq_a); freq_c = warp_sum(freq_c); freq_g = warp_sum(freq_g);
+            freq_t = warp_sum(freq_t); freq_n = warp_sum(freq_n);
+            // "MM tag refers to bases beyond sequence length": count of the complement base < sum(delta+1)
+            for (int s = 0; s < n_seg; s++) {
+                const SegInfo &g = sm.seg[s];
+                if (g.n_codes == 0) continue;
+                uint32_t c = comp_code(g.canon);
+                uint32_t f = c == 1 ? freq_a : c == 2 ? freq_c : c == 4 ? freq_g : c == 8 ? freq_t : freq_n;
+                if (g.total > f) mm_error = true;
+            }
+        }
+    }
+    if (mm_error) { status |= RS_MM_ERROR; n_mods = 0; has_implicit = false; }
+    if (has_implicit) { *need_generic = true; return 0; }
+    const uint32_t mbase = rev ? cap - n_mods : 0;  // mods occupy tmp[mbase, mbase+n_mods), ascending SEQ position
+    __syncwarp();
+
+    // ---- CIGAR walk ----
+    const uint32_t n_cigar = R.n_cigar;
+    if (n_cigar == 0 || n_mods == 0) return status;  // get_mod_poss_on_ref returns 0: record dropped
+    const int cg = rev ? -1 : 0;
+    const uint32_t qs = R.pos;
+    uint32_t clip = 0, j0 = 0;
+    {
+        uint32_t c0 = cigar[0];
+        if ((c0 & 15u) == 4u) { clip = c0 >> 4; j0 = 1; }
+    }
+    uint32_t n_out = 0;
+    uint32_t last_pos = 0;
+    bool have_last = false, unsorted = false;
+    // leading soft clip: silently consume mods inside it, emit a mod sitting exactly at the clip edge
+    uint32_t it0 = 0;
+    if (j0) {
+        // first index with t >= clip (mods ascending)
+        uint32_t lo_i = 0, hi_i = n_mods;
+        while (lo_i < hi_i) {
+            uint32_t mid = (lo_i + hi_i) >> 1;
+            if (mpos[mbase + mid] < clip) lo_i = mid + 1; else hi_i = mid;
+        }
+        it0 = lo_i;
+        if (it0 < n_mods && mpos[mbase + it0] == clip) {
+            if (lane == 0 && n_out < cap) { opos[n_out] = qs + (uint32_t)cg; ocat[n_out] = mcat[mbase + it0]; }
+            last_pos = qs + (uint32_t)cg;
+            have_last = true;
+            n_out = 1;
+            it0++;
+        }
+    }
+    bool stale = j0 && it0 >= n_mods;  // every trigger was consumed by the clip: the last one lingers
+    const uint32_t stale_t = mpos[mbase + n_mods - 1];
+    const uint8_t stale_cat = mcat[mbase + n_mods - 1];
+    const uint32_t i_ref = qs - clip;
+    uint32_t i_read = clip;
+    int32_t offset = 0;
+    uint32_t tcur = it0;
+    uint32_t n_mi = 0;
+    bool stopped = false, fatal = false, first_mi_seen = false;
+    __syncwarp();
+    for (uint32_t cbase = j0; !stopped; cbase += 32) {
+        const bool more = cbase < n_cigar;
+        uint32_t op = 0xf, L = 0;
+        bool in = false;
+        if (more) {
+            uint32_t idx = cbase + lane;
+            in = idx < n_cigar;
+            if (in) { uint32_t c = cigar[idx]; op = c & 15u; L = c >> 4; }
+        }
+        // first stopping op in this group of 32
+        unsigned stopm = __ballot_sync(FULL_MASK, in && op >= 3u);
+        int stop_lane = stopm ? __ffs(stopm) - 1 : 32;
+        if (stopm) {
+            uint32_t sop = __shfl_sync(FULL_MASK, op, stop_lane);
+            if (sop >= 5u) fatal = true;
+            stopped = true;
+        }
+        if (!more) stopped = true;
+        const bool act = in && (int)lane < stop_lane;
+        const bool isMI = act && op <= 1u;
+        uint32_t adv = isMI ? L : 0u;
+        int32_t doff = !act ? 0 : (op == 2u ? (int32_t)L : (op == 1u ? -(int32_t)L : 0));
+        uint32_t incl_adv = warp_inclusive_sum(adv);
+        int32_t incl_off = warp_inclusive_sum(doff);
+        unsigned mim = __ballot_sync(FULL_MASK, isMI);
+        if (isMI) {
+            uint32_t slot = n_mi + __popc(mim & ((1u << lane) - 1u));
+            sm.mi_end[slot] = i_read + incl_adv;
+            sm.mi_off[slot] = op == 0u ? offset + (incl_off - doff) : MI_DROP;
+        }
+        n_mi += __popc(mim);
+        i_read += __shfl_sync(FULL_MASK, incl_adv, 31);
+        offset += __shfl_sync(FULL_MASK, incl_off, 31);
+        __syncwarp();
+        // flush when the stage is nearly full or the walk is over
+        if (n_mi + 32 > DEC_MI_CAP || stopped) {
+            if (n_mi > 0) {
+                if (stale && !first_mi_seen) {
+                    // blockjoin.c:663-665 with a lingering trigger: the first M/I op handles it once
+                    int32_t o = sm.mi_off[0];
+                    if (o != MI_DROP) {
+                        uint32_t pos = i_ref + stale_t + (uint32_t)cg + (uint32_t)o;
+                        if (have_last && last_pos == pos) {
+                            if (lane == 0) ocat[n_out - 1] = stale_cat;
+                        } else {
+                            if (lane == 0 && n_out < cap) { opos[n_out] = pos; ocat[n_out] = stale_cat; }
+                            if (have_last && pos < last_pos) unsorted = true;
+                            n_out++;
+                            last_pos = pos;
+                            have_last = true;
+                        }
+                    }
+                    stale = false;
+                }
+                first_mi_seen = true;
+                const uint32_t chunk_last_end = sm.mi_end[n_mi - 1];
+                while (tcur < n_mods) {
+                    uint32_t it = tcur + lane;
+                    uint32_t t = 0;
+                    bool mine = false;
+                    if (it < n_mods) { t = mpos[mbase + it]; mine = t <= chunk_last_end; }
+                    unsigned am = __ballot_sync(FULL_MASK, mine);
+                    if (am == 0) break;
+                    bool emit = false;
+                    uint32_t pos = 0;
+                    uint8_t cat = 0;
+                    if (mine) {
+                        uint32_t lo_j = 0, hi_j = n_mi - 1;  // first op with end >= t
+                        while (lo_j < hi_j) {
+                            uint32_t mid = (lo_j + hi_j) >> 1;
+                            if (sm.mi_end[mid] >= t) hi_j = mid; else lo_j = mid + 1;
+                        }
+                        int32_t o = sm.mi_off[lo_j];
+                        if (o != MI_DROP) {
+                            emit = true;
+                            pos = i_ref + t + (uint32_t)cg + (uint32_t)o;
+                            cat = mcat[mbase + it];
+                        }
+                    }
+                    // de-duplicate against the previously emitted position (blockjoin.c:704-709)
+                    unsigned em = __ballot_sync(FULL_MASK, emit);
+                    unsigned below = em & ((1u << lane) - 1u);
+                    int prev_lane = below ? 31 - __clz((int)below) : -1;
+                    uint32_t prev_pos = __shfl_sync(FULL_MASK, pos, prev_lane < 0 ? 0 : prev_lane);
+                    bool has_prev = prev_lane >= 0 || have_last;
+                    if (prev_lane < 0) prev_pos = last_pos;
+                    bool head = emit && !(has_prev && prev_pos == pos);
+                    if (head && has_prev && pos < prev_pos) unsorted = true;
+                    unsigned hm = __ballot_sync(FULL_MASK, head);
+                    // index of the run this lane belongs to
+                    uint32_t heads_incl = __popc(hm & ((2u << lane) - 1u));
+                    uint32_t slot = n_out + heads_incl - 1;  // for a continuation of the carried run heads_incl==0 -> n_out-1
+                    unsigned above = em & ~((2u << lane) - 1u);
+                    int next_lane = above ? __ffs(above) - 1 : -1;
+                    uint32_t next_pos = __shfl_sync(FULL_MASK, pos, next_lane < 0 ? 0 : next_lane);
+                    bool last_of_run = emit && (next_lane < 0 || next_pos != pos);
+                    if (head && slot < cap) opos[slot] = pos;
+                    if (last_of_run && slot < cap) ocat[slot] = cat;
+                    n_out += __popc(hm);
+                    if (em) {
+                        int ll = 31 - __clz((int)em);
+                        last_pos = __shfl_sync(FULL_MASK, pos, ll);
+                        have_last = true;
+                    }
+                    tcur += __popc(am);
+                    __syncwarp();
+                    if (__popc(am) < 32) break;
+                }
+            }
+            n_mi = 0;
+        }
+    }
+    unsorted = __any_sync(FULL_MASK, unsorted);
+    if (fatal) return status | RS_FATAL_CIGAR;
+    if (n_out > cap) status |= RS_OVERFLOW;
+    if (unsorted) status |= RS_UNSORTED;
+    *n_calls_out = n_out;
+    return status | RS_KEPT;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General sequential path (lane 0): any number of C+m streams, more than N_MODS streams, implicit
+// canonical calls.  Follows the reference statement by statement.
+// ---------------------------------------------------------------------------------------------
+constexpr int GEN_MAXSEG = 64;
+
+struct GenSeg {
+    uint32_t list_begin, list_end, n_delta, total, ml_base;
+    uint32_t n_codes;
+    uint32_t code_begin;   // offset of the first code character
+    uint8_t canon, is_chebi;
+    // walk state
+    uint32_t cursor;       // forward: offset of the next ','; reverse: offset just past the current delta
+    uint32_t next_target;  // index among matching bases (from the left of SEQ) of the next listed base
+    uint32_t match_idx;
+    uint32_t k;            // forward: next delta index; reverse: deltas still to hand out
+};
+
+__device__ uint32_t gen_parse_uint(const uint8_t *s, uint32_t b, uint32_t e, uint32_t *next) {
+    uint32_t v = 0;
+    while (b < e && is_digit(s[b])) { v = v * 10 + (s[b] - '0'); b++; }
+    *next = b;
+    return v;
+}
+
+struct CallSink {
+    uint32_t *pos;
+    uint8_t *cat;
+    uint32_t n, cap;
+    bool unsorted;
+    __device__ void push(uint32_t p, uint8_t c) {
+        if (n > 0 && n <= cap && p <= pos[n - 1]) unsorted = true;
+        if (n < cap) { pos[n] = p; cat[n] = c; }
+        n++;
+    }
+    __device__ bool last_is(uint32_t p) const { return n > 0 && n <= cap && pos[n - 1] == p; }
+    __device__ void set_last_cat(uint8_t c) { if (n > 0 && n <= cap) cat[n - 1] = c; }
+};
+
+__device__ void gen_implicit_fill(CallSink &out, const uint8_t *seq, uint32_t len, uint32_t from, uint32_t until,
+                                  uint32_t i_ref, int32_t offset) {
+    for (uint32_t t = from; t < until; t++) {
+        if (t < len - 1 && seq_nib(seq, t) == 2u && seq_nib(seq, t + 1) == 4u) {
+            uint32_t p = i_ref + t + (uint32_t)offset;
+            if (!out.last_is(p)) out.push(p, 1);
+            t++;
+        }
+    }
+}
+
+__device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenSeg *segs, uint32_t *n_calls_out) {
+    const uint8_t *blob = P.blob;
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(blob + (size_t)R.cigar_off * 16);
+    const uint8_t *seq = blob + (size_t)R.seq_off * 16;
+    const uint8_t *mm = blob + (size_t)R.mm_off * 16;
+    const uint8_t *ml = blob + (size_t)R.ml_off * 16;
+    const uint32_t len = R.l_qseq, mm_len = R.mm_len;
+    const bool rev = (R.flags & 16u) != 0, has_ml = (R.flags & RF_HAS_ML) != 0;
+    uint32_t *mpos = P.tmp_mpos + R.calls_off;
+    uint8_t *mcat = P.tmp_mcat + R.calls_off;
+    const uint32_t cap = R.calls_cap;
+    uint32_t status = RS_SLOWPATH;
+    *n_calls_out = 0;
+    int n_seg = 0;
+    bool bad = false;
+    if (!(R.flags & RF_HAS_MM)) n_seg = 0;
+    else if (R.flags & RF_MALFORMED) bad = true;
+    else {
+        uint32_t p = 0, ml_used = 0, n_streams = 0;
+        while (p < mm_len && !bad) {
+            if (n_seg >= GEN_MAXSEG) { *n_calls_out = 0; return status | RS_MM_ERROR | RS_OVERFLOW | RS_FATAL_CIGAR; }
+            GenSeg &g = segs[n_seg];
+            int canon = base_code_of(mm[p]);
+            if (canon < 0) { bad = true; break; }
+            p++;
+            if (p >= mm_len || (mm[p] != '+' && mm[p] != '-')) { bad = true; break; }
+            p++;
+            g.code_begin = p;
+            g.is_chebi = 0;
+            g.n_codes = 0;
+            if (p < mm_len && is_digit(mm[p])) { while (p < mm_len && is_digit(mm[p])) p++; g.n_codes = 1; g.is_chebi = 1; }
+            else {
+                while (p < mm_len && is_alpha(mm[p])) { g.n_codes++; p++; }
+                if (p >= mm_len) { bad = true; break; }
+            }
+            if (p < mm_len && (mm[p] == '.' || mm[p] == '?')) p++;
+            else if (p >= mm_len || (mm[p] != ',' && mm[p] != ';')) { bad = true; break; }
+            if (g.n_codes > 0 && n_streams + g.n_codes >= 256) { bad = true; break; }
+            g.list_begin = p;
+            g.n_delta = 0;
+            g.total = 0;
+            while (p < mm_len && mm[p] == ',') {
+                p++;
+                if (p >= mm_len || !is_digit(mm[p])) { bad = true; break; }
+                uint32_t nx;
+                uint32_t v = gen_parse_uint(mm, p, mm_len, &nx);
+                p = nx;
+                g.n_delta++;
+                g.total += v + 1;
+            }
+            if (bad) break;
+            if (p >= mm_len || mm[p] != ';') { bad = true; break; }
+            g.list_end = p;
+            p++;
+            g.canon = (uint8_t)canon;
+            g.ml_base = ml_used;
+            if (has_ml && ml_used + g.n_delta * g.n_codes > R.ml_len) { bad = true; break; }
+            ml_used += g.n_delta * g.n_codes;
+            n_streams += g.n_codes;
+            n_seg++;
+        }
+        if (!bad && has_ml && ml_used != R.ml_len) bad = true;
+        if (!bad && rev) {
+            uint32_t freq[16];
+            for (int i = 0; i < 16; i++) freq[i] = 0;
+            for (uint32_t i = 0; i < len; i++) freq[seq_nib(seq, i)]++;
+            for (int s = 0; s < n_seg; s++) {
+                GenSeg &g = segs[s];
+                if (g.n_codes == 0) continue;
+                uint32_t f = freq[comp_code(g.canon)];
+                if (g.total > f) { bad = true; break; }
+                g.next_target = f - g.total;  // lead
+            }
+        }
+    }
+    if (bad) { status |= RS_MM_ERROR; n_seg = 0; }
+    // ---- walk SEQ, blockjoin.c:832-882 on top of the stateful iterator ----
+    for (int s = 0; s < n_seg; s++) {
+        GenSeg &g = segs[s];
+        g.match_idx = 0;
+        if (!rev) {
+            g.k = 0;
+            g.cursor = g.list_begin;
+            if (g.n_delta > 0) {
+                uint32_t nx;
+                uint32_t d = gen_parse_uint(mm, g.cursor + 1, mm_len, &nx);
+                g.cursor = nx;
+                g.next_target = d;
+            }
+        } else {
+            g.k = g.n_delta;          // deltas not yet handed out; the left-most listed base is delta n-1
+            g.cursor = g.list_end;    // just past the last delta
+        }
+    }
+    uint32_t n_mods = 0;
+    bool has_implicit = false, mod_overflow = false;
+    bool any_left = false;
+    for (int s = 0; s < n_seg; s++) if (segs[s].n_delta > 0 && segs[s].n_codes > 0) any_left = true;
+    for (uint32_t p = 0; p < len && any_left; p++) {
+        uint32_t code = seq_nib(seq, p);
+        uint32_t mcode = rev ? comp_code(code) : code;
+        uint32_t n_here = 0;
+        uint32_t first_new = n_mods;
+        bool imp_here = false;
+        for (int s = 0; s < n_seg; s++) {
+            GenSeg &g = segs[s];
+            if (g.n_codes == 0 || g.n_delta == 0) continue;
+            if (mcode != g.canon && g.canon != 15) continue;
+            bool done = !rev ? g.k >= g.n_delta : g.k == 0;
+            if (!done && g.match_idx == g.next_target) {
+                uint32_t which = !rev ? g.k : g.k - 1;
+                n_here += g.n_codes;
+                if (g.canon == 2 && !g.is_chebi && p < len - 1 && p > 0) {
+                    for (uint32_t c = 0; c < g.n_codes; c++) {
+                        if (mm[g.code_begin + c] != 'm') continue;
+                        bool ok = code == 2u ? seq_nib(seq, p + 1) == 4u : seq_nib(seq, p - 1) == 2u;
+                        if (!ok) { imp_here = true; continue; }
+                        uint32_t q = has_ml ? ml[g.ml_base + which * g.n_codes + c] : 255u;
+                        if (n_mods < cap) { mpos[n_mods] = p; mcat[n_mods] = q < P.lo ? 1 : (q >= P.hi ? 0 : 2); }
+                        else mod_overflow = true;
+                        n_mods++;
+                    }
+                }
+                // advance to the next listed base of this segment
+                if (!rev) {
+                    g.k++;
+                    if (g.k < g.n_delta) {
+                        uint32_t nx;
+                        uint32_t d = gen_parse_uint(mm, g.cursor + 1, mm_len, &nx);
+                        g.cursor = nx;
+                        g.next_target = g.match_idx + 1 + d;
+                    }
+                } else {
+                    // skip count before the next (further right) listed base is the delta we just consumed
+                    uint32_t b = g.cursor;  // just past delta `which`
+                    while (b > g.list_begin && mm[b - 1] != ',') b--;
+                    uint32_t nx;
+                    uint32_t d = gen_parse_uint(mm, b, mm_len, &nx);
+                    g.cursor = b - 1;       // the ',' in front of it = just past delta which-1
+                    g.k--;
+                    g.next_target = g.match_idx + 1 + d;
+                }
+            }
+            g.match_idx++;
+        }
+        if (n_here > N_MODS_LIMIT) n_mods = first_new;  // "mod reading buffer was length 10 but iter saw n": position skipped
+        else if (imp_here) has_implicit = true;
+    }
+    if (has_implicit) status |= RS_HAS_IMPLICIT;
+    if (mod_overflow) { *n_calls_out = n_mods; return status | RS_OVERFLOW; }
+
+    // ---- get_mod_poss_on_ref, blockjoin.c:605-792 ----
+    const uint32_t n_cigar = R.n_cigar;
+    if (n_cigar == 0 || n_mods == 0) return status;
+    CallSink out;
+    out.pos = P.calls_pos + R.calls_off;
+    out.cat = P.calls_cat + R.calls_off;
+    out.n = 0; out.cap = cap; out.unsorted = false;
+    const int cg = rev ? -1 : 0;
+    uint32_t i_read = 0, i_ref = R.pos, it = 0, next = mpos[0];
+    uint8_t nq = mcat[0];
+    uint32_t ic = 0;
+    if ((cigar[0] & 15u) == 4u) {
+        i_read = cigar[0] >> 4;
+        while (next < i_read) {
+            it++;
+            if (it < n_mods) { next = mpos[it]; nq = mcat[it]; } else break;
+        }
+        if (next == i_read) {
+            out.push(i_ref + (uint32_t)cg, nq);
+            it++;
+            if (it < n_mods) { next = mpos[it]; nq = mcat[it]; }
+        }
+        i_ref -= cigar[0] >> 4;
+        ic = 1;
+    }
+    int32_t offset = 0;
+    bool fatal = false;
+    for (; ic < n_cigar; ic++) {
+        uint32_t op = cigar[ic] & 15u, L = cigar[ic] >> 4;
+        if (op <= 1u) {
+            uint32_t pos_canonical = i_read;
+            while (i_read + L >= next) {
+                if (op == 0u && next != 0xffffffffu) {
+                    if (has_implicit) {
+                        uint32_t until = next - 1 < i_read + L ? next - 1 : i_read + L;
+                        gen_implicit_fill(out, seq, len, pos_canonical, until, i_ref, offset);
+                    }
+                    uint32_t pt = i_ref + next + (uint32_t)cg + (uint32_t)offset;
+                    if (out.last_is(pt)) out.set_last_cat(nq); else out.push(pt, nq);
+                    pos_canonical = cg == 0 ? next + 1 : next + 2;
+                }
+                it++;
+                if (it >= n_mods) { next = 0xffffffffu; break; }
+                next = mpos[it];
+                nq = mcat[it];
+            }
+            if (op == 0u) {
+                if (has_implicit) gen_implicit_fill(out, seq, len, pos_canonical, i_read + L, i_ref, offset);
+                i_read += L;
+            } else { i_read += L; offset -= (int32_t)L; }
+        } else if (op == 2u) offset += (int32_t)L;
+        else if (op == 3u || op == 4u) break;
+        else { fatal = true; break; }
+    }
+    if (fatal) return status | RS_FATAL_CIGAR;
+    *n_calls_out = out.n;
+    if (out.n > cap) status |= RS_OVERFLOW;
+    if (out.unsorted) status |= RS_UNSORTED;
+    return status | RS_KEPT;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel: one warp per record.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_WARPS * 32) decode_kernel(DecodeParams P) {
+    __shared__ DecodeWarpSmem smem[DEC_WARPS];
+    __shared__ GenSeg gsegs[DEC_WARPS][GEN_MAXSEG];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t ri = blockIdx.x * DEC_WARPS + warp;
+    if (ri >= P.n_reads) return;  // whole warp leaves together
+    const ReadRec R = P.reads[ri];
+    DecodeWarpSmem &sm = smem[warp];
+    // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
+    uint32_t rlen = 0;
+    for (uint32_t i = lane; i < R.n_cigar; i += 32) {
+        uint32_t c = cigar[i], op = c & 15u;
+        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) rlen += c >> 4;
+    }
+    rlen = warp_sum(rlen);
+    if (R.flags & 4u) rlen = 0;
+    if (rlen == 0) rlen = 1;
+    uint32_t n_calls = 0;
+    bool need_generic = false;
+    uint32_t status = decode_fast(P, R, sm, &n_calls, &need_generic);
+    need_generic = __any_sync(FULL_MASK, need_generic);
+    if (need_generic) {
+        if (lane == 0) status = decode_generic(P, R, gsegs[warp], &n_calls);
+        status = __shfl_sync(FULL_MASK, status, 0);
+        n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
+    }
+    if (lane == 0) {
+        P.r_ncalls[ri] = (status & RS_KEPT) || (status & RS_OVERFLOW) ? n_calls : 0;
+        P.r_status[ri] = status;
+        P.r_end[ri] = R.pos + rlen;
+    }
+}
+
+}  // namespace pomfret_gpu
+#endif

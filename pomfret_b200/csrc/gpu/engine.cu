@@ -1,0 +1,759 @@
+// libpomfret_gpu: batch staging, kernel launches and the C ABI declared in include/pomfret_gpu.h.
+//
+// One batch = one region chunk of one host worker: packed records in a pinned arena, one async H2D
+// copy, then decode -> read sets -> pileup/sites -> methmers -> greedy join on the batch's stream.
+// The only host round trips are (1) the pool-size read after methmer sizing (two integers) and
+// (2) collect().  There is no CPU fallback: without a CUDA device init() fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include "gpu_rt.h"
+#include "types.h"
+#include "decode.cuh"
+#include "readset.cuh"
+#include "pileup.cuh"
+#include "methmer.cuh"
+#include "join.cuh"
+#include "haptag.cuh"
+#include "pomfret_gpu.h"
+#include "htslib/kfunc.h"
+
+using namespace pomfret_gpu;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fprintf(stderr, "[E::pomfret_gpu] %s failed at %s:%d: %s\n", #call, __FILE__, __LINE__, \
+                    cudaGetErrorString(e_));                                                      \
+            return POMFRET_GPU_ERR_CUDA;                                                          \
+        }                                                                                         \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        if (cudaMalloc(&p, want) != cudaSuccess) return POMFRET_GPU_ERR_NOMEM;
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0, len = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        size_t want = std::max(bytes + bytes / 2, (size_t)1 << 20);
+        void *q = nullptr;
+        if (cudaMallocHost(&q, want) != cudaSuccess) return POMFRET_GPU_ERR_NOMEM;
+        if (p) { memcpy(q, p, len); cudaFreeHost(p); }
+        p = (uint8_t *)q; cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = len = 0; }
+};
+
+template <typename T> struct PinVec {
+    PinBuf b;
+    size_t n = 0;
+    int push(const T &v) {
+        if (int rc = b.reserve((n + 1) * sizeof(T))) return rc;
+        reinterpret_cast<T *>(b.p)[n++] = v;
+        b.len = n * sizeof(T);
+        return 0;
+    }
+    int resize(size_t m) {
+        if (int rc = b.reserve(m * sizeof(T))) return rc;
+        n = m; b.len = n * sizeof(T);
+        return 0;
+    }
+    T *data() { return reinterpret_cast<T *>(b.p); }
+    T &operator[](size_t i) { return reinterpret_cast<T *>(b.p)[i]; }
+    void clear() { n = 0; b.len = 0; }
+    void release() { b.release(); n = 0; }
+};
+
+enum Stage { ST_EMPTY = 0, ST_SUBMITTED = 1, ST_DECODED = 2, ST_PILED = 3, ST_JOINED = 4, ST_HAPTAGGED = 5 };
+
+}  // namespace
+
+struct pomfret_gpu_ctx {
+    std::vector<int> devices;
+    int n_workers = 1;
+    std::mutex mu;
+};
+
+struct pomfret_gpu_batch {
+    pomfret_gpu_ctx *ctx = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10] = {};
+    int stage = ST_EMPTY;
+    // host staging (pinned)
+    PinBuf h_blob;
+    PinVec<ReadRec> h_reads;
+    PinVec<WindowRec> h_win;
+    PinVec<uint32_t> h_read_win;
+    PinVec<uint32_t> h_win_base, h_win_tile_first;
+    PinVec<TileRec> h_tiles;
+    PinVec<WindowState> h_state;
+    PinVec<uint32_t> h_u32;   // scratch for small D2H reads
+    std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
+    uint64_t calls_total = 0;
+    uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
+    // device
+    DevBuf d_blob, d_reads, d_win, d_read_win, d_calls_pos, d_calls_cat, d_tmp_rank, d_tmp_mpos, d_tmp_mcat;
+    DevBuf d_r_ncalls, d_r_status, d_r_end, d_r_id, d_rs_src, d_rs_rev, d_rs_hp;
+    DevBuf d_ids[4], d_state, d_tiles, d_win_base, d_win_tile_first, d_tile_out, d_tile_count;
+    DevBuf d_site_pos, d_site_start[2], d_site_len[2];
+    DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
+    DevBuf d_tags[2], d_order[2];
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status;
+    uint32_t pool_cap = 0, tab_sites = 0, site_total = 0;
+    pomfret_gpu_config cfg = {};
+    uint32_t lo = 0, hi = 0;
+    pomfret_gpu_timing tm = {};
+    bool have_results = false;
+    std::vector<uint8_t> host_tags_fwd, host_tags_bwd;
+    std::vector<int32_t> host_rid;
+};
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+extern "C" {
+
+const char *pomfret_gpu_version(void) { return "pomfret_b200 0.1 (sm_100a)"; }
+
+const char *pomfret_gpu_strerror(int rc) {
+    switch (rc) {
+    case POMFRET_GPU_OK: return "ok";
+    case POMFRET_GPU_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case POMFRET_GPU_ERR_CUDA: return "CUDA runtime error";
+    case POMFRET_GPU_ERR_NOMEM: return "out of memory";
+    case POMFRET_GPU_ERR_ARG: return "invalid argument";
+    case POMFRET_GPU_ERR_STATE: return "call out of order";
+    case POMFRET_GPU_ERR_FATAL_CIGAR: return "fatal: unknown cigar operation";
+    case POMFRET_GPU_ERR_DUP_QNAME: return "duplicated read name";
+    case POMFRET_GPU_ERR_UNSUPPORTED: return "input outside the engine's compiled limits";
+    case POMFRET_GPU_ERR_MISSING_MD: return "MD tag missing";
+    case POMFRET_GPU_ERR_BAD_MD: return "invalid MD";
+    default: return "unknown error";
+    }
+}
+
+int pomfret_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pomfret_gpu_init(pomfret_gpu_ctx **out, const int *devices, int n_devices, int n_workers) {
+    if (!out) return POMFRET_GPU_ERR_ARG;
+    *out = nullptr;
+    int n = pomfret_gpu_device_count();
+    if (n <= 0) return POMFRET_GPU_ERR_NO_DEVICE;
+    pomfret_gpu_ctx *c = new pomfret_gpu_ctx();
+    if (devices && n_devices > 0) {
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= n) { delete c; return POMFRET_GPU_ERR_ARG; }
+            c->devices.push_back(devices[i]);
+        }
+    } else for (int i = 0; i < n; i++) c->devices.push_back(i);
+    c->n_workers = n_workers > 0 ? n_workers : 1;
+    *out = c;
+    return POMFRET_GPU_OK;
+}
+
+void pomfret_gpu_destroy(pomfret_gpu_ctx *ctx) { delete ctx; }
+
+int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfret_gpu_batch **out) {
+    (void)worker;
+    if (!ctx || !out) return POMFRET_GPU_ERR_ARG;
+    if (std::find(ctx->devices.begin(), ctx->devices.end(), device) == ctx->devices.end()) return POMFRET_GPU_ERR_ARG;
+    CK(cudaSetDevice(device));
+    pomfret_gpu_batch *b = new pomfret_gpu_batch();
+    b->ctx = ctx;
+    b->device = device;
+    CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    for (auto &e : b->ev) CK(cudaEventCreate(&e));
+#ifndef POMFRET_CUDA_EMU
+    CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
+#endif
+    *out = b;
+    return POMFRET_GPU_OK;
+}
+
+int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    b->h_blob.len = 0;
+    b->h_reads.clear(); b->h_win.clear(); b->h_read_win.clear();
+    b->h_end.clear();
+    b->calls_total = 0;
+    b->alg_decode_bytes = b->alg_haptag_bytes = 0;
+    b->stage = ST_EMPTY;
+    b->have_results = false;
+    memset(&b->tm, 0, sizeof(b->tm));
+    return POMFRET_GPU_OK;
+}
+
+void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    DevBuf *all[] = {&b->d_blob, &b->d_reads, &b->d_win, &b->d_read_win, &b->d_calls_pos, &b->d_calls_cat, &b->d_tmp_rank,
+                     &b->d_tmp_mpos, &b->d_tmp_mcat, &b->d_r_ncalls, &b->d_r_status, &b->d_r_end, &b->d_r_id, &b->d_rs_src,
+                     &b->d_rs_rev, &b->d_rs_hp, &b->d_ids[0], &b->d_ids[1], &b->d_ids[2], &b->d_ids[3], &b->d_state,
+                     &b->d_tiles, &b->d_win_base, &b->d_win_tile_first, &b->d_tile_out, &b->d_tile_count, &b->d_site_pos,
+                     &b->d_site_start[0], &b->d_site_start[1], &b->d_site_len[0], &b->d_site_len[1], &b->d_mm_xl[0],
+                     &b->d_mm_xl[1], &b->d_mm_xr[0], &b->d_mm_xr[1], &b->d_mm_off[0], &b->d_mm_off[1], &b->d_mm_n[0],
+                     &b->d_mm_n[1], &b->d_mm_start[0], &b->d_mm_start[1], &b->d_pool_total, &b->d_mmr_pool, &b->d_ent_pool,
+                     &b->d_tab, &b->d_tags[0], &b->d_tags[1], &b->d_order[0], &b->d_order[1], &b->d_known, &b->d_bases,
+                     &b->d_known_first, &b->d_hap_tag, &b->d_hap_status};
+    for (DevBuf *d : all) d->release();
+    b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
+    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release();
+    for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+static int blob_put(pomfret_gpu_batch *b, const void *src, size_t n, uint32_t *off16) {
+    size_t off = align16(b->h_blob.len);
+    size_t end = align16(off + n);
+    if (int rc = b->h_blob.reserve(end + 1024)) return rc;  // tail slack: kernels stage whole 16-byte lanes
+    if (off > b->h_blob.len) memset(b->h_blob.p + b->h_blob.len, 0, off - b->h_blob.len);
+    if (n) memcpy(b->h_blob.p + off, src, n);
+    memset(b->h_blob.p + off + n, 0, end - (off + n));
+    b->h_blob.len = end;
+    *off16 = (uint32_t)(off / 16);
+    return 0;
+}
+
+int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {
+    if (!b || !r) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+    ReadRec R;
+    memset(&R, 0, sizeof(R));
+    R.pos = r->pos; R.l_qseq = r->l_qseq; R.n_cigar = r->n_cigar;
+    R.flags = r->flag;
+    if (r->tags_malformed) R.flags |= RF_MALFORMED;
+    R.hp = r->hp; R.mn = r->mn;
+    int rc;
+    if ((rc = blob_put(b, r->cigar, (size_t)r->n_cigar * 4, &R.cigar_off))) return rc;
+    if ((rc = blob_put(b, r->seq, ((size_t)r->l_qseq + 1) / 2, &R.seq_off))) return rc;
+    if (r->mm) {
+        R.flags |= RF_HAS_MM;
+        R.mm_len = r->mm_len;
+        if ((rc = blob_put(b, r->mm, r->mm_len, &R.mm_off))) return rc;
+    }
+    if (r->ml_len >= 0) {
+        R.flags |= RF_HAS_ML;
+        R.ml_len = (uint32_t)r->ml_len;
+        if ((rc = blob_put(b, r->ml, (size_t)r->ml_len, &R.ml_off))) return rc;
+    }
+    if (r->md) {
+        R.flags |= RF_HAS_MD;
+        R.md_len = r->md_len;
+        if ((rc = blob_put(b, r->md, r->md_len, &R.md_off))) return rc;
+    }
+    // call slots: one per listed base is enough unless implicit canonical calls appear (then the engine
+    // re-runs the record with the exact count)
+    uint32_t cap = r->ml_len >= 0 ? (uint32_t)r->ml_len : r->mm_len / 2 + 1;
+    if (cap < 4) cap = 4;
+    R.calls_off = (uint32_t)b->calls_total;
+    R.calls_cap = cap;
+    b->calls_total += cap;
+    if (b->calls_total > 0xfff00000ull) return POMFRET_GPU_ERR_UNSUPPORTED;
+    // reference end (tile planning) and algorithmic byte counts
+    uint64_t rlen = 0;
+    for (uint32_t i = 0; i < r->n_cigar; i++) {
+        uint32_t op = r->cigar[i] & 15u;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += r->cigar[i] >> 4;
+    }
+    if (rlen == 0) rlen = 1;
+    b->h_end.push_back((uint32_t)(r->pos + rlen));
+    b->alg_decode_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->mm_len + (r->ml_len > 0 ? r->ml_len : 0);
+    b->alg_haptag_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->md_len + 1;
+    if ((rc = b->h_reads.push(R))) return rc;
+    if ((rc = b->h_read_win.push(0xffffffffu))) return rc;
+    return POMFRET_GPU_OK;
+}
+
+int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
+                                 uint32_t n_reads) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+    if ((uint64_t)first_read + n_reads > b->h_reads.n) return POMFRET_GPU_ERR_ARG;
+    if (n_reads >= 60000) return POMFRET_GPU_ERR_UNSUPPORTED;  // 16-bit count fields
+    WindowRec W;
+    memset(&W, 0, sizeof(W));
+    W.ref_start = ref_start; W.ref_end = ref_end; W.first_read = first_read; W.n_reads = n_reads;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        if (b->h_read_win[first_read + i] != 0xffffffffu) return POMFRET_GPU_ERR_ARG;  // windows must not share records
+        b->h_read_win[first_read + i] = (uint32_t)b->h_win.n;
+    }
+    return b->h_win.push(W);
+}
+
+static int up(pomfret_gpu_batch *b, DevBuf &d, const void *src, size_t bytes) {
+    if (int rc = d.ensure(bytes ? bytes : 16)) return rc;
+    if (bytes) {
+        CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, b->stream));
+        b->tm.bytes_h2d += bytes;
+    }
+    return 0;
+}
+
+int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+    CK(cudaSetDevice(b->device));
+    const size_t nr = b->h_reads.n, nw = b->h_win.n;
+    CK(cudaEventRecord(b->ev[0], b->stream));
+    int rc;
+    // the blob keeps 1 KB of zeroed slack behind the last field
+    if ((rc = b->h_blob.reserve(b->h_blob.len + 1024))) return rc;
+    memset(b->h_blob.p + b->h_blob.len, 0, 1024);
+    if ((rc = up(b, b->d_blob, b->h_blob.p, b->h_blob.len + 1024))) return rc;
+    if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
+    if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
+    if ((rc = up(b, b->d_read_win, b->h_read_win.data(), nr * 4))) return rc;
+    CK(cudaEventRecord(b->ev[1], b->stream));
+    b->stage = ST_SUBMITTED;
+    return POMFRET_GPU_OK;
+}
+
+static int launch_decode(pomfret_gpu_batch *b) {
+    const size_t nr = b->h_reads.n;
+    const size_t slots = (size_t)b->calls_total + 16;
+    int rc;
+    if ((rc = b->d_calls_pos.ensure(slots * 4)) || (rc = b->d_calls_cat.ensure(slots)) || (rc = b->d_tmp_rank.ensure(slots * 4)) ||
+        (rc = b->d_tmp_mpos.ensure(slots * 4)) || (rc = b->d_tmp_mcat.ensure(slots)) || (rc = b->d_r_ncalls.ensure(nr * 4 + 16)) ||
+        (rc = b->d_r_status.ensure(nr * 4 + 16)) || (rc = b->d_r_end.ensure(nr * 4 + 16)))
+        return rc;
+    DecodeParams P;
+    P.reads = b->d_reads.as<ReadRec>();
+    P.n_reads = (uint32_t)nr;
+    P.blob = b->d_blob.as<uint8_t>();
+    P.calls_pos = b->d_calls_pos.as<uint32_t>();
+    P.calls_cat = b->d_calls_cat.as<uint8_t>();
+    P.tmp_rank = b->d_tmp_rank.as<uint32_t>();
+    P.tmp_mpos = b->d_tmp_mpos.as<uint32_t>();
+    P.tmp_mcat = b->d_tmp_mcat.as<uint8_t>();
+    P.r_ncalls = b->d_r_ncalls.as<uint32_t>();
+    P.r_status = b->d_r_status.as<uint32_t>();
+    P.r_end = b->d_r_end.as<uint32_t>();
+    P.lo = b->lo; P.hi = b->hi;
+    if (nr) {
+        unsigned grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS);
+        POMFRET_LAUNCH(decode_kernel, grid, DEC_WARPS * 32, 0, b->stream, P);
+        b->tm.launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int pomfret_gpu_decode(pomfret_gpu_batch *b, uint8_t qual_lo, uint8_t qual_hi) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_SUBMITTED) return POMFRET_GPU_ERR_STATE;
+    CK(cudaSetDevice(b->device));
+    b->lo = qual_lo; b->hi = qual_hi;
+    CK(cudaEventRecord(b->ev[2], b->stream));
+    if (int rc = launch_decode(b)) return rc;
+    CK(cudaEventRecord(b->ev[3], b->stream));
+    b->stage = ST_DECODED;
+    return POMFRET_GPU_OK;
+}
+
+// read sets, pileup tiles, site layout, methmer sizing — everything up to the pool-size round trip
+static int launch_pileup_stages(pomfret_gpu_batch *b) {
+    const size_t nr = b->h_reads.n, nw = b->h_win.n;
+    const pomfret_gpu_config &cfg = b->cfg;
+    int rc;
+    // ---- plan: site capacity per window, position tiles ----
+    b->h_win_base.clear(); b->h_win_tile_first.clear(); b->h_tiles.clear();
+    uint64_t site_total = 0, tile_out_total = 0;
+    const uint32_t cov = (uint32_t)std::max(cfg.cov_for_selection, 1);
+    for (size_t w = 0; w < nw; w++) {
+        WindowRec &W = b->h_win[w];
+        uint64_t caps = 0;
+        uint32_t mn = 0xffffffffu, mx = 0;
+        for (uint32_t i = 0; i < W.n_reads; i++) {
+            const ReadRec &R = b->h_reads[W.first_read + i];
+            caps += R.calls_cap;
+            mn = std::min(mn, R.pos);
+            mx = std::max(mx, b->h_end[W.first_read + i]);
+        }
+        W.site_off = (uint32_t)site_total;
+        W.site_cap = (uint32_t)(caps / (2ull * cov) + 2);
+        site_total += W.site_cap;
+        uint32_t base = W.n_reads ? mn - 1u : 0u;  // calls lie in [read start - 1, read end]
+        uint32_t range = W.n_reads ? mx - base + 2u : 0u;
+        uint32_t n_tiles = (range + PILE_TILE - 1) / PILE_TILE;
+        if ((rc = b->h_win_base.push(base)) || (rc = b->h_win_tile_first.push((uint32_t)b->h_tiles.n))) return rc;
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            TileRec T;
+            T.window = (uint32_t)w; T.tile = t;
+            T.out_off = (uint32_t)tile_out_total;
+            T.out_cap = std::min<uint32_t>(W.site_cap, PILE_TILE);
+            tile_out_total += T.out_cap;
+            if ((rc = b->h_tiles.push(T))) return rc;
+        }
+        if (site_total > 0xfff00000ull || tile_out_total > 0xfff00000ull) return POMFRET_GPU_ERR_UNSUPPORTED;
+    }
+    if ((rc = b->h_win_tile_first.push((uint32_t)b->h_tiles.n))) return rc;
+    b->site_total = (uint32_t)site_total;
+    if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
+    if ((rc = up(b, b->d_win_base, b->h_win_base.data(), nw * 4))) return rc;
+    if ((rc = up(b, b->d_win_tile_first, b->h_win_tile_first.data(), (nw + 1) * 4))) return rc;
+    if ((rc = up(b, b->d_tiles, b->h_tiles.data(), b->h_tiles.n * sizeof(TileRec)))) return rc;
+    const size_t n4 = nr * 4 + 16;
+    if ((rc = b->d_r_id.ensure(n4)) || (rc = b->d_rs_src.ensure(n4)) || (rc = b->d_rs_rev.ensure(n4)) || (rc = b->d_rs_hp.ensure(n4)) ||
+        (rc = b->d_ids[0].ensure(n4)) || (rc = b->d_ids[1].ensure(n4)) || (rc = b->d_ids[2].ensure(n4)) || (rc = b->d_ids[3].ensure(n4)) ||
+        (rc = b->d_state.ensure(nw * sizeof(WindowState) + 16)) || (rc = b->d_tile_out.ensure(tile_out_total * 4 + 16)) ||
+        (rc = b->d_tile_count.ensure(b->h_tiles.n * 4 + 16)) || (rc = b->d_site_pos.ensure(site_total * 4 + 16)) ||
+        (rc = b->d_pool_total.ensure(16)))
+        return rc;
+    for (int d = 0; d < 2; d++) {
+        if ((rc = b->d_site_start[d].ensure(site_total * 4 + 16)) || (rc = b->d_site_len[d].ensure(site_total + 16)) ||
+            (rc = b->d_mm_xl[d].ensure(n4)) || (rc = b->d_mm_xr[d].ensure(n4)) || (rc = b->d_mm_off[d].ensure(n4)) ||
+            (rc = b->d_mm_n[d].ensure(n4)) || (rc = b->d_mm_start[d].ensure(n4)) || (rc = b->d_tags[d].ensure(nr + 16)) ||
+            (rc = b->d_order[d].ensure(n4)))
+            return rc;
+    }
+    CK(cudaMemsetAsync(b->d_pool_total.p, 0, 16, b->stream));
+    if (nw == 0) return 0;
+    // ---- read sets ----
+    ReadsetParams R;
+    R.reads = b->d_reads.as<ReadRec>(); R.win = b->d_win.as<WindowRec>(); R.state = b->d_state.as<WindowState>();
+    R.r_status = b->d_r_status.as<uint32_t>(); R.r_end = b->d_r_end.as<uint32_t>(); R.r_ncalls = b->d_r_ncalls.as<uint32_t>();
+    R.r_id = b->d_r_id.as<int32_t>(); R.rs_src = b->d_rs_src.as<uint32_t>(); R.rs_rev = b->d_rs_rev.as<uint32_t>();
+    R.ids_left = b->d_ids[0].as<uint32_t>(); R.ids_left_strict = b->d_ids[1].as<uint32_t>();
+    R.ids_right = b->d_ids[2].as<uint32_t>(); R.ids_right_strict = b->d_ids[3].as<uint32_t>();
+    R.rs_hp = b->d_rs_hp.as<int32_t>(); R.n_windows = (uint32_t)nw;
+    CK(cudaEventRecord(b->ev[4], b->stream));
+    POMFRET_LAUNCH(readset_kernel, (unsigned)nw, RS_THREADS, 0, b->stream, R);
+    b->tm.launches++;
+    CK(cudaEventRecord(b->ev[5], b->stream));
+    // ---- pileup tiles + site layout ----
+    PileupParams Q;
+    Q.win = b->d_win.as<WindowRec>(); Q.state = b->d_state.as<WindowState>(); Q.tiles = b->d_tiles.as<TileRec>();
+    Q.win_base = b->d_win_base.as<uint32_t>(); Q.reads = b->d_reads.as<ReadRec>(); Q.rs_src = b->d_rs_src.as<uint32_t>();
+    Q.r_ncalls = b->d_r_ncalls.as<uint32_t>(); Q.r_status = b->d_r_status.as<uint32_t>();
+    Q.calls_pos = b->d_calls_pos.as<uint32_t>(); Q.calls_cat = b->d_calls_cat.as<uint8_t>();
+    Q.tile_out = b->d_tile_out.as<uint32_t>(); Q.tile_count = b->d_tile_count.as<uint32_t>();
+    Q.cov = (uint32_t)cfg.cov_for_selection;
+    if (b->h_tiles.n) {
+        POMFRET_LAUNCH(pileup_tile_kernel, (unsigned)b->h_tiles.n, PILE_THREADS, PILE_TILE * 4, b->stream, Q);
+        b->tm.launches++;
+    }
+    SitesParams S;
+    S.win = b->d_win.as<WindowRec>(); S.state = b->d_state.as<WindowState>(); S.tiles = b->d_tiles.as<TileRec>();
+    S.win_tile_first = b->d_win_tile_first.as<uint32_t>(); S.tile_out = b->d_tile_out.as<uint32_t>();
+    S.tile_count = b->d_tile_count.as<uint32_t>(); S.site_pos = b->d_site_pos.as<uint32_t>();
+    for (int d = 0; d < 2; d++) { S.site_start[d] = b->d_site_start[d].as<uint32_t>(); S.site_len[d] = b->d_site_len[d].as<uint8_t>(); }
+    S.k = cfg.k; S.k_span = cfg.k_span;
+    POMFRET_LAUNCH(sites_finalize_kernel, (unsigned)nw, 256, 0, b->stream, S);
+    b->tm.launches++;
+    CK(cudaEventRecord(b->ev[6], b->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static void fill_methmer_params(pomfret_gpu_batch *b, MethmerParams &M) {
+    M.win = b->d_win.as<WindowRec>(); M.state = b->d_state.as<WindowState>(); M.read_win = b->d_read_win.as<uint32_t>();
+    M.reads = b->d_reads.as<ReadRec>(); M.rs_src = b->d_rs_src.as<uint32_t>(); M.r_ncalls = b->d_r_ncalls.as<uint32_t>();
+    M.r_status = b->d_r_status.as<uint32_t>(); M.calls_pos = b->d_calls_pos.as<uint32_t>(); M.calls_cat = b->d_calls_cat.as<uint8_t>();
+    for (int d = 0; d < 2; d++) {
+        M.site_start[d] = b->d_site_start[d].as<uint32_t>(); M.site_len[d] = b->d_site_len[d].as<uint8_t>();
+        M.mm_xl[d] = b->d_mm_xl[d].as<uint32_t>(); M.mm_xr[d] = b->d_mm_xr[d].as<uint32_t>(); M.mm_off[d] = b->d_mm_off[d].as<uint32_t>();
+        M.mm_n[d] = b->d_mm_n[d].as<uint32_t>(); M.mm_start[d] = b->d_mm_start[d].as<uint32_t>();
+    }
+    M.pool_total = b->d_pool_total.as<uint32_t>(); M.mmr_pool = b->d_mmr_pool.as<uint32_t>(); M.ent_pool = b->d_ent_pool.as<uint32_t>();
+    M.pool_cap = b->pool_cap; M.n_slots = (uint32_t)b->h_reads.n; M.k = b->cfg.k;
+}
+
+int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
+    if (!b || !cfg) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_DECODED) return POMFRET_GPU_ERR_STATE;
+    if (cfg->k < 1 || cfg->k > kMaxK || cfg->n_candidates_per_iter > JOIN_MAX_CAND || cfg->n_candidates_per_iter < 1)
+        return POMFRET_GPU_ERR_UNSUPPORTED;
+    CK(cudaSetDevice(b->device));
+    b->cfg = *cfg;
+    const size_t nr = b->h_reads.n, nw = b->h_win.n;
+    int rc;
+    if ((rc = launch_pileup_stages(b))) return rc;
+    if (nw == 0) { b->stage = ST_PILED; return POMFRET_GPU_OK; }
+    MethmerParams M;
+    fill_methmer_params(b, M);
+    POMFRET_LAUNCH(methmer_size_kernel, (unsigned)nw, RS_THREADS, 0, b->stream, M);
+    b->tm.launches++;
+    // ---- the one round trip: pool sizes (and whether any record ran out of call slots) ----
+    if ((rc = b->h_u32.resize(4))) return rc;
+    CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 8, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    const uint32_t mmr_total = b->h_u32[0], tab_sites = b->h_u32[1];
+    b->pool_cap = mmr_total + 64;
+    b->tab_sites = tab_sites;
+    const size_t row_words = ((size_t)1 << (2 * cfg->k)) + 1;
+    if ((rc = b->d_mmr_pool.ensure((size_t)b->pool_cap * 4)) || (rc = b->d_ent_pool.ensure((size_t)b->pool_cap * 4)) ||
+        (rc = b->d_tab.ensure(((size_t)tab_sites + 1) * row_words * 4)))
+        return rc;
+    fill_methmer_params(b, M);
+    unsigned grid = (unsigned)((nr * 2 + MMR_WARPS - 1) / MMR_WARPS);
+    if (grid) {
+        POMFRET_LAUNCH(methmer_fill_kernel, grid, MMR_WARPS * 32, 0, b->stream, M);
+        b->tm.launches++;
+    }
+    CK(cudaEventRecord(b->ev[7], b->stream));
+    CK(cudaGetLastError());
+    b->stage = ST_PILED;
+    return POMFRET_GPU_OK;
+}
+
+int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
+    if (!b || !cfg) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_PILED) return POMFRET_GPU_ERR_STATE;
+    if (cfg->k != b->cfg.k) return POMFRET_GPU_ERR_ARG;
+    CK(cudaSetDevice(b->device));
+    const size_t nw = b->h_win.n;
+    JoinParams J;
+    J.win = b->d_win.as<WindowRec>(); J.state = b->d_state.as<WindowState>(); J.rs_rev = b->d_rs_rev.as<uint32_t>();
+    J.rs_hp = b->d_rs_hp.as<int32_t>();
+    J.ids_left = b->d_ids[0].as<uint32_t>(); J.ids_left_strict = b->d_ids[1].as<uint32_t>();
+    J.ids_right = b->d_ids[2].as<uint32_t>(); J.ids_right_strict = b->d_ids[3].as<uint32_t>();
+    J.site_pos = b->d_site_pos.as<uint32_t>();
+    for (int d = 0; d < 2; d++) {
+        J.mm_off[d] = b->d_mm_off[d].as<uint32_t>(); J.mm_n[d] = b->d_mm_n[d].as<uint32_t>(); J.mm_start[d] = b->d_mm_start[d].as<uint32_t>();
+        J.tags[d] = b->d_tags[d].as<uint8_t>(); J.order[d] = b->d_order[d].as<uint32_t>();
+    }
+    J.mmr_pool = b->d_mmr_pool.as<uint32_t>(); J.tab = b->d_tab.as<uint32_t>();
+    J.n_cand = cfg->n_candidates_per_iter; J.cov_run = cfg->cov_for_runtime; J.k = cfg->k;
+    CK(cudaEventRecord(b->ev[8], b->stream));
+    if (nw) {
+        POMFRET_LAUNCH(join_kernel, (unsigned)(nw * 2), JOIN_THREADS, 0, b->stream, J);
+        b->tm.launches++;
+    }
+    CK(cudaEventRecord(b->ev[9], b->stream));
+    CK(cudaGetLastError());
+    b->stage = ST_JOINED;
+    return POMFRET_GPU_OK;
+}
+
+// evaluate_separation1 (reference blockjoin.c:3894-3938) on the 2x2 table tabulated by the join kernel
+static float evaluate_table(const int32_t t[4], int *join_dir) {
+    const int b00 = t[0], b01 = t[1], b10 = t[2], b11 = t[3];
+    const int buf[2][2] = {{b00, b01}, {b10, b11}};
+    auto mn2 = [](int a, int c) { return a <= c ? a : c; };
+    const int hard_cov_fail = mn2(b00, b01) > 15 || mn2(b10, b11) > 15;  // HARD_COV_THRESHOLD
+    float scores[2] = {0, 0};
+    int which_way = 0;
+    for (int i = 0; i < 2; i++) {
+        float mn, mx;
+        if (buf[i][0] > buf[i][1]) { mn = (float)buf[i][1]; mx = (float)buf[i][0]; which_way = i == 0 ? which_way + 1 : which_way - 1; }
+        else { mn = (float)buf[i][0]; mx = (float)buf[i][1]; which_way = i == 0 ? which_way - 1 : which_way + 1; }
+        if (mn2(b00, b01) > 5 || mn2(b10, b11) > 5) { *join_dir = -9; return 1.0f; }  // HARD_CONTAMINATE_THRESHOLD
+        if (mx == 0) { *join_dir = -9; return 1.0f; }
+        mn = mn == 0 ? 1 : mn;
+        if (mx / mn < 3) { *join_dir = -9; return 1.0f; }
+        scores[i] = mx / mn;
+    }
+    double l, r, two;
+    kt_fisher_exact(b00, b01, b10, b11, &l, &r, &two);
+    if (two < 0.001 && !hard_cov_fail) { *join_dir = which_way; return scores[0] <= scores[1] ? scores[0] : scores[1]; }
+    *join_dir = -9;
+    return 1.0f;
+}
+
+int pomfret_gpu_batch_collect(pomfret_gpu_batch *b, pomfret_gpu_window_result *win, uint8_t *read_tags, int32_t *read_ids) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    if (b->stage != ST_JOINED) return POMFRET_GPU_ERR_STATE;
+    CK(cudaSetDevice(b->device));
+    const size_t nr = b->h_reads.n, nw = b->h_win.n;
+    int rc;
+    if ((rc = b->h_state.resize(nw ? nw : 1))) return rc;
+    b->host_tags_fwd.resize(nr + 1);
+    b->host_rid.resize(nr + 1);
+    cudaEvent_t e0 = b->ev[0], e1 = b->ev[1];
+    (void)e0; (void)e1;
+    if (nw) {
+        CK(cudaMemcpyAsync(b->h_state.data(), b->d_state.p, nw * sizeof(WindowState), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->host_tags_fwd.data(), b->d_tags[0].p, nr, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->host_rid.data(), b->d_r_id.p, nr * 4, cudaMemcpyDeviceToHost, b->stream));
+        b->tm.bytes_d2h += nw * sizeof(WindowState) + nr * 5;
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    int first_err = 0;
+    for (size_t w = 0; w < nw; w++) {
+        const WindowState &S = b->h_state[w];
+        const WindowRec &W = b->h_win[w];
+        pomfret_gpu_window_result R;
+        memset(&R, 0, sizeof(R));
+        R.decision = R.join_fwd = R.join_bwd = -1;
+        R.n_reads = (int32_t)S.n; R.n_reads_loaded = (int32_t)S.n_loaded;
+        R.n_sites_fwd = R.n_sites_bwd = (int32_t)S.n_sites;
+        R.n_left = (int32_t)S.n_left; R.n_left_strict = (int32_t)S.n_left_strict;
+        R.n_right = (int32_t)S.n_right; R.n_right_strict = (int32_t)S.n_right_strict;
+        R.status = S.status;
+        R.score_fwd = R.score_bwd = 1.0f;
+        if (S.status != 0 && !first_err) first_err = S.status;
+        const bool ran = S.status == 0 && S.n > 0 && S.n_sites > 0;
+        if (ran) {
+            for (int t = 0; t < 4; t++) { R.table_fwd[t] = S.table[0][t]; R.table_bwd[t] = S.table[1][t]; }
+            // haplotag_region2 with one permutation (blockjoin.c:4145-4156, 4188-4205)
+            R.score_fwd = evaluate_table(S.table[0], &R.which_way_fwd);
+            R.score_bwd = evaluate_table(S.table[1], &R.which_way_bwd);
+            if (R.score_fwd >= 2 && R.which_way_fwd != 0) R.join_fwd = R.which_way_fwd > 0 ? 0 : 1;
+            if (R.score_bwd >= 2 && R.which_way_bwd != 0) R.join_bwd = R.which_way_bwd > 0 ? 0 : 1;
+            // blockjoin.c:4313-4320
+            if (R.join_fwd != R.join_bwd || (R.join_fwd == -1 && R.join_bwd == -1)) R.decision = -1;
+            else R.decision = R.join_fwd;
+        }
+        if (win) win[w] = R;
+        for (uint32_t i = 0; i < W.n_reads; i++) {
+            const size_t ri = (size_t)W.first_read + i;
+            const int32_t id = b->host_rid[ri];
+            if (read_ids) read_ids[ri] = id;
+            if (read_tags) {
+                uint8_t t = 255;
+                if (id >= 0) {
+                    if (!ran) t = (uint8_t)b->h_reads[ri].hp;                 // nothing touched the tags
+                    else if (R.decision >= 0) t = b->host_tags_fwd[W.first_read + id];  // kept from the forward pass
+                    else t = 2;                                               // set_all_as_unphased
+                }
+                read_tags[ri] = t;
+            }
+        }
+    }
+    // timings
+    float ms;
+    auto el = [&](int a, int c) { ms = 0; cudaEventElapsedTime(&ms, b->ev[a], b->ev[c]); return ms; };
+    b->tm.h2d_ms = el(0, 1);
+    b->tm.decode_ms = el(2, 3);
+    if (nw) { b->tm.readset_ms = el(4, 5); b->tm.pileup_ms = el(5, 6); b->tm.methmer_ms = el(6, 7); b->tm.join_ms = el(8, 9); }
+    b->tm.decode_bytes = b->alg_decode_bytes;
+    uint64_t calls = 0, sites = 0;
+    for (size_t w = 0; w < nw; w++) { calls += b->h_state[w].total_calls; sites += b->h_state[w].n_sites; }
+    b->tm.decode_bytes += 5 * calls;
+    b->tm.pileup_bytes = 5 * calls + 9 * sites;
+    b->have_results = true;
+    return first_err;
+}
+
+int pomfret_gpu_batch_timing(pomfret_gpu_batch *b, pomfret_gpu_timing *out) {
+    if (!b || !out) return POMFRET_GPU_ERR_ARG;
+    *out = b->tm;
+    return POMFRET_GPU_OK;
+}
+
+// ---------------- debug / parity getters ----------------
+static int dl(pomfret_gpu_batch *b, void *dst, const void *src, size_t bytes) {
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    if (bytes) CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int pomfret_gpu_debug_read_info(pomfret_gpu_batch *b, uint32_t read, uint32_t *status, uint32_t *n_calls, uint32_t *end_pos) {
+    if (!b || read >= b->h_reads.n) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_DECODED) return POMFRET_GPU_ERR_STATE;
+    int rc;
+    uint32_t v;
+    if (status) { if ((rc = dl(b, &v, b->d_r_status.as<uint32_t>() + read, 4))) return rc; *status = v & 31u; }
+    if (n_calls) { if ((rc = dl(b, &v, b->d_r_ncalls.as<uint32_t>() + read, 4))) return rc; *n_calls = v; }
+    if (end_pos) { if ((rc = dl(b, &v, b->d_r_end.as<uint32_t>() + read, 4))) return rc; *end_pos = v; }
+    return 0;
+}
+
+int pomfret_gpu_debug_get_calls(pomfret_gpu_batch *b, uint32_t read, uint32_t *pos, uint8_t *cat, uint32_t cap, uint32_t *n) {
+    if (!b || read >= b->h_reads.n || !n) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_DECODED) return POMFRET_GPU_ERR_STATE;
+    uint32_t nc = 0, st = 0;
+    int rc;
+    if ((rc = dl(b, &nc, b->d_r_ncalls.as<uint32_t>() + read, 4))) return rc;
+    if ((rc = dl(b, &st, b->d_r_status.as<uint32_t>() + read, 4))) return rc;
+    if (!(st & RS_KEPT)) nc = 0;
+    *n = nc;
+    uint32_t m = std::min(nc, cap);
+    const ReadRec &R = b->h_reads[read];
+    if (pos && (rc = dl(b, pos, b->d_calls_pos.as<uint32_t>() + R.calls_off, (size_t)m * 4))) return rc;
+    if (cat && (rc = dl(b, cat, b->d_calls_cat.as<uint8_t>() + R.calls_off, m))) return rc;
+    return 0;
+}
+
+int pomfret_gpu_debug_get_sites(pomfret_gpu_batch *b, uint32_t window, int direction, uint32_t *real_pos, uint32_t *starts,
+                                uint8_t *lens, uint32_t cap, uint32_t *n) {
+    if (!b || window >= b->h_win.n || !n || direction < 0 || direction > 1) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_PILED) return POMFRET_GPU_ERR_STATE;
+    WindowState S;
+    int rc;
+    if ((rc = dl(b, &S, b->d_state.as<WindowState>() + window, sizeof(S)))) return rc;
+    *n = S.n_sites;
+    uint32_t m = std::min(S.n_sites, cap);
+    const WindowRec &W = b->h_win[window];
+    if (real_pos && (rc = dl(b, real_pos, b->d_site_pos.as<uint32_t>() + W.site_off, (size_t)m * 4))) return rc;
+    if (starts && (rc = dl(b, starts, b->d_site_start[direction].as<uint32_t>() + W.site_off, (size_t)m * 4))) return rc;
+    if (lens && (rc = dl(b, lens, b->d_site_len[direction].as<uint8_t>() + W.site_off, m))) return rc;
+    return 0;
+}
+
+int pomfret_gpu_debug_get_mmrs(pomfret_gpu_batch *b, uint32_t read, int direction, uint32_t *mmr, uint32_t cap, uint32_t *n,
+                               uint32_t *start_i) {
+    if (!b || read >= b->h_reads.n || !n || direction < 0 || direction > 1) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_PILED) return POMFRET_GPU_ERR_STATE;
+    int rc;
+    int32_t id = -1;
+    if ((rc = dl(b, &id, b->d_r_id.as<int32_t>() + read, 4))) return rc;
+    *n = 0;
+    if (start_i) *start_i = 0;
+    if (id < 0) return 0;
+    const uint32_t w = b->h_read_win[read];
+    if (w == 0xffffffffu) return 0;
+    const uint32_t slot = b->h_win[w].first_read + (uint32_t)id;
+    uint32_t cnt = 0, off = 0, st = 0;
+    if ((rc = dl(b, &cnt, b->d_mm_n[direction].as<uint32_t>() + slot, 4))) return rc;
+    if ((rc = dl(b, &off, b->d_mm_off[direction].as<uint32_t>() + slot, 4))) return rc;
+    if ((rc = dl(b, &st, b->d_mm_start[direction].as<uint32_t>() + slot, 4))) return rc;
+    *n = cnt;
+    if (start_i) *start_i = st;
+    uint32_t m = std::min(cnt, cap);
+    if (mmr && m && (rc = dl(b, mmr, b->d_mmr_pool.as<uint32_t>() + off, (size_t)m * 4))) return rc;
+    return 0;
+}
+
+int pomfret_gpu_debug_get_tags(pomfret_gpu_batch *b, int direction, uint8_t *tags) {
+    if (!b || !tags || direction < 0 || direction > 1) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_JOINED) return POMFRET_GPU_ERR_STATE;
+    // slot-indexed (first_read + id) propagated tags of the direction
+    return dl(b, tags, b->d_tags[direction].p, b->h_reads.n);
+}
+
+int pomfret_gpu_debug_get_tag_order(pomfret_gpu_batch *b, uint32_t window, int direction, uint32_t *ids, uint32_t cap, uint32_t *n) {
+    if (!b || window >= b->h_win.n || !n || direction < 0 || direction > 1) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_JOINED) return POMFRET_GPU_ERR_STATE;
+    WindowState S;
+    int rc;
+    if ((rc = dl(b, &S, b->d_state.as<WindowState>() + window, sizeof(S)))) return rc;
+    *n = S.n_order[direction];
+    uint32_t m = std::min(S.n_order[direction], cap);
+    if (ids && m && (rc = dl(b, ids, b->d_order[direction].as<uint32_t>() + b->h_win[window].first_read, (size_t)m * 4))) return rc;
+    return 0;
+}
+
+}  // extern "C"
+
+#include "engine_haptag.inc"

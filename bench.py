@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — methphase hot-path throughput (BASELINE.json metric: reads/s and bases/s, HBM GB/s vs peak).
+
+A "step" is one pass of the hot path (decode -> read sets -> pileup -> methmers -> greedy join) over one
+batch of synthetic windows.  `value` times the device stages with inputs resident in HBM; `e2e` times
+the same through the C ABI with host buffers (staging copy + H2D + kernels + D2H inside the timed region).
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/pomfret methphase -t N) on
+the same synthetic BAM.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(float(f[0]))
+                    self.max_mhz = float(f[1])
+                    for n, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_workload(tmp, region_mb, cov, seed, tagged=True):
+    """Synthetic chr20-like haplotagged BAM + phased VCF."""
+    import conftest
+    beg = 1000000
+    end = min(64444167, beg + int(region_mb * 1e6))
+    args = ["-c", str(cov), "-s", str(seed), "-C", "chr20:64444167:%d-%d" % (beg, end), "-F", "19"]
+    if not tagged:
+        args.append("--untagged")
+    return conftest.run_synth(os.path.join(tmp, "bench_s%d" % seed), args)
+
+
+def run_reference(args, data, cov):
+    """The unmodified reference CLI built against the hts shim (oracle/_ref), all host threads it can use."""
+    import oracle_bindings as ob
+    if not os.path.exists(ob.REF_BIN):
+        return {"impl": "reference", "unavailable": "oracle/_ref/pomfret not built"}
+    ncpu = os.cpu_count() or 1
+    times = []
+    reads = bases = None
+    n_steps = args.warmup + args.steps
+    for it in range(n_steps):
+        out = os.path.join(os.path.dirname(data["bam"]), "ref_out")
+        t0 = time.perf_counter()
+        subprocess.run([ob.REF_BIN, "methphase", "-t", str(ncpu), "-c", str(cov), "-o", out, "--vcf", data["vcf"],
+                        data["bam"]], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    return times
+
+
+def count_units(host, hb, data, cfg):
+    import parity
+    wins = parity.load_windows(host, hb, data["gaps"], cfg)
+    reads = sum(n for _, n, _, _, _ in wins)
+    bases = sum(host.window_bases(w) for w, _, _, _, _ in wins)
+    return wins, reads, bases
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--region-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_MB", "16")))
+    ap.add_argument("--cov", type=int, default=30)
+    ap.add_argument("--cpu-sample-windows", type=int, default=12)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    import pomfret_b200 as pb
+    import oracle_bindings as ob
+    import parity
+    from pomfret_b200 import build
+    build.build_host()
+
+    tmp = tempfile.mkdtemp(prefix="pomfret_bench_")
+    cov = args.cov
+    cfg = pb.make_config(cov)
+    workload = "synthetic chr20-like %dx ONT reads (MM/ML+MD, haplotagged), %.0f Mb region, phased VCF; methphase -c %d" % (
+        cov, args.region_mb, cov)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        data = make_workload(tmp, args.region_mb, cov, seed=100)
+        host = pb.load_host()
+        hb = host.bam_open(data["bam"])
+        wins, reads, bases = count_units(host, hb, data, cfg)
+        times = run_reference(args, data, cov)
+        if isinstance(times, dict):
+            print(json.dumps(times))
+            return
+        mean = sum(times) / len(times)
+        ncpu = os.cpu_count() or 1
+        v = reads / mean
+        line = {"impl": "reference", "metric": "methphase reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores", "data": "synthetic",
+                "bases_per_s": bases / mean,
+                "config": {"workload": workload, "windows": len(wins), "reads_per_step": reads, "bases_per_step": bases},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": min(ncpu, 1), "kind": "reference",
+                                 "sample": "pomfret methphase -t %d on the whole workload (1 contig => 1 worker thread, "
+                                           "kt_for over contigs); includes BGZF inflate and per-window BAM open" % ncpu},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    gpu = pb.load_gpu()
+    if gpu.device_count() < 1:
+        raise RuntimeError("no CUDA device: pomfret_b200 has no CPU fallback")
+    host = pb.load_host()
+    # weak scaling: every rank owns its own contiguous region set (different seed), no data-path collective
+    data = make_workload(tmp, args.region_mb, cov, seed=100 + rank)
+    hb = host.bam_open(data["bam"])
+    wins, reads, bases = count_units(host, hb, data, cfg)
+    ctx = gpu.init([local_rank])
+    b = gpu.batch_begin(ctx, 0, local_rank)
+
+    def stage():
+        b.reset()
+        for w, n, chrom, s, e in wins:
+            first = b.add_reads(host.window_descs(w), n)
+            b.add_window(s, e, first, n)
+
+    def device_pass():
+        b.decode(cfg.lo, cfg.hi)
+        b.pileup(cfg)
+        b.join(cfg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    # device-resident timing: stage + H2D outside, kernels inside
+    dev_times, e2e_times, launches = [], [], 0
+    tsum = {}
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            sampler.start()
+        stage()
+        b.submit()
+        barrier()
+        t0 = time.perf_counter()
+        device_pass()
+        res, tags, ids, rc = b.collect()
+        barrier()
+        dt = time.perf_counter() - t0
+        tm = b.timing()
+        kern = tm.decode_ms + tm.readset_ms + tm.pileup_ms + tm.methmer_ms + tm.join_ms
+        if it >= args.warmup:
+            dev_times.append(kern / 1e3)
+            launches = tm.launches
+            for k in ("decode_ms", "readset_ms", "pileup_ms", "methmer_ms", "join_ms", "h2d_ms"):
+                tsum[k] = tsum.get(k, 0.0) + getattr(tm, k)
+            tsum["decode_bytes"] = tm.decode_bytes
+            tsum["pileup_bytes"] = tm.pileup_bytes
+            tsum["h2d"] = tm.bytes_h2d
+            tsum["d2h"] = tm.bytes_d2h
+    # end-to-end timing through the C ABI with host buffers
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        stage()
+        b.submit()
+        device_pass()
+        res, tags, ids, rc = b.collect()
+        barrier()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            e2e_times.append(dt)
+    sampler.stop_flag = True
+
+    def maxr(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sumr(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return float(x)
+
+    dev_mean = maxr(sum(dev_times) / len(dev_times))
+    e2e_mean = maxr(sum(e2e_times) / len(e2e_times))
+    tot_reads = sumr(reads)
+    tot_bases = sumr(bases)
+    if rank != 0:
+        return
+    peaks, peak_kind = measured_peaks()
+    K = args.steps
+    dec_ms = tsum["decode_ms"] / K
+    pile_ms = tsum["pileup_ms"] / K
+    dec_gbs = tsum["decode_bytes"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
+    pile_gbs = tsum["pileup_bytes"] / (pile_ms * 1e-3) / 1e9 if pile_ms > 0 else 0.0
+    kernels = {k: tsum[k] / K for k in ("decode_ms", "readset_ms", "pileup_ms", "methmer_ms", "join_ms", "h2d_ms")}
+    # CPU baseline on a bounded sample of the same windows (rank 0, N = 1 only)
+    cpu = None
+    if world == 1 and os.path.exists(ob.REF_SO):
+        ocfg = ob.make_config(cov)
+        sample = data["gaps"][:args.cpu_sample_windows]
+        t0 = time.perf_counter()
+        r_reads = 0
+        for chrom, s, e, _ in sample:
+            r = ob.ref_window(data["bam"], chrom, s, e, ocfg)
+            r_reads += r["n_reads_loaded"]
+        dtc = time.perf_counter() - t0
+        n_in = sum(n for (_, n, _, _, _) in wins[:len(sample)])
+        cpu = {"value": n_in / dtc, "unit": "reads/s", "cores": 1, "kind": "reference",
+               "sample": "first %d windows through the compiled reference's haplotag_region_given_bam call sequence "
+                         "(BAM open + inflate + decode + join), 1 thread" % len(sample)}
+    line = {"metric": "methphase reads/s", "value": tot_reads / dev_mean, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_mean * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores", "data": "synthetic",
+            "bases_per_s": tot_bases / dev_mean,
+            "config": {"workload": workload, "windows_per_gpu": len(wins), "reads_per_step": tot_reads,
+                       "bases_per_step": tot_bases, "l2": "inputs (%.0f MB per GPU) larger than L2" % (tsum["h2d"] / 1e6)},
+            "e2e": {"value": tot_reads / e2e_mean, "unit": "reads/s", "ms_per_step": e2e_mean * 1e3,
+                    "bases_per_s": tot_bases / e2e_mean, "h2d_bytes_per_step": int(tsum["h2d"]),
+                    "d2h_bytes_per_step": int(tsum["d2h"])},
+            "gpu_launches": int(launches) * K,
+            "kernel_ms": kernels,
+            "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind},
+            "roofline_pileup": {"kernel": "pileup_tile_kernel+sites_finalize_kernel", "bound": "hbm", "achieved": pile_gbs,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pile_gbs / peaks["hbm_gbs"]},
+            "clocks": sampler.summary()}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

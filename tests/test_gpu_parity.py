@@ -1,0 +1,105 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libpomfret_gpu.so, nvcc sm_100a build),
+against the oracle on the same seeded inputs.  Integer outputs, tags, decisions and the fp32 join scores
+must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+import parity
+import pomfret_b200 as pb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(built):
+    g = pb.load_gpu()  # raises if the CUDA library is missing: no fallback
+    assert g.device_count() >= 1, "no CUDA device"
+    return g
+
+
+def _run(gpu, data, cov, readlen=15000, max_windows=None, check_ref=True, **kw):
+    host = pb.load_host()
+    hb = host.bam_open(data["bam"])
+    cfg = pb.make_config(cov, readlen=readlen, **kw)
+    ocfg = ob.make_config(cov, readlen=readlen, **kw)
+    gaps = data["gaps"][:max_windows] if max_windows else data["gaps"]
+    wins = parity.load_windows(host, hb, gaps, cfg)
+    ctx = gpu.init([0])
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(gpu, ctx, host, wins, cfg)
+    assert rc == 0, gpu.strerror(rc)
+    decisions = []
+    for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+        p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+        bad = parity.compare_window(b, wi, first, n, res, tags, ids, p)
+        assert not bad, (chrom, s, e, bad[:10])
+        if check_ref and os.path.exists(ob.REF_SO):
+            r = ob.ref_window(data["bam"], chrom, s, e, ocfg)
+            assert res[wi].decision == r["decision"]
+            kept = [i for i in range(n) if ids[first + i] >= 0][:r["n_reads"]]
+            assert np.array_equal(np.array([tags[first + i] for i in kept], dtype=np.uint8), r["tags_final"])
+        decisions.append(res[wi].decision)
+        host.window_free(w)
+    b.end()
+    gpu.destroy(ctx)
+    host.bam_close(hb)
+    return decisions
+
+
+def test_gpu_matches_oracle_30x(gpu, synth30):
+    d = _run(gpu, synth30, 30)
+    assert len(d) >= 2
+
+
+def test_gpu_matches_oracle_short_reads(gpu, synth_small):
+    _run(gpu, synth_small, 36, readlen=2000)
+
+
+def test_gpu_matches_oracle_implicit(gpu, synth_implicit):
+    _run(gpu, synth_implicit, 34, readlen=1500)
+
+
+@pytest.mark.parametrize("kw", [dict(k=2, k_span=800), dict(k=4, lo=80, hi=180), dict(k=1), dict(k_span=300)])
+def test_gpu_matches_oracle_parameters(gpu, synth_small, kw):
+    _run(gpu, synth_small, 30, readlen=2000, check_ref=False, **kw)
+
+
+def test_gpu_coverage_gate_and_empty(gpu, synth_small):
+    """cov 200 => cov_for_selection 20: no site qualifies (window skipped, blockjoin.c:4266-4270);
+    a window without records => abandoned by the left-coverage gate (blockjoin.c:1161-1163)."""
+    _run(gpu, synth_small, 200, readlen=2000, check_ref=False)
+    g = gpu
+    ctx = g.init([0])
+    b = g.batch_begin(ctx)
+    b.add_window(1000, 2000, 0, 0)
+    cfg = pb.make_config(30)
+    b.submit(); b.decode(cfg.lo, cfg.hi); b.pileup(cfg); b.join(cfg)
+    res, tags, ids, rc = b.collect()
+    assert rc == 0 and res[0].decision == -1 and res[0].n_reads == 0
+    b.end()
+    g.destroy(ctx)
+
+
+def test_gpu_batch_of_many_windows_is_order_independent(gpu, synth30):
+    """Windows are independent units: a batch with the windows in reverse order gives the same answers."""
+    host = pb.load_host()
+    hb = host.bam_open(synth30["bam"])
+    cfg = pb.make_config(30)
+    wins = parity.load_windows(host, hb, synth30["gaps"], cfg)
+    ctx = gpu.init([0])
+    b1, l1, r1, t1, i1, rc1 = parity.run_gpu_batch(gpu, ctx, host, wins, cfg)
+    b2, l2, r2, t2, i2, rc2 = parity.run_gpu_batch(gpu, ctx, host, wins[::-1], cfg)
+    assert rc1 == 0 and rc2 == 0
+    nw = len(wins)
+    for wi in range(nw):
+        a, z = r1[wi], r2[nw - 1 - wi]
+        assert (a.decision, a.join_fwd, a.join_bwd, a.n_reads, a.n_sites_fwd, list(a.table_fwd), list(a.table_bwd)) == \
+               (z.decision, z.join_fwd, z.join_bwd, z.n_reads, z.n_sites_fwd, list(z.table_fwd), list(z.table_bwd))
+        f1, n1 = l1[wi]
+        f2, n2 = l2[nw - 1 - wi]
+        assert np.array_equal(t1[f1:f1 + n1], t2[f2:f2 + n2])
+    b1.end(); b2.end()
+    gpu.destroy(ctx)
+    host.bam_close(hb)

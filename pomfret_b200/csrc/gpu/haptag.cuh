@@ -1,8 +1,352 @@
-// (c) Read haplotagging kernel for untagged BAMs (-u); see engine_haptag.inc for the host side.
+// (c) Read haplotagging against the phased VCF for untagged BAMs (`-u` / --bam-is-untagged).
+// One warp per alignment record.
+//
+// Replaces parse_variants_for_one_read (reference blockjoin.c:1545-1691) and
+// haptag_one_read_with_variants (blockjoin.c:1693-1840); the known-variant set is what
+// insert_variant_from_vcf_line builds (blockjoin.c:1432-1543), the per-read i_left cursor
+// (blockjoin.c:1716-1720) is computed by the caller, first-alignment-wins (1880-1889) stays on the host.
+//
+//   A. CIGAR scan (32 ops per step, warp prefix sums): reference span, insertion list with, per
+//      insertion, its reference position, length, read position and read position net of earlier
+//      insertions (that is what the MD walk's "skip insertions" rule compares against).
+//   B. MD scan (512 chars per step): every lane classifies 16 characters; the tokenizer state
+//      (inside a number / inside a ^deletion run / neither) is handed from lane to lane, then each lane
+//      emits its tokens (mismatch with the read base, or deletion with the reference letters) with
+//      reference / read offsets from warp prefix sums.
+//   C. Vote walk (lane 0): the reference merges known and read variants with a 64-bit radix sort and
+//      walks the buffer; both read-variant lists are already position sorted, so the walk visits only the
+//      known variants and finds its neighbours in the merged order by binary search.
 #ifndef POMFRET_GPU_HAPTAG_CUH
 #define POMFRET_GPU_HAPTAG_CUH
 #include "gpu_rt.h"
 #include "types.h"
+#include "decode.cuh"
+
 namespace pomfret_gpu {
+
+constexpr int HAP_WARPS = 4;
+constexpr int HAP_MAX_UNSORTED = 64;
+
+struct KnownVar {   // mirrors pomfret_gpu_variant
+    uint32_t pos, len;
+    uint8_t op, haptag;
+    uint16_t reserved;
+    uint32_t bases_off;
+};
+
+struct HaptagParams {
+    const ReadRec *reads;
+    uint32_t n_reads;
+    const uint8_t *blob;
+    const KnownVar *known;
+    uint32_t n_known;
+    const uint8_t *bases;
+    const uint32_t *known_first;
+    // scratch, sliced per read by scr_off (insertions: n_cigar slots, MD variants: md_len slots)
+    const uint32_t *ins_off, *mdv_off;
+    uint32_t *ins_ref, *ins_len, *ins_self, *ins_q, *ins_cum;
+    uint32_t *mv_pos, *mv_info, *mv_aux;
+    uint8_t *out_tag;
+    int32_t *out_status;
+    int32_t *out_votes;  // 2 per read
+};
+
+struct HapWarpSmem {
+    __align__(16) uint8_t buf[32 + 512 + 16];
+};
+
+__device__ __forceinline__ uint8_t nt4_of_nib(uint32_t c) { return c == 1 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 8 ? 3 : 4; }
+__device__ __forceinline__ uint8_t nt4_of_char(uint32_t ch) {
+    switch (ch) {
+    case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2;
+    case 'T': case 't': case 'U': case 'u': return 3; default: return 4;
+    }
+}
+// md_op_table, blockjoin.c:94-115
+__device__ __forceinline__ int md_class(uint32_t ch) {
+    if (ch >= '0' && ch <= '9') return 0;
+    if (ch == '^') return 1;
+    switch (ch) {
+    case 'A': case 'C': case 'G': case 'T': case 'U': case 'N':
+    case 'a': case 'c': case 'g': case 't': case 'u': case 'n': return 2;
+    default: return 4;
+    }
+}
+
+// tokenizer state handed from lane to lane
+struct MdState {
+    uint32_t mode;       // 0 none, 1 inside a number, 2 inside a ^ run
+    uint32_t num;        // value of the number so far
+    uint32_t del_start;  // offset of the '^'
+    uint32_t since;      // mismatches emitted since the last number ended
+};
+
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(HAP_WARPS * 32) haptag_kernel(HaptagParams P) {
+    __shared__ HapWarpSmem smem[HAP_WARPS];
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t ri = blockIdx.x * HAP_WARPS + warp;
+    if (ri >= P.n_reads) return;
+    const ReadRec R = P.reads[ri];
+    HapWarpSmem &sm = smem[warp];
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
+    const uint8_t *seq = P.blob + (size_t)R.seq_off * 16;
+    const uint8_t *md = P.blob + (size_t)R.md_off * 16;
+    uint32_t *ins_ref = P.ins_ref + P.ins_off[ri], *ins_len = P.ins_len + P.ins_off[ri];
+    uint32_t *ins_self = P.ins_self + P.ins_off[ri], *ins_q = P.ins_q + P.ins_off[ri], *ins_cum = P.ins_cum + P.ins_off[ri];
+    uint32_t *mv_pos = P.mv_pos + P.mdv_off[ri], *mv_info = P.mv_info + P.mdv_off[ri], *mv_aux = P.mv_aux + P.mdv_off[ri];
+
+    // ---------------- A. CIGAR ----------------
+    uint32_t ref_run = R.pos, self_run = 0, ins_total = 0, n_ins = 0, rlen = 0;
+    uint32_t self_start = 0;
+    for (uint32_t base = 0; base < R.n_cigar; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t op = 15, L = 0;
+        if (i < R.n_cigar) { uint32_t c = cigar[i]; op = c & 15u; L = c >> 4; }
+        // pass 1 of the reference: N,D advance ref; S,I advance read; M,=,X advance both (blockjoin.c:1564-1589)
+        const uint32_t dref = (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) ? L : 0u;
+        const uint32_t dself = (op == 0u || op == 1u || op == 4u || op == 7u || op == 8u) ? L : 0u;
+        const uint32_t dins = op == 1u ? L : 0u;
+        uint32_t iref = warp_inclusive_sum(dref), iself = warp_inclusive_sum(dself), iins = warp_inclusive_sum(dins);
+        unsigned im = __ballot_sync(FULL_MASK, op == 1u);
+        if (op == 1u) {
+            uint32_t k = n_ins + __popc(im & ((1u << lane) - 1u));
+            uint32_t sp = self_run + iself - dself;
+            uint32_t before = ins_total + iins - dins;
+            ins_ref[k] = ref_run + iref - dref;
+            ins_len[k] = L;
+            ins_self[k] = sp;
+            ins_q[k] = sp - before;
+            ins_cum[k] = before;
+        }
+        if (i == 0 && op == 4u) self_start = L;
+        n_ins += __popc(im);
+        ref_run += __shfl_sync(FULL_MASK, iref, 31);
+        self_run += __shfl_sync(FULL_MASK, iself, 31);
+        ins_total += __shfl_sync(FULL_MASK, iins, 31);
+    }
+    self_start = __shfl_sync(FULL_MASK, self_start, 0);
+    rlen = ref_run - R.pos;
+    if (rlen == 0) rlen = 1;
+    const uint32_t end_pos = R.pos + rlen;
+    __syncwarp();
+
+    // ---------------- B. MD ----------------
+    int32_t status = 0;
+    uint32_t n_mv = 0;
+    if (!(R.flags & RF_HAS_MD)) status = -9;  // assert(tagd), blockjoin.c:1596
+    else if (R.md_len > 0) {
+        MdState carry;
+        carry.mode = 0; carry.num = 0; carry.del_start = 0; carry.since = 0;
+        uint32_t ref_base = R.pos, b_base = self_start;  // running reference / insertion-free read offsets
+        bool bad = false;
+        for (uint32_t gbase = 0; gbase < R.md_len; gbase += 512) {
+            const uint32_t off = gbase + lane * 16;
+            uint4 v = *reinterpret_cast<const uint4 *>(md + off);  // padded blob: always readable
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t nv = off >= R.md_len ? 0u : (R.md_len - off < 16u ? R.md_len - off : 16u);
+            // hand the tokenizer state from lane to lane
+            MdState in = carry, st = carry;
+            for (int l = 0; l < 32; l++) {
+                if ((int)lane == l) {
+                    st = in;
+                    for (uint32_t i = 0; i < nv; i++) {
+                        uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                        int cl = md_class(c);
+                        if (cl == 0) {
+                            if (st.mode == 1) st.num = st.num * 10 + (c - '0');
+                            else { st.mode = 1; st.num = c - '0'; }
+                        } else {
+                            if (st.mode == 1) { st.mode = 0; st.since = 0; }
+                            if (st.mode == 2) { /* the run continues through letters and carets */ }
+                            else if (cl == 1) { st.mode = 2; st.del_start = off + i; }
+                            else if (cl == 2) st.since++;
+                        }
+                    }
+                }
+                MdState nx;
+                nx.mode = __shfl_sync(FULL_MASK, st.mode, l);
+                nx.num = __shfl_sync(FULL_MASK, st.num, l);
+                nx.del_start = __shfl_sync(FULL_MASK, st.del_start, l);
+                nx.since = __shfl_sync(FULL_MASK, st.since, l);
+                if ((int)lane == l + 1) in = nx;
+                if (l == 31) carry = nx;
+            }
+            // every lane now knows its incoming state `in`: count what it emits
+            uint32_t n_tok = 0, ref_adv = 0, b_adv = 0;
+            {
+                MdState s = in;
+                for (uint32_t i = 0; i < nv; i++) {
+                    uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                    int cl = md_class(c);
+                    if (cl == 4) bad = true;
+                    if (off + i == 0 && cl >= 4) bad = true;
+                    if (cl == 0) {
+                        if (s.mode == 2) { uint32_t dl = off + i - s.del_start - 1; n_tok++; ref_adv += dl; s.mode = 1; s.num = c - '0'; }
+                        else if (s.mode == 1) s.num = s.num * 10 + (c - '0');
+                        else { s.mode = 1; s.num = c - '0'; }
+                    } else {
+                        if (s.mode == 1) { ref_adv += s.num; b_adv += s.num; s.mode = 0; s.since = 0; }
+                        if (s.mode == 2) {}
+                        else if (cl == 1) { s.mode = 2; s.del_start = off + i; }
+                        else if (cl == 2) { n_tok++; ref_adv++; b_adv++; s.since++; }
+                    }
+                }
+            }
+            uint32_t i_tok = warp_inclusive_sum(n_tok), i_ref = warp_inclusive_sum(ref_adv), i_b = warp_inclusive_sum(b_adv);
+            // emit
+            {
+                MdState s = in;
+                uint32_t slot = n_mv + i_tok - n_tok;
+                uint32_t rp = ref_base + i_ref - ref_adv;
+                uint32_t bp = b_base + i_b - b_adv;
+                for (uint32_t i = 0; i < nv; i++) {
+                    uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
+                    int cl = md_class(c);
+                    if (cl == 0) {
+                        if (s.mode == 2) {
+                            uint32_t dl = off + i - s.del_start - 1;
+                            mv_pos[slot] = rp; mv_info[slot] = (dl << 1) | 1u; mv_aux[slot] = s.del_start + 1;
+                            slot++; rp += dl;
+                            s.mode = 1; s.num = c - '0';
+                        } else if (s.mode == 1) s.num = s.num * 10 + (c - '0');
+                        else { s.mode = 1; s.num = c - '0'; }
+                    } else {
+                        if (s.mode == 1) { rp += s.num; bp += s.num; s.mode = 0; s.since = 0; }
+                        if (s.mode == 2) {}
+                        else if (cl == 1) { s.mode = 2; s.del_start = off + i; }
+                        else if (cl == 2) {
+                            // read base at self_pos = B + (insertions whose net position lies before the B reached
+                            // when the last number ended), blockjoin.c:1628-1635, 1652
+                            uint32_t b_gap = bp - s.since;
+                            uint32_t K = lower_bound_u32(ins_q, n_ins, b_gap);
+                            uint32_t skipped = K == 0 ? 0 : ins_cum[K - 1] + ins_len[K - 1];
+                            uint32_t sp = bp + skipped;
+                            uint32_t base = sp < R.l_qseq ? nt4_of_nib(seq_nib(seq, sp)) : 4u;
+                            mv_pos[slot] = rp; mv_info[slot] = (1u << 1); mv_aux[slot] = base;
+                            slot++; rp++; bp++; s.since++;
+                        }
+                    }
+                }
+            }
+            n_mv += __shfl_sync(FULL_MASK, i_tok, 31);
+            ref_base += __shfl_sync(FULL_MASK, i_ref, 31);
+            b_base += __shfl_sync(FULL_MASK, i_b, 31);
+        }
+        if (__any_sync(FULL_MASK, bad)) status = -10;  // "invalid MD", blockjoin.c:1622 / assert :1616
+    }
+    (void)sm;
+    __syncwarp();
+
+    // ---------------- C. vote walk ----------------
+    if (lane == 0) {
+        int cnt[2] = {0, 0};
+        uint8_t tag = 254;
+        if (status == 0 && P.n_known > 0) {
+            const uint32_t kf = P.known_first[ri];
+            uint32_t ke = kf;
+            bool sorted = true;
+            while (ke < P.n_known && P.known[ke].pos < end_pos) {
+                if (ke > kf && P.known[ke].pos < P.known[ke - 1].pos) sorted = false;
+                ke++;
+            }
+            const uint32_t m = ke - kf;
+            uint32_t order[HAP_MAX_UNSORTED];
+            if (!sorted) {
+                if (m > HAP_MAX_UNSORTED) status = -8;
+                else {
+                    for (uint32_t a = 0; a < m; a++) {  // insertion sort by (pos, index)
+                        uint32_t x = kf + a, b = a;
+                        while (b > 0 && P.known[order[b - 1]].pos > P.known[x].pos) { order[b] = order[b - 1]; b--; }
+                        order[b] = x;
+                    }
+                }
+            }
+            if (status == 0) {
+                for (uint32_t j = 0; j < m;) {
+                    const uint32_t vi = sorted ? kf + j : order[j];
+                    const KnownVar kv = P.known[vi];
+                    const uint32_t p = kv.pos;
+                    const uint32_t ia = lower_bound_u32(ins_ref, n_ins, p), ib = lower_bound_u32(mv_pos, n_mv, p);
+                    const bool has_a = ia < n_ins, has_b = ib < n_mv;
+                    const bool has_next_known = j + 1 < m;
+                    if (!has_next_known && !has_a && !has_b) { cnt[kv.haptag & 1]++; break; }  // last entry of the merged list
+                    const uint32_t nk = has_next_known ? (sorted ? kf + j + 1 : order[j + 1]) : 0;
+                    const uint32_t nk_pos = has_next_known ? P.known[nk].pos : 0xffffffffu;
+                    if (has_next_known && nk_pos == p) { j += 2; continue; }  // two known variants on one position
+                    uint32_t rp = 0xffffffffu;
+                    bool from_ins = false;
+                    if (has_a) { rp = ins_ref[ia]; from_ins = true; }
+                    if (has_b && mv_pos[ib] < rp) { rp = mv_pos[ib]; from_ins = false; }
+                    const bool next_is_read = (has_a || has_b) && !(has_next_known && nk_pos <= rp);
+                    if (next_is_read && rp == p) {
+                        // does the read carry the ALT allele?  (length and bases; the op type is not compared)
+                        bool ok;
+                        if (from_ins) {
+                            ok = kv.len == ins_len[ia];
+                            for (uint32_t t = 0; ok && t < kv.len; t++) {
+                                uint32_t sp = ins_self[ia] + t;
+                                uint8_t bch = sp < R.l_qseq ? nt4_of_nib(seq_nib(seq, sp)) : 4;
+                                if (P.bases[kv.bases_off + t] != bch) ok = false;
+                            }
+                        } else {
+                            const uint32_t info = mv_info[ib], vlen = info >> 1;
+                            ok = kv.len == vlen;
+                            if (ok) {
+                                if (info & 1u) {
+                                    for (uint32_t t = 0; ok && t < vlen; t++)
+                                        if (P.bases[kv.bases_off + t] != nt4_of_char(md[mv_aux[ib] + t])) ok = false;
+                                } else ok = P.bases[kv.bases_off] == (uint8_t)mv_aux[ib];
+                            }
+                        }
+                        if (ok) cnt[(kv.haptag ^ 1) & 1]++;
+                        j += 1;
+                        continue;
+                    }
+                    // next entry sits on another position: REF, unless the previous entry is a read deletion
+                    // reaching this position (blockjoin.c:1765-1784)
+                    bool skip = false;
+                    {
+                        const bool has_pa = ia > 0, has_pb = ib > 0;
+                        uint32_t ppos = 0;
+                        bool prev_is_md = false, have_prev_read = false;
+                        if (has_pa) { ppos = ins_ref[ia - 1]; have_prev_read = true; }
+                        if (has_pb && (!has_pa || mv_pos[ib - 1] >= ppos)) { ppos = mv_pos[ib - 1]; prev_is_md = true; have_prev_read = true; }
+                        // the element before the known entry is a read variant unless a known entry sorts later
+                        bool prev_known_later = false;
+                        if (j > 0) {
+                            uint32_t pk = sorted ? kf + j - 1 : order[j - 1];
+                            uint32_t pkp = P.known[pk].pos;
+                            if (!have_prev_read || pkp > ppos) prev_known_later = true;
+                        }
+                        if (have_prev_read && !prev_known_later && prev_is_md) {
+                            uint32_t info = mv_info[ib - 1];
+                            if ((info & 1u) && ppos + (info >> 1) >= p) skip = true;
+                        }
+                    }
+                    if (!skip) cnt[kv.haptag & 1]++;
+                    j += 1;
+                }
+            }
+            if (status == 0) {
+                float mx = (float)(cnt[0] > cnt[1] ? cnt[0] : cnt[1]);
+                int mn = cnt[0] <= cnt[1] ? cnt[0] : cnt[1];
+                float ratio = mn == 0 ? 0.f : __fdiv_rn(mx, (float)mn);
+                if ((cnt[0] > 3 && cnt[1] > 3 && ratio < 5.f) || cnt[0] == cnt[1]) tag = 254;
+                else tag = cnt[0] > cnt[1] ? 0 : 1;
+            }
+        }
+        P.out_tag[ri] = tag;
+        P.out_status[ri] = status;
+        P.out_votes[2 * ri] = cnt[0];
+        P.out_votes[2 * ri + 1] = cnt[1];
+    }
+}
+
 }  // namespace pomfret_gpu
 #endif

@@ -28,3 +28,97 @@ uint64_t pomfret_host_window_bases(void *w) { return ((WindowReads *)w)->n_bases
 void pomfret_host_window_free(void *w) { delete (WindowReads *)w; }
 
 }  // extern "C"
+
+// ---- interval bookkeeping hooks (tests compare them with the compiled reference) ----
+#include "intervals.h"
+#include "methphase.h"
+extern "C" {
+
+void *pomfret_host_intervals_load(const char *fn, int fmt) {
+    Storage *st = new Storage();
+    std::string fatal;
+    if (!load_intervals(fn, (IntervalFormat)fmt, st, nullptr, &fatal) || !fatal.empty()) { delete st; return nullptr; }
+    for (Ranges &r : st->ranges) { store_raw_intervals(&r); merge_close_intervals(&r, kReadback); }
+    return st;
+}
+int pomfret_host_intervals_nref(void *h) { return (int)((Storage *)h)->ref_names.size(); }
+const char *pomfret_host_intervals_refname(void *h, int i) { return ((Storage *)h)->ref_names[(size_t)i].c_str(); }
+int pomfret_host_intervals_n(void *h, int i) { return (int)((Storage *)h)->ranges[(size_t)i].n; }
+void pomfret_host_intervals_get(void *h, int i, uint32_t *starts, uint32_t *ends, uint32_t *abs_se) {
+    const Ranges &r = ((Storage *)h)->ranges[(size_t)i];
+    for (size_t j = 0; j < r.n; j++) { starts[j] = r.starts[j]; ends[j] = r.ends[j]; }
+    abs_se[0] = r.abs_start; abs_se[1] = r.abs_end;
+}
+void pomfret_host_intervals_decide(void *h, int i, const int *decisions) {
+    Ranges &r = ((Storage *)h)->ranges[(size_t)i];
+    for (size_t j = 0; j < r.n; j++) r.decisions[j] = decisions[j];
+}
+void pomfret_host_intervals_finish(void *h) {
+    Storage *st = (Storage *)h;
+    lift_decisions(st);
+    make_flips_onraw(st);
+    generate_new_phase_blocks(st);
+}
+int pomfret_host_intervals_nblocks(void *h, int i) { return (int)((Storage *)h)->ranges[(size_t)i].phaseblocks.size(); }
+void pomfret_host_intervals_blocks(void *h, int i, uint32_t *s, uint32_t *e) {
+    const Ranges &r = ((Storage *)h)->ranges[(size_t)i];
+    for (size_t j = 0; j < r.phaseblocks.size(); j++) { s[j] = r.phaseblocks[j].s; e[j] = r.phaseblocks[j].e; }
+}
+void pomfret_host_intervals_free(void *h) { delete (Storage *)h; }
+
+// known variants of one contig as the -u path sees them
+int pomfret_host_load_variants(const char *fn_vcf, const char *chrom, pomfret_gpu_variant *vars, int cap, uint8_t *bases, int bases_cap,
+                               int *n_bases) {
+    Storage st;
+    std::string fatal;
+    int n = 0, nb = 0;
+    load_intervals(fn_vcf, IntervalFormat::VCF, &st,
+                   [&](const std::string &c, KnownVariants &kv, bool) {
+                       if (c != chrom) return;
+                       for (size_t i = 0; i < kv.vars.size(); i++) {
+                           if (n < cap) {
+                               vars[n] = kv.vars[i];
+                               vars[n].bases_off = (uint32_t)nb;
+                               for (uint32_t j = 0; j < kv.vars[i].len && nb < bases_cap; j++) bases[nb++] = kv.bases[kv.vars[i].bases_off + j];
+                           }
+                           n++;
+                       }
+                   }, &fatal);
+    if (n_bases) *n_bases = nb;
+    return n;
+}
+
+// every primary record of a contig, packed for the haplotagger (tests drive pomfret_gpu_haptag with these)
+void *pomfret_host_contig_load(void *bam, const char *chrom) {
+    BamReader &b = *(BamReader *)bam;
+    WindowReads *w = new WindowReads();
+    hts_itr_t *itr = sam_itr_querys(b.idx, b.hdr, chrom);
+    if (!itr) return w;
+    std::vector<size_t> offs, lens;
+    std::vector<bam1_core_t> cores;
+    while (sam_itr_next(b.fp, itr, b.rec) >= 0) {
+        const int flag = b.rec->core.flag;
+        if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;
+        size_t off = (w->arena.size() + 15) & ~(size_t)15;
+        w->arena.resize(off + (size_t)b.rec->l_data + 16);
+        memcpy(w->arena.data() + off, b.rec->data, (size_t)b.rec->l_data);
+        offs.push_back(off); lens.push_back((size_t)b.rec->l_data); cores.push_back(b.rec->core);
+        w->qname_off.push_back((uint32_t)w->qnames.size());
+        w->qnames.append(bam_get_qname(b.rec));
+        w->qnames.push_back('\0');
+        w->n_bases += (uint64_t)b.rec->core.l_qseq;
+    }
+    hts_itr_destroy(itr);
+    w->descs.resize(offs.size());
+    bam1_t tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    for (size_t i = 0; i < offs.size(); i++) {
+        tmp.core = cores[i];
+        tmp.data = w->arena.data() + offs[i];
+        tmp.l_data = (int)lens[i];
+        describe_record(&tmp, kHaptagUnphased, &w->descs[i]);
+    }
+    return w;
+}
+
+}  // extern "C"

@@ -1,0 +1,522 @@
+// Drivers, see methphase.h.
+#include "methphase.h"
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <unordered_set>
+#include "gpu_api.h"
+#include "intervals.h"
+#include "loader.h"
+
+namespace pomfret {
+
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+[[noreturn]] void die_gpu(const GpuApi &api, int rc, const char *where) {
+    if (rc == POMFRET_GPU_ERR_FATAL_CIGAR)
+        fprintf(stderr, "[E::%s] fatal: unknown cigar operation. Bug?\n", "get_mod_poss_on_ref");  // blockjoin.c:777
+    else if (rc == POMFRET_GPU_ERR_MISSING_MD)
+        fprintf(stderr, "pomfret: parse_variants_for_one_read: Assertion `tagd' failed.\n");       // blockjoin.c:1596
+    else if (rc == POMFRET_GPU_ERR_BAD_MD)
+        fprintf(stderr, "[E::%s] invalid MD\n", "parse_variants_for_one_read");                    // blockjoin.c:1622
+    else
+        fprintf(stderr, "[E::%s] %s: %s\n", "pomfret_gpu", where, api.strerror ? api.strerror(rc) : "?");
+    exit(1);
+}
+
+struct Engine {
+    GpuApi &api = gpu_api();
+    pomfret_gpu_ctx *ctx = nullptr;
+    int n_dev = 0;
+    bool start(int want_gpus, int n_workers) {
+        std::string err;
+        if (!api.load(&err)) { fprintf(stderr, "[E::%s] %s\n", "pomfret", err.c_str()); return false; }
+        int n = api.device_count();
+        if (n <= 0) { fprintf(stderr, "[E::%s] no CUDA device visible; this build has no CPU path\n", "pomfret"); return false; }
+        n_dev = want_gpus > 0 && want_gpus < n ? want_gpus : n;
+        std::vector<int> devs;
+        for (int i = 0; i < n_dev; i++) devs.push_back(i);
+        int rc = api.init(&ctx, devs.data(), n_dev, n_workers);
+        if (rc != 0) { fprintf(stderr, "[E::%s] pomfret_gpu_init: %s\n", "pomfret", api.strerror(rc)); return false; }
+        return true;
+    }
+    ~Engine() { if (ctx) api.destroy(ctx); }
+};
+
+struct WindowJob {
+    int i_ref;
+    size_t i_win;
+    uint32_t start, end;
+};
+
+struct WindowOut {
+    int decision = -1;
+    std::vector<std::pair<std::string, int>> tags;  // kept reads in BAM order, only when decision >= 0
+};
+
+// One worker: its own BAM handle and its own batch on its own device/stream.
+struct Worker {
+    Engine *eng = nullptr;
+    int id = 0, device = 0;
+    BamReader bam;
+    pomfret_gpu_batch *batch = nullptr;
+    RunStats stats;
+    bool open(const std::string &fn_bam) {
+        if (!bam.open(fn_bam)) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "load_reads_given_interval", fn_bam.c_str()); return false; }
+        int rc = eng->api.batch_begin(eng->ctx, id, device, &batch);
+        if (rc != 0) { fprintf(stderr, "[E::%s] batch_begin: %s\n", "pomfret", eng->api.strerror(rc)); return false; }
+        return true;
+    }
+    void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; }
+
+    // haplotag_region_given_bam for a chunk of windows of one contig
+    void run_chunk(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg,
+                   const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
+        const GpuApi &api = eng->api;
+        double t0 = now_s();
+        std::vector<WindowReads> wins(jobs.size());
+        int rc = api.batch_reset(batch);
+        if (rc) die_gpu(api, rc, "batch_reset");
+        uint32_t first = 0;
+        std::vector<uint32_t> firsts;
+        for (size_t w = 0; w < jobs.size(); w++) {
+            rc = load_window(bam, chrom.c_str(), jobs[w].start, jobs[w].end, cfg.readlen_threshold, cfg.min_mapq, raw_tags, &wins[w]);
+            if (rc) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[w].start, jobs[w].end); exit(1); }
+            for (const pomfret_gpu_read_desc &d : wins[w].descs)
+                if ((rc = api.batch_add_read(batch, &d))) die_gpu(api, rc, "batch_add_read");
+            if ((rc = api.batch_add_window(batch, jobs[w].start, jobs[w].end, first, (uint32_t)wins[w].descs.size()))) die_gpu(api, rc, "batch_add_window");
+            firsts.push_back(first);
+            first += (uint32_t)wins[w].descs.size();
+            stats.n_reads += wins[w].descs.size();
+            stats.n_bases += wins[w].n_bases;
+        }
+        stats.n_windows += jobs.size();
+        double t1 = now_s();
+        stats.t_load += t1 - t0;
+        if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
+        if ((rc = api.decode(batch, (uint8_t)cfg.lo, (uint8_t)cfg.hi))) die_gpu(api, rc, "decode");
+        if ((rc = api.pileup(batch, &cfg))) die_gpu(api, rc, "pileup");
+        if ((rc = api.join(batch, &cfg))) die_gpu(api, rc, "join");
+        std::vector<pomfret_gpu_window_result> res(jobs.size() ? jobs.size() : 1);
+        std::vector<uint8_t> tags(first ? first : 1);
+        std::vector<int32_t> ids(first ? first : 1);
+        if ((rc = api.batch_collect(batch, res.data(), tags.data(), ids.data()))) die_gpu(api, rc, "batch_collect");
+        stats.t_gpu += now_s() - t1;
+        outs->assign(jobs.size(), WindowOut());
+        for (size_t w = 0; w < jobs.size(); w++) {
+            const size_t n = wins[w].descs.size();
+            // duplicated read names among the loaded records are fatal (blockjoin.c:1143-1155)
+            std::unordered_set<std::string> seen;
+            for (size_t i = 0; i < n; i++) {
+                if (ids[firsts[w] + i] < 0) continue;
+                if (!seen.insert(wins[w].qname(i)).second) {
+                    fprintf(stderr, "[E::%s] duplicated read name seen from reading bam: %s\n", "load_reads_given_interval", wins[w].qname(i));
+                    exit(1);
+                }
+            }
+            WindowOut &o = (*outs)[w];
+            o.decision = res[w].decision;
+            fprintf(stderr, "[dbg::%s] loaded %d reads (interval: %s:%u-%u), left has #ref=%d (strict: %d), right has=%d (strict: %d); "
+                            "sites n=%d; fwd join %d, bwd join %d\n", "haplotag_region_given_bam", res[w].n_reads, chrom.c_str(), jobs[w].start,
+                    jobs[w].end, res[w].n_left, res[w].n_left_strict, res[w].n_right, res[w].n_right_strict, res[w].n_sites_fwd,
+                    res[w].join_fwd, res[w].join_bwd);
+            if (o.decision >= 0)
+                for (size_t i = 0; i < n; i++)
+                    if (ids[firsts[w] + i] >= 0) o.tags.emplace_back(wins[w].qname(i), (int)tags[firsts[w] + i]);
+        }
+    }
+
+    // pre_haplotagging_read_in_one_ref (blockjoin.c:1841-1898): every primary record of the contig
+    void haptag_contig(const std::string &chrom, const KnownVariants &kv, TagMap *raw) {
+        const GpuApi &api = eng->api;
+        double t0 = now_s();
+        hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, chrom.c_str());
+        if (!itr) return;
+        struct Pending { std::string qname; };
+        std::vector<std::string> names;
+        std::vector<uint32_t> known_first;
+        std::vector<std::vector<uint8_t>> payload;  // record copies of the current batch
+        std::vector<pomfret_gpu_read_desc> descs;
+        uint32_t prev_i_left = 0;
+        size_t bytes = 0;
+        int n_new[4] = {0, 0, 0, 0};
+        auto flush = [&]() {
+            if (names.empty()) return;
+            std::vector<uint8_t> tags(names.size(), (uint8_t)kHaptagUnphased);
+            if (!kv.vars.empty()) {
+                int rc = api.batch_reset(batch);
+                if (rc) die_gpu(api, rc, "batch_reset");
+                for (const pomfret_gpu_read_desc &d : descs) if ((rc = api.batch_add_read(batch, &d))) die_gpu(api, rc, "batch_add_read");
+                if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
+                if ((rc = api.haptag(batch, kv.vars.data(), (uint32_t)kv.vars.size(), kv.bases.data(), (uint32_t)kv.bases.size(), known_first.data())))
+                    die_gpu(api, rc, "haptag");
+                std::vector<int32_t> st(names.size());
+                if ((rc = api.batch_collect_haptags(batch, tags.data(), st.data()))) die_gpu(api, rc, "collect_haptags");
+            }
+            for (size_t i = 0; i < names.size(); i++) {
+                auto ins = raw->emplace(names[i], (int)tags[i]);  // first alignment wins (blockjoin.c:1880-1889)
+                if (ins.second) n_new[tags[i] == 0 ? 0 : tags[i] == 1 ? 1 : 2]++; else n_new[3]++;
+            }
+            names.clear(); known_first.clear(); payload.clear(); descs.clear(); bytes = 0;
+        };
+        bam1_t *b = bam.rec;
+        while (sam_itr_next(bam.fp, itr, b) >= 0) {
+            const int flag = b->core.flag;
+            if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;
+            if (!bam_aux_get(b, "MD")) die_gpu(api, POMFRET_GPU_ERR_MISSING_MD, "haptag");
+            names.emplace_back(bam_get_qname(b));
+            stats.n_haptag_reads++;
+            stats.n_haptag_bases += (uint64_t)b->core.l_qseq;
+            if (!kv.vars.empty()) {
+                // i_left cursor, blockjoin.c:1716-1720
+                uint32_t i = prev_i_left;
+                const uint32_t start_pos = (uint32_t)b->core.pos;
+                while (i < kv.vars.size() && kv.vars[i].pos < start_pos) i++;
+                prev_i_left = i == 0 ? 0 : i - 1;
+                known_first.push_back(i);
+                payload.emplace_back(b->data, b->data + b->l_data);
+                bam1_t tmp = *b;
+                tmp.data = payload.back().data();
+                pomfret_gpu_read_desc d;
+                describe_record(&tmp, kHaptagUnphased, &d);
+                d.mm = nullptr; d.mm_len = 0; d.ml = nullptr; d.ml_len = -1;  // the haplotagger needs CIGAR, SEQ and MD only
+                descs.push_back(d);
+                bytes += (size_t)b->l_data;
+            }
+            if (names.size() >= 16384 || bytes >= ((size_t)512 << 20)) flush();
+        }
+        flush();
+        hts_itr_destroy(itr);
+        fprintf(stderr, "[dbg::%s] tagged: %d new hap0, %d new hap1, %d new unphased, %d dup\n", "pre_haplotagging_read_in_one_ref",
+                n_new[0], n_new[1], n_new[2], n_new[3]);
+        stats.t_haptag += now_s() - t0;
+    }
+};
+
+pomfret_gpu_config base_config(const Options &o) {
+    pomfret_gpu_config c;
+    memset(&c, 0, sizeof(c));
+    c.lo = o.lo; c.hi = o.hi; c.min_mapq = o.mapq; c.k = o.k; c.k_span = o.k_span;
+    c.cov_known = o.cov; c.cov_for_selection = o.cov_for_selection;
+    c.cov_for_runtime = c.cov_for_selection * 2;  // blockjoin.c:4657
+    c.readlen_threshold = o.readlen_threshold;
+    c.n_candidates_per_iter = o.n_candidates_per_iter;
+    return c;
+}
+
+bool files_exist(const Options &o) {  // sancheck_cliopt_t_files_exist, blockjoin.c:4606-4641
+    htsFile *fp = hts_open(o.fn_bam.c_str(), "rb");
+    if (!fp || !fp->is_bgzf) { fprintf(stderr, "[E::%s] cannot open bam file: %s\n", "sancheck_cliopt_t_files_exist", o.fn_bam.c_str()); if (fp) hts_close(fp); return false; }
+    hts_close(fp);
+    for (const std::string *f : {&o.fn_vcf, &o.fn_tsv, &o.fn_gtf}) {
+        if (f->empty()) continue;
+        FILE *t = fopen(f->c_str(), "r");
+        if (!t) { fprintf(stderr, "[E::%s] cannot open %s\n", "sancheck_cliopt_t_files_exist", f->c_str()); return false; }
+        fclose(t);
+    }
+    return true;
+}
+
+void check_limits(const pomfret_gpu_config &c) {
+    if (c.k > 4 || c.n_candidates_per_iter > 128) {
+        fprintf(stderr, "[E::%s] this build supports methmer k <= 4 and <= 128 candidates per iteration (got k=%d, n=%d)\n", "pomfret",
+                c.k, c.n_candidates_per_iter);
+        exit(1);
+    }
+}
+
+// Run all windows of all contigs; chunks of consecutive windows are independent jobs.
+void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const std::vector<pomfret_gpu_config> &cfg_per_ref,
+                 std::vector<std::vector<WindowOut>> *results, RunStats *stats) {
+    struct Chunk { int i_ref; std::vector<WindowJob> jobs; };
+    std::vector<Chunk> chunks;
+    const int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 64;
+    results->assign(ps.st.ref_names.size(), {});
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        const Ranges &rg = ps.st.ranges[r];
+        (*results)[r].assign(rg.n, WindowOut());
+        for (size_t i = 0; i < rg.n; i += (size_t)per) {
+            Chunk c;
+            c.i_ref = (int)r;
+            for (size_t j = i; j < rg.n && j < i + (size_t)per; j++) c.jobs.push_back({(int)r, j, rg.starts[j], rg.ends[j]});
+            chunks.push_back(std::move(c));
+        }
+    }
+    const int n_workers = std::max(1, std::min<int>(opt.threads, (int)chunks.size()));
+    std::atomic<size_t> next(0);
+    std::mutex mu;
+    auto body = [&](int wid) {
+        Worker wk;
+        wk.eng = &eng; wk.id = wid; wk.device = wid % eng.n_dev;
+        if (!wk.open(opt.fn_bam)) exit(1);
+        for (;;) {
+            size_t c = next.fetch_add(1);
+            if (c >= chunks.size()) break;
+            const Chunk &ch = chunks[c];
+            std::vector<WindowOut> outs;
+            wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
+            for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
+        }
+        wk.close();
+        std::lock_guard<std::mutex> lock(mu);
+        stats->n_windows += wk.stats.n_windows; stats->n_reads += wk.stats.n_reads; stats->n_bases += wk.stats.n_bases;
+        stats->t_load += wk.stats.t_load; stats->t_gpu += wk.stats.t_gpu;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_workers; t++) th.emplace_back(body, t);
+    body(0);
+    for (auto &t : th) t.join();
+}
+
+// load_intervals_from_file with the -u pre-pass hooked in (blockjoin.c:4446-4468)
+bool load_all_intervals(Engine &eng, const Options &opt, PhaseState *ps, RunStats *stats) {
+    std::string fatal;
+    const std::string fn_interval = !opt.fn_tsv.empty() ? opt.fn_tsv : !opt.fn_gtf.empty() ? opt.fn_gtf : opt.fn_vcf;
+    const IntervalFormat fmt = !opt.fn_tsv.empty() ? IntervalFormat::TSV : !opt.fn_gtf.empty() ? IntervalFormat::GTF : IntervalFormat::VCF;
+    if (opt.bam_needs_haplotagging) {
+        Worker wk;
+        wk.eng = &eng; wk.id = 0; wk.device = 0;
+        if (!wk.open(opt.fn_bam)) return false;
+        ps->stores_raw_tag = true;
+        bool ok = load_intervals(opt.fn_vcf, IntervalFormat::VCF, &ps->st,
+                                 [&](const std::string &chrom, KnownVariants &kv, bool) { wk.haptag_contig(chrom, kv, &ps->qname2haptag_raw); },
+                                 &fatal);
+        wk.close();
+        stats->n_haptag_reads += wk.stats.n_haptag_reads; stats->n_haptag_bases += wk.stats.n_haptag_bases; stats->t_haptag += wk.stats.t_haptag;
+        if (!ok) { fprintf(stderr, "[E::%s] failed to open file for phase blocks: %s\n", "load_intervals_from_file", opt.fn_vcf.c_str()); exit(1); }
+        if (!fatal.empty()) { fprintf(stderr, "%s\n", fatal.c_str()); exit(1); }
+        size_t n_loaded = 0;
+        for (const Ranges &r : ps->st.ranges) n_loaded += r.n;
+        if (n_loaded == 0) {
+            fprintf(stderr, "[E::%s] Nothing loaded from vcf (ref_n=%d), cannot haptag the input bam. Terminating.\n", "blockjoin_parallel", (int)ps->st.ref_names.size());
+            exit(1);
+        }
+        if (fmt != IntervalFormat::VCF) {  // gtf/tsv override the vcf's phase blocks
+            ps->st = Storage();
+            if (!load_intervals(fn_interval, fmt, &ps->st, nullptr, &fatal)) { fprintf(stderr, "[E::%s] failed to open file for phase blocks: %s\n", "load_intervals_from_file", fn_interval.c_str()); exit(1); }
+        }
+    } else {
+        if (!load_intervals(fn_interval, fmt, &ps->st, nullptr, &fatal)) { fprintf(stderr, "[E::%s] failed to open file for phase blocks: %s\n", "load_intervals_from_file", fn_interval.c_str()); exit(1); }
+        if (!fatal.empty()) { fprintf(stderr, "%s\n", fatal.c_str()); exit(1); }
+    }
+    return true;
+}
+
+}  // namespace
+
+std::vector<int> estimate_read_coverage(const std::string &fn_bam) {
+    BamReader bam;
+    std::vector<int> covs;
+    if (!bam.open(fn_bam)) return covs;
+    covs.assign((size_t)bam.hdr->n_targets, 0);
+    hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, ".");
+    fprintf(stderr, "[M::%s] estimate read depths...\n", "estimate_read_coverage_dirtyfast");
+    const int mod = 5000;
+    std::vector<uint64_t> buf;
+    int prev = -1, refID = -1;
+    auto close_ref = [&](int id) {
+        if (buf.empty()) { covs[id] = 0; return; }
+        uint64_t tot = 0;
+        for (uint64_t v : buf) tot += v;
+        covs[id] = (int)(tot / buf.size());
+    };
+    bam1_t *b = bam.rec;
+    while (sam_itr_next(bam.fp, itr, b) >= 0) {
+        refID = b->core.tid;
+        if (refID < 0) continue;
+        if (refID > bam.hdr->n_targets) continue;
+        if (refID != prev) {
+            if (prev >= 0) close_ref(prev);
+            buf.assign((size_t)(bam.hdr->target_len[refID] / mod), 0);
+            prev = refID;
+        }
+        const int flag = b->core.flag;
+        if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;
+        if (b->core.qual < 5) continue;
+        float de = -1;
+        uint8_t *t = bam_aux_get(b, "de");
+        if (t) de = (float)bam_aux2f(t);
+        if ((uint32_t)b->core.l_qseq < 15000) continue;
+        if (de > kMinAlnDe) continue;
+        const uint32_t s = (uint32_t)b->core.pos, e = (uint32_t)bam_endpos(b);
+        for (int i = (int)s; i < (int)e; i += mod) {
+            size_t bin = (size_t)(i / mod);
+            if (bin < buf.size()) buf[bin]++;  // the reference can write one bin past the end here
+        }
+    }
+    if (refID >= 0) close_ref(refID);
+    hts_itr_destroy(itr);
+    for (int i = 0; i < bam.hdr->n_targets; i++)
+        fprintf(stderr, "[M::%s] %s est. coverage is %d\n", "estimate_read_coverage_dirtyfast", bam.hdr->target_name[i], covs[(size_t)i]);
+    return covs;
+}
+
+int run_methphase(const Options &opt, RunStats *stats) {
+    const double T = now_s();
+    if (!files_exist(opt)) return 1;
+    Engine eng;
+    if (!eng.start(opt.gpus, opt.threads)) return 1;
+    PhaseState ps;
+    if (!load_all_intervals(eng, opt, &ps, stats)) return 1;
+    size_t n_loaded = 0;
+    for (const Ranges &r : ps.st.ranges) n_loaded += r.n;
+    if (n_loaded == 0) { fprintf(stderr, "[E::%s] No intervals loaded, terminating.\n", "blockjoin_parallel"); exit(1); }
+    fprintf(stderr, "[M::%s] input has %d references\n", "blockjoin_parallel", (int)ps.st.ref_names.size());
+    for (Ranges &r : ps.st.ranges) { store_raw_intervals(&r); merge_close_intervals(&r, kReadback); }
+    fprintf(stderr, "[M::%s] loaded phase block gaps.\n\n\n", "blockjoin_parallel");
+
+    // per-contig parameters (blockjoin_one_chrom_callback, blockjoin.c:4357-4392)
+    pomfret_gpu_config base = base_config(opt);
+    std::vector<int> covs;
+    BamReader hdr_only;
+    if (base.cov_for_selection <= 0) {
+        covs = estimate_read_coverage(opt.fn_bam);
+        if (!hdr_only.open(opt.fn_bam)) return 1;
+    }
+    std::vector<pomfret_gpu_config> cfgs;
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        pomfret_gpu_config c = base;
+        if (c.cov_for_selection <= 0) {
+            int ref_i = sam_hdr_name2tid(hdr_only.hdr, ps.st.ref_names[r].c_str());
+            if (ref_i < 0) { fprintf(stderr, "pomfret: blockjoin_one_chrom_callback: Assertion `ref_i>=0' failed.\n"); abort(); }
+            const int coverage = covs[(size_t)ref_i];
+            c.cov_for_selection = coverage / 10 + 1;
+            c.cov_for_runtime = c.cov_for_selection * 2;
+            c.n_candidates_per_iter = coverage / 4 + 1;
+        }
+        if (c.cov_for_selection <= 0) { fprintf(stderr, "[W::%s] had to clamp cov_for_selection (ref: %s)\n", "blockjoin_one_chrom_callback", ps.st.ref_names[r].c_str()); c.cov_for_selection = 1; }
+        if (c.n_candidates_per_iter <= 1) { fprintf(stderr, "[W::%s] had to clamp n_candidates_per_iter (ref: %s)\n", "blockjoin_one_chrom_callback", ps.st.ref_names[r].c_str()); c.n_candidates_per_iter = 2; }
+        fprintf(stderr, "[dbg::%s] ref %s using: cov_for_selection=%d, n_cand_per_iter=%d\n", "blockjoin_one_chrom_callback", ps.st.ref_names[r].c_str(), c.cov_for_selection, c.n_candidates_per_iter);
+        check_limits(c);
+        cfgs.push_back(c);
+    }
+    std::vector<std::vector<WindowOut>> results;
+    run_windows(eng, opt, ps, cfgs, &results, stats);
+    // decisions + per-contig tag tables, then the global table in contig order (first insert wins both times)
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        Ranges &rg = ps.st.ranges[r];
+        TagMap local;
+        for (size_t i = 0; i < rg.n; i++) {
+            rg.decisions[i] = results[r][i].decision;
+            for (auto &kv : results[r][i].tags) local.emplace(kv.first, kv.second);
+        }
+        for (auto &kv : local) ps.qname2haptag.emplace(kv.first, kv.second);
+    }
+    fprintf(stderr, "\n\n[M::%s] done, used %.1fs.\n", "blockjoin_parallel", now_s() - T);
+
+    lift_decisions(&ps.st);
+    make_flips_onraw(&ps.st);
+    generate_new_phase_blocks(&ps.st);
+    if (opt.write_debug_files) output_debug_read2tag(ps, opt.output_prefix);
+    output_gtf(ps, opt.output_prefix);
+    fprintf(stderr, "[M::%s] gtf written.\n", "main_blockjoin");
+    if (opt.do_output_tsv) { output_tsv(ps, opt.output_prefix); fprintf(stderr, "[M::%s] tsv written.\n", "main_blockjoin"); }
+    if (!opt.fn_vcf.empty()) {
+        fprintf(stderr, "[M::%s] writing vcf...\n", "main_blockjoin");
+        recover_variant_phase_in_dropped_intervals(&ps, opt.fn_bam, opt.fn_vcf);
+        output_modify_vcf(opt.fn_vcf, ps, opt.output_prefix);
+        fprintf(stderr, "[M::%s] vcf written.\n", "main_blockjoin");
+    }
+    if (opt.do_output_bam) {
+        const std::string fn_bam_out = opt.output_prefix + ".mp.bam", fn_bai_out = opt.output_prefix + ".mp.bam.bai";
+        output_modify_bam(opt.fn_bam, ps, fn_bam_out);
+        fprintf(stderr, "[M::%s] bam written. now indexing...\n", "main_blockjoin");
+        int stat = sam_index_build3(fn_bam_out.c_str(), fn_bai_out.c_str(), 0, opt.threads_bam);
+        if (stat != 0) fprintf(stderr, "[W::%s] failed to build index for output bam (status code=%d)\n", "main_blockjoin", stat);
+        fprintf(stderr, "[M::%s] bam index written.\n", "main_blockjoin");
+    }
+    stats->t_total = now_s() - T;
+    return 0;
+}
+
+int run_report(const Options &opt, RunStats *stats) {
+    const double T = now_s();
+    if (opt.fn_bam.empty()) { fprintf(stderr, "[E::%s] input bam file name missing\n", "main_methreport"); exit(1); }
+    if (opt.fn_vcf.empty()) { fprintf(stderr, "[E::%s] input vcf file name missing\n", "main_methreport"); exit(1); }
+    {
+        BamReader probe;
+        if (!probe.open(opt.fn_bam)) { fprintf(stderr, "[E::%s] failed to open input bam: %s\n", "main_methreport", opt.fn_bam.c_str()); exit(1); }
+    }
+    const std::string fn_out = opt.output_prefix + ".report.tsv";
+    FILE *fp_out = fopen(fn_out.c_str(), "w");
+    if (!fp_out) { fprintf(stderr, "[E::%s] failed to open output file\n", "main_methreport"); exit(1); }
+    Engine eng;
+    if (!eng.start(opt.gpus, opt.threads)) return 1;
+    PhaseState ps;
+    Options o2 = opt;
+    o2.fn_tsv.clear(); o2.fn_gtf.clear();  // report always derives its blocks from the vcf (blockjoin.c:4958)
+    if (!load_all_intervals(eng, o2, &ps, stats)) return 1;
+    // replace the gaps by windows inside the phased stretches (blockjoin.c:4961-4993)
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        Ranges &rg = ps.st.ranges[r];
+        std::vector<uint32_t> starts, ends;
+        uint32_t prev = rg.abs_start;
+        for (size_t i = 0; i < rg.n; i++) {
+            const uint32_t start = rg.starts[i], end = rg.ends[i];
+            if ((uint32_t)(start - prev) > (uint32_t)opt.chunk_size)
+                for (uint32_t p = prev; p + (uint32_t)opt.chunk_stride < start; p += (uint32_t)opt.chunk_stride) {
+                    starts.push_back(p);
+                    ends.push_back(p + (uint32_t)opt.chunk_size);
+                }
+            prev = end;
+        }
+        rg.starts = starts; rg.ends = ends; rg.n = starts.size();
+        rg.decisions.assign(starts.size(), -1); rg.n_decisions = starts.size();
+        fprintf(stderr, "[M::%s] %s has %d intervals\n", "main_methreport", ps.st.ref_names[r].c_str(), (int)starts.size());
+    }
+    const int read_coverage = opt.cov;
+    std::vector<int> covs;
+    BamReader hdr_only;
+    if (read_coverage <= 0) {
+        fprintf(stderr, "[M::%s] estimating read depths..\n", "main_methreport");
+        covs = estimate_read_coverage(opt.fn_bam);
+        if (!hdr_only.open(opt.fn_bam)) return 1;
+    }
+    std::vector<pomfret_gpu_config> cfgs;
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        pomfret_gpu_config c = base_config(opt);
+        // the reference indexes covs[] by contig order of the vcf here (blockjoin.c:5045-5051)
+        const int cov = read_coverage <= 0 ? (r < covs.size() ? covs[r] : 0) : read_coverage;
+        c.cov_for_selection = cov / 10 + 1;
+        c.cov_for_runtime = c.cov_for_selection * 2;
+        c.n_candidates_per_iter = cov / 4 + 1;
+        check_limits(c);
+        cfgs.push_back(c);
+    }
+    std::vector<std::vector<WindowOut>> results;
+    run_windows(eng, opt, ps, cfgs, &results, stats);
+    float n_switch = 0, n_fail = 0, n_correct = 0;
+    int tot = 0;
+    for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
+        const Ranges &rg = ps.st.ranges[r];
+        for (size_t i = 0; i < rg.n; i++) {
+            const int start = (int)rg.starts[i], end = (int)rg.ends[i], decision = results[r][i].decision;
+            fprintf(fp_out, "%s\t%d\t%d\t", ps.st.ref_names[r].c_str(), start, end);
+            if (decision == 0) { n_correct++; fprintf(fp_out, "correct\n"); }
+            else if (decision == 1) { n_switch++; fprintf(fp_out, "switch\n"); }
+            else { n_fail++; fprintf(fp_out, "fail\n"); }
+            tot++;
+            if (tot % 100 == 0)
+                fprintf(stdout, "Parsed N=%d regions, currently at %s:%d-%d, correct/(correct+switch)=%.2f%%, correct/N=%.2f%%\n", tot,
+                        ps.st.ref_names[r].c_str(), start, end, n_correct / (n_correct + n_switch) * 100.0, n_correct / (float)tot * 100.0);
+        }
+    }
+    fprintf(stdout, "Total N=%d regions, correct/(correct+switch)=%.2f%%, correct/N=%.2f%%\n", tot,
+            n_correct / (n_correct + n_switch) * 100.0, n_correct / (float)tot * 100.0);
+    fprintf(stderr, "[M::%s] Total N=%d regions, correct/(correct+switch)=%.2f%%, correct/N=%.2f%%\n", "main_methreport", tot,
+            n_correct / (n_correct + n_switch) * 100.0, n_correct / (float)tot * 100.0);
+    fclose(fp_out);
+    fprintf(stderr, "[M::%s] done, used %.1fs\n", "main_methreport", now_s() - T);
+    stats->t_total = now_s() - T;
+    return 0;
+}
+
+}  // namespace pomfret

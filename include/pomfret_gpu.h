@@ -183,6 +183,8 @@ int pomfret_gpu_debug_get_tags(pomfret_gpu_batch *b, int direction, uint8_t *tag
 /* tagging order of the greedy loop: read ids (within window) in the order they were tagged */
 int pomfret_gpu_debug_get_tag_order(pomfret_gpu_batch *b, uint32_t window, int direction, uint32_t *ids,
                                     uint32_t cap, uint32_t *n);
+/* hp_cnt[0], hp_cnt[1] of haptag_one_read_with_variants (blockjoin.c:1746), two per read */
+int pomfret_gpu_debug_get_votes(pomfret_gpu_batch *b, int32_t *votes);
 
 #ifdef __cplusplus
 }

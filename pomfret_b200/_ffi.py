@@ -188,9 +188,10 @@ class Batch:
             self.gpu.check(rc, "batch_collect")
         return list(res)[:self.n_windows], tags[:self.n_reads], ids[:self.n_reads], rc
 
-    def haptag(self, variants, bases, known_first):
-        self.gpu.check(self.gpu.lib.pomfret_gpu_haptag(self.h, variants.ctypes.data if len(variants) else None,
-                                                       len(variants), bases.ctypes.data if len(bases) else None,
+    def haptag(self, variants, n_variants, bases, known_first):
+        """variants: numpy byte buffer holding n_variants pomfret_gpu_variant records"""
+        self.gpu.check(self.gpu.lib.pomfret_gpu_haptag(self.h, variants.ctypes.data if n_variants else None,
+                                                       n_variants, bases.ctypes.data if len(bases) else None,
                                                        len(bases), known_first.ctypes.data), "haptag")
 
     def collect_haptags(self):

@@ -43,7 +43,7 @@ def haptag_parity(gpu, data, chrom):
     b = gpu.batch_begin(ctx)
     b.add_reads(descs, n)
     b.submit()
-    b.haptag(known.view(np.uint8), bases[:nb.value], kf)
+    b.haptag(known, nk, bases[:nb.value], kf)
     tags, status = b.collect_haptags()
     votes = np.zeros(2 * n, np.int32)
     gpu.lib.pomfret_gpu_debug_get_votes.argtypes = [C.c_void_p, C.c_void_p]

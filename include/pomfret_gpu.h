@@ -134,6 +134,8 @@ const char *pomfret_gpu_version(void);
 int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfret_gpu_batch **out);
 int pomfret_gpu_batch_reset(pomfret_gpu_batch *b);
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r);
+/* the same for an array of n descriptors (one call per window instead of one per record) */
+int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n);
 /* reads [first_read, first_read+n_reads) are the records of the region query
  * chrom:(ref_start-50000)-(ref_end+50000) in BAM order */
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,

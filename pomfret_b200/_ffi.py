@@ -92,6 +92,7 @@ class GpuLib:
         lib.pomfret_gpu_batch_begin.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
         lib.pomfret_gpu_batch_reset.argtypes = [vp]
         lib.pomfret_gpu_batch_add_read.argtypes = [vp, vp]
+        lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
         lib.pomfret_gpu_decode.argtypes = [vp, C.c_uint8, C.c_uint8]
@@ -154,10 +155,8 @@ class Batch:
 
     def add_reads(self, descs_ptr, n):
         """descs_ptr: address of an array of pomfret_gpu_read_desc"""
-        sz = C.sizeof(ReadDesc)
         base = descs_ptr if isinstance(descs_ptr, int) else C.cast(descs_ptr, C.c_void_p).value
-        for i in range(n):
-            self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_read(self.h, base + i * sz), "batch_add_read")
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_reads(self.h, base, n), "batch_add_reads")
         first = self.n_reads
         self.n_reads += n
         return first

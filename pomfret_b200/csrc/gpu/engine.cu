@@ -293,6 +293,13 @@ int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc
     return POMFRET_GPU_OK;
 }
 
+int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n) {
+    if (!b || (n && !r)) return POMFRET_GPU_ERR_ARG;
+    for (uint32_t i = 0; i < n; i++)
+        if (int rc = pomfret_gpu_batch_add_read(b, r + i)) return rc;
+    return POMFRET_GPU_OK;
+}
+
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
                                  uint32_t n_reads) {
     if (!b) return POMFRET_GPU_ERR_ARG;

@@ -16,6 +16,7 @@ struct GpuApi {
     int (*batch_begin)(pomfret_gpu_ctx *, int, int, pomfret_gpu_batch **) = nullptr;
     int (*batch_reset)(pomfret_gpu_batch *) = nullptr;
     int (*batch_add_read)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *) = nullptr;
+    int (*batch_add_reads)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *, uint32_t) = nullptr;
     int (*batch_add_window)(pomfret_gpu_batch *, uint32_t, uint32_t, uint32_t, uint32_t) = nullptr;
     int (*batch_submit)(pomfret_gpu_batch *) = nullptr;
     int (*decode)(pomfret_gpu_batch *, uint8_t, uint8_t) = nullptr;

@@ -90,8 +90,7 @@ struct Worker {
         for (size_t w = 0; w < jobs.size(); w++) {
             rc = load_window(bam, chrom.c_str(), jobs[w].start, jobs[w].end, cfg.readlen_threshold, cfg.min_mapq, raw_tags, &wins[w]);
             if (rc) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[w].start, jobs[w].end); exit(1); }
-            for (const pomfret_gpu_read_desc &d : wins[w].descs)
-                if ((rc = api.batch_add_read(batch, &d))) die_gpu(api, rc, "batch_add_read");
+            if ((rc = api.batch_add_reads(batch, wins[w].descs.data(), (uint32_t)wins[w].descs.size()))) die_gpu(api, rc, "batch_add_reads");
             if ((rc = api.batch_add_window(batch, jobs[w].start, jobs[w].end, first, (uint32_t)wins[w].descs.size()))) die_gpu(api, rc, "batch_add_window");
             firsts.push_back(first);
             first += (uint32_t)wins[w].descs.size();

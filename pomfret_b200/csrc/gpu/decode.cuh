@@ -44,6 +44,7 @@ struct DecodeParams {
     uint32_t *tmp_mpos;
     uint8_t *tmp_mcat;
     uint32_t *r_ncalls, *r_status, *r_end;
+    uint32_t *n_overflow;  // records that ran out of call slots (the engine re-runs them with more room)
     uint32_t lo, hi;
 };
 
@@ -909,6 +910,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_kernel(DecodeParams P) 
         n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
     }
     if (lane == 0) {
+        if (status & RS_OVERFLOW) atomicAdd(P.n_overflow, 1u);
         P.r_ncalls[ri] = (status & RS_KEPT) || (status & RS_OVERFLOW) ? n_calls : 0;
         P.r_status[ri] = status;
         P.r_end[ri] = R.pos + rlen;

@@ -122,7 +122,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -222,7 +222,7 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
                      &b->d_mm_xl[1], &b->d_mm_xr[0], &b->d_mm_xr[1], &b->d_mm_off[0], &b->d_mm_off[1], &b->d_mm_n[0],
                      &b->d_mm_n[1], &b->d_mm_start[0], &b->d_mm_start[1], &b->d_pool_total, &b->d_mmr_pool, &b->d_ent_pool,
                      &b->d_tab, &b->d_tags[0], &b->d_tags[1], &b->d_order[0], &b->d_order[1], &b->d_known, &b->d_bases,
-                     &b->d_known_first, &b->d_hap_tag, &b->d_hap_status};
+                     &b->d_known_first, &b->d_hap_tag, &b->d_hap_status, &b->d_flags};
     for (DevBuf *d : all) d->release();
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
     b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release();
@@ -350,8 +350,9 @@ static int launch_decode(pomfret_gpu_batch *b) {
     int rc;
     if ((rc = b->d_calls_pos.ensure(slots * 4)) || (rc = b->d_calls_cat.ensure(slots)) || (rc = b->d_tmp_rank.ensure(slots * 4)) ||
         (rc = b->d_tmp_mpos.ensure(slots * 4)) || (rc = b->d_tmp_mcat.ensure(slots)) || (rc = b->d_r_ncalls.ensure(nr * 4 + 16)) ||
-        (rc = b->d_r_status.ensure(nr * 4 + 16)) || (rc = b->d_r_end.ensure(nr * 4 + 16)))
+        (rc = b->d_r_status.ensure(nr * 4 + 16)) || (rc = b->d_r_end.ensure(nr * 4 + 16)) || (rc = b->d_flags.ensure(16)))
         return rc;
+    CK(cudaMemsetAsync(b->d_flags.p, 0, 16, b->stream));
     DecodeParams P;
     P.reads = b->d_reads.as<ReadRec>();
     P.n_reads = (uint32_t)nr;
@@ -364,6 +365,7 @@ static int launch_decode(pomfret_gpu_batch *b) {
     P.r_ncalls = b->d_r_ncalls.as<uint32_t>();
     P.r_status = b->d_r_status.as<uint32_t>();
     P.r_end = b->d_r_end.as<uint32_t>();
+    P.n_overflow = b->d_flags.as<uint32_t>();
     P.lo = b->lo; P.hi = b->hi;
     if (nr) {
         unsigned grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS);
@@ -510,9 +512,33 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     POMFRET_LAUNCH(methmer_size_kernel, (unsigned)nw, RS_THREADS, 0, b->stream, M);
     b->tm.launches++;
     // ---- the one round trip: pool sizes (and whether any record ran out of call slots) ----
-    if ((rc = b->h_u32.resize(4))) return rc;
-    CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 8, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
+    if ((rc = b->h_u32.resize(8))) return rc;
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 8, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->h_u32.data() + 4, b->d_flags.p, 4, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        if (b->h_u32[4] == 0) break;
+        if (attempt > 0) return POMFRET_GPU_ERR_UNSUPPORTED;
+        // Implicit canonical calls (blockjoin.c:666-700) can exceed one slot per listed base: give the affected
+        // records the hard upper bound (every second base + every listed base) and run the stages again.
+        std::vector<uint32_t> st(nr);
+        CK(cudaMemcpy(st.data(), b->d_r_status.p, nr * 4, cudaMemcpyDeviceToHost));
+        uint64_t total = 0;
+        for (size_t i = 0; i < nr; i++) {
+            ReadRec &R = b->h_reads[i];
+            if (st[i] & RS_OVERFLOW) R.calls_cap = R.calls_cap + R.l_qseq / 2 + 16;
+            R.calls_off = (uint32_t)total;
+            total += R.calls_cap;
+        }
+        if (total > 0xfff00000ull) return POMFRET_GPU_ERR_UNSUPPORTED;
+        b->calls_total = total;
+        if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
+        if ((rc = launch_decode(b))) return rc;
+        if ((rc = launch_pileup_stages(b))) return rc;
+        fill_methmer_params(b, M);
+        POMFRET_LAUNCH(methmer_size_kernel, (unsigned)nw, RS_THREADS, 0, b->stream, M);
+        b->tm.launches += 1;
+    }
     const uint32_t mmr_total = b->h_u32[0], tab_sites = b->h_u32[1];
     b->pool_cap = mmr_total + 64;
     b->tab_sites = tab_sites;

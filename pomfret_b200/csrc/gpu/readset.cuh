@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(RS_THREADS) readset_kernel(ReadsetParams P) {
         if (i < nr) {
             uint32_t st = P.r_status[first + i];
             keep = (st & RS_KEPT) ? 1u : 0u;
-            if (st & (RS_FATAL_CIGAR | RS_OVERFLOW)) fatal = 1;
+            if (st & RS_FATAL_CIGAR) fatal = 1;
         }
         uint32_t tot;
         uint32_t ex = block_exclusive_scan(keep, &tot, s_warp);

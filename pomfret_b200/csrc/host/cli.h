@@ -21,7 +21,7 @@ struct Options {
     int verbose = 0;
     // additions of this implementation (do not change results)
     int gpus = 0;                // 0 = all visible devices
-    int windows_per_batch = 64;
+    int windows_per_batch = 8;
 };
 
 void print_help_main();

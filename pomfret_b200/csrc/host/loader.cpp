@@ -89,72 +89,78 @@ void describe_record(const bam1_t *b, int hp, pomfret_gpu_read_desc *d) {
     }
 }
 
-int load_window(BamReader &bam, const char *chrom, uint32_t ref_start, uint32_t ref_end, int readlen_threshold,
-                int min_mapq, const RawTagMap *raw_tags, WindowReads *out) {
-    out->clear();
-    out->ref_start = ref_start;
-    out->ref_end = ref_end;
+int for_each_window_record(BamReader &bam, const char *chrom, uint32_t ref_start, uint32_t ref_end, int readlen_threshold,
+                           int min_mapq, const RawTagMap *raw_tags, const std::function<void(const bam1_t *, int hp)> &fn) {
     const int itvl_s = (int)ref_start, itvl_e = (int)ref_end;
     char region[1024];
     snprintf(region, sizeof(region), "%s:%d-%d", chrom, (itvl_s - kReadback) > 0 ? itvl_s - kReadback : 0,
              itvl_e + kReadback);
     hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, region);
     if (!itr) return POMFRET_GPU_ERR_ARG;
-    struct Pending { size_t off; size_t len; int hp; };
-    std::vector<Pending> pending;
     bam1_t *b = bam.rec;
     while (sam_itr_next(bam.fp, itr, b) >= 0) {
         const int flag = b->core.flag;
         const uint32_t mapq = b->core.qual;
         const uint32_t len = (uint32_t)b->core.l_qseq;
-        float de = -1;
-        uint8_t *t = bam_aux_get(b, "de");
-        if (t) de = (float)bam_aux2f(t);
         if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;
         if (mapq < (uint32_t)min_mapq) continue;
         if (len < 2 || len < (uint32_t)readlen_threshold) continue;
+        float de = -1;
+        uint8_t *t = bam_aux_get(b, "de");
+        if (t) de = (float)bam_aux2f(t);
         if (de > kMinAlnDe) continue;
-        int hp = hp_from_record(b);
-        const char *qn = bam_get_qname(b);
+        int hp;
         if (raw_tags) {
-            auto it = raw_tags->find(qn);
+            auto it = raw_tags->find(bam_get_qname(b));
             hp = it != raw_tags->end() ? it->second : kHaptagUnphased;
-        }
-        // keep a 16-byte aligned copy of the record payload
-        size_t off = (out->arena.size() + 15) & ~(size_t)15;
-        out->arena.resize(off + (size_t)b->l_data + 16);
-        memcpy(out->arena.data() + off, b->data, (size_t)b->l_data);
-        pending.push_back({off, (size_t)b->l_data, hp});
-        out->qname_off.push_back((uint32_t)out->qnames.size());
-        out->qnames.append(qn);
-        out->qnames.push_back('\0');
-        out->n_bases += len;
-        // core fields are needed again when the pointers are fixed up below
-        pomfret_gpu_read_desc d;
-        memset(&d, 0, sizeof(d));
-        d.pos = (uint32_t)b->core.pos;
-        d.l_qseq = len;
-        d.n_cigar = b->core.n_cigar;
-        d.flag = b->core.flag;
-        d.mapq = b->core.qual;
-        d.reserved = (uint32_t)b->core.l_qname;  // scratch until fix-up
-        out->descs.push_back(d);
+        } else hp = hp_from_record(b);
+        fn(b, hp);
     }
     hts_itr_destroy(itr);
-    // arena is final: describe each stored record in place
-    bam1_t tmp;
-    memset(&tmp, 0, sizeof(tmp));
-    for (size_t i = 0; i < pending.size(); i++) {
+    return 0;
+}
+
+// Copies only what the engine reads (CIGAR, SEQ, MM, ML, MD): base qualities and the other tags stay behind.
+int load_window(BamReader &bam, const char *chrom, uint32_t ref_start, uint32_t ref_end, int readlen_threshold,
+                int min_mapq, const RawTagMap *raw_tags, WindowReads *out) {
+    out->clear();
+    out->ref_start = ref_start;
+    out->ref_end = ref_end;
+    struct Off { size_t cigar, seq, mm, ml, md; };
+    std::vector<Off> offs;
+    auto put = [&](const void *p, size_t n) {
+        size_t off = (out->arena.size() + 15) & ~(size_t)15;
+        out->arena.resize(off + n + 1);
+        if (n) memcpy(out->arena.data() + off, p, n);
+        out->arena[off + n] = 0;
+        return off;
+    };
+    int rc = for_each_window_record(bam, chrom, ref_start, ref_end, readlen_threshold, min_mapq, raw_tags,
+                                    [&](const bam1_t *b, int hp) {
+        pomfret_gpu_read_desc d;
+        describe_record(b, hp, &d);
+        Off o;
+        o.cigar = put(d.cigar, (size_t)d.n_cigar * 4);
+        o.seq = put(d.seq, ((size_t)d.l_qseq + 1) / 2);
+        o.mm = d.mm ? put(d.mm, d.mm_len) : 0;
+        o.ml = d.ml_len >= 0 ? put(d.ml, (size_t)d.ml_len) : 0;
+        o.md = d.md ? put(d.md, d.md_len) : 0;
+        offs.push_back(o);
+        out->descs.push_back(d);
+        out->qname_off.push_back((uint32_t)out->qnames.size());
+        out->qnames.append(bam_get_qname(b));
+        out->qnames.push_back('\0');
+        out->n_bases += d.l_qseq;
+    });
+    if (rc) return rc;
+    const uint8_t *base = out->arena.data();
+    for (size_t i = 0; i < offs.size(); i++) {
         pomfret_gpu_read_desc &d = out->descs[i];
-        tmp.data = out->arena.data() + pending[i].off;
-        tmp.l_data = (int)pending[i].len;
-        tmp.core.pos = d.pos;
-        tmp.core.l_qseq = (int32_t)d.l_qseq;
-        tmp.core.n_cigar = d.n_cigar;
-        tmp.core.flag = d.flag;
-        tmp.core.qual = d.mapq;
-        tmp.core.l_qname = (uint16_t)d.reserved;
-        describe_record(&tmp, pending[i].hp, &d);
+        d.cigar = (const uint32_t *)(base + offs[i].cigar);
+        d.seq = base + offs[i].seq;
+        if (d.mm) d.mm = (const char *)(base + offs[i].mm);
+        if (d.ml_len >= 0) d.ml = base + offs[i].ml;
+        if (d.md) d.md = (const char *)(base + offs[i].md);
     }
     return 0;
 }

@@ -5,6 +5,7 @@
 #ifndef POMFRET_HOST_LOADER_H
 #define POMFRET_HOST_LOADER_H
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -48,6 +49,11 @@ int hp_from_record(const bam1_t *b);
 
 // Fill `desc` from a record. Pointers address b's data.
 void describe_record(const bam1_t *b, int hp, pomfret_gpu_read_desc *desc);
+
+// Query chrom:(s-50000)-(e+50000) and hand every record that passes the filters (blockjoin.c:1081-1084) to
+// `fn` together with its haplotag; the record is only valid during the call.  Returns 0 or an error code.
+int for_each_window_record(BamReader &bam, const char *chrom, uint32_t ref_start, uint32_t ref_end, int readlen_threshold,
+                           int min_mapq, const RawTagMap *raw_tags, const std::function<void(const bam1_t *, int hp)> &fn);
 
 // Query chrom:(s-50000)-(e+50000), filter (blockjoin.c:1081-1084) and pack.
 // raw_tags: the -u override (blockjoin.c:1114-1122), may be null.

@@ -82,20 +82,34 @@ struct Worker {
                    const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
         const GpuApi &api = eng->api;
         double t0 = now_s();
-        std::vector<WindowReads> wins(jobs.size());
+        // records go from the BAM reader straight into the batch's pinned arena (one copy); only names are kept
+        struct Win { std::vector<uint32_t> qname_off; std::string qnames; size_t n = 0;
+                     const char *qname(size_t i) const { return qnames.data() + qname_off[i]; } };
+        std::vector<Win> wins(jobs.size());
         int rc = api.batch_reset(batch);
         if (rc) die_gpu(api, rc, "batch_reset");
         uint32_t first = 0;
         std::vector<uint32_t> firsts;
         for (size_t w = 0; w < jobs.size(); w++) {
-            rc = load_window(bam, chrom.c_str(), jobs[w].start, jobs[w].end, cfg.readlen_threshold, cfg.min_mapq, raw_tags, &wins[w]);
+            Win &W = wins[w];
+            rc = for_each_window_record(bam, chrom.c_str(), jobs[w].start, jobs[w].end, cfg.readlen_threshold, cfg.min_mapq, raw_tags,
+                                        [&](const bam1_t *b, int hp) {
+                pomfret_gpu_read_desc d;
+                describe_record(b, hp, &d);
+                d.md = nullptr; d.md_len = 0;  // the window engine does not read MD
+                int rc2 = api.batch_add_read(batch, &d);
+                if (rc2) die_gpu(api, rc2, "batch_add_read");
+                W.qname_off.push_back((uint32_t)W.qnames.size());
+                W.qnames.append(bam_get_qname(b));
+                W.qnames.push_back('\0');
+                W.n++;
+                stats.n_bases += d.l_qseq;
+            });
             if (rc) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[w].start, jobs[w].end); exit(1); }
-            if ((rc = api.batch_add_reads(batch, wins[w].descs.data(), (uint32_t)wins[w].descs.size()))) die_gpu(api, rc, "batch_add_reads");
-            if ((rc = api.batch_add_window(batch, jobs[w].start, jobs[w].end, first, (uint32_t)wins[w].descs.size()))) die_gpu(api, rc, "batch_add_window");
+            if ((rc = api.batch_add_window(batch, jobs[w].start, jobs[w].end, first, (uint32_t)W.n))) die_gpu(api, rc, "batch_add_window");
             firsts.push_back(first);
-            first += (uint32_t)wins[w].descs.size();
-            stats.n_reads += wins[w].descs.size();
-            stats.n_bases += wins[w].n_bases;
+            first += (uint32_t)W.n;
+            stats.n_reads += W.n;
         }
         stats.n_windows += jobs.size();
         double t1 = now_s();
@@ -111,7 +125,7 @@ struct Worker {
         stats.t_gpu += now_s() - t1;
         outs->assign(jobs.size(), WindowOut());
         for (size_t w = 0; w < jobs.size(); w++) {
-            const size_t n = wins[w].descs.size();
+            const size_t n = wins[w].n;
             // duplicated read names among the loaded records are fatal (blockjoin.c:1143-1155)
             std::unordered_set<std::string> seen;
             for (size_t i = 0; i < n; i++) {
@@ -237,7 +251,7 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
                  std::vector<std::vector<WindowOut>> *results, RunStats *stats) {
     struct Chunk { int i_ref; std::vector<WindowJob> jobs; };
     std::vector<Chunk> chunks;
-    const int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 64;
+    const int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 8;
     results->assign(ps.st.ref_names.size(), {});
     for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
         const Ranges &rg = ps.st.ranges[r];
@@ -255,7 +269,9 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
     auto body = [&](int wid) {
         Worker wk;
         wk.eng = &eng; wk.id = wid; wk.device = wid % eng.n_dev;
+        const double tw0 = now_s();
         if (!wk.open(opt.fn_bam)) exit(1);
+        const double tw1 = now_s();
         for (;;) {
             size_t c = next.fetch_add(1);
             if (c >= chunks.size()) break;
@@ -264,7 +280,10 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
             wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
             for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
         }
+        const double tw2 = now_s();
         wk.close();
+        fprintf(stderr, "[T::worker %d] open %.2fs, chunks %.2fs (load %.2fs, gpu %.2fs), close %.2fs\n", wid, tw1 - tw0, tw2 - tw1,
+                wk.stats.t_load, wk.stats.t_gpu, now_s() - tw2);
         std::lock_guard<std::mutex> lock(mu);
         stats->n_windows += wk.stats.n_windows; stats->n_reads += wk.stats.n_reads; stats->n_bases += wk.stats.n_bases;
         stats->t_load += wk.stats.t_load; stats->t_gpu += wk.stats.t_gpu;
@@ -398,7 +417,9 @@ int run_methphase(const Options &opt, RunStats *stats) {
         cfgs.push_back(c);
     }
     std::vector<std::vector<WindowOut>> results;
+    fprintf(stderr, "[T::%s] setup + intervals %.2fs\n", "run_methphase", now_s() - T);
     run_windows(eng, opt, ps, cfgs, &results, stats);
+    fprintf(stderr, "[T::%s] windows done at %.2fs\n", "run_methphase", now_s() - T);
     // decisions + per-contig tag tables, then the global table in contig order (first insert wins both times)
     for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
         Ranges &rg = ps.st.ranges[r];
@@ -424,6 +445,7 @@ int run_methphase(const Options &opt, RunStats *stats) {
         output_modify_vcf(opt.fn_vcf, ps, opt.output_prefix);
         fprintf(stderr, "[M::%s] vcf written.\n", "main_blockjoin");
     }
+    fprintf(stderr, "[T::%s] gtf/vcf written at %.2fs\n", "run_methphase", now_s() - T);
     if (opt.do_output_bam) {
         const std::string fn_bam_out = opt.output_prefix + ".mp.bam", fn_bai_out = opt.output_prefix + ".mp.bam.bai";
         output_modify_bam(opt.fn_bam, ps, fn_bam_out);

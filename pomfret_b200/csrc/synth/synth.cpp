@@ -253,6 +253,7 @@ extern "C" void pomfret_synth_default_config(synth_config *c) {
     c->frac_multicode = 0.05;
     c->frac_noncpg_calls = 0.0;
     c->n_header_contigs_before = 0;
+    c->frac_cpg_listed = 1.0;
 }
 
 namespace {
@@ -474,14 +475,14 @@ struct ReadSim {
                 for (int i = 0; i < n; i++) {
                     if (seq[i] != 'C') continue;
                     bool cpg = i + 1 < n && seq[i + 1] == 'G';
-                    if (cpg || rng.chance(cfg.frac_noncpg_calls)) emit(seq2ref[i], cpg);
+                    if ((cpg && (cfg.frac_cpg_listed >= 1.0 || rng.chance(cfg.frac_cpg_listed))) || (!cpg && rng.chance(cfg.frac_noncpg_calls))) emit(seq2ref[i], cpg);
                     else skipped++;
                 }
             } else {
                 for (int i = n - 1; i >= 0; i--) {
                     if (seq[i] != 'G') continue;
                     bool cpg = i > 0 && seq[i - 1] == 'C';
-                    if (cpg || rng.chance(cfg.frac_noncpg_calls)) emit(seq2ref[i] >= 0 ? seq2ref[i] - 1 : -1, cpg);
+                    if ((cpg && (cfg.frac_cpg_listed >= 1.0 || rng.chance(cfg.frac_cpg_listed))) || (!cpg && rng.chance(cfg.frac_noncpg_calls))) emit(seq2ref[i] >= 0 ? seq2ref[i] - 1 : -1, cpg);
                     else skipped++;
                 }
             }

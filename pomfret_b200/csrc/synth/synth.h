@@ -28,6 +28,7 @@ typedef struct synth_config {
     double frac_low_mapq, frac_high_de, frac_secondary, frac_no_mm;
     double frac_two_segments, frac_multicode, frac_noncpg_calls;
     int n_header_contigs_before; /* filler @SQ lines so target ids are not 0 */
+    double frac_cpg_listed;      /* fraction of CpG cytosines that appear in the MM list (1 = all) */
 } synth_config;
 
 void pomfret_synth_default_config(synth_config *c);

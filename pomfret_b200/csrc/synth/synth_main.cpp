@@ -18,6 +18,7 @@ static void usage() {
             "  --untagged    do not write HP/PS tags (for methphase -u)\n"
             "  --qual        write pseudo-random base qualities instead of 0xff\n"
             "  --implicit F  fraction of non-CpG C positions that also get a C+m call [0]\n"
+            "  --listed F    fraction of CpG cytosines present in the MM list [1]\n"
             "  --err F       per-base error rate [0.01]\n"
             "  --readlen F   mean read length [20000]\n"
             "  --gap A-B     phase-block gap length range [20000-150000]\n"
@@ -44,6 +45,7 @@ int main(int argc, char **argv) {
         else if (a == "--untagged") cfg.tagged = 0;
         else if (a == "--qual") cfg.qual_mode = 1;
         else if (a == "--implicit") cfg.frac_noncpg_calls = atof(need("--implicit"));
+        else if (a == "--listed") cfg.frac_cpg_listed = atof(need("--listed"));
         else if (a == "--err") cfg.err_rate = atof(need("--err"));
         else if (a == "--readlen") cfg.read_len_mean = atof(need("--readlen"));
         else if (a == "--block") cfg.block_len_median = atof(need("--block"));

@@ -59,3 +59,12 @@ def synth_implicit(built, tmp_path_factory):
     d = tmp_path_factory.mktemp("synthimp")
     return run_synth(str(d / "imp"), ["-c", "34", "-s", "5", "-C", "chrI:300000:0-200000", "--readlen", "3000",
                                       "--block", "70000", "--gap", "8000-10000", "--implicit", "0.01"])
+
+
+@pytest.fixture(scope="session")
+def synth_sparse_implicit(built, tmp_path_factory):
+    """MM lists that name only 40% of the CpGs plus a few non-CpG cytosines: the implicit-canonical fill
+    produces far more calls than listed bases (call-slot overflow path of the engine)."""
+    d = tmp_path_factory.mktemp("synthsparse")
+    return run_synth(str(d / "sp"), ["-c", "34", "-s", "6", "-C", "chrS:300000:0-200000", "--readlen", "3000",
+                                     "--block", "70000", "--gap", "8000-10000", "--implicit", "0.01", "--listed", "0.4"])

@@ -45,3 +45,7 @@ def test_emulated_kernels_implicit_mode(emu_gpu, synth_implicit):
 
 def test_emulated_kernels_k2(emu_gpu, synth_small):
     _run(emu_gpu, synth_small, 24, 2000, k=2, k_span=900)
+
+
+def test_emulated_kernels_call_slot_overflow(emu_gpu, synth_sparse_implicit):
+    _run(emu_gpu, synth_sparse_implicit, 34, 1500)

@@ -61,6 +61,10 @@ def test_gpu_matches_oracle_implicit(gpu, synth_implicit):
     _run(gpu, synth_implicit, 34, readlen=1500)
 
 
+def test_gpu_matches_oracle_call_slot_overflow(gpu, synth_sparse_implicit):
+    _run(gpu, synth_sparse_implicit, 34, readlen=1500)
+
+
 @pytest.mark.parametrize("kw", [dict(k=2, k_span=800), dict(k=4, lo=80, hi=180), dict(k=1), dict(k_span=300)])
 def test_gpu_matches_oracle_parameters(gpu, synth_small, kw):
     _run(gpu, synth_small, 30, readlen=2000, check_ref=False, **kw)

@@ -47,6 +47,11 @@ def test_port_matches_reference_implicit_calls(synth_implicit):
 
 
 @needs_ref
+def test_port_matches_reference_sparse_lists(synth_sparse_implicit):
+    assert _check(synth_sparse_implicit, 34, readlen=1500) >= 1
+
+
+@needs_ref
 def test_port_matches_reference_other_parameters(synth_small):
     assert _check(synth_small, 20, readlen=2000, k=2, k_span=800) >= 1
     assert _check(synth_small, 50, readlen=2000, k=4, lo=80, hi=180) >= 1

@@ -36,28 +36,68 @@ using namespace pomfret_gpu;
 
 namespace {
 
+// Device memory of a batch comes from one arena: a bump allocator over a few large cudaMalloc chunks that
+// is rewound by batch_reset().  cudaMalloc / cudaFree serialise across host threads in the driver, so the
+// steady state (one chunk, no allocation calls per batch) is what lets several workers share a device.
+struct DevArena {
+    struct Chunk { uint8_t *p; size_t cap, used; };
+    std::vector<Chunk> chunks;
+    uint64_t epoch = 1;
+    size_t high_water = 0, used_total = 0;
+    void *alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!chunks.empty()) {
+            Chunk &c = chunks.back();
+            if (c.used + bytes <= c.cap) { void *r = c.p + c.used; c.used += bytes; used_total += bytes; return r; }
+        }
+        size_t want = std::max<size_t>(bytes, std::max<size_t>((size_t)64 << 20, chunks.empty() ? 0 : chunks.back().cap));
+        void *p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+        chunks.push_back({(uint8_t *)p, want, bytes});
+        used_total += bytes;
+        return p;
+    }
+    void rewind() {
+        high_water = std::max(high_water, used_total);
+        if (chunks.size() > 1) {  // coalesce: next batch of this size fits one chunk
+            for (Chunk &c : chunks) cudaFree(c.p);
+            chunks.clear();
+            void *p = nullptr;
+            size_t want = high_water + high_water / 4;
+            if (cudaMalloc(&p, want) == cudaSuccess) chunks.push_back({(uint8_t *)p, want, 0});
+        } else if (!chunks.empty()) chunks[0].used = 0;
+        used_total = 0;
+        epoch++;
+    }
+    void release() { for (Chunk &c : chunks) cudaFree(c.p); chunks.clear(); }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    uint64_t epoch = 0;
+    DevArena *arena = nullptr;
+    // contents survive only while the request fits the current allocation of the current batch epoch
     int ensure(size_t bytes) {
-        if (bytes <= cap) return 0;
-        size_t want = bytes + bytes / 4 + 4096;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        if (cudaMalloc(&p, want) != cudaSuccess) return POMFRET_GPU_ERR_NOMEM;
+        if (epoch == arena->epoch && bytes <= cap) return 0;
+        size_t want = bytes + bytes / 8 + 256;
+        p = arena->alloc(want);
+        if (!p) { cap = 0; return POMFRET_GPU_ERR_NOMEM; }
         cap = want;
+        epoch = arena->epoch;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { p = nullptr; cap = 0; epoch = 0; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
 struct PinBuf {
     uint8_t *p = nullptr;
     size_t cap = 0, len = 0;
+    size_t min_cap = (size_t)1 << 20;  // cudaMallocHost is slow and serialises: grow in big steps
     int reserve(size_t bytes) {
         if (bytes <= cap) return 0;
-        size_t want = std::max(bytes + bytes / 2, (size_t)1 << 20);
+        size_t want = std::max(std::max(bytes + bytes / 2, cap * 2), min_cap);
         void *q = nullptr;
         if (cudaMallocHost(&q, want) != cudaSuccess) return POMFRET_GPU_ERR_NOMEM;
         if (p) { memcpy(q, p, len); cudaFreeHost(p); }
@@ -116,6 +156,7 @@ struct pomfret_gpu_batch {
     uint64_t calls_total = 0;
     uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
     // device
+    DevArena arena;
     DevBuf d_blob, d_reads, d_win, d_read_win, d_calls_pos, d_calls_cat, d_tmp_rank, d_tmp_mpos, d_tmp_mcat;
     DevBuf d_r_ncalls, d_r_status, d_r_end, d_r_id, d_rs_src, d_rs_rev, d_rs_hp;
     DevBuf d_ids[4], d_state, d_tiles, d_win_base, d_win_tile_first, d_tile_out, d_tile_count;
@@ -130,6 +171,17 @@ struct pomfret_gpu_batch {
     bool have_results = false;
     std::vector<uint8_t> host_tags_fwd, host_tags_bwd;
     std::vector<int32_t> host_rid;
+    std::vector<DevBuf *> all_bufs() {
+        return {&d_blob, &d_reads, &d_win, &d_read_win, &d_calls_pos, &d_calls_cat, &d_tmp_rank,
+                     &d_tmp_mpos, &d_tmp_mcat, &d_r_ncalls, &d_r_status, &d_r_end, &d_r_id, &d_rs_src,
+                     &d_rs_rev, &d_rs_hp, &d_ids[0], &d_ids[1], &d_ids[2], &d_ids[3], &d_state,
+                     &d_tiles, &d_win_base, &d_win_tile_first, &d_tile_out, &d_tile_count, &d_site_pos,
+                     &d_site_start[0], &d_site_start[1], &d_site_len[0], &d_site_len[1], &d_mm_xl[0],
+                     &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
+                     &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
+                     &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags};
+    }
 };
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -188,6 +240,8 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
     pomfret_gpu_batch *b = new pomfret_gpu_batch();
     b->ctx = ctx;
     b->device = device;
+    for (DevBuf *d : b->all_bufs()) d->arena = &b->arena;
+    b->h_blob.min_cap = (size_t)64 << 20;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     for (auto &e : b->ev) CK(cudaEventCreate(&e));
 #ifndef POMFRET_CUDA_EMU
@@ -207,6 +261,9 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     b->stage = ST_EMPTY;
     b->have_results = false;
     memset(&b->tm, 0, sizeof(b->tm));
+    if (cudaSetDevice(b->device) != cudaSuccess) return POMFRET_GPU_ERR_CUDA;
+    cudaStreamSynchronize(b->stream);
+    b->arena.rewind();
     return POMFRET_GPU_OK;
 }
 
@@ -214,16 +271,9 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
-    DevBuf *all[] = {&b->d_blob, &b->d_reads, &b->d_win, &b->d_read_win, &b->d_calls_pos, &b->d_calls_cat, &b->d_tmp_rank,
-                     &b->d_tmp_mpos, &b->d_tmp_mcat, &b->d_r_ncalls, &b->d_r_status, &b->d_r_end, &b->d_r_id, &b->d_rs_src,
-                     &b->d_rs_rev, &b->d_rs_hp, &b->d_ids[0], &b->d_ids[1], &b->d_ids[2], &b->d_ids[3], &b->d_state,
-                     &b->d_tiles, &b->d_win_base, &b->d_win_tile_first, &b->d_tile_out, &b->d_tile_count, &b->d_site_pos,
-                     &b->d_site_start[0], &b->d_site_start[1], &b->d_site_len[0], &b->d_site_len[1], &b->d_mm_xl[0],
-                     &b->d_mm_xl[1], &b->d_mm_xr[0], &b->d_mm_xr[1], &b->d_mm_off[0], &b->d_mm_off[1], &b->d_mm_n[0],
-                     &b->d_mm_n[1], &b->d_mm_start[0], &b->d_mm_start[1], &b->d_pool_total, &b->d_mmr_pool, &b->d_ent_pool,
-                     &b->d_tab, &b->d_tags[0], &b->d_tags[1], &b->d_order[0], &b->d_order[1], &b->d_known, &b->d_bases,
-                     &b->d_known_first, &b->d_hap_tag, &b->d_hap_status, &b->d_flags};
+    std::vector<DevBuf *> all = b->all_bufs();
     for (DevBuf *d : all) d->release();
+    b->arena.release();
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
     b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);

@@ -122,6 +122,8 @@ typedef struct pomfret_gpu_window_result {
 #define POMFRET_GPU_READ_FATAL_CIGAR 4u
 #define POMFRET_GPU_READ_MM_ERROR 8u      /* malformed MM/ML: record has no modifications */
 #define POMFRET_GPU_READ_SLOWPATH 16u     /* decoded by the single-lane general path */
+#define POMFRET_GPU_READ_UNSORTED 32u     /* internal: calls not strictly ascending */
+#define POMFRET_GPU_READ_OVERFLOW 64u     /* internal: ran out of call slots; pileup() re-runs the record with more room */
 
 /* ---- context ---- */
 int pomfret_gpu_init(pomfret_gpu_ctx **out, const int *devices, int n_devices, int n_workers);

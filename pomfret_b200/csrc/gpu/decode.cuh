@@ -30,8 +30,10 @@ namespace pomfret_gpu {
 
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_MAXSEG = 16;
-constexpr int DEC_MI_CAP = 768;       // M/I ops staged per chunk
+constexpr int DEC_MI_CAP = 256;       // M/I ops staged per chunk
 constexpr int DEC_MM_CHUNK = 512;     // MM bytes staged per step
+constexpr int DEC_T = 2;              // SEQ tiles (512 B = 1024 bases each) per scan step
+constexpr int DEC_BM_WORDS = 128;     // target bitmap window: 4096 canonical-base ranks (>= DEC_T * 1024)
 constexpr int N_MODS_LIMIT = 10;      // reference N_MODS, blockjoin.c:34
 
 struct DecodeParams {
@@ -63,28 +65,65 @@ struct SegInfo {
 
 struct DecodeWarpSmem {
     __align__(16) uint8_t mmbuf[DEC_MM_CHUNK + 16];
-    uint32_t s_first[32];
-    uint32_t s_cnt[32];
-    uint32_t s_m[32][4];
+    uint32_t bm[DEC_BM_WORDS + 1];    // bit (r - window base) set iff canonical base number r is listed
+    uint32_t bm_k[DEC_BM_WORDS + 1];  // index (in list order) of the first listed base at or after bit 0 of the word
     uint32_t mi_end[DEC_MI_CAP];
     int32_t mi_off[DEC_MI_CAP];
     SegInfo seg[DEC_MAXSEG];
 };
 
 constexpr int32_t MI_DROP = (int32_t)0x80000000;
+// Deltas and their running sums saturate here: far beyond any SEQ length the engine accepts (add_read
+// rejects l_qseq >= 2^28), so a saturated rank is simply "never found" — what the reference's 64-bit
+// arithmetic yields for such lists.
+constexpr uint32_t DEC_SAT = 0x40000000u;
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b) {  // a, b <= DEC_SAT
+    uint32_t s = a + b;
+    return s > DEC_SAT ? DEC_SAT : s;
+}
+__device__ __forceinline__ uint32_t warp_inclusive_sat_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL_MASK, v, o);
+        if (lane_id() >= (unsigned)o) v = sat_add(v, t);
+    }
+    return v;
+}
 
 __device__ __forceinline__ uint32_t seq_nib(const uint8_t *seq, uint32_t i) {
     return (seq[i >> 1] >> ((~i & 1u) << 2)) & 0xfu;
 }
 
-// flags word: bit 4*i set iff base i (0..7) of the 32-bit SEQ word equals nibble value `want`
-__device__ __forceinline__ uint32_t nib_match_flags(uint32_t w, uint32_t want) {
-    // put base i into bits [4i,4i+3]: swap the nibbles of every byte (BAM packs the first base high)
-    uint32_t x = ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu);
-    x ^= want * 0x11111111u;
+// flags word: bit 4*i set iff nibble i of the 32-bit SEQ word equals the nibble replicated in `pat`
+// (nibble i holds base i^1: BAM packs the first base of a byte high).  Zero padding never matches.
+__device__ __forceinline__ uint32_t nib_eq_flags(uint32_t w, uint32_t pat) {
+    uint32_t x = w ^ pat;
     x |= x >> 1;
     x |= x >> 2;
     return ~x & 0x11111111u;
+}
+// base index (0..7) of the n-th (0-based, base order) flagged base of a flags word
+__device__ __forceinline__ uint32_t select_base_in_word(uint32_t f, uint32_t n) {
+    uint32_t g = ((f & 0x01010101u) << 4) | ((f >> 4) & 0x01010101u);  // bit 4b <-> base b
+    uint32_t b = 0;
+    uint32_t c = (uint32_t)__popc(g & 0xffffu);
+    if (n >= c) { n -= c; g >>= 16; b = 4; }
+    c = (uint32_t)__popc(g & 0xffu);
+    if (n >= c) { n -= c; g >>= 8; b += 2; }
+    c = (uint32_t)__popc(g & 0xfu);
+    if (n >= c) b += 1;
+    return b;
+}
+// number of SEQ nibbles equal to `code` (code != 0), whole warp
+__device__ uint32_t count_base(const uint8_t *seq, uint32_t n_bytes, uint32_t code) {
+    const uint32_t pat = code * 0x11111111u;
+    uint32_t c = 0;
+    for (uint32_t off = lane_id() * 16; off < n_bytes; off += 512) {
+        uint4 v = *reinterpret_cast<const uint4 *>(seq + off);
+        c += __popc(nib_eq_flags(v.x, pat)) + __popc(nib_eq_flags(v.y, pat)) + __popc(nib_eq_flags(v.z, pat)) +
+             __popc(nib_eq_flags(v.w, pat));
+    }
+    return warp_sum(c);
 }
 
 __device__ __forceinline__ int base_code_of(int ch) {
@@ -221,30 +260,33 @@ __device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm,
                     while (base + q < le && nd < 10) {
                         uint32_t d = sm.mmbuf[q];
                         if (d < '0' || d > '9') break;
-                        val = val * 10 + (d - '0');
+                        val = val >= DEC_SAT / 10 ? DEC_SAT : val * 10 + (d - '0');
                         q++; nd++;
                     }
+                    if (val >= DEC_SAT) val = DEC_SAT - 1;
                     if (nd == 0) bad = true;
                     if (nv < 8) vals[nv] = val;
                     nv++;
-                    lsum += val + 1;
+                    lsum = sat_add(lsum, val + 1);
                 } else if (c < '0' || c > '9') bad = true;
             }
         }
         uint32_t cnt = (uint32_t)nv;
         uint32_t incl_c = warp_inclusive_sum(cnt);
-        uint32_t incl_s = warp_inclusive_sum(lsum);
+        uint32_t incl_s = warp_inclusive_sat_sum(lsum);
         if (rank_out) {
             uint32_t k = n_delta + incl_c - cnt;
-            uint32_t run = total + incl_s - lsum;
+            uint32_t excl_s = __shfl_up_sync(FULL_MASK, incl_s, 1);
+            if (lane == 0) excl_s = 0;
+            uint32_t run = sat_add(total, excl_s);
             for (int j = 0; j < nv && j < 8; j++) {
-                run += vals[j] + 1;
+                run = sat_add(run, vals[j] + 1);
                 if (k < rank_cap) rank_out[k] = run - 1;
                 k++;
             }
         }
         n_delta += __shfl_sync(FULL_MASK, incl_c, 31);
-        total += __shfl_sync(FULL_MASK, incl_s, 31);
+        total = sat_add(total, __shfl_sync(FULL_MASK, incl_s, 31));
         __syncwarp();
     }
     bad = __any_sync(FULL_MASK, bad);
@@ -317,143 +359,160 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
     }
 
     // ---- SEQ scan: select the listed canonical bases of the relevant segment ----
-    uint32_t n_mods = 0;
+    // Lane-centric: every lane flags the canonical bases of its 32-base chunk, a warp scan gives the rank of
+    // its first one, and the lane pulls "which of my bases are listed" out of a shared-memory bitmap indexed
+    // by rank (built from the cumulative delta sums, refreshed every 4096 ranks).  Reverse-strand records
+    // are scanned from the right end of SEQ so ranks count from the read's own 5' end (htslib walks the
+    // delta list backwards instead).
+    uint32_t n_mods = 0, mbase = 0;
     bool has_implicit = false;
-    uint32_t freq_a = 0, freq_c = 0, freq_g = 0, freq_t = 0, freq_n = 0;  // reverse strand only
     const bool do_select = !mm_error && rel >= 0 && sm.seg[rel].n_delta > 0;
-    if ((do_select || (rev && !mm_error && n_seg > 0)) && len > 0) {
-        const uint32_t want = rev ? 4u : 2u;  // C on the read strand is G in SEQ for reverse alignments
+    // reverse strand: "MM tag refers to bases beyond sequence length" iff count(complement base) < sum(delta+1)
+    uint32_t need_c = 0;
+    const uint32_t n_bytes = (len + 1) >> 1;
+    if (rev && !mm_error && len > 0) {
+        for (int s = 0; s < n_seg; s++) {
+            const SegInfo &g = sm.seg[s];
+            if (g.n_codes == 0) continue;
+            if (g.canon == 2) need_c = g.total > need_c ? g.total : need_c;
+            else if (g.total > 0 && g.total > count_base(seq, n_bytes, comp_code(g.canon))) mm_error = true;
+        }
+    }
+    if (!mm_error && len > 0 && (do_select || need_c > 0)) {
+        const uint32_t pat = (rev ? 4u : 2u) * 0x11111111u;  // C on the read strand is G in SEQ for reverse alignments
         const uint32_t n_targets = do_select ? sm.seg[rel].n_delta : 0;
         const uint32_t ml_base = do_select ? sm.seg[rel].ml_base : 0;
         const uint32_t stride = do_select ? sm.seg[rel].n_codes : 0;
         const uint32_t m_idx = do_select ? (uint32_t)sm.seg[rel].m_idx : 0;
-        const uint32_t n_bytes = (len + 1) >> 1;
-        const uint32_t n_tiles = (n_bytes + 511) / 512;
-        uint32_t run = 0;   // matches seen so far in scan order
-        uint32_t tcur = 0;  // next target (targets are in scan order for both strands)
-        for (uint32_t ti = 0; ti < n_tiles; ti++) {
-            if (!rev && tcur >= n_targets) break;  // forward: nothing left to find
-            const uint32_t tile = rev ? n_tiles - 1 - ti : ti;
-            const uint32_t byte_off = tile * 512 + lane * 16;
-            const uint32_t base0 = byte_off * 2;  // first base of this lane's chunk
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (byte_off < n_bytes) v = *reinterpret_cast<const uint4 *>(seq + byte_off);
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t m[4];
-            uint32_t C = 0;
+        const int n_tiles = (int)((n_bytes + 511) / 512);
+        const int n_steps = (n_tiles + DEC_T - 1) / DEC_T;
+        uint32_t run = 0;        // canonical bases seen so far, in scan order
+        uint32_t tcur = 0;       // listed bases with rank < run (list order == scan order on both strands)
+        uint32_t wb = 0, wend = 0;  // rank window covered by the bitmap
+        bool drop_first = false, drop_last = false, implicit = false;
+        if (lane == 0) sm.bm[DEC_BM_WORDS] = 0;
+        uint4 cur[DEC_T], nxt[DEC_T];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t b0 = base0 + j * 8;
-                uint32_t valid = b0 >= len ? 0u : (len - b0 >= 8 ? 0x11111111u : ((1u << ((len - b0) * 4)) - 1u) & 0x11111111u);
-                m[j] = nib_match_flags(w[j], want) & valid;
-                C += __popc(m[j]);
-                if (rev) {
-                    freq_a += __popc(nib_match_flags(w[j], 1u) & valid);
-                    freq_c += __popc(nib_match_flags(w[j], 2u) & valid);
-                    freq_t += __popc(nib_match_flags(w[j], 8u) & valid);
-                    freq_n += __popc(nib_match_flags(w[j], 15u) & valid);
-                }
-            }
-            if (rev) freq_g += C;
-            uint32_t incl = warp_inclusive_sum(C);
-            uint32_t tile_total = __shfl_sync(FULL_MASK, incl, 31);
-            // rank (in scan order) of this lane's first match
-            uint32_t first = rev ? run + (tile_total - incl) : run + (incl - C);
-            sm.s_first[lane] = first;
-            sm.s_cnt[lane] = C;
+        for (int t = 0; t < DEC_T; t++) {
+            const int tile = rev ? n_tiles - 1 - t : t;
+            const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
+            cur[t] = make_uint4(0, 0, 0, 0);
+            if (tile >= 0 && tile < n_tiles && byte_off < n_bytes) cur[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
+        }
+        for (int step = 0; step < n_steps; step++) {
+            if (tcur >= n_targets && run >= need_c) break;  // everything listed was found (and counted, reverse)
 #pragma unroll
-            for (int j = 0; j < 4; j++) sm.s_m[lane][j] = m[j];
-            __syncwarp();
-            // hand out the targets that fall into this tile
-            while (tcur < n_targets) {
-                uint32_t k = tcur + lane;
-                uint32_t r = 0xffffffffu;
-                if (k < n_targets) r = rank[k];
-                bool mine = k < n_targets && r < run + tile_total && r >= run;
-                // a malformed list could repeat a rank (delta = -1 is impossible: digits only), so ranks
-                // strictly increase; `mine` lanes are a prefix
-                unsigned act = __ballot_sync(FULL_MASK, mine);
-                if (act == 0) break;
-                uint32_t p = 0;
-                bool keep = false, implicit = false;
-                uint8_t cat = 0;
-                if (mine) {
-                    // owner lane L: first[L] <= r < first[L] + cnt[L]
-                    int lo_l = 0, hi_l = 31;
-                    if (!rev) {  // first[] ascending with lane
-                        while (lo_l < hi_l) {
-                            int mid = (lo_l + hi_l + 1) >> 1;
-                            if (sm.s_first[mid] <= r) lo_l = mid; else hi_l = mid - 1;
-                        }
-                        // skip empty lanes that share the same first rank: take the last lane with first<=r that has matches
-                        while (sm.s_cnt[lo_l] == 0 && lo_l > 0) lo_l--;
-                    } else {     // first[] descending with lane
-                        while (lo_l < hi_l) {
-                            int mid = (lo_l + hi_l) >> 1;
-                            if (sm.s_first[mid] <= r) hi_l = mid; else lo_l = mid + 1;
-                        }
-                        while (sm.s_cnt[lo_l] == 0 && lo_l < 31) lo_l++;
-                    }
-                    const int L = lo_l;
-                    uint32_t local = r - sm.s_first[L];
-                    int bitpos = -1, wj = 0;
-                    if (!rev) {
-                        for (wj = 0; wj < 4; wj++) {
-                            uint32_t c = __popc(sm.s_m[L][wj]);
-                            if (local < c) { bitpos = (int)__fns(sm.s_m[L][wj], 0, (int)local + 1); break; }
-                            local -= c;
-                        }
-                    } else {
-                        for (wj = 3; wj >= 0; wj--) {
-                            uint32_t c = __popc(sm.s_m[L][wj]);
-                            if (local < c) { bitpos = (int)__fns(sm.s_m[L][wj], 31, -((int)local + 1)); break; }
-                            local -= c;
-                        }
-                    }
-                    p = tile * 1024 + (uint32_t)L * 32 + (uint32_t)wj * 8 + (uint32_t)(bitpos >> 2);
-                    // blockjoin.c:846-858
-                    if (p < len - 1 && p > 0) {
-                        bool ok = seq_nib(seq, p) == 2u ? seq_nib(seq, p + 1) == 4u : seq_nib(seq, p - 1) == 2u;
-                        if (ok) {
-                            keep = true;
-                            // targets are in scan order on both strands: reverse records are scanned from the
-                            // right end of SEQ, i.e. from the read's own 5' end, so target k is delta k
-                            uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
-                            cat = q < P.lo ? 1 : (q >= P.hi ? 0 : 2);
-                        } else implicit = true;
-                    }
-                }
-                unsigned km = __ballot_sync(FULL_MASK, keep);
-                if (__any_sync(FULL_MASK, implicit)) has_implicit = true;
-                if (keep) {
-                    uint32_t j = n_mods + __popc(km & ((1u << lane) - 1u));
-                    uint32_t slot = rev ? cap - 1 - j : j;
-                    mpos[slot] = p;
-                    mcat[slot] = cat;
-                }
-                n_mods += __popc(km);
-                tcur += __popc(act);
-                if (__popc(act) < 32) break;
+            for (int t = 0; t < DEC_T; t++) {  // prefetch the next step
+                const int idx = (step + 1) * DEC_T + t;
+                const int tile = rev ? n_tiles - 1 - idx : idx;
+                const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
+                nxt[t] = make_uint4(0, 0, 0, 0);
+                if (tile >= 0 && tile < n_tiles && byte_off < n_bytes) nxt[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
             }
-            run += tile_total;
-            __syncwarp();
-        }
-        if (rev) {
-            freq_a = warp_sum(freq_a); freq_c = warp_sum(freq_c); freq_g = warp_sum(freq_g);
-            freq_t = warp_sum(freq_t); freq_n = warp_sum(freq_n);
-            // "MM tag refers to bases beyond sequence length": count of the complement base < sum(delta+1)
-            for (int s = 0; s < n_seg; s++) {
-                const SegInfo &g = sm.seg[s];
-                if (g.n_codes == 0) continue;
-                uint32_t c = comp_code(g.canon);
-                uint32_t f = c == 1 ? freq_a : c == 2 ? freq_c : c == 4 ? freq_g : c == 8 ? freq_t : freq_n;
-                if (g.total > f) mm_error = true;
+            uint32_t m[DEC_T][4], C[DEC_T];
+            uint32_t packed = 0;
+#pragma unroll
+            for (int t = 0; t < DEC_T; t++) {
+                m[t][0] = nib_eq_flags(cur[t].x, pat); m[t][1] = nib_eq_flags(cur[t].y, pat);
+                m[t][2] = nib_eq_flags(cur[t].z, pat); m[t][3] = nib_eq_flags(cur[t].w, pat);
+                C[t] = (uint32_t)(__popc(m[t][0]) + __popc(m[t][1]) + __popc(m[t][2]) + __popc(m[t][3]));
+                packed |= C[t] << (16 * t);  // a tile holds at most 1024 matches: 16 bits per tile
             }
+            const uint32_t incl = warp_inclusive_sum(packed);
+            const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+            uint32_t step_total = 0;
+#pragma unroll
+            for (int t = 0; t < DEC_T; t++) step_total += (tot >> (16 * t)) & 0xffffu;
+            if (tcur < n_targets && step_total > 0) {
+                if (run + step_total > wend) {
+                    // ---- refresh the bitmap: ranks [run, run + 4096) ----
+                    wb = run;
+                    wend = wb + DEC_BM_WORDS * 32u;
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < DEC_BM_WORDS / 32; i++) sm.bm[lane + 32 * i] = 0;
+                    __syncwarp();
+                    for (uint32_t t0 = tcur;; t0 += 32) {
+                        const uint32_t k = t0 + lane;
+                        const uint32_t r = k < n_targets ? rank[k] : 0xffffffffu;
+                        const bool in = r < wend;  // ranks ascend strictly and every rank below `run` is consumed
+                        if (in) atomicOr(&sm.bm[(r - wb) >> 5], 1u << ((r - wb) & 31u));
+                        if (__popc(__ballot_sync(FULL_MASK, in)) < 32) break;
+                    }
+                    __syncwarp();
+                    constexpr int WPL = DEC_BM_WORDS / 32;
+                    uint32_t c[WPL], s_l = 0;
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) { c[i] = (uint32_t)__popc(sm.bm[lane * WPL + i]); s_l += c[i]; }
+                    const uint32_t in_l = warp_inclusive_sum(s_l);
+                    uint32_t kk = tcur + in_l - s_l;
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) { sm.bm_k[lane * WPL + i] = kk; kk += c[i]; }
+                    if (lane == 31) sm.bm_k[DEC_BM_WORDS] = kk;
+                    __syncwarp();
+                }
+                uint32_t before = 0;  // matches of earlier tiles of this step
+#pragma unroll
+                for (int t = 0; t < DEC_T; t++) {
+                    const uint32_t tile_total = (tot >> (16 * t)) & 0xffffu;
+                    const uint32_t incl_t = (incl >> (16 * t)) & 0xffffu;
+                    const uint32_t Ct = C[t];
+                    // rank of this lane's first match in scan order
+                    const uint32_t first = run + before + (rev ? tile_total - incl_t : incl_t - Ct);
+                    before += tile_total;
+                    if (Ct == 0) continue;
+                    const uint32_t idx = first - wb, word = idx >> 5, sh = idx & 31u;
+                    const uint32_t lo_w = sm.bm[word], hi_w = sm.bm[word + 1];
+                    uint32_t tw = __funnelshift_r(lo_w, hi_w, sh);
+                    tw &= Ct >= 32u ? 0xffffffffu : (1u << Ct) - 1u;  // bit j <-> this lane's j-th match in scan order
+                    if (tw == 0) continue;
+                    uint32_t k = sm.bm_k[word] + (uint32_t)__popc(lo_w & ((1u << sh) - 1u));
+                    const uint32_t c0 = (uint32_t)__popc(m[t][0]), c1 = (uint32_t)__popc(m[t][1]), c2 = (uint32_t)__popc(m[t][2]);
+                    const int tile = rev ? n_tiles - 1 - (step * DEC_T + t) : step * DEC_T + t;
+                    do {
+                        const uint32_t j = (uint32_t)__ffs((int)tw) - 1u;
+                        tw &= tw - 1u;
+                        uint32_t n = rev ? Ct - 1u - j : j;  // index in base order inside the lane's chunk
+                        uint32_t wj = 0, f = m[t][0];
+                        if (n >= c0) {
+                            n -= c0; wj = 1; f = m[t][1];
+                            if (n >= c1) {
+                                n -= c1; wj = 2; f = m[t][2];
+                                if (n >= c2) { n -= c2; wj = 3; f = m[t][3]; }
+                            }
+                        }
+                        const uint32_t p = (uint32_t)tile * 1024u + lane * 32u + wj * 8u + select_base_in_word(f, n);
+                        // blockjoin.c:846-858: C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
+                        if (p > 0 && p < len - 1) {
+                            const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
+                            if (ok) {
+                                const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
+                                const uint32_t slot = rev ? cap - 1u - k : k;
+                                mpos[slot] = p;
+                                mcat[slot] = (uint8_t)(q < P.lo ? 1 : (q >= P.hi ? 0 : 2));
+                            } else implicit = true;
+                        } else if (k == 0) drop_first = true;
+                        else drop_last = true;
+                        k++;
+                    } while (tw);
+                }
+                // listed bases consumed so far = those with rank < run + step_total
+                const uint32_t e = run + step_total - wb;
+                tcur = sm.bm_k[e >> 5] + (uint32_t)__popc(sm.bm[e >> 5] & ((1u << (e & 31u)) - 1u));
+            }
+            run += step_total;
+#pragma unroll
+            for (int t = 0; t < DEC_T; t++) cur[t] = nxt[t];
         }
+        if (rev && run < need_c) mm_error = true;
+        has_implicit = __any_sync(FULL_MASK, implicit);
+        // only the first and the last base of SEQ can be listed and silently dropped (0 < pos < len-1)
+        const uint32_t d0 = __any_sync(FULL_MASK, drop_first) ? 1u : 0u, d1 = __any_sync(FULL_MASK, drop_last) ? 1u : 0u;
+        n_mods = tcur - d0 - d1;
+        mbase = rev ? cap - tcur + d1 : d0;  // mods occupy tmp[mbase, mbase+n_mods), ascending SEQ position
     }
     if (mm_error) { status |= RS_MM_ERROR; n_mods = 0; has_implicit = false; }
     if (has_implicit) { *need_generic = true; return 0; }
-    const uint32_t mbase = rev ? cap - n_mods : 0;  // mods occupy tmp[mbase, mbase+n_mods), ascending SEQ position
     __syncwarp();
 
     // ---- CIGAR walk ----
@@ -637,9 +696,9 @@ struct GenSeg {
 
 __device__ uint32_t gen_parse_uint(const uint8_t *s, uint32_t b, uint32_t e, uint32_t *next) {
     uint32_t v = 0;
-    while (b < e && is_digit(s[b])) { v = v * 10 + (s[b] - '0'); b++; }
+    while (b < e && is_digit(s[b])) { v = v >= DEC_SAT / 10 ? DEC_SAT : v * 10 + (s[b] - '0'); b++; }
     *next = b;
-    return v;
+    return v >= DEC_SAT ? DEC_SAT - 1 : v;
 }
 
 struct CallSink {
@@ -715,7 +774,7 @@ __device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenS
                 uint32_t v = gen_parse_uint(mm, p, mm_len, &nx);
                 p = nx;
                 g.n_delta++;
-                g.total += v + 1;
+                g.total = sat_add(g.total, v + 1);
             }
             if (bad) break;
             if (p >= mm_len || mm[p] != ';') { bad = true; break; }
@@ -797,7 +856,7 @@ __device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenS
                         uint32_t nx;
                         uint32_t d = gen_parse_uint(mm, g.cursor + 1, mm_len, &nx);
                         g.cursor = nx;
-                        g.next_target = g.match_idx + 1 + d;
+                        g.next_target = sat_add(g.match_idx + 1, d);
                     }
                 } else {
                     // skip count before the next (further right) listed base is the delta we just consumed
@@ -807,7 +866,7 @@ __device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenS
                     uint32_t d = gen_parse_uint(mm, b, mm_len, &nx);
                     g.cursor = b - 1;       // the ',' in front of it = just past delta which-1
                     g.k--;
-                    g.next_target = g.match_idx + 1 + d;
+                    g.next_target = sat_add(g.match_idx + 1, d);
                 }
             }
             g.match_idx++;
@@ -882,9 +941,10 @@ __device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenS
 // ---------------------------------------------------------------------------------------------
 // Kernel: one warp per record.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DEC_WARPS * 32) decode_kernel(DecodeParams P) {
+static_assert(sizeof(DecodeWarpSmem) >= sizeof(GenSeg) * GEN_MAXSEG, "the general path reuses the warp's staging area");
+
+__global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams P) {
     __shared__ DecodeWarpSmem smem[DEC_WARPS];
-    __shared__ GenSeg gsegs[DEC_WARPS][GEN_MAXSEG];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t ri = blockIdx.x * DEC_WARPS + warp;
     if (ri >= P.n_reads) return;  // whole warp leaves together
@@ -905,7 +965,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_kernel(DecodeParams P) 
     uint32_t status = decode_fast(P, R, sm, &n_calls, &need_generic);
     need_generic = __any_sync(FULL_MASK, need_generic);
     if (need_generic) {
-        if (lane == 0) status = decode_generic(P, R, gsegs[warp], &n_calls);
+        __syncwarp();
+        if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
         status = __shfl_sync(FULL_MASK, status, 0);
         n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
     }

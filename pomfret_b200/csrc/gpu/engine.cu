@@ -296,6 +296,7 @@ static int blob_put(pomfret_gpu_batch *b, const void *src, size_t n, uint32_t *o
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {
     if (!b || !r) return POMFRET_GPU_ERR_ARG;
     if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+    if (r->l_qseq >= (1u << 28)) return POMFRET_GPU_ERR_UNSUPPORTED;  // decode.cuh: DEC_SAT
     ReadRec R;
     memset(&R, 0, sizeof(R));
     R.pos = r->pos; R.l_qseq = r->l_qseq; R.n_cigar = r->n_cigar;
@@ -305,6 +306,8 @@ int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc
     int rc;
     if ((rc = blob_put(b, r->cigar, (size_t)r->n_cigar * 4, &R.cigar_off))) return rc;
     if ((rc = blob_put(b, r->seq, ((size_t)r->l_qseq + 1) / 2, &R.seq_off))) return rc;
+    // the unused low nibble of an odd-length SEQ must read as "no base" (the kernels do not mask the tail)
+    if (r->l_qseq & 1u) b->h_blob.p[(size_t)R.seq_off * 16 + r->l_qseq / 2] &= 0xf0u;
     if (r->mm) {
         R.flags |= RF_HAS_MM;
         R.mm_len = r->mm_len;
@@ -756,7 +759,7 @@ int pomfret_gpu_debug_read_info(pomfret_gpu_batch *b, uint32_t read, uint32_t *s
     if (b->stage < ST_DECODED) return POMFRET_GPU_ERR_STATE;
     int rc;
     uint32_t v;
-    if (status) { if ((rc = dl(b, &v, b->d_r_status.as<uint32_t>() + read, 4))) return rc; *status = v & 31u; }
+    if (status) { if ((rc = dl(b, &v, b->d_r_status.as<uint32_t>() + read, 4))) return rc; *status = v & 127u; }
     if (n_calls) { if ((rc = dl(b, &v, b->d_r_ncalls.as<uint32_t>() + read, 4))) return rc; *n_calls = v; }
     if (end_pos) { if ((rc = dl(b, &v, b->d_r_end.as<uint32_t>() + read, 4))) return rc; *end_pos = v; }
     return 0;

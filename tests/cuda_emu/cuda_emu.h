@@ -148,6 +148,14 @@ static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
     } else if ((mask >> base) & 1u) return base;
     return 0xffffffffu;
 }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)(v >> (shift & 31u));
+}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (unsigned)((v << (shift & 31u)) >> 32);
+}
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     uint64_t v = ((uint64_t)y << 32) | x;
     unsigned r = 0;

@@ -22,9 +22,11 @@
 
 namespace pomfret_gpu {
 
-constexpr int JOIN_THREADS = 256;
+constexpr int JOIN_THREADS = 512;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
 constexpr int JOIN_MAX_CAND = 128;
+constexpr int JOIN_U = 8;                 // methmer sub-chunks (32 each) whose loads are issued together
+constexpr int JOIN_CHUNK = JOIN_U * 32;   // values staged per warp before the ordered sum
 
 struct JoinParams {
     const WindowRec *win;
@@ -47,13 +49,44 @@ __device__ __forceinline__ uint32_t *site_row(uint32_t *tab, uint32_t tab_base, 
     return tab + ((size_t)tab_base + site) * row_words;
 }
 
+// Range growth of update_available_methmer_range (blockjoin.c:3669-3691), warp-parallel: the left edge
+// walks down from `mn` while the site's coverage reaches cov, the right edge walks up from `mx`.
+__device__ __forceinline__ void grow_range(uint32_t *tab, uint32_t tab_base, uint32_t row_words, uint32_t n_keys,
+                                           uint32_t n_sites, int cov, uint32_t &mn, uint32_t &mx) {
+    const int lane = (int)lane_id();
+    for (int i0 = (int)mn;; i0 -= 32) {
+        const int i = i0 - lane;
+        bool ok = false;
+        if (i >= 0) {
+            const uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
+            ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
+        }
+        const unsigned bad = ~__ballot_sync(FULL_MASK, ok);  // first lane that stops the walk (or ran past site 0)
+        const int f = bad ? __ffs((int)bad) - 1 : 32;
+        if (f > 0) mn = (uint32_t)(i0 - (f - 1));
+        if (f < 32) break;
+    }
+    for (int i0 = (int)mx;; i0 += 32) {
+        const int i = i0 + lane;
+        bool ok = false;
+        if (i < (int)n_sites) {
+            const uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
+            ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
+        }
+        const unsigned bad = ~__ballot_sync(FULL_MASK, ok);
+        const int f = bad ? __ffs((int)bad) - 1 : 32;
+        if (f > 0) mx = (uint32_t)(i0 + (f - 1));
+        if (f < 32) break;
+    }
+}
+
 __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
-    __shared__ int s_i_last, s_failed, s_done, s_ncand, s_best, s_best_tag;
+    __shared__ int s_i_last, s_failed, s_done, s_ncand, s_cursor;
     __shared__ uint32_t s_min, s_max;
     __shared__ uint32_t s_cand[JOIN_MAX_CAND];
     __shared__ float s_score[JOIN_MAX_CAND];
     __shared__ int s_tag[JOIN_MAX_CAND];
-    __shared__ float s_val[JOIN_WARPS][2][32];
+    __shared__ float s_val[JOIN_WARPS][2][JOIN_CHUNK];
     __shared__ int s_tbl[4];
 
     const uint32_t w = blockIdx.x >> 1, d = blockIdx.x & 1u;
@@ -72,6 +105,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     const uint32_t *pool = P.mmr_pool;
     const uint32_t *site_pos = P.site_pos + W.site_off;
     const uint32_t *ref_ids = (d == 0 ? P.ids_left : P.ids_right) + first;
+    const uint32_t *rev = P.rs_rev + first;
     const uint32_t n_ref = d == 0 ? S.n_left : S.n_right;
     const int n_cand = P.n_cand;
 
@@ -98,18 +132,19 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     }
     __syncthreads();
     // ---- seed with the reference reads of the starting side, in list order, :3793-3803 ----
-    for (uint32_t r = 0; r < n_ref; r++) {
+    // (every read touches each site at most once, and the u16 halves add independently: order is irrelevant)
+    for (uint32_t r = warp; r < n_ref; r += JOIN_WARPS) {
         const uint32_t id = ref_ids[r];
         const int hap = P.rs_hp[first + id];
         if (hap == 0 || hap == 1) {
             const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
-            for (uint32_t i0 = tid; i0 < nm; i0 += JOIN_THREADS) {
+            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
+            for (uint32_t i0 = lane; i0 < nm; i0 += 32) {
                 uint32_t *row = site_row(tab, tab_base, st + i0, row_words);
-                row[pool[off + i0]] += hap == 0 ? 1u : 0x10000u;
-                row[n_keys] += hap == 0 ? 1u : 0x10000u;
+                atomicAdd(&row[pool[off + i0]], inc);
+                atomicAdd(&row[n_keys], inc);
             }
         }
-        __syncthreads();
     }
     // ---- un-tag everything but the reference reads, :4010-4025 (with the (id<<2)|hp packing) ----
     for (uint32_t i = tid; i < n; i += JOIN_THREADS) tags[i] = 2;
@@ -121,95 +156,130 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             uint32_t tid2 = packed >> 2;
             if (tid2 < n) tags[tid2] = (uint8_t)(packed & 3u);
         }
-        // update_available_methmer_range(cov_for_runtime), :3669-3691
-        uint32_t mn = s_min, mx = s_max;
-        for (int i = (int)mn; i >= 0; i--) {
-            uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
-            if ((int)((sm & 0xffffu) + (sm >> 16)) >= P.cov_run) mn = (uint32_t)i; else break;
-        }
-        for (int i = (int)mx; i < (int)n_sites; i++) {
-            uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
-            if ((int)((sm & 0xffffu) + (sm >> 16)) >= P.cov_run) mx = (uint32_t)i; else break;
-        }
-        s_min = mn; s_max = mx;
     }
     __syncthreads();
 
     // ---- extension loop, :4032-4071 ----
+    // Warp 0 owns the loop state between the barriers: available range, candidate list, failure count.
+    // The candidate list ("the first n_cand untagged reads in scan order from i_last", :4039-4045) is kept
+    // incrementally: a success removes the tagged read and appends the next untagged one behind the scan
+    // cursor; a failure moves i_last (:4064-4068) and rebuilds it.
     uint32_t n_order = 0;
+    int nc = 0, cursor = 0;          // warp 0 only (uniform)
+    bool rebuild = true, grow = true;  // first pass: update_available_methmer_range after seeding, fresh list
+    int last_best = -1;
     for (;;) {
-        // 1) candidates: the first n_cand untagged reads in scan order from i_last (warp 0)
         if (warp == 0) {
-            int i_last = s_i_last;
-            int nc = 0;
-            bool done = (d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0);
+            uint32_t mn = s_min, mx = s_max;
+            if (grow) { grow_range(tab, tab_base, row_words, n_keys, n_sites, P.cov_run, mn, mx); if (lane == 0) { s_min = mn; s_max = mx; } }
+            const int i_last = s_i_last;
+            const bool done = (d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0);
             if (!done) {
-                int pos = i_last;
+                if (rebuild) { nc = 0; cursor = i_last; }
+                else if (last_best >= 0) {
+                    // drop entry last_best, keep the order of the rest
+                    for (int c0 = 0; c0 < nc; c0 += 32) {
+                        const int c = c0 + (int)lane;
+                        uint32_t v = 0;
+                        const bool mv = c > last_best && c < nc;
+                        if (mv) v = s_cand[c];
+                        __syncwarp();
+                        if (mv) s_cand[c - 1] = v;
+                    }
+                    nc--;
+                    __syncwarp();
+                }
+                // refill from the cursor
                 while (nc < n_cand) {
-                    int i0 = d == 0 ? pos + (int)lane : pos - (int)lane;
-                    bool in = d == 0 ? i0 < (int)n : i0 >= 0;
+                    const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
+                    const bool in = d == 0 ? i0 < (int)n : i0 >= 0;
                     uint32_t id = 0;
                     bool unt = false;
                     if (in) {
-                        id = d == 0 ? (uint32_t)i0 : P.rs_rev[first + i0];
-                        uint8_t t = tags[id];
+                        id = d == 0 ? (uint32_t)i0 : rev[i0];
+                        const uint8_t t = tags[id];
                         unt = t != 0 && t != 1;
                     }
-                    unsigned um = __ballot_sync(FULL_MASK, unt);
-                    int rank = __popc(um & ((1u << lane) - 1u));
-                    if (unt && nc + rank < n_cand) s_cand[nc + rank] = id;
-                    nc += __popc(um);
-                    if (nc > n_cand) nc = n_cand;
-                    unsigned inm = __ballot_sync(FULL_MASK, in);
-                    if (inm != FULL_MASK) break;
-                    pos += d == 0 ? 32 : -32;
+                    const unsigned um = __ballot_sync(FULL_MASK, unt);
+                    const int rank = __popc(um & ((1u << lane) - 1u));
+                    const int room = n_cand - nc;
+                    if (unt && rank < room) s_cand[nc + rank] = id;
+                    const int found = __popc(um);
+                    if (found >= room) {
+                        // the list is full: the cursor stops right behind the read that filled it
+                        const int fill_lane = (int)__fns(um, 0, room);
+                        cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
+                        nc = n_cand;
+                        break;
+                    }
+                    nc += found;
+                    cursor += d == 0 ? 32 : -32;
+                    if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
                 }
+                __syncwarp();
             }
-            if (lane == 0) { s_ncand = nc; s_done = done ? 1 : 0; }
+            if (lane == 0) { s_ncand = nc; if (done) s_done = 1; }
         }
         __syncthreads();
         if (s_done) break;
         const int ncand = s_ncand;
         const uint32_t rmin = s_min, rmax = s_max;
-        // 2) score the candidates, one warp each
+        // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
         for (int c = (int)warp; c < ncand; c += JOIN_WARPS) {
             const uint32_t id = s_cand[c];
             const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
-            float score0 = 0.f, score1 = 0.f;  // live in lane 0 / lane 1
+            float sc_h = 0.f;  // lane 0: haplotype 0, lane 1: haplotype 1
             int l0 = 0, l1 = 0;
-            for (uint32_t base = 0; base < nm; base += 32) {
-                const uint32_t i0 = base + lane;
-                float v0 = 0.f, v1 = 0.f;
-                bool p0 = false, p1 = false;
-                if (i0 < nm) {
+            for (uint32_t base = 0; base < nm; base += JOIN_CHUNK) {
+                uint32_t key[JOIN_U], cnt[JOIN_U], sums[JOIN_U];
+                bool inr[JOIN_U];
+#pragma unroll
+                for (int u = 0; u < JOIN_U; u++) {
+                    const uint32_t i0 = base + u * 32 + lane;
                     const uint32_t site = st + i0;
-                    if (!(site < rmin || site >= rmax)) {
-                        const uint32_t *row = site_row(tab, tab_base, site, row_words);
-                        const uint32_t cnt = row[pool[off + i0]];
-                        if (cnt != 0) {  // key present at this site
-                            const uint32_t sums = row[n_keys];
-                            const uint32_t sum0 = sums & 0xffffu, sum1 = sums >> 16;
-                            if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt & 0xffffu), (float)sum0); }
-                            if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt >> 16), (float)sum1); }
-                        }
+                    inr[u] = i0 < nm && !(site < rmin || site >= rmax);
+                    key[u] = inr[u] ? pool[off + i0] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < JOIN_U; u++) {
+                    cnt[u] = 0; sums[u] = 0;
+                    if (inr[u]) {
+                        const uint32_t *row = site_row(tab, tab_base, st + base + u * 32 + lane, row_words);
+                        cnt[u] = row[key[u]];
+                        sums[u] = row[n_keys];
                     }
                 }
-                l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(__ballot_sync(FULL_MASK, v0 > 0.f));
-                l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(__ballot_sync(FULL_MASK, v1 > 0.f));
-                s_val[warp][0][lane] = v0;
-                s_val[warp][1][lane] = v1;
+                int n0 = 0, n1 = 0;  // non-zero terms staged so far (adding +0.0f is exact, so zeros are skipped)
+#pragma unroll
+                for (int u = 0; u < JOIN_U; u++) {
+                    if (base + u * 32 >= nm) break;
+                    float v0 = 0.f, v1 = 0.f;
+                    bool p0 = false, p1 = false;
+                    if (cnt[u] != 0) {  // key present at this site
+                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
+                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt[u] & 0xffffu), (float)sum0); }
+                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt[u] >> 16), (float)sum1); }
+                    }
+                    const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
+                    l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
+                    l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (v0 > 0.f) s_val[warp][0][n0 + __popc(z0 & lt)] = v0;
+                    if (v1 > 0.f) s_val[warp][1][n1 + __popc(z1 & lt)] = v1;
+                    n0 += __popc(z0);
+                    n1 += __popc(z1);
+                }
                 __syncwarp();
-                if (lane < 2) {
-                    float s = lane == 0 ? score0 : score1;
+                if (lane < 2) {  // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636)
+                    const int nn = lane == 0 ? n0 : n1;
                     const float *v = s_val[warp][lane];
-#pragma unroll 8
-                    for (int t = 0; t < 32; t++) s = __fadd_rn(s, v[t]);  // + 0.0f is exact for skipped entries
-                    if (lane == 0) score0 = s; else score1 = s;
+#pragma unroll 4
+                    for (int t = 0; t < nn; t++) sc_h = __fadd_rn(sc_h, v[t]);
                 }
                 __syncwarp();
             }
-            score1 = __shfl_sync(FULL_MASK, score1, 1);
-            score0 = __shfl_sync(FULL_MASK, score0, 0);
+            const float score1 = __shfl_sync(FULL_MASK, sc_h, 1);
+            const float score0 = __shfl_sync(FULL_MASK, sc_h, 0);
             if (lane == 0) {
                 float diff = score0 > score1 ? __fsub_rn(score0, score1) : __fsub_rn(score1, score0);
                 int tag;
@@ -221,28 +291,34 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             }
         }
         __syncthreads();
-        // 3) stable ascending sort + scan from the top == max score, ties to the later candidate
-        if (tid == 0) {
-            int best = -1;
-            float bs = 0.f;
-            for (int c = 0; c < ncand; c++) {
-                if (s_tag[c] == 0 || s_tag[c] == 1) {
-                    if (best < 0 || s_score[c] >= bs) { best = c; bs = s_score[c]; }
+        // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
+        //      every warp finds it on its own ----
+        int best = -1;
+        {
+            unsigned long long bk = 0;
+            for (int c = (int)lane; c < ncand; c += 32) {
+                const int t = s_tag[c];
+                if (t == 0 || t == 1) {
+                    const unsigned long long k = (((unsigned long long)__float_as_uint(s_score[c]) << 32) | (unsigned)c) + 1ull;
+                    bk = k > bk ? k : bk;
                 }
             }
-            s_best = best;
-            s_best_tag = best >= 0 ? s_tag[best] : -1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long t = __shfl_xor_sync(FULL_MASK, bk, o);
+                bk = t > bk ? t : bk;
+            }
+            if (bk) best = (int)((bk - 1ull) & 0xffffffffull);
         }
-        __syncthreads();
-        const int best = s_best;
         if (best >= 0) {
             const uint32_t id = s_cand[best];
-            const int hap = s_best_tag;
+            const int hap = s_tag[best];
             const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
+            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
             for (uint32_t i0 = tid; i0 < nm; i0 += JOIN_THREADS) {
                 uint32_t *row = site_row(tab, tab_base, st + i0, row_words);
-                row[pool[off + i0]] += hap == 0 ? 1u : 0x10000u;
-                row[n_keys] += hap == 0 ? 1u : 0x10000u;
+                row[pool[off + i0]] += inc;
+                row[n_keys] += inc;
             }
             if (tid == 0) {
                 tags[id] = (uint8_t)hap;
@@ -250,24 +326,16 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             }
             n_order++;
         }
-        __syncthreads();
-        if (tid == 0) {
-            if (best >= 0) {
-                uint32_t mn = s_min, mx = s_max;
-                for (int i = (int)mn; i >= 0; i--) {
-                    uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
-                    if ((int)((sm & 0xffffu) + (sm >> 16)) >= P.cov_run) mn = (uint32_t)i; else break;
+        if (warp == 0) {
+            last_best = best;
+            if (best >= 0) { rebuild = false; grow = true; if (lane == 0) s_failed = 0; }
+            else {
+                rebuild = true; grow = false;
+                if (lane == 0) {
+                    s_failed++;
+                    if (s_failed > 10) s_done = 1;
+                    s_i_last += d == 0 ? n_cand : -n_cand;
                 }
-                for (int i = (int)mx; i < (int)n_sites; i++) {
-                    uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
-                    if ((int)((sm & 0xffffu) + (sm >> 16)) >= P.cov_run) mx = (uint32_t)i; else break;
-                }
-                s_min = mn; s_max = mx;
-                s_failed = 0;
-            } else {
-                s_failed++;
-                if (s_failed > 10) s_done = 1;
-                s_i_last += d == 0 ? n_cand : -n_cand;
             }
         }
         __syncthreads();

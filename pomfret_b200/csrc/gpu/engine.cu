@@ -8,7 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <algorithm>
 #include "gpu_rt.h"
@@ -127,6 +131,67 @@ template <typename T> struct PinVec {
     void release() { b.release(); n = 0; }
 };
 
+// Helper threads for the gather copy of add_reads(): record payloads are scattered over the caller's
+// memory (one BAM record each) and have to land in the pinned arena before the DMA engine can take
+// them; one core moves ~10 GB/s, PCIe 5 wants ~55 GB/s.  Helpers spin briefly between calls (a loader
+// calls add_reads back to back) and then block on a condition variable.
+class StagePool {
+ public:
+    explicit StagePool(int n_helpers) {
+        for (int i = 0; i < n_helpers; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~StagePool() {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; gen_.fetch_add(1); }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int helpers() const { return (int)th_.size(); }
+    void run(size_t n, const std::function<void(size_t)> &fn) {
+        if (th_.empty() || n < 2) { for (size_t i = 0; i < n; i++) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            fn_ = &fn; n_ = n; next_.store(0); active_.store((int)th_.size());
+            gen_.fetch_add(1);
+        }
+        cv_.notify_all();
+        for (size_t i; (i = next_.fetch_add(1)) < n;) fn(i);
+        while (active_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    }
+
+ private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            // spin, then sleep
+            bool got = false;
+            for (int spin = 0; spin < 20000 && !got; spin++) got = gen_.load(std::memory_order_acquire) != seen;
+            if (!got) {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_.load() != seen; });
+            }
+            const std::function<void(size_t)> *fn;
+            size_t n;
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                seen = gen_.load();
+                if (stop_) return;
+                fn = fn_; n = n_;
+            }
+            for (size_t i; (i = next_.fetch_add(1)) < n;) (*fn)(i);
+            active_.fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t n_ = 0;
+    std::atomic<size_t> next_{0};
+    std::atomic<uint64_t> gen_{0};
+    std::atomic<int> active_{0};
+    bool stop_ = false;
+};
+
 enum Stage { ST_EMPTY = 0, ST_SUBMITTED = 1, ST_DECODED = 2, ST_PILED = 3, ST_JOINED = 4, ST_HAPTAGGED = 5 };
 
 }  // namespace
@@ -155,6 +220,10 @@ struct pomfret_gpu_batch {
     std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
     uint64_t calls_total = 0;
     uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
+    StagePool *pool = nullptr;      // gather-copy helpers (created on first bulk add)
+    size_t blob_hint = 0;           // blob size of the previous batch: device buffer is ready before staging starts
+    size_t blob_sent = 0;           // bytes of the blob already handed to the DMA engine while staging
+    bool streaming = false, h2d_started = false;
     // device
     DevArena arena;
     DevBuf d_blob, d_reads, d_win, d_read_win, d_calls_pos, d_calls_cat, d_tmp_rank, d_tmp_mpos, d_tmp_mcat;
@@ -264,6 +333,11 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     if (cudaSetDevice(b->device) != cudaSuccess) return POMFRET_GPU_ERR_CUDA;
     cudaStreamSynchronize(b->stream);
     b->arena.rewind();
+    // A batch of about the size of the previous one gets its device blob up front, so that add_reads()
+    // can hand finished parts of the pinned arena to the DMA engine while the caller is still staging.
+    b->blob_sent = 0;
+    b->h2d_started = false;
+    b->streaming = b->blob_hint > 0 && b->d_blob.ensure(b->blob_hint + 1024) == 0;
     return POMFRET_GPU_OK;
 }
 
@@ -278,24 +352,13 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
+    delete b->pool;
     delete b;
 }
 
-static int blob_put(pomfret_gpu_batch *b, const void *src, size_t n, uint32_t *off16) {
-    size_t off = align16(b->h_blob.len);
-    size_t end = align16(off + n);
-    if (int rc = b->h_blob.reserve(end + 1024)) return rc;  // tail slack: kernels stage whole 16-byte lanes
-    if (off > b->h_blob.len) memset(b->h_blob.p + b->h_blob.len, 0, off - b->h_blob.len);
-    if (n) memcpy(b->h_blob.p + off, src, n);
-    memset(b->h_blob.p + off + n, 0, end - (off + n));
-    b->h_blob.len = end;
-    *off16 = (uint32_t)(off / 16);
-    return 0;
-}
-
-int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {
-    if (!b || !r) return POMFRET_GPU_ERR_ARG;
-    if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+// Phase 1 of staging (serial, no payload touched): lay the record's fields out in the blob and reserve
+// its call slots.  Every field starts on a 16-byte boundary and is zero padded to the next one.
+static int plan_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, size_t *len) {
     if (r->l_qseq >= (1u << 28)) return POMFRET_GPU_ERR_UNSUPPORTED;  // decode.cuh: DEC_SAT
     ReadRec R;
     memset(&R, 0, sizeof(R));
@@ -303,26 +366,13 @@ int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc
     R.flags = r->flag;
     if (r->tags_malformed) R.flags |= RF_MALFORMED;
     R.hp = r->hp; R.mn = r->mn;
-    int rc;
-    if ((rc = blob_put(b, r->cigar, (size_t)r->n_cigar * 4, &R.cigar_off))) return rc;
-    if ((rc = blob_put(b, r->seq, ((size_t)r->l_qseq + 1) / 2, &R.seq_off))) return rc;
-    // the unused low nibble of an odd-length SEQ must read as "no base" (the kernels do not mask the tail)
-    if (r->l_qseq & 1u) b->h_blob.p[(size_t)R.seq_off * 16 + r->l_qseq / 2] &= 0xf0u;
-    if (r->mm) {
-        R.flags |= RF_HAS_MM;
-        R.mm_len = r->mm_len;
-        if ((rc = blob_put(b, r->mm, r->mm_len, &R.mm_off))) return rc;
-    }
-    if (r->ml_len >= 0) {
-        R.flags |= RF_HAS_ML;
-        R.ml_len = (uint32_t)r->ml_len;
-        if ((rc = blob_put(b, r->ml, (size_t)r->ml_len, &R.ml_off))) return rc;
-    }
-    if (r->md) {
-        R.flags |= RF_HAS_MD;
-        R.md_len = r->md_len;
-        if ((rc = blob_put(b, r->md, r->md_len, &R.md_off))) return rc;
-    }
+    auto place = [&](size_t n, uint32_t *off16) { *off16 = (uint32_t)(*len / 16); *len = align16(*len + n); };
+    place((size_t)r->n_cigar * 4, &R.cigar_off);
+    place(((size_t)r->l_qseq + 1) / 2, &R.seq_off);
+    if (r->mm) { R.flags |= RF_HAS_MM; R.mm_len = r->mm_len; place(r->mm_len, &R.mm_off); }
+    if (r->ml_len >= 0) { R.flags |= RF_HAS_ML; R.ml_len = (uint32_t)r->ml_len; place((size_t)r->ml_len, &R.ml_off); }
+    if (r->md) { R.flags |= RF_HAS_MD; R.md_len = r->md_len; place(r->md_len, &R.md_off); }
+    if (*len / 16 > 0xfffffff0ull) return POMFRET_GPU_ERR_UNSUPPORTED;  // 32-bit offsets in units of 16 bytes
     // call slots: one per listed base is enough unless implicit canonical calls appear (then the engine
     // re-runs the record with the exact count)
     uint32_t cap = r->ml_len >= 0 ? (uint32_t)r->ml_len : r->mm_len / 2 + 1;
@@ -331,26 +381,93 @@ int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc
     R.calls_cap = cap;
     b->calls_total += cap;
     if (b->calls_total > 0xfff00000ull) return POMFRET_GPU_ERR_UNSUPPORTED;
-    // reference end (tile planning) and algorithmic byte counts
+    // algorithmic byte counts
+    b->alg_decode_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->mm_len + (r->ml_len > 0 ? r->ml_len : 0);
+    b->alg_haptag_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->md_len + 1;
+    int rc;
+    if ((rc = b->h_reads.push(R))) return rc;
+    if ((rc = b->h_read_win.push(0xffffffffu))) return rc;
+    return POMFRET_GPU_OK;
+}
+
+// Phase 2 (any thread): copy the payload of one planned record into the pinned blob.
+static void copy_read(uint8_t *blob, const ReadRec &R, const pomfret_gpu_read_desc *r, uint32_t *end_out) {
+    auto put = [&](uint32_t off16, const void *src, size_t n) {
+        uint8_t *dst = blob + (size_t)off16 * 16;
+        if (n) memcpy(dst, src, n);
+        memset(dst + n, 0, align16(n) - n);
+    };
+    put(R.cigar_off, r->cigar, (size_t)r->n_cigar * 4);
+    put(R.seq_off, r->seq, ((size_t)r->l_qseq + 1) / 2);
+    // the unused low nibble of an odd-length SEQ must read as "no base" (the kernels do not mask the tail)
+    if (r->l_qseq & 1u) blob[(size_t)R.seq_off * 16 + r->l_qseq / 2] &= 0xf0u;
+    if (R.flags & RF_HAS_MM) put(R.mm_off, r->mm, r->mm_len);
+    if (R.flags & RF_HAS_ML) put(R.ml_off, r->ml, (size_t)r->ml_len);
+    if (R.flags & RF_HAS_MD) put(R.md_off, r->md, r->md_len);
+    // reference end (tile planning on the host)
     uint64_t rlen = 0;
     for (uint32_t i = 0; i < r->n_cigar; i++) {
         uint32_t op = r->cigar[i] & 15u;
         if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += r->cigar[i] >> 4;
     }
     if (rlen == 0) rlen = 1;
-    b->h_end.push_back((uint32_t)(r->pos + rlen));
-    b->alg_decode_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->mm_len + (r->ml_len > 0 ? r->ml_len : 0);
-    b->alg_haptag_bytes += ((uint64_t)r->l_qseq + 1) / 2 + 4ull * r->n_cigar + r->md_len + 1;
-    if ((rc = b->h_reads.push(R))) return rc;
-    if ((rc = b->h_read_win.push(0xffffffffu))) return rc;
-    return POMFRET_GPU_OK;
+    *end_out = (uint32_t)(r->pos + rlen);
+}
+
+// Hand the finished part of the blob to the copy engine (only while the device buffer of this batch is
+// known to be large enough; submit() sends whatever is left).
+static int stream_blob(pomfret_gpu_batch *b, bool force) {
+    if (!b->streaming) return 0;
+    if (b->h_blob.len + 2048 > b->d_blob.cap) { b->streaming = false; return 0; }  // larger than planned: submit() copies all
+    const size_t ready = b->h_blob.len;
+    if (ready <= b->blob_sent || (!force && ready - b->blob_sent < ((size_t)8 << 20))) return 0;
+    if (cudaSetDevice(b->device) != cudaSuccess) return POMFRET_GPU_ERR_CUDA;
+    if (!b->h2d_started) { CK(cudaEventRecord(b->ev[0], b->stream)); b->h2d_started = true; }
+    CK(cudaMemcpyAsync(b->d_blob.as<uint8_t>() + b->blob_sent, b->h_blob.p + b->blob_sent, ready - b->blob_sent,
+                       cudaMemcpyHostToDevice, b->stream));
+    b->tm.bytes_h2d += ready - b->blob_sent;
+    b->blob_sent = ready;
+    return 0;
 }
 
 int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n) {
     if (!b || (n && !r)) return POMFRET_GPU_ERR_ARG;
-    for (uint32_t i = 0; i < n; i++)
-        if (int rc = pomfret_gpu_batch_add_read(b, r + i)) return rc;
-    return POMFRET_GPU_OK;
+    if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
+    if (n == 0) return POMFRET_GPU_OK;
+    const size_t first = b->h_reads.n;
+    size_t len = b->h_blob.len;
+    for (uint32_t i = 0; i < n; i++) {
+        if (int rc = plan_read(b, r + i, &len)) {
+            // roll back the partially planned call
+            b->h_reads.n = first; b->h_reads.b.len = first * sizeof(ReadRec);
+            b->h_read_win.n = first; b->h_read_win.b.len = first * 4;
+            return rc;
+        }
+    }
+    if (len + 2048 > b->h_blob.cap) {
+        // growing the pinned arena moves it: no DMA may still be reading the old one
+        if (b->blob_sent) { CK(cudaSetDevice(b->device)); CK(cudaStreamSynchronize(b->stream)); }
+        if (int rc = b->h_blob.reserve(len + 2048)) return rc;
+    }
+    b->h_end.resize(first + n);
+    uint8_t *blob = b->h_blob.p;
+    const ReadRec *recs = b->h_reads.data() + first;
+    uint32_t *ends = b->h_end.data() + first;
+    if (n >= 16 && !b->pool) {
+        unsigned hw = std::thread::hardware_concurrency();
+        int per = (int)(hw ? hw : 1) / std::max(1, b->ctx->n_workers);
+        if (const char *e = getenv("POMFRET_GPU_STAGE_THREADS")) per = atoi(e);
+        b->pool = new StagePool(std::max(0, std::min(per, 12) - 1));
+    }
+    if (b->pool && n >= 16) b->pool->run(n, [&](size_t i) { copy_read(blob, recs[i], r + i, ends + i); });
+    else for (uint32_t i = 0; i < n; i++) copy_read(blob, recs[i], r + i, ends + i);
+    b->h_blob.len = len;
+    return stream_blob(b, false);
+}
+
+int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {
+    if (!r) return POMFRET_GPU_ERR_ARG;
+    return pomfret_gpu_batch_add_reads(b, r, 1);
 }
 
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
@@ -383,12 +500,22 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
     CK(cudaSetDevice(b->device));
     const size_t nr = b->h_reads.n, nw = b->h_win.n;
-    CK(cudaEventRecord(b->ev[0], b->stream));
     int rc;
     // the blob keeps 1 KB of zeroed slack behind the last field
-    if ((rc = b->h_blob.reserve(b->h_blob.len + 1024))) return rc;
+    if (b->h_blob.len + 2048 > b->h_blob.cap) {
+        if (b->blob_sent) CK(cudaStreamSynchronize(b->stream));
+        if ((rc = b->h_blob.reserve(b->h_blob.len + 2048))) return rc;
+    }
     memset(b->h_blob.p + b->h_blob.len, 0, 1024);
-    if ((rc = up(b, b->d_blob, b->h_blob.p, b->h_blob.len + 1024))) return rc;
+    b->h_blob.len += 1024;
+    if ((rc = stream_blob(b, true))) return rc;
+    if (!b->h2d_started) { CK(cudaEventRecord(b->ev[0], b->stream)); b->h2d_started = true; }
+    if (!b->streaming) {
+        b->blob_sent = 0;
+        if ((rc = up(b, b->d_blob, b->h_blob.p, b->h_blob.len))) return rc;
+    }
+    b->blob_hint = std::max(b->h_blob.len, b->blob_hint - b->blob_hint / 16);  // follows the batch size, decays slowly
+    b->h_blob.len -= 1024;
     if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
     if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
     if ((rc = up(b, b->d_read_win, b->h_read_win.data(), nr * 4))) return rc;

@@ -24,7 +24,7 @@ def build(verbose=False, opt="-O1"):
            "-Wno-unused-function", "-Wno-unused-variable", "-Wno-sign-compare",
            "-I", HERE, "-I", gpu, "-I", os.path.join(ROOT, "include"), "-I", hts,
            "-x", "c++", srcs[0], "-x", "c++", os.path.join(HERE, "cuda_emu.cpp"),
-           "-x", "c", os.path.join(hts, "fisher.c"), "-lm", "-o", so]
+           "-x", "c", os.path.join(hts, "fisher.c"), "-lm", "-pthread", "-o", so]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -233,7 +233,7 @@ struct pomfret_gpu_batch {
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
     DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags;
-    uint32_t pool_cap = 0, tab_sites = 0, site_total = 0;
+    uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
     pomfret_gpu_timing tm = {};
@@ -694,7 +694,7 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     // ---- the one round trip: pool sizes (and whether any record ran out of call slots) ----
     if ((rc = b->h_u32.resize(8))) return rc;
     for (int attempt = 0;; attempt++) {
-        CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 8, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 12, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaMemcpyAsync(b->h_u32.data() + 4, b->d_flags.p, 4, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         if (b->h_u32[4] == 0) break;
@@ -722,7 +722,8 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     const uint32_t mmr_total = b->h_u32[0], tab_sites = b->h_u32[1];
     b->pool_cap = mmr_total + 64;
     b->tab_sites = tab_sites;
-    const size_t row_words = ((size_t)1 << (2 * cfg->k)) + 1;
+    b->max_sites = b->h_u32[2];
+    const size_t row_words = join_row_stride(cfg->k);
     if ((rc = b->d_mmr_pool.ensure((size_t)b->pool_cap * 4)) || (rc = b->d_ent_pool.ensure((size_t)b->pool_cap * 4)) ||
         (rc = b->d_tab.ensure(((size_t)tab_sites + 1) * row_words * 4)))
         return rc;
@@ -756,9 +757,21 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     }
     J.mmr_pool = b->d_mmr_pool.as<uint32_t>(); J.tab = b->d_tab.as<uint32_t>();
     J.n_cand = cfg->n_candidates_per_iter; J.cov_run = cfg->cov_for_runtime; J.k = cfg->k;
+    // shared-memory plan: per-read state of the largest window, look-ahead key cache, and — if they fit — the
+    // count tables of the largest window (otherwise that launch keeps them in the global pool)
+    uint32_t max_reads = 0;
+    for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
+    J.meta_cap = max_reads <= 4096 ? max_reads : 0;
+    const size_t smem_limit = (size_t)225 * 1024;
+    const size_t want_tab = (size_t)b->max_sites * join_row_stride(cfg->k);
+    J.smem_tab_words = join_smem_bytes((uint32_t)want_tab, J.meta_cap, J.n_cand) <= smem_limit ? (uint32_t)want_tab : 0;
+    const size_t smem = join_smem_bytes(J.smem_tab_words, J.meta_cap, J.n_cand);
     CK(cudaEventRecord(b->ev[8], b->stream));
     if (nw) {
-        POMFRET_LAUNCH(join_kernel, (unsigned)(nw * 2), JOIN_THREADS, 0, b->stream, J);
+#ifndef POMFRET_CUDA_EMU
+        CK(cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+        POMFRET_LAUNCH(join_kernel, (unsigned)(nw * 2), JOIN_THREADS, smem, b->stream, J);
         b->tm.launches++;
     }
     CK(cudaEventRecord(b->ev[9], b->stream));

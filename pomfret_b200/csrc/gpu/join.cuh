@@ -26,7 +26,7 @@ constexpr int JOIN_THREADS = 512;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
 constexpr int JOIN_MAX_CAND = 128;
 constexpr int JOIN_U = 8;                 // methmer sub-chunks (32 each) whose loads are issued together
-constexpr int JOIN_CHUNK = JOIN_U * 32;   // values staged per warp before the ordered sum
+constexpr int JOIN_CHUNK = JOIN_U * 32;   // methmers of a candidate whose keys are cached in shared memory
 
 struct JoinParams {
     const WindowRec *win;
@@ -37,28 +37,41 @@ struct JoinParams {
     const uint32_t *site_pos;
     const uint32_t *mm_off[2], *mm_n[2], *mm_start[2];
     const uint32_t *mmr_pool;
-    uint32_t *tab;         // table pool: per site (n_keys + 1) words
+    uint32_t *tab;         // table pool (used by windows whose tables do not fit shared memory)
     uint8_t *tags[2];      // propagated tags per slot and direction
     uint32_t *order[2];    // tagging order per direction (slot-indexed slices)
     int32_t n_cand;
     int32_t cov_run;
     int32_t k;
+    uint32_t smem_tab_words;  // shared-memory words reserved for the count tables
+    uint32_t meta_cap;        // reads whose per-read state fits the shared-memory arrays
 };
 
-__device__ __forceinline__ uint32_t *site_row(uint32_t *tab, uint32_t tab_base, uint32_t site, uint32_t row_words) {
-    return tab + ((size_t)tab_base + site) * row_words;
+// Count tables: per site one row of 3^k key words (lo16 = haplotype 0 count, hi16 = haplotype 1 count)
+// plus one word with the two sums.  Methmer symbols are m=0, u=1, -=2 (blockjoin.c:3186-3194), so a key's
+// base-4 digits never contain 3 and the row is indexed by the same digits read in base 3.  The row stride
+// is odd so that consecutive sites fall into different shared-memory banks.
+__host__ __device__ __forceinline__ uint32_t join_n_keys(int k) { uint32_t v = 1; for (int i = 0; i < k; i++) v *= 3u; return v; }
+__host__ __device__ __forceinline__ uint32_t join_row_stride(int k) { return (join_n_keys(k) + 1u) | 1u; }
+__device__ __forceinline__ uint32_t compact_key(uint32_t key) {  // k <= 4
+    return ((key >> 6) & 3u) * 27u + ((key >> 4) & 3u) * 9u + ((key >> 2) & 3u) * 3u + (key & 3u);
+}
+// dynamic shared memory of join_kernel for the given capacities (bytes)
+__host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_words, uint32_t meta_cap, int n_cand) {
+    return (size_t)tab_words * 4 + (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 + (size_t)((meta_cap + 31) / 32) * 4 +
+           (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
 }
 
 // Range growth of update_available_methmer_range (blockjoin.c:3669-3691), warp-parallel: the left edge
 // walks down from `mn` while the site's coverage reaches cov, the right edge walks up from `mx`.
-__device__ __forceinline__ void grow_range(uint32_t *tab, uint32_t tab_base, uint32_t row_words, uint32_t n_keys,
-                                           uint32_t n_sites, int cov, uint32_t &mn, uint32_t &mx) {
+__device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride, uint32_t n_keys, uint32_t n_sites, int cov,
+                                           uint32_t &mn, uint32_t &mx) {
     const int lane = (int)lane_id();
     for (int i0 = (int)mn;; i0 -= 32) {
         const int i = i0 - lane;
         bool ok = false;
         if (i >= 0) {
-            const uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
+            const uint32_t sm = tab[(size_t)i * stride + n_keys];
             ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
         }
         const unsigned bad = ~__ballot_sync(FULL_MASK, ok);  // first lane that stops the walk (or ran past site 0)
@@ -70,7 +83,7 @@ __device__ __forceinline__ void grow_range(uint32_t *tab, uint32_t tab_base, uin
         const int i = i0 + lane;
         bool ok = false;
         if (i < (int)n_sites) {
-            const uint32_t sm = site_row(tab, tab_base, (uint32_t)i, row_words)[n_keys];
+            const uint32_t sm = tab[(size_t)i * stride + n_keys];
             ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
         }
         const unsigned bad = ~__ballot_sync(FULL_MASK, ok);
@@ -81,13 +94,14 @@ __device__ __forceinline__ void grow_range(uint32_t *tab, uint32_t tab_base, uin
 }
 
 __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
-    __shared__ int s_i_last, s_failed, s_done, s_ncand, s_cursor;
+    __shared__ int s_i_last, s_failed, s_done, s_ncand;
     __shared__ uint32_t s_min, s_max;
-    __shared__ uint32_t s_cand[JOIN_MAX_CAND];
+    __shared__ uint32_t s_cand[JOIN_MAX_CAND + 1];
+    __shared__ uint8_t s_slot[JOIN_MAX_CAND + 1];
     __shared__ float s_score[JOIN_MAX_CAND];
     __shared__ int s_tag[JOIN_MAX_CAND];
-    __shared__ float s_val[JOIN_WARPS][2][JOIN_CHUNK];
     __shared__ int s_tbl[4];
+    POMFRET_DYN_SMEM(uint32_t, dyn);
 
     const uint32_t w = blockIdx.x >> 1, d = blockIdx.x & 1u;
     const WindowRec W = P.win[w];
@@ -96,12 +110,10 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
     if (n == 0 || n_sites == 0 || S.status != 0) return;
     const uint32_t first = W.first_read;
-    const uint32_t n_keys = 1u << (2 * P.k);
-    const uint32_t row_words = n_keys + 1;
-    const uint32_t tab_base = S.tab_base[d];
-    uint32_t *tab = P.tab;
+    const uint32_t n_keys = join_n_keys(P.k);
+    const uint32_t stride = join_row_stride(P.k);
     uint8_t *tags = P.tags[d] + first;
-    const uint32_t *mm_off = P.mm_off[d] + first, *mm_n = P.mm_n[d] + first, *mm_start = P.mm_start[d] + first;
+    const uint32_t *g_off = P.mm_off[d] + first, *g_n = P.mm_n[d] + first, *g_start = P.mm_start[d] + first;
     const uint32_t *pool = P.mmr_pool;
     const uint32_t *site_pos = P.site_pos + W.site_off;
     const uint32_t *ref_ids = (d == 0 ? P.ids_left : P.ids_right) + first;
@@ -109,11 +121,26 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     const uint32_t n_ref = d == 0 ? S.n_left : S.n_right;
     const int n_cand = P.n_cand;
 
-    // ---- wipe the tables (insert_ref_reads_methmer_counts, :3780-3789) ----
-    {
-        uint32_t *t0 = site_row(tab, tab_base, 0, row_words);
-        const size_t words = (size_t)n_sites * row_words;
-        for (size_t i = tid; i < words; i += JOIN_THREADS) t0[i] = 0;
+    // ---- shared-memory carve-up ----
+    uint32_t *s_tab = dyn;
+    uint32_t *s_moff = s_tab + P.smem_tab_words;               // per read: offset of its keys in the methmer pool
+    uint32_t *s_mn = s_moff + P.meta_cap;                      // per read: number of methmers
+    uint32_t *s_mst = s_mn + P.meta_cap;                       // per read: site index of the first one
+    uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
+    uint32_t *s_tagged = reinterpret_cast<uint32_t *>(s_scan) + (P.meta_cap + 1) / 2;  // bit per read: tagged 0/1
+    uint8_t *s_keys = reinterpret_cast<uint8_t *>(s_tagged + (P.meta_cap + 31) / 32);   // [n_cand + 1][JOIN_CHUNK]
+    const bool tab_in_smem = (size_t)n_sites * stride <= P.smem_tab_words;
+    const bool meta_in_smem = n <= P.meta_cap;
+    uint32_t *tab = tab_in_smem ? s_tab : P.tab + (size_t)S.tab_base[d] * stride;
+
+    // ---- wipe the tables (insert_ref_reads_methmer_counts, :3780-3789), load the per-read state ----
+    for (size_t i = tid, words = (size_t)n_sites * stride; i < words; i += JOIN_THREADS) tab[i] = 0;
+    if (meta_in_smem) {
+        for (uint32_t i = tid; i < n; i += JOIN_THREADS) {
+            s_moff[i] = g_off[i]; s_mn[i] = g_n[i]; s_mst[i] = g_start[i];
+            s_scan[i] = (uint16_t)(d == 0 ? i : rev[i]);
+        }
+        for (uint32_t i = tid; i < (n + 31) / 32; i += JOIN_THREADS) s_tagged[i] = 0;
     }
     // ---- available range, :3976-4004 ----
     if (tid == 0) {
@@ -131,17 +158,17 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         s_tbl[0] = s_tbl[1] = s_tbl[2] = s_tbl[3] = 0;
     }
     __syncthreads();
-    // ---- seed with the reference reads of the starting side, in list order, :3793-3803 ----
-    // (every read touches each site at most once, and the u16 halves add independently: order is irrelevant)
+    // ---- seed with the reference reads of the starting side, :3793-3803 ----
+    // (a read touches each site at most once and the 16-bit halves add independently: order is irrelevant)
     for (uint32_t r = warp; r < n_ref; r += JOIN_WARPS) {
         const uint32_t id = ref_ids[r];
         const int hap = P.rs_hp[first + id];
         if (hap == 0 || hap == 1) {
-            const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
+            const uint32_t nm = g_n[id], st = g_start[id], off = g_off[id];
             const uint32_t inc = hap == 0 ? 1u : 0x10000u;
             for (uint32_t i0 = lane; i0 < nm; i0 += 32) {
-                uint32_t *row = site_row(tab, tab_base, st + i0, row_words);
-                atomicAdd(&row[pool[off + i0]], inc);
+                uint32_t *row = tab + (size_t)(st + i0) * stride;
+                atomicAdd(&row[compact_key(pool[off + i0])], inc);
                 atomicAdd(&row[n_keys], inc);
             }
         }
@@ -154,62 +181,90 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             uint32_t id = ref_ids[r];
             uint32_t packed = (id << 2) | (uint32_t)P.rs_hp[first + id];
             uint32_t tid2 = packed >> 2;
-            if (tid2 < n) tags[tid2] = (uint8_t)(packed & 3u);
+            if (tid2 < n) {
+                const uint8_t t = (uint8_t)(packed & 3u);
+                tags[tid2] = t;
+                if (meta_in_smem && t < 2) s_tagged[tid2 >> 5] |= 1u << (tid2 & 31u);
+            }
         }
     }
     __syncthreads();
+
+    auto is_untagged = [&](uint32_t id) -> bool {
+        if (meta_in_smem) return !((s_tagged[id >> 5] >> (id & 31u)) & 1u);
+        const uint8_t t = tags[id];
+        return t != 0 && t != 1;
+    };
 
     // ---- extension loop, :4032-4071 ----
     // Warp 0 owns the loop state between the barriers: available range, candidate list, failure count.
     // The candidate list ("the first n_cand untagged reads in scan order from i_last", :4039-4045) is kept
     // incrementally: a success removes the tagged read and appends the next untagged one behind the scan
-    // cursor; a failure moves i_last (:4064-4068) and rebuilds it.
+    // cursor; a failure moves i_last (:4064-4068) and rebuilds it.  The list carries one entry more than is
+    // scored: the look-ahead entry's methmer keys travel from global to shared memory one iteration before
+    // they are first needed, so no iteration waits for L2.
     uint32_t n_order = 0;
-    int nc = 0, cursor = 0;          // warp 0 only (uniform)
+    int nc = 0, cursor = 0;            // warp 0 only (uniform): list length incl. look-ahead, scan cursor
     bool rebuild = true, grow = true;  // first pass: update_available_methmer_range after seeding, fresh list
     int last_best = -1;
+    int pend_slot = -1;                // warp 0: keys in flight for this cache slot
+    uint32_t pend_nm = 0, pend[JOIN_U];
     for (;;) {
         if (warp == 0) {
             uint32_t mn = s_min, mx = s_max;
-            if (grow) { grow_range(tab, tab_base, row_words, n_keys, n_sites, P.cov_run, mn, mx); if (lane == 0) { s_min = mn; s_max = mx; } }
+            if (grow) { grow_range(tab, stride, n_keys, n_sites, P.cov_run, mn, mx); if (lane == 0) { s_min = mn; s_max = mx; } }
+            if (pend_slot >= 0) {
+#pragma unroll
+                for (int u = 0; u < JOIN_U; u++) {
+                    const uint32_t i = u * 32 + lane;
+                    if (i < pend_nm) s_keys[pend_slot * JOIN_CHUNK + i] = (uint8_t)compact_key(pend[u]);
+                }
+                pend_slot = -1;
+            }
             const int i_last = s_i_last;
             const bool done = (d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0);
             if (!done) {
-                if (rebuild) { nc = 0; cursor = i_last; }
+                int free_slot = -1, n_old = nc;
+                if (rebuild) { nc = 0; cursor = i_last; n_old = 0; }
                 else if (last_best >= 0) {
                     // drop entry last_best, keep the order of the rest
+                    free_slot = s_slot[last_best];
                     for (int c0 = 0; c0 < nc; c0 += 32) {
                         const int c = c0 + (int)lane;
                         uint32_t v = 0;
+                        uint8_t sl = 0;
                         const bool mv = c > last_best && c < nc;
-                        if (mv) v = s_cand[c];
+                        if (mv) { v = s_cand[c]; sl = s_slot[c]; }
                         __syncwarp();
-                        if (mv) s_cand[c - 1] = v;
+                        if (mv) { s_cand[c - 1] = v; s_slot[c - 1] = sl; }
                     }
                     nc--;
+                    n_old = nc;
                     __syncwarp();
                 }
                 // refill from the cursor
-                while (nc < n_cand) {
+                while (nc < n_cand + 1) {
                     const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
                     const bool in = d == 0 ? i0 < (int)n : i0 >= 0;
                     uint32_t id = 0;
                     bool unt = false;
                     if (in) {
-                        id = d == 0 ? (uint32_t)i0 : rev[i0];
-                        const uint8_t t = tags[id];
-                        unt = t != 0 && t != 1;
+                        id = d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]);
+                        unt = is_untagged(id);
                     }
                     const unsigned um = __ballot_sync(FULL_MASK, unt);
                     const int rank = __popc(um & ((1u << lane) - 1u));
-                    const int room = n_cand - nc;
-                    if (unt && rank < room) s_cand[nc + rank] = id;
+                    const int room = n_cand + 1 - nc;
+                    if (unt && rank < room) {
+                        s_cand[nc + rank] = id;
+                        s_slot[nc + rank] = (uint8_t)(rebuild ? nc + rank : free_slot);
+                    }
                     const int found = __popc(um);
                     if (found >= room) {
                         // the list is full: the cursor stops right behind the read that filled it
                         const int fill_lane = (int)__fns(um, 0, room);
                         cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
-                        nc = n_cand;
+                        nc = n_cand + 1;
                         break;
                     }
                     nc += found;
@@ -217,8 +272,29 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
                 }
                 __syncwarp();
+                // keys of the new entries: a rebuilt list loads them now, the look-ahead entry in the background
+                for (int c = n_old; c < nc; c++) {
+                    const uint32_t id = s_cand[c];
+                    const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
+                    if (nm > JOIN_CHUNK) continue;  // too long to cache: scored straight from the pool
+                    uint32_t kk[JOIN_U];
+#pragma unroll
+                    for (int u = 0; u < JOIN_U; u++) { const uint32_t i = u * 32 + lane; kk[u] = i < nm ? pool[off + i] : 0u; }
+                    if (!rebuild && c == nc - 1 && c >= n_cand) {
+                        pend_slot = s_slot[c]; pend_nm = nm;
+#pragma unroll
+                        for (int u = 0; u < JOIN_U; u++) pend[u] = kk[u];
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < JOIN_U; u++) {
+                            const uint32_t i = u * 32 + lane;
+                            if (i < nm) s_keys[s_slot[c] * JOIN_CHUNK + i] = (uint8_t)compact_key(kk[u]);
+                        }
+                    }
+                }
+                __syncwarp();
             }
-            if (lane == 0) { s_ncand = nc; if (done) s_done = 1; }
+            if (lane == 0) { s_ncand = nc < n_cand ? nc : n_cand; if (done) s_done = 1; }
         }
         __syncthreads();
         if (s_done) break;
@@ -227,8 +303,11 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
         for (int c = (int)warp; c < ncand; c += JOIN_WARPS) {
             const uint32_t id = s_cand[c];
-            const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
-            float sc_h = 0.f;  // lane 0: haplotype 0, lane 1: haplotype 1
+            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
+            const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
+            const bool cached = nm <= JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
+            float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
             int l0 = 0, l1 = 0;
             for (uint32_t base = 0; base < nm; base += JOIN_CHUNK) {
                 uint32_t key[JOIN_U], cnt[JOIN_U], sums[JOIN_U];
@@ -238,18 +317,17 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     const uint32_t i0 = base + u * 32 + lane;
                     const uint32_t site = st + i0;
                     inr[u] = i0 < nm && !(site < rmin || site >= rmax);
-                    key[u] = inr[u] ? pool[off + i0] : 0u;
+                    key[u] = !inr[u] ? 0u : (cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0]));
                 }
 #pragma unroll
                 for (int u = 0; u < JOIN_U; u++) {
                     cnt[u] = 0; sums[u] = 0;
                     if (inr[u]) {
-                        const uint32_t *row = site_row(tab, tab_base, st + base + u * 32 + lane, row_words);
+                        const uint32_t *row = tab + (size_t)(st + base + u * 32 + lane) * stride;
                         cnt[u] = row[key[u]];
                         sums[u] = row[n_keys];
                     }
                 }
-                int n0 = 0, n1 = 0;  // non-zero terms staged so far (adding +0.0f is exact, so zeros are skipped)
 #pragma unroll
                 for (int u = 0; u < JOIN_U; u++) {
                     if (base + u * 32 >= nm) break;
@@ -263,29 +341,25 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
                     l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
                     l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
-                    const unsigned lt = (1u << lane) - 1u;
-                    if (v0 > 0.f) s_val[warp][0][n0 + __popc(z0 & lt)] = v0;
-                    if (v1 > 0.f) s_val[warp][1][n1 + __popc(z1 & lt)] = v1;
-                    n0 += __popc(z0);
-                    n1 += __popc(z1);
-                }
-                __syncwarp();
-                if (lane < 2) {  // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636)
-                    const int nn = lane == 0 ? n0 : n1;
-                    const float *v = s_val[warp][lane];
+                    // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); adding +0.0f is
+                    // exact, so only the span of lanes that hold a non-zero term is walked
+                    const unsigned z = z0 | z1;
+                    if (z) {
+                        const int t_hi = 31 - __clz((int)z);
 #pragma unroll 4
-                    for (int t = 0; t < nn; t++) sc_h = __fadd_rn(sc_h, v[t]);
+                        for (int t = __ffs((int)z) - 1; t <= t_hi; t++) {
+                            sc0 = __fadd_rn(sc0, __shfl_sync(FULL_MASK, v0, t));
+                            sc1 = __fadd_rn(sc1, __shfl_sync(FULL_MASK, v1, t));
+                        }
+                    }
                 }
-                __syncwarp();
             }
-            const float score1 = __shfl_sync(FULL_MASK, sc_h, 1);
-            const float score0 = __shfl_sync(FULL_MASK, sc_h, 0);
             if (lane == 0) {
-                float diff = score0 > score1 ? __fsub_rn(score0, score1) : __fsub_rn(score1, score0);
+                float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
                 int tag;
                 float sc;
                 if (diff < 3.0f && (l0 < 3 || l1 < 3)) { tag = -1; sc = 0.f; }
-                else { tag = score0 > score1 ? 0 : 1; sc = diff; }
+                else { tag = sc0 > sc1 ? 0 : 1; sc = diff; }
                 s_score[c] = sc;
                 s_tag[c] = tag;
             }
@@ -313,15 +387,19 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         if (best >= 0) {
             const uint32_t id = s_cand[best];
             const int hap = s_tag[best];
-            const uint32_t nm = mm_n[id], st = mm_start[id], off = mm_off[id];
+            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
+            const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
+            const bool cached = nm <= JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)s_slot[best] * JOIN_CHUNK;
             const uint32_t inc = hap == 0 ? 1u : 0x10000u;
             for (uint32_t i0 = tid; i0 < nm; i0 += JOIN_THREADS) {
-                uint32_t *row = site_row(tab, tab_base, st + i0, row_words);
-                row[pool[off + i0]] += inc;
+                uint32_t *row = tab + (size_t)(st + i0) * stride;
+                row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
                 row[n_keys] += inc;
             }
             if (tid == 0) {
                 tags[id] = (uint8_t)hap;
+                if (meta_in_smem) s_tagged[id >> 5] |= 1u << (id & 31u);
                 P.order[d][first + n_order] = id;
             }
             n_order++;
@@ -331,6 +409,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             if (best >= 0) { rebuild = false; grow = true; if (lane == 0) s_failed = 0; }
             else {
                 rebuild = true; grow = false;
+                pend_slot = -1;
                 if (lane == 0) {
                     s_failed++;
                     if (s_failed > 10) s_done = 1;

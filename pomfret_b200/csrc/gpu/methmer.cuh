@@ -31,7 +31,7 @@ struct MethmerParams {
     const uint32_t *site_start[2];
     const uint8_t *site_len[2];
     uint32_t *mm_xl[2], *mm_xr[2], *mm_off[2], *mm_n[2], *mm_start[2];
-    uint32_t *pool_total;          // [0] methmer slots, [1] table sites
+    uint32_t *pool_total;          // [0] methmer slots, [1] table sites, [2] largest site count of a window
     uint32_t *mmr_pool;            // keys
     uint32_t *ent_pool;            // scratch: (site index << 2 | symbol) per entry
     uint32_t pool_cap;
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams 
         uint32_t tb = atomicAdd(&P.pool_total[1], active ? 2 * n_sites : 0);
         S.tab_base[0] = tb;
         S.tab_base[1] = tb + n_sites;
+        if (active) atomicMax(&P.pool_total[2], n_sites);
     }
     __syncthreads();
     const uint32_t gbase = s_base;

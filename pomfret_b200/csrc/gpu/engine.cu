@@ -205,8 +205,10 @@ struct pomfret_gpu_ctx {
 struct pomfret_gpu_batch {
     pomfret_gpu_ctx *ctx = nullptr;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second join launch (large-table windows)
     cudaEvent_t ev[10] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int sm_count = 148;
     int stage = ST_EMPTY;
     // host staging (pinned)
     PinBuf h_blob;
@@ -217,6 +219,7 @@ struct pomfret_gpu_batch {
     PinVec<TileRec> h_tiles;
     PinVec<WindowState> h_state;
     PinVec<uint32_t> h_u32;   // scratch for small D2H reads
+    PinVec<uint32_t> h_cta;   // join launch order: window * 2 + direction
     std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
     uint64_t calls_total = 0;
     uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
@@ -232,7 +235,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -249,11 +252,13 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta};
     }
 };
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+// dynamic shared memory of join_kernel: one CTA per SM may take kJoinSmemMax, two CTAs per SM kJoinSmemHalf each
+static const size_t kJoinSmemMax = (size_t)224 * 1024, kJoinSmemHalf = (size_t)110 * 1024;
 
 extern "C" {
 
@@ -312,9 +317,17 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
     for (DevBuf *d : b->all_bufs()) d->arena = &b->arena;
     b->h_blob.min_cap = (size_t)64 << 20;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
     for (auto &e : b->ev) CK(cudaEventCreate(&e));
+    CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) b->sm_count = prop.multiProcessorCount;
+    }
 #ifndef POMFRET_CUDA_EMU
     CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
+    CK(cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
 #endif
     *out = b;
     return POMFRET_GPU_OK;
@@ -349,8 +362,11 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     for (DevBuf *d : all) d->release();
     b->arena.release();
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
-    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release();
+    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->stream2) cudaStreamDestroy(b->stream2);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b->pool;
     delete b;
@@ -692,8 +708,9 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     POMFRET_LAUNCH(methmer_size_kernel, (unsigned)nw, RS_THREADS, 0, b->stream, M);
     b->tm.launches++;
     // ---- the one round trip: pool sizes (and whether any record ran out of call slots) ----
-    if ((rc = b->h_u32.resize(8))) return rc;
+    if ((rc = b->h_u32.resize(8)) || (rc = b->h_state.resize(nw))) return rc;
     for (int attempt = 0;; attempt++) {
+        CK(cudaMemcpyAsync(b->h_state.data(), b->d_state.p, nw * sizeof(WindowState), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaMemcpyAsync(b->h_u32.data(), b->d_pool_total.p, 12, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaMemcpyAsync(b->h_u32.data() + 4, b->d_flags.p, 4, cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
@@ -757,23 +774,50 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     }
     J.mmr_pool = b->d_mmr_pool.as<uint32_t>(); J.tab = b->d_tab.as<uint32_t>();
     J.n_cand = cfg->n_candidates_per_iter; J.cov_run = cfg->cov_for_runtime; J.k = cfg->k;
-    // shared-memory plan: per-read state of the largest window, look-ahead key cache, and — if they fit — the
-    // count tables of the largest window (otherwise that launch keeps them in the global pool)
+    // Shared-memory plan.  Every CTA carries the per-read state of the largest window and the look-ahead key
+    // cache; the count tables of a window go to shared memory if they fit.  With more CTAs than SMs the windows
+    // are split into two launches on two streams: those whose tables fit beside a second CTA on the same SM
+    // (or fit nowhere: they use the global pool) and those that need most of an SM for themselves.
     uint32_t max_reads = 0;
     for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
     J.meta_cap = max_reads <= 4096 ? max_reads : 0;
-    const size_t smem_limit = (size_t)225 * 1024;
-    const size_t want_tab = (size_t)b->max_sites * join_row_stride(cfg->k);
-    J.smem_tab_words = join_smem_bytes((uint32_t)want_tab, J.meta_cap, J.n_cand) <= smem_limit ? (uint32_t)want_tab : 0;
-    const size_t smem = join_smem_bytes(J.smem_tab_words, J.meta_cap, J.n_cand);
+    const uint32_t stride = join_row_stride(cfg->k);
+    const size_t small_limit = nw * 2 <= (size_t)b->sm_count ? kJoinSmemMax : kJoinSmemHalf;
+    if (int rc = b->h_cta.resize(nw * 2 + 1)) return rc;
+    size_t n_a = 0, n_b = 0;
+    uint32_t tab_a = 0, tab_b = 0;
+    std::vector<uint32_t> big;
+    for (size_t w = 0; w < nw; w++) {
+        const WindowState &S = b->h_state[w];
+        if (S.n == 0 || S.n_sites == 0 || S.status != 0) continue;  // nothing to propagate: no CTA
+        const uint32_t words = S.n_sites * stride;
+        const size_t need = join_smem_bytes(words, J.meta_cap, J.n_cand);
+        if (need > small_limit && need <= kJoinSmemMax) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
+        else {
+            if (need <= small_limit) tab_a = std::max(tab_a, words);
+            b->h_cta[n_a++] = (uint32_t)w * 2; b->h_cta[n_a++] = (uint32_t)w * 2 + 1;
+        }
+    }
+    for (uint32_t w : big) { b->h_cta[n_a + n_b++] = w * 2; b->h_cta[n_a + n_b++] = w * 2 + 1; }
+    if (int rc = up(b, b->d_cta, b->h_cta.data(), (n_a + n_b) * 4)) return rc;
     CK(cudaEventRecord(b->ev[8], b->stream));
-    if (nw) {
-#ifndef POMFRET_CUDA_EMU
-        CK(cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-#endif
-        POMFRET_LAUNCH(join_kernel, (unsigned)(nw * 2), JOIN_THREADS, smem, b->stream, J);
+    if (n_b) {
+        CK(cudaEventRecord(b->ev_fork, b->stream));
+        CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
+        JoinParams JB = J;
+        JB.cta_map = b->d_cta.as<uint32_t>() + n_a;
+        JB.smem_tab_words = tab_b;
+        POMFRET_LAUNCH(join_kernel, (unsigned)n_b, JOIN_THREADS, join_smem_bytes(tab_b, J.meta_cap, J.n_cand), b->stream2, JB);
+        b->tm.launches++;
+        CK(cudaEventRecord(b->ev_join, b->stream2));
+    }
+    if (n_a) {
+        J.cta_map = b->d_cta.as<uint32_t>();
+        J.smem_tab_words = tab_a;
+        POMFRET_LAUNCH(join_kernel, (unsigned)n_a, JOIN_THREADS, join_smem_bytes(tab_a, J.meta_cap, J.n_cand), b->stream, J);
         b->tm.launches++;
     }
+    if (n_b) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
     CK(cudaEventRecord(b->ev[9], b->stream));
     CK(cudaGetLastError());
     b->stage = ST_JOINED;

@@ -43,6 +43,7 @@ struct JoinParams {
     int32_t n_cand;
     int32_t cov_run;
     int32_t k;
+    const uint32_t *cta_map;  // blockIdx.x -> window * 2 + direction
     uint32_t smem_tab_words;  // shared-memory words reserved for the count tables
     uint32_t meta_cap;        // reads whose per-read state fits the shared-memory arrays
 };
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
 
-    const uint32_t w = blockIdx.x >> 1, d = blockIdx.x & 1u;
+    const uint32_t wd = P.cta_map[blockIdx.x];
+    const uint32_t w = wd >> 1, d = wd & 1u;
     const WindowRec W = P.win[w];
     WindowState &S = P.state[w];
     const uint32_t n = S.n, n_sites = S.n_sites;
@@ -309,48 +311,36 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             const uint8_t *ck = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
             float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
             int l0 = 0, l1 = 0;
-            for (uint32_t base = 0; base < nm; base += JOIN_CHUNK) {
-                uint32_t key[JOIN_U], cnt[JOIN_U], sums[JOIN_U];
-                bool inr[JOIN_U];
-#pragma unroll
-                for (int u = 0; u < JOIN_U; u++) {
-                    const uint32_t i0 = base + u * 32 + lane;
-                    const uint32_t site = st + i0;
-                    inr[u] = i0 < nm && !(site < rmin || site >= rmax);
-                    key[u] = !inr[u] ? 0u : (cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0]));
-                }
-#pragma unroll
-                for (int u = 0; u < JOIN_U; u++) {
-                    cnt[u] = 0; sums[u] = 0;
-                    if (inr[u]) {
-                        const uint32_t *row = tab + (size_t)(st + base + u * 32 + lane) * stride;
-                        cnt[u] = row[key[u]];
-                        sums[u] = row[n_keys];
+            // only methmers whose site lies in the available range [rmin, rmax) are looked up (:3499-3502)
+            const uint32_t i_lo = rmin > st ? rmin - st : 0u;
+            const uint32_t i_hi = rmax > st ? (rmax - st < nm ? rmax - st : nm) : 0u;
+            for (uint32_t base = i_lo; base < i_hi; base += 32) {
+                const uint32_t i0 = base + lane;
+                float v0 = 0.f, v1 = 0.f;
+                bool p0 = false, p1 = false;
+                if (i0 < i_hi) {
+                    const uint32_t key = cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0]);
+                    const uint32_t *row = tab + (size_t)(st + i0) * stride;
+                    const uint32_t cnt = row[key];
+                    if (cnt != 0) {  // key present at this site
+                        const uint32_t sums = row[n_keys];
+                        const uint32_t sum0 = sums & 0xffffu, sum1 = sums >> 16;
+                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt & 0xffffu), (float)sum0); }
+                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt >> 16), (float)sum1); }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < JOIN_U; u++) {
-                    if (base + u * 32 >= nm) break;
-                    float v0 = 0.f, v1 = 0.f;
-                    bool p0 = false, p1 = false;
-                    if (cnt[u] != 0) {  // key present at this site
-                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
-                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt[u] & 0xffffu), (float)sum0); }
-                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt[u] >> 16), (float)sum1); }
-                    }
-                    const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
-                    l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
-                    l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
-                    // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); adding +0.0f is
-                    // exact, so only the span of lanes that hold a non-zero term is walked
-                    const unsigned z = z0 | z1;
-                    if (z) {
-                        const int t_hi = 31 - __clz((int)z);
+                const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
+                l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
+                l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
+                // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); adding +0.0f is
+                // exact, so only the span of lanes that hold a non-zero term is walked
+                const unsigned z = z0 | z1;
+                if (z) {
+                    const int t_hi = 31 - __clz((int)z);
 #pragma unroll 4
-                        for (int t = __ffs((int)z) - 1; t <= t_hi; t++) {
-                            sc0 = __fadd_rn(sc0, __shfl_sync(FULL_MASK, v0, t));
-                            sc1 = __fadd_rn(sc1, __shfl_sync(FULL_MASK, v1, t));
-                        }
+                    for (int t = __ffs((int)z) - 1; t <= t_hi; t++) {
+                        sc0 = __fadd_rn(sc0, __shfl_sync(FULL_MASK, v0, t));
+                        sc1 = __fadd_rn(sc1, __shfl_sync(FULL_MASK, v1, t));
                     }
                 }
             }
@@ -366,23 +356,20 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         }
         __syncthreads();
         // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
-        //      every warp finds it on its own ----
+        //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
         int best = -1;
         {
-            unsigned long long bk = 0;
+            uint32_t bs = 0;
+            int bc = -1;
             for (int c = (int)lane; c < ncand; c += 32) {
                 const int t = s_tag[c];
                 if (t == 0 || t == 1) {
-                    const unsigned long long k = (((unsigned long long)__float_as_uint(s_score[c]) << 32) | (unsigned)c) + 1ull;
-                    bk = k > bk ? k : bk;
+                    const uint32_t sb = __float_as_uint(s_score[c]);
+                    if (bc < 0 || sb >= bs) { bs = sb; bc = c; }
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long t = __shfl_xor_sync(FULL_MASK, bk, o);
-                bk = t > bk ? t : bk;
-            }
-            if (bk) best = (int)((bk - 1ull) & 0xffffffffull);
+            const uint32_t top = __reduce_max_sync(FULL_MASK, bc >= 0 ? bs : 0u);
+            best = (int)__reduce_max_sync(FULL_MASK, (uint32_t)((bc >= 0 && bs == top) ? bc + 1 : 0)) - 1;
         }
         if (best >= 0) {
             const uint32_t id = s_cand[best];

@@ -778,6 +778,8 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     // cache; the count tables of a window go to shared memory if they fit.  With more CTAs than SMs the windows
     // are split into two launches on two streams: those whose tables fit beside a second CTA on the same SM
     // (or fit nowhere: they use the global pool) and those that need most of an SM for themselves.
+    // one warp per candidate plus one that fills the look-ahead key cache while the others score
+    const unsigned join_threads = 32u * (unsigned)std::min(JOIN_WARPS, std::max(4, J.n_cand + 1));
     uint32_t max_reads = 0;
     for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
     J.meta_cap = max_reads <= 4096 ? max_reads : 0;
@@ -791,7 +793,7 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         const WindowState &S = b->h_state[w];
         if (S.n == 0 || S.n_sites == 0 || S.status != 0) continue;  // nothing to propagate: no CTA
         const uint32_t words = S.n_sites * stride;
-        const size_t need = join_smem_bytes(words, J.meta_cap, J.n_cand);
+        const size_t need = join_smem_bytes(words + 1, J.meta_cap, J.n_cand, (int)join_threads / 32);
         if (need > small_limit && need <= kJoinSmemMax) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
         else {
             if (need <= small_limit) tab_a = std::max(tab_a, words);
@@ -807,14 +809,14 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         JoinParams JB = J;
         JB.cta_map = b->d_cta.as<uint32_t>() + n_a;
         JB.smem_tab_words = tab_b;
-        POMFRET_LAUNCH(join_kernel, (unsigned)n_b, JOIN_THREADS, join_smem_bytes(tab_b, J.meta_cap, J.n_cand), b->stream2, JB);
+        POMFRET_LAUNCH(join_kernel, (unsigned)n_b, join_threads, join_smem_bytes(tab_b + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream2, JB);
         b->tm.launches++;
         CK(cudaEventRecord(b->ev_join, b->stream2));
     }
     if (n_a) {
         J.cta_map = b->d_cta.as<uint32_t>();
         J.smem_tab_words = tab_a;
-        POMFRET_LAUNCH(join_kernel, (unsigned)n_a, JOIN_THREADS, join_smem_bytes(tab_a, J.meta_cap, J.n_cand), b->stream, J);
+        POMFRET_LAUNCH(join_kernel, (unsigned)n_a, join_threads, join_smem_bytes(tab_a + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream, J);
         b->tm.launches++;
     }
     if (n_b) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));

@@ -27,6 +27,7 @@ constexpr int JOIN_WARPS = JOIN_THREADS / 32;
 constexpr int JOIN_MAX_CAND = 128;
 constexpr int JOIN_U = 8;                 // methmer sub-chunks (32 each) whose loads are issued together
 constexpr int JOIN_CHUNK = JOIN_U * 32;   // methmers of a candidate whose keys are cached in shared memory
+constexpr int JOIN_STAGE = 128;           // score terms staged per warp between two runs of the ordered sum
 
 struct JoinParams {
     const WindowRec *win;
@@ -58,9 +59,9 @@ __device__ __forceinline__ uint32_t compact_key(uint32_t key) {  // k <= 4
     return ((key >> 6) & 3u) * 27u + ((key >> 4) & 3u) * 9u + ((key >> 2) & 3u) * 3u + (key & 3u);
 }
 // dynamic shared memory of join_kernel for the given capacities (bytes)
-__host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_words, uint32_t meta_cap, int n_cand) {
-    return (size_t)tab_words * 4 + (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 + (size_t)((meta_cap + 31) / 32) * 4 +
-           (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
+__host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_words, uint32_t meta_cap, int n_cand, int n_warps) {
+    return (size_t)tab_words * 4 + (size_t)n_warps * JOIN_STAGE * 8 + (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 +
+           (size_t)((meta_cap + 31) / 32) * 4 + (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
 }
 
 // Range growth of update_available_methmer_range (blockjoin.c:3669-3691), warp-parallel: the left edge
@@ -95,7 +96,7 @@ __device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride,
 }
 
 __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
-    __shared__ int s_i_last, s_failed, s_done, s_ncand;
+    __shared__ int s_i_last, s_failed, s_done, s_ncand, s_fill;
     __shared__ uint32_t s_min, s_max;
     __shared__ uint32_t s_cand[JOIN_MAX_CAND + 1];
     __shared__ uint8_t s_slot[JOIN_MAX_CAND + 1];
@@ -104,12 +105,23 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
 
+#ifdef POMFRET_JOIN_PROF
+    long long pf_t0 = clock64(), pf_setup = 0, pf_w0 = 0, pf_score = 0, pf_rest = 0, pf_t = 0;
+    int pf_iter = 0;
+#define PF_MARK(acc) do { long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; pf_s = now_; } while (0)
+    long long pf_sub[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pf_s = 0;
+#define PF_SUB(i) do { long long now_ = clock64(); pf_sub[i] += now_ - pf_s; pf_s = now_; } while (0)
+#else
+#define PF_MARK(acc) do {} while (0)
+#define PF_SUB(i) do {} while (0)
+#endif
     const uint32_t wd = P.cta_map[blockIdx.x];
     const uint32_t w = wd >> 1, d = wd & 1u;
     const WindowRec W = P.win[w];
     WindowState &S = P.state[w];
     const uint32_t n = S.n, n_sites = S.n_sites;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    const uint32_t nthreads = blockDim.x, nwarps = nthreads >> 5;
     if (n == 0 || n_sites == 0 || S.status != 0) return;
     const uint32_t first = W.first_read;
     const uint32_t n_keys = join_n_keys(P.k);
@@ -125,7 +137,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
 
     // ---- shared-memory carve-up ----
     uint32_t *s_tab = dyn;
-    uint32_t *s_moff = s_tab + P.smem_tab_words;               // per read: offset of its keys in the methmer pool
+    float2 *s_stage = reinterpret_cast<float2 *>(s_tab + (P.smem_tab_words + (P.smem_tab_words & 1u)));  // [nwarps][JOIN_STAGE]
+    uint32_t *s_moff = reinterpret_cast<uint32_t *>(s_stage + (size_t)nwarps * JOIN_STAGE);  // per read: offset of its keys in the pool
     uint32_t *s_mn = s_moff + P.meta_cap;                      // per read: number of methmers
     uint32_t *s_mst = s_mn + P.meta_cap;                       // per read: site index of the first one
     uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
@@ -136,13 +149,13 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     uint32_t *tab = tab_in_smem ? s_tab : P.tab + (size_t)S.tab_base[d] * stride;
 
     // ---- wipe the tables (insert_ref_reads_methmer_counts, :3780-3789), load the per-read state ----
-    for (size_t i = tid, words = (size_t)n_sites * stride; i < words; i += JOIN_THREADS) tab[i] = 0;
+    for (size_t i = tid, words = (size_t)n_sites * stride; i < words; i += nthreads) tab[i] = 0;
     if (meta_in_smem) {
-        for (uint32_t i = tid; i < n; i += JOIN_THREADS) {
+        for (uint32_t i = tid; i < n; i += nthreads) {
             s_moff[i] = g_off[i]; s_mn[i] = g_n[i]; s_mst[i] = g_start[i];
             s_scan[i] = (uint16_t)(d == 0 ? i : rev[i]);
         }
-        for (uint32_t i = tid; i < (n + 31) / 32; i += JOIN_THREADS) s_tagged[i] = 0;
+        for (uint32_t i = tid; i < (n + 31) / 32; i += nthreads) s_tagged[i] = 0;
     }
     // ---- available range, :3976-4004 ----
     if (tid == 0) {
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     __syncthreads();
     // ---- seed with the reference reads of the starting side, :3793-3803 ----
     // (a read touches each site at most once and the 16-bit halves add independently: order is irrelevant)
-    for (uint32_t r = warp; r < n_ref; r += JOIN_WARPS) {
+    for (uint32_t r = warp; r < n_ref; r += nwarps) {
         const uint32_t id = ref_ids[r];
         const int hap = P.rs_hp[first + id];
         if (hap == 0 || hap == 1) {
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         }
     }
     // ---- un-tag everything but the reference reads, :4010-4025 (with the (id<<2)|hp packing) ----
-    for (uint32_t i = tid; i < n; i += JOIN_THREADS) tags[i] = 2;
+    for (uint32_t i = tid; i < n; i += nthreads) tags[i] = 2;
     __syncthreads();
     if (tid == 0) {
         for (uint32_t r = 0; r < n_ref; r++) {
@@ -205,24 +218,18 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     // cursor; a failure moves i_last (:4064-4068) and rebuilds it.  The list carries one entry more than is
     // scored: the look-ahead entry's methmer keys travel from global to shared memory one iteration before
     // they are first needed, so no iteration waits for L2.
+#ifdef POMFRET_JOIN_PROF
+    pf_t = clock64(); pf_setup = pf_t - pf_t0;
+#endif
     uint32_t n_order = 0;
     int nc = 0, cursor = 0;            // warp 0 only (uniform): list length incl. look-ahead, scan cursor
     bool rebuild = true, grow = true;  // first pass: update_available_methmer_range after seeding, fresh list
     int last_best = -1;
-    int pend_slot = -1;                // warp 0: keys in flight for this cache slot
-    uint32_t pend_nm = 0, pend[JOIN_U];
     for (;;) {
         if (warp == 0) {
             uint32_t mn = s_min, mx = s_max;
             if (grow) { grow_range(tab, stride, n_keys, n_sites, P.cov_run, mn, mx); if (lane == 0) { s_min = mn; s_max = mx; } }
-            if (pend_slot >= 0) {
-#pragma unroll
-                for (int u = 0; u < JOIN_U; u++) {
-                    const uint32_t i = u * 32 + lane;
-                    if (i < pend_nm) s_keys[pend_slot * JOIN_CHUNK + i] = (uint8_t)compact_key(pend[u]);
-                }
-                pend_slot = -1;
-            }
+            PF_SUB(0);  // grow
             const int i_last = s_i_last;
             const bool done = (d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0);
             if (!done) {
@@ -244,6 +251,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     n_old = nc;
                     __syncwarp();
                 }
+                PF_SUB(1);  // pend store + shift
                 // refill from the cursor
                 while (nc < n_cand + 1) {
                     const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
@@ -264,7 +272,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     const int found = __popc(um);
                     if (found >= room) {
                         // the list is full: the cursor stops right behind the read that filled it
-                        const int fill_lane = (int)__fns(um, 0, room);
+                        unsigned fm = um;
+                        for (int r = 1; r < room; r++) fm &= fm - 1u;  // drop the room-1 lowest set bits
+                        const int fill_lane = __ffs((int)fm) - 1;
                         cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
                         nc = n_cand + 1;
                         break;
@@ -274,36 +284,31 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
                 }
                 __syncwarp();
-                // keys of the new entries: a rebuilt list loads them now, the look-ahead entry in the background
+                PF_SUB(2);  // refill
+                // keys of the new entries: a rebuilt list needs them before it is scored; the look-ahead entry of a
+                // running list is filled by the last warp while the others score (s_fill)
+                int fill = -1;
                 for (int c = n_old; c < nc; c++) {
+                    if (!rebuild && c >= n_cand) { fill = c; continue; }
                     const uint32_t id = s_cand[c];
                     const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
                     if (nm > JOIN_CHUNK) continue;  // too long to cache: scored straight from the pool
-                    uint32_t kk[JOIN_U];
-#pragma unroll
-                    for (int u = 0; u < JOIN_U; u++) { const uint32_t i = u * 32 + lane; kk[u] = i < nm ? pool[off + i] : 0u; }
-                    if (!rebuild && c == nc - 1 && c >= n_cand) {
-                        pend_slot = s_slot[c]; pend_nm = nm;
-#pragma unroll
-                        for (int u = 0; u < JOIN_U; u++) pend[u] = kk[u];
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < JOIN_U; u++) {
-                            const uint32_t i = u * 32 + lane;
-                            if (i < nm) s_keys[s_slot[c] * JOIN_CHUNK + i] = (uint8_t)compact_key(kk[u]);
-                        }
-                    }
+                    uint8_t *dst = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
+                    for (uint32_t i = lane; i < nm; i += 32) dst[i] = (uint8_t)compact_key(pool[off + i]);
                 }
+                if (lane == 0) s_fill = fill;
                 __syncwarp();
-            }
+            } else if (lane == 0) s_fill = -1;
+            PF_SUB(3);  // key loads
             if (lane == 0) { s_ncand = nc < n_cand ? nc : n_cand; if (done) s_done = 1; }
         }
         __syncthreads();
+        PF_MARK(pf_w0);
         if (s_done) break;
         const int ncand = s_ncand;
         const uint32_t rmin = s_min, rmax = s_max;
         // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
-        for (int c = (int)warp; c < ncand; c += JOIN_WARPS) {
+        for (int c = (int)warp; c < ncand; c += (int)nwarps) {
             const uint32_t id = s_cand[c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
@@ -312,37 +317,58 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
             int l0 = 0, l1 = 0;
             // only methmers whose site lies in the available range [rmin, rmax) are looked up (:3499-3502)
+            PF_SUB(4);  // scoring meta
             const uint32_t i_lo = rmin > st ? rmin - st : 0u;
             const uint32_t i_hi = rmax > st ? (rmax - st < nm ? rmax - st : nm) : 0u;
-            for (uint32_t base = i_lo; base < i_hi; base += 32) {
-                const uint32_t i0 = base + lane;
-                float v0 = 0.f, v1 = 0.f;
-                bool p0 = false, p1 = false;
-                if (i0 < i_hi) {
-                    const uint32_t key = cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0]);
-                    const uint32_t *row = tab + (size_t)(st + i0) * stride;
-                    const uint32_t cnt = row[key];
-                    if (cnt != 0) {  // key present at this site
-                        const uint32_t sums = row[n_keys];
-                        const uint32_t sum0 = sums & 0xffffu, sum1 = sums >> 16;
-                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt & 0xffffu), (float)sum0); }
-                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt >> 16), (float)sum1); }
+            float2 *stage = s_stage + (size_t)warp * JOIN_STAGE;
+            for (uint32_t base = i_lo; base < i_hi; base += JOIN_STAGE) {
+                // four sub-chunks of 32 methmers at a time: their shared-memory lookups overlap
+                uint32_t key[4], cnt[4], sums[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i0 = base + u * 32 + lane;
+                    key[u] = i0 < i_hi ? (cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    cnt[u] = 0; sums[u] = 0;
+                    if (key[u] != 0xffffffffu) {
+                        const uint32_t *row = tab + (size_t)(st + base + u * 32 + lane) * stride;
+                        cnt[u] = row[key[u]];
+                        sums[u] = row[n_keys];
                     }
                 }
-                const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
-                l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
-                l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
-                // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); adding +0.0f is
-                // exact, so only the span of lanes that hold a non-zero term is walked
-                const unsigned z = z0 | z1;
-                if (z) {
-                    const int t_hi = 31 - __clz((int)z);
-#pragma unroll 4
-                    for (int t = __ffs((int)z) - 1; t <= t_hi; t++) {
-                        sc0 = __fadd_rn(sc0, __shfl_sync(FULL_MASK, v0, t));
-                        sc1 = __fadd_rn(sc1, __shfl_sync(FULL_MASK, v1, t));
+                uint32_t nz = 0;  // non-zero terms staged (adding +0.0f is exact, so zero terms are dropped)
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (base + u * 32 >= i_hi) break;
+                    float v0 = 0.f, v1 = 0.f;
+                    bool p0 = false, p1 = false;
+                    if (cnt[u] != 0) {  // key present at this site
+                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
+                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt[u] & 0xffffu), (float)sum0); }
+                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt[u] >> 16), (float)sum1); }
+                    }
+                    const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
+                    l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
+                    l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
+                    const unsigned zz = z0 | z1;
+                    if ((zz >> lane) & 1u) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0, v1);
+                    nz += __popc(zz);
+                }
+                __syncwarp();
+                // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); every lane walks the
+                // staged terms (broadcast reads), eight loads in flight ahead of the two add chains
+                for (uint32_t t0 = 0; t0 < nz; t0 += 8) {
+                    float2 r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) r[j] = stage[t0 + j < JOIN_STAGE ? t0 + j : JOIN_STAGE - 1];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (t0 + j < nz) { sc0 = __fadd_rn(sc0, r[j].x); sc1 = __fadd_rn(sc1, r[j].y); }
                     }
                 }
+                __syncwarp();
             }
             if (lane == 0) {
                 float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
@@ -354,7 +380,17 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                 s_tag[c] = tag;
             }
         }
+        if (warp == nwarps - 1 && s_fill >= 0) {
+            const int c = s_fill;
+            const uint32_t id = s_cand[c];
+            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
+            if (nm <= JOIN_CHUNK) {
+                uint8_t *dst = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
+                for (uint32_t i = lane; i < nm; i += 32) dst[i] = (uint8_t)compact_key(pool[off + i]);
+            }
+        }
         __syncthreads();
+        PF_MARK(pf_score);
         // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
         //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
         int best = -1;
@@ -371,6 +407,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             const uint32_t top = __reduce_max_sync(FULL_MASK, bc >= 0 ? bs : 0u);
             best = (int)__reduce_max_sync(FULL_MASK, (uint32_t)((bc >= 0 && bs == top) ? bc + 1 : 0)) - 1;
         }
+        PF_SUB(6);  // best
         if (best >= 0) {
             const uint32_t id = s_cand[best];
             const int hap = s_tag[best];
@@ -379,7 +416,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             const bool cached = nm <= JOIN_CHUNK;
             const uint8_t *ck = s_keys + (size_t)s_slot[best] * JOIN_CHUNK;
             const uint32_t inc = hap == 0 ? 1u : 0x10000u;
-            for (uint32_t i0 = tid; i0 < nm; i0 += JOIN_THREADS) {
+            for (uint32_t i0 = tid; i0 < nm; i0 += nthreads) {
                 uint32_t *row = tab + (size_t)(st + i0) * stride;
                 row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
                 row[n_keys] += inc;
@@ -391,12 +428,12 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             }
             n_order++;
         }
+        PF_SUB(7);  // insert done
         if (warp == 0) {
             last_best = best;
             if (best >= 0) { rebuild = false; grow = true; if (lane == 0) s_failed = 0; }
             else {
                 rebuild = true; grow = false;
-                pend_slot = -1;
                 if (lane == 0) {
                     s_failed++;
                     if (s_failed > 10) s_done = 1;
@@ -405,13 +442,23 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             }
         }
         __syncthreads();
+        PF_MARK(pf_rest);
+#ifdef POMFRET_JOIN_PROF
+        pf_iter++;
+#endif
         if (s_done) break;
     }
+#ifdef POMFRET_JOIN_PROF
+    if (tid == 0) printf("JOINPROF w %u d %u n %u sites %u iters %d tagged %u total %lld setup %lld w0 %lld score %lld rest %lld\n", w, d, n,
+                         n_sites, pf_iter, n_order, clock64() - pf_t0, pf_setup, pf_w0, pf_score, pf_rest);
+    if (tid == 0) printf("JOINSUB w %u d %u grow %lld pend+shift %lld refill %lld keyload %lld meta %lld scoreloop %lld best %lld insert %lld\n", w, d,
+                         pf_sub[0], pf_sub[1], pf_sub[2], pf_sub[3], pf_sub[4], pf_sub[5], pf_sub[6], pf_sub[7]);
+#endif
     // ---- 2x2 table over the far-side strict reads, :3888-3893 and :3940-3951 ----
     {
         const uint32_t *sid = (d == 0 ? P.ids_right_strict : P.ids_left_strict) + first;
         const uint32_t ns = d == 0 ? S.n_right_strict : S.n_left_strict;
-        for (uint32_t i = tid; i < ns; i += JOIN_THREADS) {
+        for (uint32_t i = tid; i < ns; i += nthreads) {
             const uint32_t id = sid[i];
             const uint8_t ref = (uint8_t)P.rs_hp[first + id];
             const uint8_t q = tags[id];

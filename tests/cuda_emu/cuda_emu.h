@@ -39,6 +39,8 @@ struct uint4 { uint32_t x, y, z, w; } __attribute__((aligned(16)));
 struct uint2 { uint32_t x, y; } __attribute__((aligned(8)));
 struct int2 { int x, y; } __attribute__((aligned(8)));
 struct ushort2 { uint16_t x, y; };
+struct float2 { float x, y; } __attribute__((aligned(8)));
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 

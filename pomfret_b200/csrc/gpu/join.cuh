@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     long long pf_t0 = clock64(), pf_setup = 0, pf_w0 = 0, pf_score = 0, pf_rest = 0, pf_t = 0;
     int pf_iter = 0;
 #define PF_MARK(acc) do { long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; pf_s = now_; } while (0)
-    long long pf_sub[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pf_s = 0;
+    long long pf_sub[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pf_s = 0;
 #define PF_SUB(i) do { long long now_ = clock64(); pf_sub[i] += now_ - pf_s; pf_s = now_; } while (0)
 #else
 #define PF_MARK(acc) do {} while (0)
@@ -338,25 +338,35 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                         sums[u] = row[n_keys];
                     }
                 }
+                PF_SUB(8);  // key/cnt/sums lookups
+                // the divisions of the four sub-chunks are independent and branch-free, so they overlap
+                float v0[4], v1[4];
+                bool p0[4], p1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
+                    p0[u] = cnt[u] != 0 && sum0 != 0;  // key present at this site and the haplotype has counts
+                    p1[u] = cnt[u] != 0 && sum1 != 0;
+                    // (zero operands are replaced by 1 so that the division always takes its fast path)
+                    const uint32_t c0 = cnt[u] & 0xffffu, c1 = cnt[u] >> 16;
+                    const float q0 = __fdiv_rn((float)(c0 ? c0 : 1u), (float)(sum0 ? sum0 : 1u));
+                    const float q1 = __fdiv_rn((float)(c1 ? c1 : 1u), (float)(sum1 ? sum1 : 1u));
+                    v0[u] = p0[u] && c0 ? q0 : 0.f;
+                    v1[u] = p1[u] && c1 ? q1 : 0.f;
+                }
                 uint32_t nz = 0;  // non-zero terms staged (adding +0.0f is exact, so zero terms are dropped)
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (base + u * 32 >= i_hi) break;
-                    float v0 = 0.f, v1 = 0.f;
-                    bool p0 = false, p1 = false;
-                    if (cnt[u] != 0) {  // key present at this site
-                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
-                        if (sum0 != 0) { p0 = true; v0 = __fdiv_rn((float)(cnt[u] & 0xffffu), (float)sum0); }
-                        if (sum1 != 0) { p1 = true; v1 = __fdiv_rn((float)(cnt[u] >> 16), (float)sum1); }
-                    }
-                    const unsigned z0 = __ballot_sync(FULL_MASK, v0 > 0.f), z1 = __ballot_sync(FULL_MASK, v1 > 0.f);
-                    l0 += __popc(__ballot_sync(FULL_MASK, p0)) + __popc(z0);
-                    l1 += __popc(__ballot_sync(FULL_MASK, p1)) + __popc(z1);
+                    const unsigned z0 = __ballot_sync(FULL_MASK, v0[u] > 0.f), z1 = __ballot_sync(FULL_MASK, v1[u] > 0.f);
+                    l0 += __popc(__ballot_sync(FULL_MASK, p0[u])) + __popc(z0);
+                    l1 += __popc(__ballot_sync(FULL_MASK, p1[u])) + __popc(z1);
                     const unsigned zz = z0 | z1;
-                    if ((zz >> lane) & 1u) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0, v1);
+                    if ((zz >> lane) & 1u) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0[u], v1[u]);
                     nz += __popc(zz);
                 }
                 __syncwarp();
+                PF_SUB(9);  // values + staging
                 // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); every lane walks the
                 // staged terms (broadcast reads), eight loads in flight ahead of the two add chains
                 for (uint32_t t0 = 0; t0 < nz; t0 += 8) {
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     }
                 }
                 __syncwarp();
+                PF_SUB(10);  // chain
             }
             if (lane == 0) {
                 float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
@@ -380,7 +391,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                 s_tag[c] = tag;
             }
         }
+        PF_SUB(5);  // own scoring done
         if (warp == nwarps - 1 && s_fill >= 0) {
+            PF_SUB(5);
             const int c = s_fill;
             const uint32_t id = s_cand[c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
@@ -388,6 +401,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                 uint8_t *dst = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
                 for (uint32_t i = lane; i < nm; i += 32) dst[i] = (uint8_t)compact_key(pool[off + i]);
             }
+            PF_SUB(11);
         }
         __syncthreads();
         PF_MARK(pf_score);
@@ -451,8 +465,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
 #ifdef POMFRET_JOIN_PROF
     if (tid == 0) printf("JOINPROF w %u d %u n %u sites %u iters %d tagged %u total %lld setup %lld w0 %lld score %lld rest %lld\n", w, d, n,
                          n_sites, pf_iter, n_order, clock64() - pf_t0, pf_setup, pf_w0, pf_score, pf_rest);
-    if (tid == 0) printf("JOINSUB w %u d %u grow %lld pend+shift %lld refill %lld keyload %lld meta %lld scoreloop %lld best %lld insert %lld\n", w, d,
-                         pf_sub[0], pf_sub[1], pf_sub[2], pf_sub[3], pf_sub[4], pf_sub[5], pf_sub[6], pf_sub[7]);
+    if (tid == 0) printf("JOINSUB w %u d %u grow %lld pend+shift %lld refill %lld keyload %lld meta %lld lookups %lld values %lld chain %lld tail %lld best %lld insert %lld\n", w, d,
+                         pf_sub[0], pf_sub[1], pf_sub[2], pf_sub[3], pf_sub[4], pf_sub[8], pf_sub[9], pf_sub[10], pf_sub[5], pf_sub[6], pf_sub[7]);
+    if (tid == nthreads - 32) printf("JOINHELP w %u d %u fill %lld\n", w, d, pf_sub[11]);
 #endif
     // ---- 2x2 table over the far-side strict reads, :3888-3893 and :3940-3951 ----
     {

@@ -29,6 +29,20 @@ def env_int(name, default):
         return default
 
 
+def measured_traffic(kernel, reads_per_launch):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/traffic.json, written from the .ncu-rep by profiles/summarize_ncu.py); None if there is no capture
+    of a launch of this size."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p)).get(kernel)
+        if t and abs(t["reads_per_launch"] - reads_per_launch) <= 0.02 * reads_per_launch:
+            return t["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -177,6 +191,8 @@ def main():
     gpu = pb.load_gpu()
     if gpu.device_count() < 1:
         raise RuntimeError("no CUDA device: pomfret_b200 has no CPU fallback")
+    # the staging helper threads of all ranks share the host's cores
+    os.environ.setdefault("POMFRET_GPU_STAGE_THREADS", str(max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))))
     host = pb.load_host()
     # weak scaling: every rank owns its own contiguous region set (different seed), no data-path collective
     data = make_workload(tmp, args.region_mb, cov, seed=100 + rank)
@@ -297,7 +313,9 @@ def main():
             "gpu_launches": int(launches) * K,
             "kernel_ms": kernels,
             "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind},
+                         "unit": "GB/s", "frac": dec_gbs / peaks["hbm_gbs"],
+                         "traffic": measured_traffic("decode_kernel", reads), "algorithmic_bytes": int(tsum["decode_bytes"]),
+                         "launch_ms": dec_ms, "peak_kind": peak_kind},
             "roofline_pileup": {"kernel": "pileup_tile_kernel+sites_finalize_kernel", "bound": "hbm", "achieved": pile_gbs,
                                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pile_gbs / peaks["hbm_gbs"]},
             "clocks": sampler.summary()}

@@ -34,6 +34,7 @@ constexpr int DEC_MI_CAP = 256;       // M/I ops staged per chunk
 constexpr int DEC_MM_CHUNK = 512;     // MM bytes staged per step
 constexpr int DEC_T = 2;              // SEQ tiles (512 B = 1024 bases each) per scan step
 constexpr int DEC_BM_WORDS = 128;     // target bitmap window: 4096 canonical-base ranks (>= DEC_T * 1024)
+constexpr uint32_t DEC_Q = 64;        // listed bases queued between two dense passes (power of two, >= 2 * 32)
 constexpr int N_MODS_LIMIT = 10;      // reference N_MODS, blockjoin.c:34
 
 struct DecodeParams {
@@ -65,8 +66,9 @@ struct SegInfo {
 
 struct DecodeWarpSmem {
     __align__(16) uint8_t mmbuf[DEC_MM_CHUNK + 16];
-    uint32_t bm[DEC_BM_WORDS + 1];    // bit (r - window base) set iff canonical base number r is listed
+    uint32_t bm[DEC_BM_WORDS + 2];    // bit (r - window base) set iff canonical base number r is listed
     uint32_t bm_k[DEC_BM_WORDS + 1];  // index (in list order) of the first listed base at or after bit 0 of the word
+    uint32_t q[DEC_Q];                // ring of queued listed bases: (16-byte SEQ chunk << 5) | index among the chunk's matches
     uint32_t mi_end[DEC_MI_CAP];
     int32_t mi_off[DEC_MI_CAP];
     SegInfo seg[DEC_MAXSEG];
@@ -137,6 +139,20 @@ __device__ __forceinline__ bool is_alpha(int c) { return (c >= 'a' && c <= 'z') 
 __device__ __forceinline__ uint32_t comp_code(uint32_t c) {
     // complement of a 4-bit base code: reverse the 4 bits (A1<->T8, C2<->G4, N15 fixed)
     return ((c & 1u) << 3) | ((c & 2u) << 1) | ((c & 4u) >> 1) | ((c & 8u) >> 3);
+}
+
+// SWAR byte classification of four characters at a time
+__device__ __forceinline__ uint32_t byte_eq_mask4(uint32_t w, uint32_t pat) {  // 0x80 in every byte of w equal to pat's
+    const uint32_t x = w ^ pat;
+    const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return ~(t | x | 0x7f7f7f7fu);
+}
+__device__ __forceinline__ uint32_t nondigit_mask4(uint32_t w) {  // 0x80 in every byte outside '0'..'9'
+    const uint32_t y = w ^ 0x30303030u;
+    return (((y & 0x7f7f7f7fu) + 0x76767676u) | y) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t pack4(uint32_t m80) {  // 0x80 flags of four bytes -> four bits
+    return (((m80 >> 7) * 0x00204081u) >> 21) & 0xfu;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,34 +258,61 @@ __device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm,
         *reinterpret_cast<uint4 *>(sm.mmbuf + lane * 16) = v;
         if (lane == 0) *reinterpret_cast<uint4 *>(sm.mmbuf + DEC_MM_CHUNK) = *reinterpret_cast<const uint4 *>(mm + base + DEC_MM_CHUNK);
         __syncwarp();
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // byte classes of this lane's 16 characters as bit masks (SWAR, no per-character loop)
+        const uint32_t comma16 = pack4(byte_eq_mask4(v.x, 0x2c2c2c2cu)) | pack4(byte_eq_mask4(v.y, 0x2c2c2c2cu)) << 4 |
+                                 pack4(byte_eq_mask4(v.z, 0x2c2c2c2cu)) << 8 | pack4(byte_eq_mask4(v.w, 0x2c2c2c2cu)) << 12;
+        const uint32_t nd16 = pack4(nondigit_mask4(v.x)) | pack4(nondigit_mask4(v.y)) << 4 | pack4(nondigit_mask4(v.z)) << 8 |
+                              pack4(nondigit_mask4(v.w)) << 12;
+        const uint32_t lo_i = lb > off ? (lb - off < 16u ? lb - off : 16u) : 0u;
+        const uint32_t hi_i = le > off ? (le - off < 16u ? le - off : 16u) : 0u;
+        const uint32_t below_hi = (1u << hi_i) - 1u;                          // positions before the terminating ';'
+        const uint32_t range = hi_i > lo_i ? below_hi & ~((1u << lo_i) - 1u) : 0u;  // positions inside the list
+        if (nd16 & ~comma16 & range) bad = true;                              // neither digit nor comma
+        // a digit run ends at the first non-digit or at the end of the list; runs may continue in the next
+        // lane's characters (for lane 31: the 16 characters staged behind the chunk)
+        const uint32_t t16 = (nd16 | ~below_hi) & 0xffffu;
+        uint32_t ext_t16 = 0xffffu;
+        if (lane == 0) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(sm.mmbuf + DEC_MM_CHUNK);
+            const uint32_t e_nd = pack4(nondigit_mask4(x.x)) | pack4(nondigit_mask4(x.y)) << 4 | pack4(nondigit_mask4(x.z)) << 8 |
+                                  pack4(nondigit_mask4(x.w)) << 12;
+            const uint32_t e_off = base + DEC_MM_CHUNK;
+            const uint32_t e_hi = le > e_off ? (le - e_off < 16u ? le - e_off : 16u) : 0u;
+            ext_t16 = (e_nd | ~((1u << e_hi) - 1u)) & 0xffffu;
+        }
+        ext_t16 = __shfl_sync(FULL_MASK, ext_t16, 0);
+        uint32_t next_t16 = __shfl_down_sync(FULL_MASK, t16, 1);
+        if (lane == 31) next_t16 = ext_t16;
+        const uint32_t t32 = t16 | (next_t16 << 16);
         // commas owned by this lane, parsed values
         uint32_t vals[8];
         int nv = 0;
         uint32_t lsum = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            uint32_t pos = off + i;
-            uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-            if (pos >= lb && pos < le) {
-                if (c == ',') {
-                    // digits follow at pos+1.. (stop at le)
-                    uint32_t q = lane * 16 + i + 1;  // index into mmbuf
-                    uint32_t val = 0;
-                    int nd = 0;
-                    while (base + q < le && nd < 10) {
-                        uint32_t d = sm.mmbuf[q];
-                        if (d < '0' || d > '9') break;
-                        val = val >= DEC_SAT / 10 ? DEC_SAT : val * 10 + (d - '0');
-                        q++; nd++;
-                    }
-                    if (val >= DEC_SAT) val = DEC_SAT - 1;
-                    if (nd == 0) bad = true;
-                    if (nv < 8) vals[nv] = val;
-                    nv++;
-                    lsum = sat_add(lsum, val + 1);
-                } else if (c < '0' || c > '9') bad = true;
+        const uint32_t *mmbuf32 = reinterpret_cast<const uint32_t *>(sm.mmbuf);
+        for (uint32_t cm = comma16 & range; cm; cm &= cm - 1u) {
+            const uint32_t i = (uint32_t)__ffs((int)cm) - 1u;
+            const uint32_t run = t32 >> (i + 1u);
+            const uint32_t L = run ? (uint32_t)__ffs((int)run) - 1u : 31u - i;  // digits that follow the comma
+            const uint32_t q = lane * 16 + i + 1;                              // index of the first one in mmbuf
+            uint32_t val;
+            if (L <= 4u) {
+                // up to four ASCII digits -> value, without a loop
+                const uint32_t x = __funnelshift_r(mmbuf32[q >> 2], mmbuf32[(q >> 2) + 1], (q & 3u) * 8u);
+                const uint32_t mask = L >= 4u ? 0xffffffffu : (1u << (8u * L)) - 1u;
+                const uint32_t y = ((x & mask) - (0x30303030u & mask)) << (8u * (4u - L));  // last digit in the top byte
+                val = (y >> 24) + ((y >> 16) & 0xffu) * 10u + ((y >> 8) & 0xffu) * 100u + (y & 0xffu) * 1000u;
+                if (L == 0u) bad = true;
+            } else {
+                val = 0;
+                for (uint32_t nd = 0; nd < L && nd < 10u; nd++) {
+                    const uint32_t d = sm.mmbuf[q + nd];
+                    val = val >= DEC_SAT / 10 ? DEC_SAT : val * 10 + (d - '0');
+                }
+                if (val >= DEC_SAT) val = DEC_SAT - 1;
             }
+            if (nv < 8) vals[nv] = val;
+            nv++;
+            lsum = sat_add(lsum, val + 1);
         }
         uint32_t cnt = (uint32_t)nv;
         uint32_t incl_c = warp_inclusive_sum(cnt);
@@ -294,6 +337,47 @@ __device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm,
     g.total = total;
     __syncwarp();
     return !bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense pass over `nq` (<= 32) queued listed bases, one lane each: position in SEQ, CpG context
+// (blockjoin.c:846-858), ML byte -> category (blockjoin.c:876-878), coalesced stores in list order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dec_drain(DecodeWarpSmem &sm, const uint8_t *seq, const uint8_t *ml, uint32_t len, bool rev,
+                                          bool has_ml, uint32_t pat, uint32_t ml_base, uint32_t stride, uint32_t m_idx, uint32_t cap,
+                                          uint32_t lo, uint32_t hi, uint32_t *mpos, uint8_t *mcat, uint32_t k0, uint32_t nq,
+                                          bool &implicit, bool &drop_first, bool &drop_last) {
+    const unsigned lane = lane_id();
+    if (lane < nq) {
+        const uint32_t k = k0 + lane;
+        const uint32_t e = sm.q[k & (DEC_Q - 1)];
+        const uint32_t chunk = e >> 5;
+        uint32_t n = e & 31u;
+        const uint4 v = *reinterpret_cast<const uint4 *>(seq + (size_t)chunk * 16);
+        const uint32_t f0 = nib_eq_flags(v.x, pat), f1 = nib_eq_flags(v.y, pat), f2 = nib_eq_flags(v.z, pat), f3 = nib_eq_flags(v.w, pat);
+        const uint32_t c0 = (uint32_t)__popc(f0), c1 = (uint32_t)__popc(f1), c2 = (uint32_t)__popc(f2);
+        uint32_t wj = 0, f = f0;
+        if (n >= c0) {
+            n -= c0; wj = 1; f = f1;
+            if (n >= c1) {
+                n -= c1; wj = 2; f = f2;
+                if (n >= c2) { n -= c2; wj = 3; f = f3; }
+            }
+        }
+        const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
+        // C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
+        if (p > 0 && p < len - 1) {
+            const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
+            if (ok) {
+                const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
+                const uint32_t slot = rev ? cap - 1u - k : k;
+                mpos[slot] = p;
+                mcat[slot] = (uint8_t)(q < lo ? 1 : (q >= hi ? 0 : 2));
+            } else implicit = true;
+        } else if (k == 0) drop_first = true;
+        else drop_last = true;
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,6 +473,7 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
         uint32_t run = 0;        // canonical bases seen so far, in scan order
         uint32_t tcur = 0;       // listed bases with rank < run (list order == scan order on both strands)
         uint32_t wb = 0, wend = 0;  // rank window covered by the bitmap
+        uint32_t drained = 0;    // listed bases already resolved by dec_drain (drained <= tcur)
         bool drop_first = false, drop_last = false, implicit = false;
         if (lane == 0) sm.bm[DEC_BM_WORDS] = 0;
         uint4 cur[DEC_T], nxt[DEC_T];
@@ -451,6 +536,11 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
                     if (lane == 31) sm.bm_k[DEC_BM_WORDS] = kk;
                     __syncwarp();
                 }
+                // ---- every lane finds which of its matches are listed and queues (chunk, index in chunk) under the
+                //      base's list index k; full groups of 32 queued bases are then resolved densely (dec_drain) ----
+                const uint32_t e = run + step_total - wb;
+                const uint32_t k_end = sm.bm_k[e >> 5] + (uint32_t)__popc(sm.bm[e >> 5] & ((1u << (e & 31u)) - 1u));
+                uint32_t tw[DEC_T], kk[DEC_T];
                 uint32_t before = 0;  // matches of earlier tiles of this step
 #pragma unroll
                 for (int t = 0; t < DEC_T; t++) {
@@ -460,49 +550,45 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
                     // rank of this lane's first match in scan order
                     const uint32_t first = run + before + (rev ? tile_total - incl_t : incl_t - Ct);
                     before += tile_total;
-                    if (Ct == 0) continue;
                     const uint32_t idx = first - wb, word = idx >> 5, sh = idx & 31u;
                     const uint32_t lo_w = sm.bm[word], hi_w = sm.bm[word + 1];
-                    uint32_t tw = __funnelshift_r(lo_w, hi_w, sh);
-                    tw &= Ct >= 32u ? 0xffffffffu : (1u << Ct) - 1u;  // bit j <-> this lane's j-th match in scan order
-                    if (tw == 0) continue;
-                    uint32_t k = sm.bm_k[word] + (uint32_t)__popc(lo_w & ((1u << sh) - 1u));
-                    const uint32_t c0 = (uint32_t)__popc(m[t][0]), c1 = (uint32_t)__popc(m[t][1]), c2 = (uint32_t)__popc(m[t][2]);
-                    const int tile = rev ? n_tiles - 1 - (step * DEC_T + t) : step * DEC_T + t;
-                    do {
-                        const uint32_t j = (uint32_t)__ffs((int)tw) - 1u;
-                        tw &= tw - 1u;
-                        uint32_t n = rev ? Ct - 1u - j : j;  // index in base order inside the lane's chunk
-                        uint32_t wj = 0, f = m[t][0];
-                        if (n >= c0) {
-                            n -= c0; wj = 1; f = m[t][1];
-                            if (n >= c1) {
-                                n -= c1; wj = 2; f = m[t][2];
-                                if (n >= c2) { n -= c2; wj = 3; f = m[t][3]; }
-                            }
-                        }
-                        const uint32_t p = (uint32_t)tile * 1024u + lane * 32u + wj * 8u + select_base_in_word(f, n);
-                        // blockjoin.c:846-858: C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
-                        if (p > 0 && p < len - 1) {
-                            const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
-                            if (ok) {
-                                const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
-                                const uint32_t slot = rev ? cap - 1u - k : k;
-                                mpos[slot] = p;
-                                mcat[slot] = (uint8_t)(q < P.lo ? 1 : (q >= P.hi ? 0 : 2));
-                            } else implicit = true;
-                        } else if (k == 0) drop_first = true;
-                        else drop_last = true;
-                        k++;
-                    } while (tw);
+                    tw[t] = __funnelshift_r(lo_w, hi_w, sh) & (Ct >= 32u ? 0xffffffffu : (1u << Ct) - 1u);  // bit j <-> j-th match in scan order
+                    kk[t] = sm.bm_k[word] + (uint32_t)__popc(lo_w & ((1u << sh) - 1u));
                 }
-                // listed bases consumed so far = those with rank < run + step_total
-                const uint32_t e = run + step_total - wb;
-                tcur = sm.bm_k[e >> 5] + (uint32_t)__popc(sm.bm[e >> 5] & ((1u << (e & 31u)) - 1u));
+                for (;;) {
+                    const uint32_t lim = k_end - drained <= DEC_Q ? k_end : drained + DEC_Q;  // queue capacity
+#pragma unroll
+                    for (int t = 0; t < DEC_T; t++) {
+                        const int tile = rev ? n_tiles - 1 - (step * DEC_T + t) : step * DEC_T + t;
+                        const uint32_t chunk = (uint32_t)tile * 32u + lane;
+                        while (tw[t] && kk[t] < lim) {
+                            const uint32_t j = (uint32_t)__ffs((int)tw[t]) - 1u;
+                            tw[t] &= tw[t] - 1u;
+                            sm.q[kk[t] & (DEC_Q - 1)] = (chunk << 5) | (rev ? C[t] - 1u - j : j);  // index in base order
+                            kk[t]++;
+                        }
+                    }
+                    __syncwarp();
+                    while (lim - drained >= 32u) {
+                        dec_drain(sm, seq, ml, len, rev, has_ml, pat, ml_base, stride, m_idx, cap, P.lo, P.hi, mpos, mcat, drained, 32u,
+                                  implicit, drop_first, drop_last);
+                        drained += 32u;
+                    }
+                    if (lim == k_end) break;
+                }
+                tcur = k_end;  // listed bases consumed so far = those with rank < run + step_total
+
             }
             run += step_total;
 #pragma unroll
             for (int t = 0; t < DEC_T; t++) cur[t] = nxt[t];
+        }
+        __syncwarp();
+        while (drained < tcur) {
+            const uint32_t nq = tcur - drained < 32u ? tcur - drained : 32u;
+            dec_drain(sm, seq, ml, len, rev, has_ml, pat, ml_base, stride, m_idx, cap, P.lo, P.hi, mpos, mcat, drained, nq, implicit,
+                      drop_first, drop_last);
+            drained += nq;
         }
         if (rev && run < need_c) mm_error = true;
         has_implicit = __any_sync(FULL_MASK, implicit);

@@ -202,6 +202,8 @@ def build_records(seed, n_random=60, max_len=9000, long_lens=(70000,)):
         one("fatal_head", 600, rev, "uniform", "fatal_head", "m", "cpg")
         one("fatal_mid", 3000, rev, "uniform", "fatal_mid", "m", "cpg")
         one("dense_cigar", 6000, rev, "uniform", "dense", "m", "cpg")
+        one("dense_cpg_list", 9000, rev, "crich", "plain", "m", "cpg")      # > 64 listed bases per SEQ tile
+        one("big_deltas", 30000, rev, "crich", "plain", "m", "cpg", 0.002)  # 3- to 5-digit deltas
         for style in ("hm", "mh", "h;m", "a;m", "m;a;N", "chebi", "m;m", "onlyh", "minus"):
             one("style_" + style, 2500, rev, "uniform", "plain", style, "cpg")
             one("style_" + style + "_iupac", 1800, rev, "iupac", "clip", style, "cpg", 0.7)

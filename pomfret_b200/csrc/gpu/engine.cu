@@ -658,7 +658,7 @@ static int launch_pileup_stages(pomfret_gpu_batch *b) {
     PileupParams Q;
     Q.win = b->d_win.as<WindowRec>(); Q.state = b->d_state.as<WindowState>(); Q.tiles = b->d_tiles.as<TileRec>();
     Q.win_base = b->d_win_base.as<uint32_t>(); Q.reads = b->d_reads.as<ReadRec>(); Q.rs_src = b->d_rs_src.as<uint32_t>();
-    Q.r_ncalls = b->d_r_ncalls.as<uint32_t>(); Q.r_status = b->d_r_status.as<uint32_t>();
+    Q.r_ncalls = b->d_r_ncalls.as<uint32_t>(); Q.r_status = b->d_r_status.as<uint32_t>(); Q.r_end = b->d_r_end.as<uint32_t>();
     Q.calls_pos = b->d_calls_pos.as<uint32_t>(); Q.calls_cat = b->d_calls_cat.as<uint8_t>();
     Q.tile_out = b->d_tile_out.as<uint32_t>(); Q.tile_count = b->d_tile_count.as<uint32_t>();
     Q.cov = (uint32_t)cfg.cov_for_selection;

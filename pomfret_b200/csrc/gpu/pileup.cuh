@@ -39,7 +39,7 @@ struct PileupParams {
     const uint32_t *win_base;     // per window: position that maps to counter 0 (min read start - 1)
     const ReadRec *reads;
     const uint32_t *rs_src;
-    const uint32_t *r_ncalls, *r_status;
+    const uint32_t *r_ncalls, *r_status, *r_end;
     const uint32_t *calls_pos;
     const uint8_t *calls_cat;
     uint32_t *tile_out;           // selected positions per tile, ascending
@@ -58,26 +58,36 @@ __global__ void __launch_bounds__(PILE_THREADS) pileup_tile_kernel(PileupParams 
     const uint32_t t0 = T.tile * PILE_TILE;  // window-relative
     for (uint32_t i = tid; i < PILE_TILE; i += PILE_THREADS) cnt[i] = 0;
     __syncthreads();
+    // Positions are handled relative to the window base in wrapping 32-bit arithmetic, compared as signed:
+    // the reference's position arithmetic wraps too, and a call that a clipped record
+    // maps left of the base stays ordered (negative) instead of turning into a huge offset.
     for (uint32_t id = warp; id < n; id += n_warps) {
         const uint32_t src = P.rs_src[W.first_read + id];
         const uint32_t nc = P.r_ncalls[src];
         if (nc == 0) continue;
+        const bool sorted = !(P.r_status[src] & RS_UNSORTED);
         const uint32_t *cp = P.calls_pos + P.reads[src].calls_off;
         const uint8_t *cc = P.calls_cat + P.reads[src].calls_off;
-        uint32_t a = 0, b = nc;
-        if (!(P.r_status[src] & RS_UNSORTED)) {
-            // window-relative positions ascend: [a,b) = calls with rel in [t0, t0+PILE_TILE)
+        uint32_t a = 0;
+        if (sorted) {
+            // most records of the window miss this tile altogether: look at their first and last call
+            if ((int32_t)(cp[nc - 1] - wbase) < (int32_t)t0 || (int32_t)(cp[0] - wbase) >= (int32_t)(t0 + PILE_TILE)) continue;
+            // first call at or behind the tile start, then stream until the tile ends
             uint32_t lo = 0, hi = nc;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cp[mid] - wbase < t0) lo = mid + 1; else hi = mid; }
+            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)(cp[mid] - wbase) < (int32_t)t0) lo = mid + 1; else hi = mid; }
             a = lo;
-            hi = nc;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (cp[mid] - wbase < t0 + PILE_TILE) lo = mid + 1; else hi = mid; }
-            b = lo;
         }
-        for (uint32_t j = a + lane; j < b; j += 32) {
-            uint32_t rel = cp[j] - wbase - t0;
-            uint32_t cat = cc[j];
-            if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
+        for (uint32_t j0 = a; j0 < nc; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool past = false;
+            if (j < nc) {
+                const uint32_t rel = cp[j] - wbase - t0;
+                const uint32_t cat = cc[j];
+                if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
+                past = (int32_t)rel >= (int32_t)PILE_TILE;
+            }
+            // sorted: once a lane is past the tile, so is everything behind it
+            if (sorted && __any_sync(FULL_MASK, past)) break;
         }
     }
     __syncthreads();

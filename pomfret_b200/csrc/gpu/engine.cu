@@ -327,7 +327,8 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
     }
 #ifndef POMFRET_CUDA_EMU
     CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
-    CK(cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+    CK(cudaFuncSetAttribute(join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+    CK(cudaFuncSetAttribute(join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
 #endif
     *out = b;
     return POMFRET_GPU_OK;
@@ -788,6 +789,7 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     if (int rc = b->h_cta.resize(nw * 2 + 1)) return rc;
     size_t n_a = 0, n_b = 0;
     uint32_t tab_a = 0, tab_b = 0;
+    bool a_all_fit = true;
     std::vector<uint32_t> big;
     for (size_t w = 0; w < nw; w++) {
         const WindowState &S = b->h_state[w];
@@ -797,6 +799,7 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         if (need > small_limit && need <= kJoinSmemMax) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
         else {
             if (need <= small_limit) tab_a = std::max(tab_a, words);
+            else a_all_fit = false;  // larger than a whole SM's shared memory: this window keeps its tables in the global pool
             b->h_cta[n_a++] = (uint32_t)w * 2; b->h_cta[n_a++] = (uint32_t)w * 2 + 1;
         }
     }
@@ -809,14 +812,16 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         JoinParams JB = J;
         JB.cta_map = b->d_cta.as<uint32_t>() + n_a;
         JB.smem_tab_words = tab_b;
-        POMFRET_LAUNCH(join_kernel, (unsigned)n_b, join_threads, join_smem_bytes(tab_b + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream2, JB);
+        POMFRET_LAUNCH(join_kernel<true>, (unsigned)n_b, join_threads, join_smem_bytes(tab_b + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream2, JB);
         b->tm.launches++;
         CK(cudaEventRecord(b->ev_join, b->stream2));
     }
     if (n_a) {
         J.cta_map = b->d_cta.as<uint32_t>();
         J.smem_tab_words = tab_a;
-        POMFRET_LAUNCH(join_kernel, (unsigned)n_a, join_threads, join_smem_bytes(tab_a + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream, J);
+        const size_t smem_a = join_smem_bytes(tab_a + 1, J.meta_cap, J.n_cand, (int)join_threads / 32);
+        if (a_all_fit) POMFRET_LAUNCH(join_kernel<true>, (unsigned)n_a, join_threads, smem_a, b->stream, J);
+        else POMFRET_LAUNCH(join_kernel<false>, (unsigned)n_a, join_threads, smem_a, b->stream, J);
         b->tm.launches++;
     }
     if (n_b) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));

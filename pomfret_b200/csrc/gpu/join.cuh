@@ -95,26 +95,19 @@ __device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride,
     }
 }
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
-    __shared__ int s_i_last, s_failed, s_done, s_ncand, s_fill;
+// kTabSmem: every window of the launch keeps its count tables in shared memory (the compiler then emits
+// shared-memory loads/stores for them); otherwise windows that do not fit use the global pool.
+template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
+    __shared__ int s_i_last, s_failed, s_done, s_fill;
+    __shared__ int s_ncand[2];
     __shared__ uint32_t s_min, s_max;
-    __shared__ uint32_t s_cand[JOIN_MAX_CAND + 1];
-    __shared__ uint8_t s_slot[JOIN_MAX_CAND + 1];
+    __shared__ uint32_t s_cand[2][JOIN_MAX_CAND + 1];   // candidate lists of two consecutive iterations (ping-pong)
+    __shared__ uint8_t s_slot[2][JOIN_MAX_CAND + 1];
     __shared__ float s_score[JOIN_MAX_CAND];
     __shared__ int s_tag[JOIN_MAX_CAND];
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
 
-#ifdef POMFRET_JOIN_PROF
-    long long pf_t0 = clock64(), pf_setup = 0, pf_w0 = 0, pf_score = 0, pf_rest = 0, pf_t = 0;
-    int pf_iter = 0;
-#define PF_MARK(acc) do { long long now_ = clock64(); acc += now_ - pf_t; pf_t = now_; pf_s = now_; } while (0)
-    long long pf_sub[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pf_s = 0;
-#define PF_SUB(i) do { long long now_ = clock64(); pf_sub[i] += now_ - pf_s; pf_s = now_; } while (0)
-#else
-#define PF_MARK(acc) do {} while (0)
-#define PF_SUB(i) do {} while (0)
-#endif
     const uint32_t wd = P.cta_map[blockIdx.x];
     const uint32_t w = wd >> 1, d = wd & 1u;
     const WindowRec W = P.win[w];
@@ -144,9 +137,9 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
     uint32_t *s_tagged = reinterpret_cast<uint32_t *>(s_scan) + (P.meta_cap + 1) / 2;  // bit per read: tagged 0/1
     uint8_t *s_keys = reinterpret_cast<uint8_t *>(s_tagged + (P.meta_cap + 31) / 32);   // [n_cand + 1][JOIN_CHUNK]
-    const bool tab_in_smem = (size_t)n_sites * stride <= P.smem_tab_words;
+    const bool tab_in_smem = kTabSmem || (size_t)n_sites * stride <= P.smem_tab_words;
     const bool meta_in_smem = n <= P.meta_cap;
-    uint32_t *tab = tab_in_smem ? s_tab : P.tab + (size_t)S.tab_base[d] * stride;
+    uint32_t *tab = kTabSmem ? s_tab : (tab_in_smem ? s_tab : P.tab + (size_t)S.tab_base[d] * stride);
 
     // ---- wipe the tables (insert_ref_reads_methmer_counts, :3780-3789), load the per-read state ----
     for (size_t i = tid, words = (size_t)n_sites * stride; i < words; i += nthreads) tab[i] = 0;
@@ -157,20 +150,34 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         }
         for (uint32_t i = tid; i < (n + 31) / 32; i += nthreads) s_tagged[i] = 0;
     }
-    // ---- available range, :3976-4004 ----
-    if (tid == 0) {
+    // ---- available range, :3976-4004 (warp-parallel count of the sites on the starting side of the gap) ----
+    if (warp == 0) {
         uint32_t mn, mx;
         if (d == 0) {
             mn = 0; mx = 0;
-            for (int i = 0; i < (int)n_sites; i++) { if (site_pos[i] <= W.ref_start) mx++; else break; }
+            for (uint32_t i0 = 0; i0 < n_sites; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const unsigned ok = __ballot_sync(FULL_MASK, i < n_sites && site_pos[i] <= W.ref_start);
+                if (ok == FULL_MASK) { mx += 32; continue; }
+                mx += (uint32_t)__ffs((int)~ok) - 1u;
+                break;
+            }
         } else {
             mn = n_sites - 1; mx = n_sites - 1;
-            for (int i = (int)mn; i >= 0; i--) { if (site_pos[i] > W.ref_end) mn--; else break; }
+            for (int i0 = (int)n_sites - 1; i0 >= 0; i0 -= 32) {
+                const int i = i0 - (int)lane;
+                const unsigned ok = __ballot_sync(FULL_MASK, i >= 0 && site_pos[i] > W.ref_end);
+                if (ok == FULL_MASK) { mn -= 32; continue; }
+                mn -= (uint32_t)__ffs((int)~ok) - 1u;
+                break;
+            }
         }
-        s_min = mn; s_max = mx;
-        s_failed = 0; s_done = 0;
-        s_i_last = d == 0 ? 0 : (int)n - 1;
-        s_tbl[0] = s_tbl[1] = s_tbl[2] = s_tbl[3] = 0;
+        if (lane == 0) {
+            s_min = mn; s_max = mx;
+            s_failed = 0; s_done = 0; s_fill = -1;
+            s_i_last = d == 0 ? 0 : (int)n - 1;
+            s_tbl[0] = s_tbl[1] = s_tbl[2] = s_tbl[3] = 0;
+        }
     }
     __syncthreads();
     // ---- seed with the reference reads of the starting side, :3793-3803 ----
@@ -191,16 +198,29 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
     // ---- un-tag everything but the reference reads, :4010-4025 (with the (id<<2)|hp packing) ----
     for (uint32_t i = tid; i < n; i += nthreads) tags[i] = 2;
     __syncthreads();
-    if (tid == 0) {
-        for (uint32_t r = 0; r < n_ref; r++) {
-            uint32_t id = ref_ids[r];
-            uint32_t packed = (id << 2) | (uint32_t)P.rs_hp[first + id];
-            uint32_t tid2 = packed >> 2;
-            if (tid2 < n) {
-                const uint8_t t = (uint8_t)(packed & 3u);
-                tags[tid2] = t;
-                if (meta_in_smem && t < 2) s_tagged[tid2 >> 5] |= 1u << (tid2 & 31u);
+    // The reference re-tags the list sequentially, and with hp = 254 the packing corrupts the id (the write
+    // lands on read id | 63): a later entry may overwrite an earlier one.  One warp walks the list in order,
+    // 32 entries at a time; inside a group the highest lane writing to a read wins.
+    if (warp == 0) {
+        for (uint32_t r0 = 0; r0 < n_ref; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            uint32_t tid2 = 0xffffffffu - lane;  // distinct dummies for idle lanes
+            uint8_t t = 0;
+            bool act = false;
+            if (r < n_ref) {
+                const uint32_t id = ref_ids[r];
+                const uint32_t packed = (id << 2) | (uint32_t)P.rs_hp[first + id];
+                if ((packed >> 2) < n) { act = true; tid2 = packed >> 2; t = (uint8_t)(packed & 3u); }
             }
+            const unsigned same = __match_any_sync(FULL_MASK, tid2);
+            if (act && (same >> lane) <= 1u) {  // no higher lane targets the same read
+                tags[tid2] = t;
+                if (meta_in_smem) {
+                    if (t < 2) atomicOr(&s_tagged[tid2 >> 5], 1u << (tid2 & 31u));
+                    else atomicAnd(&s_tagged[tid2 >> 5], ~(1u << (tid2 & 31u)));
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -210,119 +230,113 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
         const uint8_t t = tags[id];
         return t != 0 && t != 1;
     };
+    // Candidate-list maintenance (warp 0).  The list is "the first n_cand untagged reads in scan order from
+    // i_last" (:4039-4045) plus one look-ahead entry whose methmer keys are fetched from global memory one
+    // iteration before they are first needed.  `src` < 0 rebuilds it from i_last; otherwise entry `drop` of
+    // list `src` is removed and the next untagged read behind the scan cursor is appended.
+    int cursor = 0;  // warp 0, uniform: scan position right behind the last listed read
+    auto build_list = [&](int dst, int src, int drop) {
+        int nc = 0, free_slot = -1;
+        const bool rebuild = src < 0;
+        if (rebuild) cursor = s_i_last;
+        else {
+            const int nc_old = s_ncand[src];  // (look-ahead included, see below)
+            free_slot = s_slot[src][drop];
+            for (int c0 = 0; c0 < nc_old; c0 += 32) {
+                const int c = c0 + (int)lane;
+                if (c < nc_old && c != drop) {
+                    const int to = c < drop ? c : c - 1;
+                    s_cand[dst][to] = s_cand[src][c];
+                    s_slot[dst][to] = s_slot[src][c];
+                }
+            }
+            nc = nc_old - 1;
+        }
+        const int n_old = nc;
+        while (nc < n_cand + 1) {
+            const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
+            const bool in = d == 0 ? i0 < (int)n : i0 >= 0;
+            uint32_t id = 0;
+            bool unt = false;
+            if (in) {
+                id = d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]);
+                unt = is_untagged(id);
+            }
+            const unsigned um = __ballot_sync(FULL_MASK, unt);
+            const int rank = __popc(um & ((1u << lane) - 1u));
+            const int room = n_cand + 1 - nc;
+            if (unt && rank < room) {
+                s_cand[dst][nc + rank] = id;
+                s_slot[dst][nc + rank] = (uint8_t)(rebuild ? nc + rank : free_slot);
+            }
+            const int found = __popc(um);
+            if (found >= room) {
+                // the list is full: the cursor stops right behind the read that filled it
+                unsigned fm = um;
+                for (int r = 1; r < room; r++) fm &= fm - 1u;  // drop the room-1 lowest set bits
+                const int fill_lane = __ffs((int)fm) - 1;
+                cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
+                nc = n_cand + 1;
+                break;
+            }
+            nc += found;
+            cursor += d == 0 ? 32 : -32;
+            if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
+        }
+        __syncwarp();
+        // keys of the new entries: a rebuilt list needs them before it is scored; the look-ahead entry of a
+        // running list is filled by the last warp while the others score (s_fill)
+        int fill = -1;
+        for (int c = n_old; c < nc; c++) {
+            if (!rebuild && c >= n_cand) { fill = c; continue; }
+            const uint32_t id = s_cand[dst][c];
+            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
+            if (nm > JOIN_CHUNK) continue;  // too long to cache: scored straight from the pool
+            uint8_t *dk = s_keys + (size_t)s_slot[dst][c] * JOIN_CHUNK;
+            for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
+        }
+        if (lane == 0) { s_ncand[dst] = nc; s_fill = fill; }
+        __syncwarp();
+    };
 
     // ---- extension loop, :4032-4071 ----
-    // Warp 0 owns the loop state between the barriers: available range, candidate list, failure count.
-    // The candidate list ("the first n_cand untagged reads in scan order from i_last", :4039-4045) is kept
-    // incrementally: a success removes the tagged read and appends the next untagged one behind the scan
-    // cursor; a failure moves i_last (:4064-4068) and rebuilds it.  The list carries one entry more than is
-    // scored: the look-ahead entry's methmer keys travel from global to shared memory one iteration before
-    // they are first needed, so no iteration waits for L2.
-#ifdef POMFRET_JOIN_PROF
-    pf_t = clock64(); pf_setup = pf_t - pf_t0;
-#endif
+    // Two barriers per iteration.  Between them: (1) every warp grows the available range on its own (the
+    // walk is idempotent) and scores one candidate; (2) every warp finds the best candidate on its own, then
+    // warp 0 maintains the loop state and writes the next candidate list into the other buffer while the
+    // remaining warps insert the tagged read's methmers.
     uint32_t n_order = 0;
-    int nc = 0, cursor = 0;            // warp 0 only (uniform): list length incl. look-ahead, scan cursor
-    bool rebuild = true, grow = true;  // first pass: update_available_methmer_range after seeding, fresh list
-    int last_best = -1;
+    int cur = 0;
+    bool grow = true;  // update_available_methmer_range after seeding / after every insertion (:3770, :3806)
+    if (warp == 0) {
+        const int i_last = s_i_last;
+        if ((d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0)) { if (lane == 0) s_done = 1; }
+        else build_list(0, -1, 0);
+    }
+    __syncthreads();
     for (;;) {
-        if (warp == 0) {
-            uint32_t mn = s_min, mx = s_max;
-            if (grow) { grow_range(tab, stride, n_keys, n_sites, P.cov_run, mn, mx); if (lane == 0) { s_min = mn; s_max = mx; } }
-            PF_SUB(0);  // grow
-            const int i_last = s_i_last;
-            const bool done = (d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0);
-            if (!done) {
-                int free_slot = -1, n_old = nc;
-                if (rebuild) { nc = 0; cursor = i_last; n_old = 0; }
-                else if (last_best >= 0) {
-                    // drop entry last_best, keep the order of the rest
-                    free_slot = s_slot[last_best];
-                    for (int c0 = 0; c0 < nc; c0 += 32) {
-                        const int c = c0 + (int)lane;
-                        uint32_t v = 0;
-                        uint8_t sl = 0;
-                        const bool mv = c > last_best && c < nc;
-                        if (mv) { v = s_cand[c]; sl = s_slot[c]; }
-                        __syncwarp();
-                        if (mv) { s_cand[c - 1] = v; s_slot[c - 1] = sl; }
-                    }
-                    nc--;
-                    n_old = nc;
-                    __syncwarp();
-                }
-                PF_SUB(1);  // pend store + shift
-                // refill from the cursor
-                while (nc < n_cand + 1) {
-                    const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
-                    const bool in = d == 0 ? i0 < (int)n : i0 >= 0;
-                    uint32_t id = 0;
-                    bool unt = false;
-                    if (in) {
-                        id = d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]);
-                        unt = is_untagged(id);
-                    }
-                    const unsigned um = __ballot_sync(FULL_MASK, unt);
-                    const int rank = __popc(um & ((1u << lane) - 1u));
-                    const int room = n_cand + 1 - nc;
-                    if (unt && rank < room) {
-                        s_cand[nc + rank] = id;
-                        s_slot[nc + rank] = (uint8_t)(rebuild ? nc + rank : free_slot);
-                    }
-                    const int found = __popc(um);
-                    if (found >= room) {
-                        // the list is full: the cursor stops right behind the read that filled it
-                        unsigned fm = um;
-                        for (int r = 1; r < room; r++) fm &= fm - 1u;  // drop the room-1 lowest set bits
-                        const int fill_lane = __ffs((int)fm) - 1;
-                        cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
-                        nc = n_cand + 1;
-                        break;
-                    }
-                    nc += found;
-                    cursor += d == 0 ? 32 : -32;
-                    if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
-                }
-                __syncwarp();
-                PF_SUB(2);  // refill
-                // keys of the new entries: a rebuilt list needs them before it is scored; the look-ahead entry of a
-                // running list is filled by the last warp while the others score (s_fill)
-                int fill = -1;
-                for (int c = n_old; c < nc; c++) {
-                    if (!rebuild && c >= n_cand) { fill = c; continue; }
-                    const uint32_t id = s_cand[c];
-                    const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
-                    if (nm > JOIN_CHUNK) continue;  // too long to cache: scored straight from the pool
-                    uint8_t *dst = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
-                    for (uint32_t i = lane; i < nm; i += 32) dst[i] = (uint8_t)compact_key(pool[off + i]);
-                }
-                if (lane == 0) s_fill = fill;
-                __syncwarp();
-            } else if (lane == 0) s_fill = -1;
-            PF_SUB(3);  // key loads
-            if (lane == 0) { s_ncand = nc < n_cand ? nc : n_cand; if (done) s_done = 1; }
-        }
-        __syncthreads();
-        PF_MARK(pf_w0);
         if (s_done) break;
-        const int ncand = s_ncand;
-        const uint32_t rmin = s_min, rmax = s_max;
+        const int nc_all = s_ncand[cur];
+        const int ncand = nc_all < n_cand ? nc_all : n_cand;  // the look-ahead entry is not scored
+        uint32_t rmin = s_min, rmax = s_max;
+        if (grow) {
+            grow_range(tab, stride, n_keys, n_sites, P.cov_run, rmin, rmax);
+            if (tid == 0) { s_min = rmin; s_max = rmax; }  // others may still read the old pair: growing again is harmless
+        }
         // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
         for (int c = (int)warp; c < ncand; c += (int)nwarps) {
-            const uint32_t id = s_cand[c];
+            const uint32_t id = s_cand[cur][c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
             const bool cached = nm <= JOIN_CHUNK;
-            const uint8_t *ck = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)s_slot[cur][c] * JOIN_CHUNK;
             float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
             int l0 = 0, l1 = 0;
             // only methmers whose site lies in the available range [rmin, rmax) are looked up (:3499-3502)
-            PF_SUB(4);  // scoring meta
             const uint32_t i_lo = rmin > st ? rmin - st : 0u;
             const uint32_t i_hi = rmax > st ? (rmax - st < nm ? rmax - st : nm) : 0u;
             float2 *stage = s_stage + (size_t)warp * JOIN_STAGE;
             for (uint32_t base = i_lo; base < i_hi; base += JOIN_STAGE) {
-                // four sub-chunks of 32 methmers at a time: their shared-memory lookups overlap
+                // up to four sub-chunks of 32 methmers at a time: their lookups and divisions overlap
                 uint32_t key[4], cnt[4], sums[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -338,21 +352,22 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                         sums[u] = row[n_keys];
                     }
                 }
-                PF_SUB(8);  // key/cnt/sums lookups
-                // the divisions of the four sub-chunks are independent and branch-free, so they overlap
                 float v0[4], v1[4];
                 bool p0[4], p1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
-                    p0[u] = cnt[u] != 0 && sum0 != 0;  // key present at this site and the haplotype has counts
-                    p1[u] = cnt[u] != 0 && sum1 != 0;
-                    // (zero operands are replaced by 1 so that the division always takes its fast path)
-                    const uint32_t c0 = cnt[u] & 0xffffu, c1 = cnt[u] >> 16;
-                    const float q0 = __fdiv_rn((float)(c0 ? c0 : 1u), (float)(sum0 ? sum0 : 1u));
-                    const float q1 = __fdiv_rn((float)(c1 ? c1 : 1u), (float)(sum1 ? sum1 : 1u));
-                    v0[u] = p0[u] && c0 ? q0 : 0.f;
-                    v1[u] = p1[u] && c1 ? q1 : 0.f;
+                    v0[u] = v1[u] = 0.f; p0[u] = p1[u] = false;
+                    if (base + u * 32 < i_hi) {  // uniform
+                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
+                        const uint32_t c0 = cnt[u] & 0xffffu, c1 = cnt[u] >> 16;
+                        p0[u] = cnt[u] != 0 && sum0 != 0;  // key present at this site and the haplotype has counts
+                        p1[u] = cnt[u] != 0 && sum1 != 0;
+                        // (zero operands are replaced by 1 so that the division always takes its fast path)
+                        const float q0 = __fdiv_rn((float)(c0 ? c0 : 1u), (float)(sum0 ? sum0 : 1u));
+                        const float q1 = __fdiv_rn((float)(c1 ? c1 : 1u), (float)(sum1 ? sum1 : 1u));
+                        v0[u] = p0[u] && c0 ? q0 : 0.f;
+                        v1[u] = p1[u] && c1 ? q1 : 0.f;
+                    }
                 }
                 uint32_t nz = 0;  // non-zero terms staged (adding +0.0f is exact, so zero terms are dropped)
 #pragma unroll
@@ -366,7 +381,6 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     nz += __popc(zz);
                 }
                 __syncwarp();
-                PF_SUB(9);  // values + staging
                 // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); every lane walks the
                 // staged terms (broadcast reads), eight loads in flight ahead of the two add chains
                 for (uint32_t t0 = 0; t0 < nz; t0 += 8) {
@@ -379,7 +393,6 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                     }
                 }
                 __syncwarp();
-                PF_SUB(10);  // chain
             }
             if (lane == 0) {
                 float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
@@ -391,20 +404,16 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
                 s_tag[c] = tag;
             }
         }
-        PF_SUB(5);  // own scoring done
-        if (warp == nwarps - 1 && s_fill >= 0) {
-            PF_SUB(5);
+        if (warp == nwarps - 1 && s_fill >= 0) {  // look-ahead entry: keys global -> shared, off the critical path
             const int c = s_fill;
-            const uint32_t id = s_cand[c];
+            const uint32_t id = s_cand[cur][c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
             if (nm <= JOIN_CHUNK) {
-                uint8_t *dst = s_keys + (size_t)s_slot[c] * JOIN_CHUNK;
-                for (uint32_t i = lane; i < nm; i += 32) dst[i] = (uint8_t)compact_key(pool[off + i]);
+                uint8_t *dk = s_keys + (size_t)s_slot[cur][c] * JOIN_CHUNK;
+                for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
             }
-            PF_SUB(11);
         }
         __syncthreads();
-        PF_MARK(pf_score);
         // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
         //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
         int best = -1;
@@ -421,54 +430,49 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
             const uint32_t top = __reduce_max_sync(FULL_MASK, bc >= 0 ? bs : 0u);
             best = (int)__reduce_max_sync(FULL_MASK, (uint32_t)((bc >= 0 && bs == top) ? bc + 1 : 0)) - 1;
         }
-        PF_SUB(6);  // best
-        if (best >= 0) {
-            const uint32_t id = s_cand[best];
-            const int hap = s_tag[best];
-            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
-            const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
-            const bool cached = nm <= JOIN_CHUNK;
-            const uint8_t *ck = s_keys + (size_t)s_slot[best] * JOIN_CHUNK;
-            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
-            for (uint32_t i0 = tid; i0 < nm; i0 += nthreads) {
-                uint32_t *row = tab + (size_t)(st + i0) * stride;
-                row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
-                row[n_keys] += inc;
+        const uint32_t best_id = best >= 0 ? s_cand[cur][best] : 0u;
+        const int hap = best >= 0 ? s_tag[best] : -1;
+        if (warp == 0) {
+            // ---- loop state and the next candidate list ----
+            if (best >= 0) {
+                if (lane == 0) {
+                    tags[best_id] = (uint8_t)hap;
+                    if (meta_in_smem) s_tagged[best_id >> 5] |= 1u << (best_id & 31u);
+                    P.order[d][first + n_order] = best_id;
+                    s_failed = 0;
+                }
+                __syncwarp();
+                build_list(cur ^ 1, cur, best);
+            } else {
+                int fl = s_failed + 1, il = s_i_last + (d == 0 ? n_cand : -n_cand);
+                const bool done = fl > 10 || (d == 0 && il >= (int)n) || (d != 0 && il <= 0);
+                __syncwarp();
+                if (lane == 0) { s_failed = fl; s_i_last = il; if (done) s_done = 1; }
+                __syncwarp();
+                if (!done) build_list(cur ^ 1, -1, 0);
             }
-            if (tid == 0) {
-                tags[id] = (uint8_t)hap;
-                if (meta_in_smem) s_tagged[id >> 5] |= 1u << (id & 31u);
-                P.order[d][first + n_order] = id;
+        }
+        if (best >= 0) {
+            // ---- insert_mmrs_to_counts (:3453-3486) by the other warps (all of them if there is only one) ----
+            const uint32_t nm = meta_in_smem ? s_mn[best_id] : g_n[best_id], st = meta_in_smem ? s_mst[best_id] : g_start[best_id];
+            const uint32_t off = meta_in_smem ? s_moff[best_id] : g_off[best_id];
+            const bool cached = nm <= JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)s_slot[cur][best] * JOIN_CHUNK;
+            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
+            const uint32_t t_first = nwarps > 1 ? 32u : 0u;
+            if (tid >= t_first) {
+                for (uint32_t i0 = tid - t_first; i0 < nm; i0 += nthreads - t_first) {
+                    uint32_t *row = tab + (size_t)(st + i0) * stride;
+                    row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
+                    row[n_keys] += inc;
+                }
             }
             n_order++;
         }
-        PF_SUB(7);  // insert done
-        if (warp == 0) {
-            last_best = best;
-            if (best >= 0) { rebuild = false; grow = true; if (lane == 0) s_failed = 0; }
-            else {
-                rebuild = true; grow = false;
-                if (lane == 0) {
-                    s_failed++;
-                    if (s_failed > 10) s_done = 1;
-                    s_i_last += d == 0 ? n_cand : -n_cand;
-                }
-            }
-        }
+        grow = best >= 0;
+        cur ^= 1;
         __syncthreads();
-        PF_MARK(pf_rest);
-#ifdef POMFRET_JOIN_PROF
-        pf_iter++;
-#endif
-        if (s_done) break;
     }
-#ifdef POMFRET_JOIN_PROF
-    if (tid == 0) printf("JOINPROF w %u d %u n %u sites %u iters %d tagged %u total %lld setup %lld w0 %lld score %lld rest %lld\n", w, d, n,
-                         n_sites, pf_iter, n_order, clock64() - pf_t0, pf_setup, pf_w0, pf_score, pf_rest);
-    if (tid == 0) printf("JOINSUB w %u d %u grow %lld pend+shift %lld refill %lld keyload %lld meta %lld lookups %lld values %lld chain %lld tail %lld best %lld insert %lld\n", w, d,
-                         pf_sub[0], pf_sub[1], pf_sub[2], pf_sub[3], pf_sub[4], pf_sub[8], pf_sub[9], pf_sub[10], pf_sub[5], pf_sub[6], pf_sub[7]);
-    if (tid == nthreads - 32) printf("JOINHELP w %u d %u fill %lld\n", w, d, pf_sub[11]);
-#endif
     // ---- 2x2 table over the far-side strict reads, :3888-3893 and :3940-3951 ----
     {
         const uint32_t *sid = (d == 0 ? P.ids_right_strict : P.ids_left_strict) + first;

@@ -304,6 +304,13 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
     // walk is idempotent) and scores one candidate; (2) every warp finds the best candidate on its own, then
     // warp 0 maintains the loop state and writes the next candidate list into the other buffer while the
     // remaining warps insert the tagged read's methmers.
+#ifdef POMFRET_JOIN_PROF
+    long long pf_t0 = clock64(), pf[6] = {0, 0, 0, 0, 0, 0}, pf_t = pf_t0;
+    int pf_iter = 0;
+#define PF_MARK(i) do { long long now_ = clock64(); pf[i] += now_ - pf_t; pf_t = now_; } while (0)
+#else
+#define PF_MARK(i) do {} while (0)
+#endif
     uint32_t n_order = 0;
     int cur = 0;
     bool grow = true;  // update_available_methmer_range after seeding / after every insertion (:3770, :3806)
@@ -322,6 +329,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
             grow_range(tab, stride, n_keys, n_sites, P.cov_run, rmin, rmax);
             if (tid == 0) { s_min = rmin; s_max = rmax; }  // others may still read the old pair: growing again is harmless
         }
+        PF_MARK(0);  // grow
         // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
         for (int c = (int)warp; c < ncand; c += (int)nwarps) {
             const uint32_t id = s_cand[cur][c];
@@ -404,6 +412,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                 s_tag[c] = tag;
             }
         }
+        PF_MARK(1);  // own scoring
         if (warp == nwarps - 1 && s_fill >= 0) {  // look-ahead entry: keys global -> shared, off the critical path
             const int c = s_fill;
             const uint32_t id = s_cand[cur][c];
@@ -414,6 +423,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
             }
         }
         __syncthreads();
+        PF_MARK(2);  // wait for the slowest scorer / the key fill
         // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
         //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
         int best = -1;
@@ -432,6 +442,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         }
         const uint32_t best_id = best >= 0 ? s_cand[cur][best] : 0u;
         const int hap = best >= 0 ? s_tag[best] : -1;
+        PF_MARK(3);  // best
         if (warp == 0) {
             // ---- loop state and the next candidate list ----
             if (best >= 0) {
@@ -471,8 +482,18 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         }
         grow = best >= 0;
         cur ^= 1;
+        PF_MARK(4);  // list maintenance (warp 0) / insertion (others)
         __syncthreads();
+        PF_MARK(5);  // wait
+#ifdef POMFRET_JOIN_PROF
+        pf_iter++;
+#endif
     }
+#ifdef POMFRET_JOIN_PROF
+    if (lane == 0 && (warp == 0 || warp == 1 || warp == nwarps - 1))
+        printf("JOINPROF w %u d %u warp %u n %u sites %u iters %d total %lld grow %lld score %lld wait2 %lld best %lld phaseD %lld wait3 %lld\n", w, d, warp, n,
+               n_sites, pf_iter, clock64() - pf_t0, pf[0], pf[1], pf[2], pf[3], pf[4], pf[5]);
+#endif
     // ---- 2x2 table over the far-side strict reads, :3888-3893 and :3940-3951 ----
     {
         const uint32_t *sid = (d == 0 ? P.ids_right_strict : P.ids_left_strict) + first;

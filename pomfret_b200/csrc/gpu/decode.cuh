@@ -33,8 +33,7 @@ constexpr int DEC_MAXSEG = 16;
 constexpr int DEC_MI_CAP = 256;       // M/I ops staged per chunk
 constexpr int DEC_MM_CHUNK = 512;     // MM bytes staged per step
 constexpr int DEC_T = 2;              // SEQ tiles (512 B = 1024 bases each) per scan step
-constexpr int DEC_BM_WORDS = 128;     // target bitmap window: 4096 canonical-base ranks (>= DEC_T * 1024)
-constexpr uint32_t DEC_Q = 64;        // listed bases queued between two dense passes (power of two, >= 2 * 32)
+constexpr int DEC_FC = 768;           // chunks (32 bases each) per SEQ section: 24 tiles, 24576 bases
 constexpr int N_MODS_LIMIT = 10;      // reference N_MODS, blockjoin.c:34
 
 struct DecodeParams {
@@ -66,11 +65,13 @@ struct SegInfo {
 
 struct DecodeWarpSmem {
     __align__(16) uint8_t mmbuf[DEC_MM_CHUNK + 16];
-    uint32_t bm[DEC_BM_WORDS + 2];    // bit (r - window base) set iff canonical base number r is listed
-    uint32_t bm_k[DEC_BM_WORDS + 1];  // index (in list order) of the first listed base at or after bit 0 of the word
-    uint32_t q[DEC_Q];                // ring of queued listed bases: (16-byte SEQ chunk << 5) | index among the chunk's matches
-    uint32_t mi_end[DEC_MI_CAP];
-    int32_t mi_off[DEC_MI_CAP];
+    union {
+        uint32_t first[DEC_FC + 1];   // SEQ scan: rank of the first canonical base of every 32-base chunk of the section
+        struct {                      // CIGAR walk (afterwards): staged M/I ops
+            uint32_t mi_end[DEC_MI_CAP];
+            int32_t mi_off[DEC_MI_CAP];
+        };
+    };
     SegInfo seg[DEC_MAXSEG];
 };
 
@@ -340,47 +341,6 @@ __device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Dense pass over `nq` (<= 32) queued listed bases, one lane each: position in SEQ, CpG context
-// (blockjoin.c:846-858), ML byte -> category (blockjoin.c:876-878), coalesced stores in list order.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dec_drain(DecodeWarpSmem &sm, const uint8_t *seq, const uint8_t *ml, uint32_t len, bool rev,
-                                          bool has_ml, uint32_t pat, uint32_t ml_base, uint32_t stride, uint32_t m_idx, uint32_t cap,
-                                          uint32_t lo, uint32_t hi, uint32_t *mpos, uint8_t *mcat, uint32_t k0, uint32_t nq,
-                                          bool &implicit, bool &drop_first, bool &drop_last) {
-    const unsigned lane = lane_id();
-    if (lane < nq) {
-        const uint32_t k = k0 + lane;
-        const uint32_t e = sm.q[k & (DEC_Q - 1)];
-        const uint32_t chunk = e >> 5;
-        uint32_t n = e & 31u;
-        const uint4 v = *reinterpret_cast<const uint4 *>(seq + (size_t)chunk * 16);
-        const uint32_t f0 = nib_eq_flags(v.x, pat), f1 = nib_eq_flags(v.y, pat), f2 = nib_eq_flags(v.z, pat), f3 = nib_eq_flags(v.w, pat);
-        const uint32_t c0 = (uint32_t)__popc(f0), c1 = (uint32_t)__popc(f1), c2 = (uint32_t)__popc(f2);
-        uint32_t wj = 0, f = f0;
-        if (n >= c0) {
-            n -= c0; wj = 1; f = f1;
-            if (n >= c1) {
-                n -= c1; wj = 2; f = f2;
-                if (n >= c2) { n -= c2; wj = 3; f = f3; }
-            }
-        }
-        const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
-        // C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
-        if (p > 0 && p < len - 1) {
-            const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
-            if (ok) {
-                const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
-                const uint32_t slot = rev ? cap - 1u - k : k;
-                mpos[slot] = p;
-                mcat[slot] = (uint8_t)(q < lo ? 1 : (q >= hi ? 0 : 2));
-            } else implicit = true;
-        } else if (k == 0) drop_first = true;
-        else drop_last = true;
-    }
-    __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------
 // The warp-parallel fast path.  Returns status bits; n_calls_out receives the number of calls.
 // ---------------------------------------------------------------------------------------------
 __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeWarpSmem &sm, uint32_t *n_calls_out,
@@ -443,11 +403,13 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
     }
 
     // ---- SEQ scan: select the listed canonical bases of the relevant segment ----
-    // Lane-centric: every lane flags the canonical bases of its 32-base chunk, a warp scan gives the rank of
-    // its first one, and the lane pulls "which of my bases are listed" out of a shared-memory bitmap indexed
-    // by rank (built from the cumulative delta sums, refreshed every 4096 ranks).  Reverse-strand records
-    // are scanned from the right end of SEQ so ranks count from the read's own 5' end (htslib walks the
-    // delta list backwards instead).
+    // Pass 1 streams SEQ (two 512-byte tiles per step, next step prefetched): every lane counts the canonical
+    // bases of its 32-base chunk and a warp scan gives the rank of the chunk's first one, kept in shared
+    // memory.  Pass 2 is dense over the listed bases: one lane per base binary-searches the chunk that holds
+    // its rank, selects the base inside the chunk, checks the CpG context and turns the ML byte into a
+    // category; ML reads and the stores are coalesced in list order.  Reverse-strand records are scanned
+    // from the right end of SEQ so ranks count from the read's own 5' end (htslib walks the delta list
+    // backwards instead).
     uint32_t n_mods = 0, mbase = 0;
     bool has_implicit = false;
     const bool do_select = !mm_error && rel >= 0 && sm.seg[rel].n_delta > 0;
@@ -469,126 +431,110 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
         const uint32_t stride = do_select ? sm.seg[rel].n_codes : 0;
         const uint32_t m_idx = do_select ? (uint32_t)sm.seg[rel].m_idx : 0;
         const int n_tiles = (int)((n_bytes + 511) / 512);
-        const int n_steps = (n_tiles + DEC_T - 1) / DEC_T;
         uint32_t run = 0;        // canonical bases seen so far, in scan order
         uint32_t tcur = 0;       // listed bases with rank < run (list order == scan order on both strands)
-        uint32_t wb = 0, wend = 0;  // rank window covered by the bitmap
-        uint32_t drained = 0;    // listed bases already resolved by dec_drain (drained <= tcur)
         bool drop_first = false, drop_last = false, implicit = false;
-        if (lane == 0) sm.bm[DEC_BM_WORDS] = 0;
-        uint4 cur[DEC_T], nxt[DEC_T];
-#pragma unroll
-        for (int t = 0; t < DEC_T; t++) {
-            const int tile = rev ? n_tiles - 1 - t : t;
-            const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
-            cur[t] = make_uint4(0, 0, 0, 0);
-            if (tile >= 0 && tile < n_tiles && byte_off < n_bytes) cur[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
-        }
-        for (int step = 0; step < n_steps; step++) {
+        // SEQ is walked in sections of up to DEC_FC chunks (16 bytes = 32 bases each), in scan order
+        for (int tile0 = 0; tile0 < n_tiles; tile0 += DEC_FC / 32) {
             if (tcur >= n_targets && run >= need_c) break;  // everything listed was found (and counted, reverse)
-#pragma unroll
-            for (int t = 0; t < DEC_T; t++) {  // prefetch the next step
-                const int idx = (step + 1) * DEC_T + t;
-                const int tile = rev ? n_tiles - 1 - idx : idx;
-                const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
-                nxt[t] = make_uint4(0, 0, 0, 0);
-                if (tile >= 0 && tile < n_tiles && byte_off < n_bytes) nxt[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
-            }
-            uint32_t m[DEC_T][4], C[DEC_T];
-            uint32_t packed = 0;
+            const int sec_tiles = n_tiles - tile0 < DEC_FC / 32 ? n_tiles - tile0 : DEC_FC / 32;
+            const int n_steps = (sec_tiles + DEC_T - 1) / DEC_T;
+            const uint32_t run0 = run;
+            // ---- pass 1: stream the section, rank of every chunk's first match -> sm.first[] ----
+            uint4 cur[DEC_T], nxt[DEC_T];
 #pragma unroll
             for (int t = 0; t < DEC_T; t++) {
-                m[t][0] = nib_eq_flags(cur[t].x, pat); m[t][1] = nib_eq_flags(cur[t].y, pat);
-                m[t][2] = nib_eq_flags(cur[t].z, pat); m[t][3] = nib_eq_flags(cur[t].w, pat);
-                C[t] = (uint32_t)(__popc(m[t][0]) + __popc(m[t][1]) + __popc(m[t][2]) + __popc(m[t][3]));
-                packed |= C[t] << (16 * t);  // a tile holds at most 1024 matches: 16 bits per tile
+                const int ts = tile0 + t;  // tile in scan order
+                const int tile = rev ? n_tiles - 1 - ts : ts;
+                const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
+                cur[t] = make_uint4(0, 0, 0, 0);
+                if (t < sec_tiles && byte_off < n_bytes) cur[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
             }
-            const uint32_t incl = warp_inclusive_sum(packed);
-            const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
-            uint32_t step_total = 0;
+            for (int step = 0; step < n_steps; step++) {
 #pragma unroll
-            for (int t = 0; t < DEC_T; t++) step_total += (tot >> (16 * t)) & 0xffffu;
-            if (tcur < n_targets && step_total > 0) {
-                if (run + step_total > wend) {
-                    // ---- refresh the bitmap: ranks [run, run + 4096) ----
-                    wb = run;
-                    wend = wb + DEC_BM_WORDS * 32u;
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < DEC_BM_WORDS / 32; i++) sm.bm[lane + 32 * i] = 0;
-                    __syncwarp();
-                    for (uint32_t t0 = tcur;; t0 += 32) {
-                        const uint32_t k = t0 + lane;
-                        const uint32_t r = k < n_targets ? rank[k] : 0xffffffffu;
-                        const bool in = r < wend;  // ranks ascend strictly and every rank below `run` is consumed
-                        if (in) atomicOr(&sm.bm[(r - wb) >> 5], 1u << ((r - wb) & 31u));
-                        if (__popc(__ballot_sync(FULL_MASK, in)) < 32) break;
-                    }
-                    __syncwarp();
-                    constexpr int WPL = DEC_BM_WORDS / 32;
-                    uint32_t c[WPL], s_l = 0;
-#pragma unroll
-                    for (int i = 0; i < WPL; i++) { c[i] = (uint32_t)__popc(sm.bm[lane * WPL + i]); s_l += c[i]; }
-                    const uint32_t in_l = warp_inclusive_sum(s_l);
-                    uint32_t kk = tcur + in_l - s_l;
-#pragma unroll
-                    for (int i = 0; i < WPL; i++) { sm.bm_k[lane * WPL + i] = kk; kk += c[i]; }
-                    if (lane == 31) sm.bm_k[DEC_BM_WORDS] = kk;
-                    __syncwarp();
+                for (int t = 0; t < DEC_T; t++) {  // prefetch the next step
+                    const int tl = (step + 1) * DEC_T + t;  // tile inside the section
+                    const int tile = rev ? n_tiles - 1 - (tile0 + tl) : tile0 + tl;
+                    const uint32_t byte_off = (uint32_t)tile * 512u + lane * 16u;
+                    nxt[t] = make_uint4(0, 0, 0, 0);
+                    if (tl < sec_tiles && byte_off < n_bytes) nxt[t] = *reinterpret_cast<const uint4 *>(seq + byte_off);
                 }
-                // ---- every lane finds which of its matches are listed and queues (chunk, index in chunk) under the
-                //      base's list index k; full groups of 32 queued bases are then resolved densely (dec_drain) ----
-                const uint32_t e = run + step_total - wb;
-                const uint32_t k_end = sm.bm_k[e >> 5] + (uint32_t)__popc(sm.bm[e >> 5] & ((1u << (e & 31u)) - 1u));
-                uint32_t tw[DEC_T], kk[DEC_T];
-                uint32_t before = 0;  // matches of earlier tiles of this step
+                uint32_t C[DEC_T], packed = 0;
+#pragma unroll
+                for (int t = 0; t < DEC_T; t++) {
+                    C[t] = (uint32_t)(__popc(nib_eq_flags(cur[t].x, pat)) + __popc(nib_eq_flags(cur[t].y, pat)) +
+                                      __popc(nib_eq_flags(cur[t].z, pat)) + __popc(nib_eq_flags(cur[t].w, pat)));
+                    packed |= C[t] << (16 * t);  // a tile holds at most 1024 matches: 16 bits per tile
+                }
+                const uint32_t incl = warp_inclusive_sum(packed);
+                const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+                uint32_t before = 0;
 #pragma unroll
                 for (int t = 0; t < DEC_T; t++) {
                     const uint32_t tile_total = (tot >> (16 * t)) & 0xffffu;
                     const uint32_t incl_t = (incl >> (16 * t)) & 0xffffu;
-                    const uint32_t Ct = C[t];
-                    // rank of this lane's first match in scan order
-                    const uint32_t first = run + before + (rev ? tile_total - incl_t : incl_t - Ct);
+                    // rank of this lane's first match; the chunk's index in scan order
+                    const uint32_t fr = run + before + (rev ? tile_total - incl_t : incl_t - C[t]);
+                    const uint32_t ci = (uint32_t)(step * DEC_T + t) * 32u + (rev ? 31u - lane : lane);
+                    if (step * DEC_T + t < sec_tiles) sm.first[ci] = fr;
                     before += tile_total;
-                    const uint32_t idx = first - wb, word = idx >> 5, sh = idx & 31u;
-                    const uint32_t lo_w = sm.bm[word], hi_w = sm.bm[word + 1];
-                    tw[t] = __funnelshift_r(lo_w, hi_w, sh) & (Ct >= 32u ? 0xffffffffu : (1u << Ct) - 1u);  // bit j <-> j-th match in scan order
-                    kk[t] = sm.bm_k[word] + (uint32_t)__popc(lo_w & ((1u << sh) - 1u));
                 }
-                for (;;) {
-                    const uint32_t lim = k_end - drained <= DEC_Q ? k_end : drained + DEC_Q;  // queue capacity
+                run += before;
 #pragma unroll
-                    for (int t = 0; t < DEC_T; t++) {
-                        const int tile = rev ? n_tiles - 1 - (step * DEC_T + t) : step * DEC_T + t;
-                        const uint32_t chunk = (uint32_t)tile * 32u + lane;
-                        while (tw[t] && kk[t] < lim) {
-                            const uint32_t j = (uint32_t)__ffs((int)tw[t]) - 1u;
-                            tw[t] &= tw[t] - 1u;
-                            sm.q[kk[t] & (DEC_Q - 1)] = (chunk << 5) | (rev ? C[t] - 1u - j : j);  // index in base order
-                            kk[t]++;
+                for (int t = 0; t < DEC_T; t++) cur[t] = nxt[t];
+            }
+            const uint32_t n_ch = (uint32_t)sec_tiles * 32u;
+            if (lane == 0) sm.first[n_ch] = run;
+            __syncwarp();
+            // ---- pass 2: the listed bases whose rank falls into the section, 32 at a time ----
+            while (tcur < n_targets) {
+                const uint32_t k = tcur + lane;
+                const uint32_t r = k < n_targets ? rank[k] : 0xffffffffu;
+                const bool mine = r < run;  // ranks ascend strictly and every rank below run0 is consumed
+                const unsigned act = __ballot_sync(FULL_MASK, mine);
+                if (act == 0) break;
+                if (mine) {
+                    // last chunk whose first rank is <= r (empty chunks share the rank of their successor)
+                    uint32_t lo = 0, hi = n_ch;  // first[lo] <= r < first[hi]
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sm.first[mid] <= r) lo = mid; else hi = mid;
+                    }
+                    const uint32_t f0 = sm.first[lo], cnt = sm.first[lo + 1] - f0;
+                    const uint32_t ts = (uint32_t)tile0 + (lo >> 5);
+                    const uint32_t tile = rev ? (uint32_t)n_tiles - 1u - ts : ts;
+                    const uint32_t chunk = tile * 32u + (rev ? 31u - (lo & 31u) : lo & 31u);
+                    uint32_t n = rev ? cnt - 1u - (r - f0) : r - f0;  // index in base order inside the chunk
+                    const uint4 v = *reinterpret_cast<const uint4 *>(seq + (size_t)chunk * 16);
+                    const uint32_t g0 = nib_eq_flags(v.x, pat), g1 = nib_eq_flags(v.y, pat), g2 = nib_eq_flags(v.z, pat),
+                                   g3 = nib_eq_flags(v.w, pat);
+                    const uint32_t c0 = (uint32_t)__popc(g0), c1 = (uint32_t)__popc(g1), c2 = (uint32_t)__popc(g2);
+                    uint32_t wj = 0, f = g0;
+                    if (n >= c0) {
+                        n -= c0; wj = 1; f = g1;
+                        if (n >= c1) {
+                            n -= c1; wj = 2; f = g2;
+                            if (n >= c2) { n -= c2; wj = 3; f = g3; }
                         }
                     }
-                    __syncwarp();
-                    while (lim - drained >= 32u) {
-                        dec_drain(sm, seq, ml, len, rev, has_ml, pat, ml_base, stride, m_idx, cap, P.lo, P.hi, mpos, mcat, drained, 32u,
-                                  implicit, drop_first, drop_last);
-                        drained += 32u;
-                    }
-                    if (lim == k_end) break;
+                    const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
+                    // blockjoin.c:846-858: C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
+                    if (p > 0 && p < len - 1) {
+                        const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
+                        if (ok) {
+                            const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
+                            const uint32_t slot = rev ? cap - 1u - k : k;
+                            mpos[slot] = p;
+                            mcat[slot] = (uint8_t)(q < P.lo ? 1 : (q >= P.hi ? 0 : 2));  // blockjoin.c:876-878
+                        } else implicit = true;
+                    } else if (k == 0) drop_first = true;
+                    else drop_last = true;
                 }
-                tcur = k_end;  // listed bases consumed so far = those with rank < run + step_total
-
+                tcur += (uint32_t)__popc(act);
+                if (act != FULL_MASK) break;
             }
-            run += step_total;
-#pragma unroll
-            for (int t = 0; t < DEC_T; t++) cur[t] = nxt[t];
-        }
-        __syncwarp();
-        while (drained < tcur) {
-            const uint32_t nq = tcur - drained < 32u ? tcur - drained : 32u;
-            dec_drain(sm, seq, ml, len, rev, has_ml, pat, ml_base, stride, m_idx, cap, P.lo, P.hi, mpos, mcat, drained, nq, implicit,
-                      drop_first, drop_last);
-            drained += nq;
+            __syncwarp();
+            (void)run0;
         }
         if (rev && run < need_c) mm_error = true;
         has_implicit = __any_sync(FULL_MASK, implicit);

@@ -15,6 +15,10 @@
 #include <thread>
 #include <vector>
 #include <algorithm>
+#if defined(__x86_64__) && !defined(POMFRET_CUDA_EMU)
+#include <emmintrin.h>
+#define POMFRET_NT_COPY 1
+#endif
 #include "gpu_rt.h"
 #include "types.h"
 #include "decode.cuh"
@@ -407,11 +411,32 @@ static int plan_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, size_
     return POMFRET_GPU_OK;
 }
 
+// Copy into the pinned arena with non-temporal stores: the destination is written once and next read by
+// the DMA engine, so it should neither be fetched for ownership nor displace the source from the caches
+// (one third less host memory traffic on the staging path, which is what bounds it).  dst is 16-byte aligned.
+static inline void copy_stream(uint8_t *dst, const void *src, size_t n) {
+#ifdef POMFRET_NT_COPY
+    if (n >= 256) {
+        const uint8_t *s = (const uint8_t *)src;
+        size_t i = 0;
+        for (; i + 64 <= n; i += 64) {
+            __m128i a = _mm_loadu_si128((const __m128i *)(s + i)), b = _mm_loadu_si128((const __m128i *)(s + i + 16));
+            __m128i c = _mm_loadu_si128((const __m128i *)(s + i + 32)), d = _mm_loadu_si128((const __m128i *)(s + i + 48));
+            _mm_stream_si128((__m128i *)(dst + i), a); _mm_stream_si128((__m128i *)(dst + i + 16), b);
+            _mm_stream_si128((__m128i *)(dst + i + 32), c); _mm_stream_si128((__m128i *)(dst + i + 48), d);
+        }
+        if (i < n) memcpy(dst + i, s + i, n - i);
+        return;
+    }
+#endif
+    if (n) memcpy(dst, src, n);
+}
+
 // Phase 2 (any thread): copy the payload of one planned record into the pinned blob.
 static void copy_read(uint8_t *blob, const ReadRec &R, const pomfret_gpu_read_desc *r, uint32_t *end_out) {
     auto put = [&](uint32_t off16, const void *src, size_t n) {
         uint8_t *dst = blob + (size_t)off16 * 16;
-        if (n) memcpy(dst, src, n);
+        copy_stream(dst, src, n);
         memset(dst + n, 0, align16(n) - n);
     };
     put(R.cigar_off, r->cigar, (size_t)r->n_cigar * 4);
@@ -429,6 +454,9 @@ static void copy_read(uint8_t *blob, const ReadRec &R, const pomfret_gpu_read_de
     }
     if (rlen == 0) rlen = 1;
     *end_out = (uint32_t)(r->pos + rlen);
+#ifdef POMFRET_NT_COPY
+    _mm_sfence();  // the streamed payload is globally visible before the copy engine is pointed at it
+#endif
 }
 
 // Hand the finished part of the blob to the copy engine (only while the device buffer of this batch is

@@ -254,13 +254,28 @@ def main():
     chunks = [wins[cuts[i]:cuts[i + 1]] for i in range(nb)]
     batches = [b] + [gpu.batch_begin(ctx, i, local_rank) for i in range(1, nb)]
     e2e_results = [None] * nb
+    # the loader's descriptors of a chunk as one array (72-byte records pointing at the host copies of the BAM
+    # records): one add_reads() call per chunk
+    from pomfret_b200 import _ffi
+    chunk_descs = []
+    for ws in chunks:
+        tot = sum(n for _, n, _, _, _ in ws)
+        arr = (_ffi.ReadDesc * max(tot, 1))()
+        o = 0
+        for w, n, chrom, s, e in ws:
+            C.memmove(C.byref(arr, o * C.sizeof(_ffi.ReadDesc)), host.window_descs(w), n * C.sizeof(_ffi.ReadDesc))
+            o += n
+        chunk_descs.append((arr, tot))
 
     def produce(q):
         for i, (bt, ws) in enumerate(zip(batches, chunks)):
             bt.reset()
+            arr, tot = chunk_descs[i]
+            bt.add_reads(arr, tot)
+            first = 0
             for w, n, chrom, s, e in ws:
-                first = bt.add_reads(host.window_descs(w), n)
                 bt.add_window(s, e, first, n)
+                first += n
             bt.submit()
             q.put(i)
 

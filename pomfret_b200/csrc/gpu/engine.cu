@@ -168,7 +168,7 @@ class StagePool {
         for (;;) {
             // spin, then sleep
             bool got = false;
-            for (int spin = 0; spin < 20000 && !got; spin++) got = gen_.load(std::memory_order_acquire) != seen;
+            for (int spin = 0; spin < 400000 && !got; spin++) got = gen_.load(std::memory_order_acquire) != seen;  // ~0.2 ms
             if (!got) {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [&] { return gen_.load() != seen; });
@@ -504,10 +504,18 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
         if (const char *e = getenv("POMFRET_GPU_STAGE_THREADS")) per = atoi(e);
         b->pool = new StagePool(std::max(0, std::min(per, 12) - 1));
     }
-    if (b->pool && n >= 16) b->pool->run(n, [&](size_t i) { copy_read(blob, recs[i], r + i, ends + i); });
-    else for (uint32_t i = 0; i < n; i++) copy_read(blob, recs[i], r + i, ends + i);
-    b->h_blob.len = len;
-    return stream_blob(b, false);
+    // Groups of ~4 MB: the helpers copy one group while the DMA engine already moves the previous ones.
+    for (uint32_t g0 = 0; g0 < n;) {
+        uint32_t g1 = g0;
+        const size_t from = (size_t)recs[g0].cigar_off * 16;
+        while (g1 < n && (g1 - g0 < 16 || (size_t)recs[g1].cigar_off * 16 - from < ((size_t)4 << 20))) g1++;
+        if (b->pool && g1 - g0 >= 16) b->pool->run(g1 - g0, [&](size_t i) { copy_read(blob, recs[g0 + i], r + g0 + i, ends + g0 + i); });
+        else for (uint32_t i = g0; i < g1; i++) copy_read(blob, recs[i], r + i, ends + i);
+        b->h_blob.len = g1 < n ? (size_t)recs[g1].cigar_off * 16 : len;
+        if (int rc = stream_blob(b, false)) return rc;
+        g0 = g1;
+    }
+    return POMFRET_GPU_OK;
 }
 
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {

@@ -98,13 +98,15 @@ __device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride,
 // kTabSmem: every window of the launch keeps its count tables in shared memory (the compiler then emits
 // shared-memory loads/stores for them); otherwise windows that do not fit use the global pool.
 template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
-    __shared__ int s_i_last, s_failed, s_done, s_fill;
-    __shared__ int s_ncand[2];
-    __shared__ uint32_t s_min, s_max;
-    __shared__ uint32_t s_cand[2][JOIN_MAX_CAND + 1];   // candidate lists of two consecutive iterations (ping-pong)
-    __shared__ uint8_t s_slot[2][JOIN_MAX_CAND + 1];
-    __shared__ float s_score[JOIN_MAX_CAND];
-    __shared__ int s_tag[JOIN_MAX_CAND];
+    __shared__ int s_i_last, s_failed, s_done, s_fill, s_cursor, s_next_id;
+    __shared__ int s_newest[2], s_nocc[2];
+    __shared__ uint32_t s_min, s_max, s_seq;
+    // candidate slots, two copies: an iteration reads one and writes the other (no barrier between the warps that
+    // still look for the best candidate and the one that already recycles its slot)
+    __shared__ uint32_t s_sid[2][JOIN_MAX_CAND + 1];    // read id
+    __shared__ uint32_t s_sseq[2][JOIN_MAX_CAND + 1];   // position in scan order (monotone counter), SLOT_FREE if empty
+    __shared__ float s_score[JOIN_MAX_CAND + 1];
+    __shared__ int s_tag[JOIN_MAX_CAND + 1];
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
 
@@ -230,80 +232,68 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         const uint8_t t = tags[id];
         return t != 0 && t != 1;
     };
-    // Candidate-list maintenance (warp 0).  The list is "the first n_cand untagged reads in scan order from
-    // i_last" (:4039-4045) plus one look-ahead entry whose methmer keys are fetched from global memory one
-    // iteration before they are first needed.  `src` < 0 rebuilds it from i_last; otherwise entry `drop` of
-    // list `src` is removed and the next untagged read behind the scan cursor is appended.
-    int cursor = 0;  // warp 0, uniform: scan position right behind the last listed read
-    auto build_list = [&](int dst, int src, int drop) {
-        int nc = 0, free_slot = -1;
-        const bool rebuild = src < 0;
-        if (rebuild) cursor = s_i_last;
-        else {
-            const int nc_old = s_ncand[src];  // (look-ahead included, see below)
-            free_slot = s_slot[src][drop];
-            for (int c0 = 0; c0 < nc_old; c0 += 32) {
-                const int c = c0 + (int)lane;
-                if (c < nc_old && c != drop) {
-                    const int to = c < drop ? c : c - 1;
-                    s_cand[dst][to] = s_cand[src][c];
-                    s_slot[dst][to] = s_slot[src][c];
-                }
-            }
-            nc = nc_old - 1;
+    // Candidates ("the first n_cand untagged reads in scan order from i_last", :4039-4045) live in n_cand + 1
+    // fixed slots, each with its read id, its position in scan order (a running counter: ties between equal
+    // scores go to the later candidate, :3729-3760) and a cache of its methmer keys.  The extra slot holds the
+    // look-ahead entry: the next untagged read behind the scan cursor, found and fetched from global memory by
+    // the last warp while the others score, one iteration before it is first scored.  A tagged read simply
+    // frees its slot for the next look-ahead entry; only a failure (i_last moves, :4064-4068) rebuilds the slots.
+    constexpr uint32_t SLOT_FREE = 0xffffffffu;
+    const int n_slots = n_cand + 1;
+    auto scan_id = [&](int i0) -> uint32_t { return d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]); };
+    auto fill_keys = [&](int buf, int slot) {  // one warp: keys of the slot's read, global -> shared (compact u8)
+        const uint32_t id = s_sid[buf][slot];
+        const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
+        if (nm <= JOIN_CHUNK) {  // longer reads are scored straight from the pool
+            uint8_t *dk = s_keys + (size_t)slot * JOIN_CHUNK;
+            for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
         }
-        const int n_old = nc;
-        while (nc < n_cand + 1) {
+    };
+    // next untagged read at or behind scan position `cursor` (one warp); returns its id or -1, moves the cursor behind it
+    auto next_untagged = [&](int &cursor) -> int {
+        for (;;) {
             const int i0 = d == 0 ? cursor + (int)lane : cursor - (int)lane;
             const bool in = d == 0 ? i0 < (int)n : i0 >= 0;
             uint32_t id = 0;
             bool unt = false;
-            if (in) {
-                id = d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]);
-                unt = is_untagged(id);
-            }
+            if (in) { id = scan_id(i0); unt = is_untagged(id); }
             const unsigned um = __ballot_sync(FULL_MASK, unt);
-            const int rank = __popc(um & ((1u << lane) - 1u));
-            const int room = n_cand + 1 - nc;
-            if (unt && rank < room) {
-                s_cand[dst][nc + rank] = id;
-                s_slot[dst][nc + rank] = (uint8_t)(rebuild ? nc + rank : free_slot);
+            if (um) {
+                const int fl = __ffs((int)um) - 1;
+                cursor += d == 0 ? fl + 1 : -(fl + 1);
+                return (int)__shfl_sync(FULL_MASK, id, fl);
             }
-            const int found = __popc(um);
-            if (found >= room) {
-                // the list is full: the cursor stops right behind the read that filled it
-                unsigned fm = um;
-                for (int r = 1; r < room; r++) fm &= fm - 1u;  // drop the room-1 lowest set bits
-                const int fill_lane = __ffs((int)fm) - 1;
-                cursor += d == 0 ? fill_lane + 1 : -(fill_lane + 1);
-                nc = n_cand + 1;
-                break;
-            }
-            nc += found;
             cursor += d == 0 ? 32 : -32;
-            if (__ballot_sync(FULL_MASK, in) != FULL_MASK) break;  // ran past the last read
+            if (__ballot_sync(FULL_MASK, in) != FULL_MASK) return -1;  // ran past the last read
         }
+    };
+    // (re)build all slots from i_last (warp 0): keys are fetched at once, the look-ahead entry included
+    auto rebuild_slots = [&](int buf) {
+        int cursor = s_i_last, nocc = 0;
+        uint32_t seq = 0;
+        for (int sl = lane; sl < n_slots; sl += 32) s_sseq[buf][sl] = SLOT_FREE;
         __syncwarp();
-        // keys of the new entries: a rebuilt list needs them before it is scored; the look-ahead entry of a
-        // running list is filled by the last warp while the others score (s_fill)
-        int fill = -1;
-        for (int c = n_old; c < nc; c++) {
-            if (!rebuild && c >= n_cand) { fill = c; continue; }
-            const uint32_t id = s_cand[dst][c];
-            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
-            if (nm > JOIN_CHUNK) continue;  // too long to cache: scored straight from the pool
-            uint8_t *dk = s_keys + (size_t)s_slot[dst][c] * JOIN_CHUNK;
-            for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
+        while (nocc < n_slots) {
+            const int id = next_untagged(cursor);
+            if (id < 0) break;
+            if (lane == 0) { s_sid[buf][nocc] = (uint32_t)id; s_sseq[buf][nocc] = seq; }
+            __syncwarp();
+            fill_keys(buf, nocc);
+            nocc++; seq++;
         }
-        if (lane == 0) { s_ncand[dst] = nc; s_fill = fill; }
+        if (lane == 0) {
+            s_nocc[buf] = nocc; s_seq = seq; s_cursor = cursor; s_fill = -1;
+            s_newest[buf] = nocc == n_slots ? n_slots - 1 : -1;
+            s_next_id = -2;  // unknown: the last warp looks for it while the others score
+        }
         __syncwarp();
     };
 
     // ---- extension loop, :4032-4071 ----
     // Two barriers per iteration.  Between them: (1) every warp grows the available range on its own (the
-    // walk is idempotent) and scores one candidate; (2) every warp finds the best candidate on its own, then
-    // warp 0 maintains the loop state and writes the next candidate list into the other buffer while the
-    // remaining warps insert the tagged read's methmers.
+    // walk is idempotent) and scores the candidate of its slot; the last warp also serves the look-ahead slot;
+    // (2) every warp finds the best candidate on its own, all threads insert its methmers, one thread updates
+    // the slot.
 #ifdef POMFRET_JOIN_PROF
     long long pf_t0 = clock64(), pf[6] = {0, 0, 0, 0, 0, 0}, pf_t = pf_t0;
     int pf_iter = 0;
@@ -317,26 +307,27 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
     if (warp == 0) {
         const int i_last = s_i_last;
         if ((d == 0 && i_last >= (int)n) || (d != 0 && i_last <= 0)) { if (lane == 0) s_done = 1; }
-        else build_list(0, -1, 0);
+        else rebuild_slots(0);
     }
     __syncthreads();
     for (;;) {
         if (s_done) break;
-        const int nc_all = s_ncand[cur];
-        const int ncand = nc_all < n_cand ? nc_all : n_cand;  // the look-ahead entry is not scored
+        const int nocc = s_nocc[cur], newest = s_newest[cur];
+        const bool full = nocc == n_slots;
         uint32_t rmin = s_min, rmax = s_max;
         if (grow) {
             grow_range(tab, stride, n_keys, n_sites, P.cov_run, rmin, rmax);
             if (tid == 0) { s_min = rmin; s_max = rmax; }  // others may still read the old pair: growing again is harmless
         }
         PF_MARK(0);  // grow
-        // ---- score the candidates, one warp each (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
-        for (int c = (int)warp; c < ncand; c += (int)nwarps) {
-            const uint32_t id = s_cand[cur][c];
+        // ---- score the candidates, one warp per slot (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
+        for (int c = (int)warp; c < n_slots; c += (int)nwarps) {
+            if (s_sseq[cur][c] == SLOT_FREE || (full && c == newest)) { if (lane == 0) s_tag[c] = -2; continue; }  // empty / look-ahead
+            const uint32_t id = s_sid[cur][c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
             const bool cached = nm <= JOIN_CHUNK;
-            const uint8_t *ck = s_keys + (size_t)s_slot[cur][c] * JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)c * JOIN_CHUNK;
             float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
             int l0 = 0, l1 = 0;
             // only methmers whose site lies in the available range [rmin, rmax) are looked up (:3499-3502)
@@ -413,76 +404,86 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
             }
         }
         PF_MARK(1);  // own scoring
-        if (warp == nwarps - 1 && s_fill >= 0) {  // look-ahead entry: keys global -> shared, off the critical path
-            const int c = s_fill;
-            const uint32_t id = s_cand[cur][c];
-            const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
-            if (nm <= JOIN_CHUNK) {
-                uint8_t *dk = s_keys + (size_t)s_slot[cur][c] * JOIN_CHUNK;
-                for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
+        if (warp == nwarps - 1) {
+            // look-ahead service, off the critical path: keys of the entry placed last iteration, then the read
+            // that will take the next freed slot
+            if (s_fill >= 0) fill_keys(cur, s_fill);
+            if (s_next_id == -2 || s_fill >= 0) {
+                int cursor = s_cursor;
+                const int nx = full ? next_untagged(cursor) : -1;  // a list that is not full has run out of reads
+                if (lane == 0) { s_next_id = nx; s_cursor = cursor; }
             }
         }
         __syncthreads();
-        PF_MARK(2);  // wait for the slowest scorer / the key fill
+        PF_MARK(2);  // wait for the slowest scorer / the look-ahead service
         // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
         //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
         int best = -1;
         {
-            uint32_t bs = 0;
+            uint32_t bs = 0, bq = 0;
             int bc = -1;
-            for (int c = (int)lane; c < ncand; c += 32) {
+            for (int c = (int)lane; c < n_slots; c += 32) {
                 const int t = s_tag[c];
                 if (t == 0 || t == 1) {
-                    const uint32_t sb = __float_as_uint(s_score[c]);
-                    if (bc < 0 || sb >= bs) { bs = sb; bc = c; }
+                    const uint32_t sb = __float_as_uint(s_score[c]), sq = s_sseq[cur][c];
+                    if (bc < 0 || sb > bs || (sb == bs && sq > bq)) { bs = sb; bq = sq; bc = c; }
                 }
             }
             const uint32_t top = __reduce_max_sync(FULL_MASK, bc >= 0 ? bs : 0u);
-            best = (int)__reduce_max_sync(FULL_MASK, (uint32_t)((bc >= 0 && bs == top) ? bc + 1 : 0)) - 1;
+            const bool cand = bc >= 0 && bs == top;
+            const uint32_t topq = __reduce_max_sync(FULL_MASK, cand ? bq + 1u : 0u);
+            const unsigned who = __ballot_sync(FULL_MASK, cand && bq + 1u == topq);
+            if (who) best = __shfl_sync(FULL_MASK, bc, __ffs((int)who) - 1);
         }
-        const uint32_t best_id = best >= 0 ? s_cand[cur][best] : 0u;
+        const uint32_t best_id = best >= 0 ? s_sid[cur][best] : 0u;
         const int hap = best >= 0 ? s_tag[best] : -1;
         PF_MARK(3);  // best
-        if (warp == 0) {
-            // ---- loop state and the next candidate list ----
-            if (best >= 0) {
-                if (lane == 0) {
+        if (best >= 0) {
+            // ---- insert_mmrs_to_counts (:3453-3486), all threads ----
+            const uint32_t nm = meta_in_smem ? s_mn[best_id] : g_n[best_id], st = meta_in_smem ? s_mst[best_id] : g_start[best_id];
+            const uint32_t off = meta_in_smem ? s_moff[best_id] : g_off[best_id];
+            const bool cached = nm <= JOIN_CHUNK;
+            const uint8_t *ck = s_keys + (size_t)best * JOIN_CHUNK;
+            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
+            for (uint32_t i0 = tid; i0 < nm; i0 += nthreads) {
+                uint32_t *row = tab + (size_t)(st + i0) * stride;
+                row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
+                row[n_keys] += inc;
+            }
+            if (warp == nwarps - 1) {
+                // next iteration's slots: a copy, with the freed slot taking the look-ahead entry found during
+                // scoring (its keys follow next iteration)
+                const int nx = s_next_id;
+                const uint32_t seq_new = s_seq;
+                for (int c = (int)lane; c < n_slots; c += 32) {
+                    uint32_t sid = s_sid[cur][c], sq = s_sseq[cur][c];
+                    if (c == best) { if (nx >= 0) { sid = (uint32_t)nx; sq = seq_new; } else sq = SLOT_FREE; }
+                    s_sid[cur ^ 1][c] = sid;
+                    s_sseq[cur ^ 1][c] = sq;
+                }
+                __syncwarp();
+                if (lane == 31) {
                     tags[best_id] = (uint8_t)hap;
                     if (meta_in_smem) s_tagged[best_id >> 5] |= 1u << (best_id & 31u);
                     P.order[d][first + n_order] = best_id;
                     s_failed = 0;
-                }
-                __syncwarp();
-                build_list(cur ^ 1, cur, best);
-            } else {
-                int fl = s_failed + 1, il = s_i_last + (d == 0 ? n_cand : -n_cand);
-                const bool done = fl > 10 || (d == 0 && il >= (int)n) || (d != 0 && il <= 0);
-                __syncwarp();
-                if (lane == 0) { s_failed = fl; s_i_last = il; if (done) s_done = 1; }
-                __syncwarp();
-                if (!done) build_list(cur ^ 1, -1, 0);
-            }
-        }
-        if (best >= 0) {
-            // ---- insert_mmrs_to_counts (:3453-3486) by the other warps (all of them if there is only one) ----
-            const uint32_t nm = meta_in_smem ? s_mn[best_id] : g_n[best_id], st = meta_in_smem ? s_mst[best_id] : g_start[best_id];
-            const uint32_t off = meta_in_smem ? s_moff[best_id] : g_off[best_id];
-            const bool cached = nm <= JOIN_CHUNK;
-            const uint8_t *ck = s_keys + (size_t)s_slot[cur][best] * JOIN_CHUNK;
-            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
-            const uint32_t t_first = nwarps > 1 ? 32u : 0u;
-            if (tid >= t_first) {
-                for (uint32_t i0 = tid - t_first; i0 < nm; i0 += nthreads - t_first) {
-                    uint32_t *row = tab + (size_t)(st + i0) * stride;
-                    row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
-                    row[n_keys] += inc;
+                    if (nx >= 0) { s_seq = seq_new + 1; s_nocc[cur ^ 1] = nocc; s_newest[cur ^ 1] = best; s_fill = best; }
+                    else { s_nocc[cur ^ 1] = nocc - 1; s_newest[cur ^ 1] = -1; s_fill = -1; }
                 }
             }
             n_order++;
+        } else if (warp == 0) {
+            // ---- nothing could be tagged: move i_last (:4064-4068) and start over from there ----
+            const int fl = s_failed + 1, il = s_i_last + (d == 0 ? n_cand : -n_cand);
+            const bool done = fl > 10 || (d == 0 && il >= (int)n) || (d != 0 && il <= 0);
+            __syncwarp();
+            if (lane == 0) { s_failed = fl; s_i_last = il; if (done) s_done = 1; }
+            __syncwarp();
+            if (!done) rebuild_slots(cur ^ 1);
         }
         grow = best >= 0;
         cur ^= 1;
-        PF_MARK(4);  // list maintenance (warp 0) / insertion (others)
+        PF_MARK(4);  // insertion / rebuild
         __syncthreads();
         PF_MARK(5);  // wait
 #ifdef POMFRET_JOIN_PROF

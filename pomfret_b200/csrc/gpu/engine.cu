@@ -262,7 +262,7 @@ struct pomfret_gpu_batch {
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 // dynamic shared memory of join_kernel: one CTA per SM may take kJoinSmemMax, two CTAs per SM kJoinSmemHalf each
-static const size_t kJoinSmemMax = (size_t)224 * 1024, kJoinSmemHalf = (size_t)110 * 1024;
+static const size_t kJoinSmemMax = (size_t)216 * 1024, kJoinSmemHalf = (size_t)108 * 1024;
 
 extern "C" {
 

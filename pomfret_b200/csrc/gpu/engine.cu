@@ -815,8 +815,8 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     // cache; the count tables of a window go to shared memory if they fit.  With more CTAs than SMs the windows
     // are split into two launches on two streams: those whose tables fit beside a second CTA on the same SM
     // (or fit nowhere: they use the global pool) and those that need most of an SM for themselves.
-    // one warp per candidate plus one that fills the look-ahead key cache while the others score
-    const unsigned join_threads = 32u * (unsigned)std::min(JOIN_WARPS, std::max(4, J.n_cand + 1));
+    // one warp per candidate slot (n_cand + 1) plus one that serves the look-ahead slot while the others score
+    const unsigned join_threads = 32u * (unsigned)std::min(JOIN_WARPS, std::max(4, J.n_cand + 2));
     uint32_t max_reads = 0;
     for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
     J.meta_cap = max_reads <= 4096 ? max_reads : 0;

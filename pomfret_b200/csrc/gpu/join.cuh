@@ -372,11 +372,12 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (base + u * 32 >= i_hi) break;
-                    const unsigned z0 = __ballot_sync(FULL_MASK, v0[u] > 0.f), z1 = __ballot_sync(FULL_MASK, v1[u] > 0.f);
-                    l0 += __popc(__ballot_sync(FULL_MASK, p0[u])) + __popc(z0);
-                    l1 += __popc(__ballot_sync(FULL_MASK, p1[u])) + __popc(z1);
-                    const unsigned zz = z0 | z1;
-                    if ((zz >> lane) & 1u) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0[u], v1[u]);
+                    // (the counts behind score_h_l, :3620-3636, are kept per lane and reduced once per candidate)
+                    l0 += (int)p0[u] + (int)(v0[u] > 0.f);
+                    l1 += (int)p1[u] + (int)(v1[u] > 0.f);
+                    const bool nzv = v0[u] > 0.f || v1[u] > 0.f;
+                    const unsigned zz = __ballot_sync(FULL_MASK, nzv);
+                    if (nzv) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0[u], v1[u]);
                     nz += __popc(zz);
                 }
                 __syncwarp();
@@ -393,6 +394,8 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                 }
                 __syncwarp();
             }
+            l0 = (int)__reduce_add_sync(FULL_MASK, (unsigned)l0);
+            l1 = (int)__reduce_add_sync(FULL_MASK, (unsigned)l1);
             if (lane == 0) {
                 float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
                 int tag;

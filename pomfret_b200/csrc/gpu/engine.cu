@@ -821,7 +821,14 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
     J.meta_cap = max_reads <= 4096 ? max_reads : 0;
     const uint32_t stride = join_row_stride(cfg->k);
-    const size_t small_limit = nw * 2 <= (size_t)b->sm_count ? kJoinSmemMax : kJoinSmemHalf;
+    size_t small_limit = nw * 2 <= (size_t)b->sm_count ? kJoinSmemMax : kJoinSmemHalf;
+    size_t big_limit = kJoinSmemMax;
+    if (const char *e = getenv("POMFRET_GPU_JOIN_SMEM")) {
+        // test hook: "0" keeps per-read state and count tables in global memory (the paths very large windows
+        // take), "half" forbids the one-CTA-per-SM launch
+        if (!strcmp(e, "0")) { J.meta_cap = 0; small_limit = big_limit = 0; }
+        else if (!strcmp(e, "half")) big_limit = small_limit;
+    }
     if (int rc = b->h_cta.resize(nw * 2 + 1)) return rc;
     size_t n_a = 0, n_b = 0;
     uint32_t tab_a = 0, tab_b = 0;
@@ -832,7 +839,7 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         if (S.n == 0 || S.n_sites == 0 || S.status != 0) continue;  // nothing to propagate: no CTA
         const uint32_t words = S.n_sites * stride;
         const size_t need = join_smem_bytes(words + 1, J.meta_cap, J.n_cand, (int)join_threads / 32);
-        if (need > small_limit && need <= kJoinSmemMax) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
+        if (need > small_limit && need <= big_limit) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
         else {
             if (need <= small_limit) tab_a = std::max(tab_a, words);
             else a_all_fit = false;  // larger than a whole SM's shared memory: this window keeps its tables in the global pool

@@ -49,3 +49,38 @@ def test_emulated_kernels_k2(emu_gpu, synth_small):
 
 def test_emulated_kernels_call_slot_overflow(emu_gpu, synth_sparse_implicit):
     _run(emu_gpu, synth_sparse_implicit, 34, 1500)
+
+
+def _run_cfg(emu_gpu, data, cov, readlen, tweak):
+    """like _run, with the engine / oracle configurations adjusted by tweak(cfg)"""
+    host = pb.load_host()
+    hb = host.bam_open(data["bam"])
+    cfg, ocfg = pb.make_config(cov, readlen=readlen), ob.make_config(cov, readlen=readlen)
+    tweak(cfg); tweak(ocfg)
+    wins = parity.load_windows(host, hb, data["gaps"][:1], cfg)
+    ctx = emu_gpu.init()
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(emu_gpu, ctx, host, wins, cfg)
+    assert rc == 0
+    for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+        p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+        bad = parity.compare_window(b, wi, first, n, res, tags, ids, p, deep=False)
+        assert not bad, (chrom, s, e, bad[:10])
+        host.window_free(w)
+    b.end()
+    emu_gpu.destroy(ctx)
+    host.bam_close(hb)
+
+
+@pytest.mark.parametrize("n_cand", [1, 2, 40, 128])
+def test_emulated_join_candidate_counts(emu_gpu, synth_small, n_cand):
+    # fewer slots than warps, more slots than warps, more slots than lanes
+    def tweak(cfg):
+        cfg.n_candidates_per_iter = n_cand
+    _run_cfg(emu_gpu, synth_small, 36, 2000, tweak)
+
+
+@pytest.mark.parametrize("mode", ["0", "half"])
+def test_emulated_join_global_memory_paths(emu_gpu, synth_small, mode, monkeypatch):
+    # windows too large for shared memory keep tables / per-read state in global memory
+    monkeypatch.setenv("POMFRET_GPU_JOIN_SMEM", mode)
+    _run_cfg(emu_gpu, synth_small, 36, 2000, lambda cfg: None)

@@ -107,3 +107,39 @@ def test_gpu_batch_of_many_windows_is_order_independent(gpu, synth30):
     b1.end(); b2.end()
     gpu.destroy(ctx)
     host.bam_close(hb)
+
+
+def _run_tweaked(gpu, data, cov, readlen, tweak, max_windows=None):
+    host = pb.load_host()
+    hb = host.bam_open(data["bam"])
+    cfg, ocfg = pb.make_config(cov, readlen=readlen), ob.make_config(cov, readlen=readlen)
+    tweak(cfg); tweak(ocfg)
+    gaps = data["gaps"][:max_windows] if max_windows else data["gaps"]
+    wins = parity.load_windows(host, hb, gaps, cfg)
+    ctx = gpu.init([0])
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(gpu, ctx, host, wins, cfg)
+    assert rc == 0, gpu.strerror(rc)
+    for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+        p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+        bad = parity.compare_window(b, wi, first, n, res, tags, ids, p, deep=False)
+        assert not bad, (chrom, s, e, bad[:10])
+        host.window_free(w)
+    b.end()
+    gpu.destroy(ctx)
+    host.bam_close(hb)
+
+
+@pytest.mark.parametrize("n_cand", [1, 3, 15, 40, 128])
+def test_gpu_join_candidate_counts(gpu, synth30, synth_small, n_cand):
+    # fewer candidate slots than warps, more slots than warps, more slots than lanes
+    def tweak(cfg):
+        cfg.n_candidates_per_iter = n_cand
+    _run_tweaked(gpu, synth_small, 36, 2000, tweak)
+    _run_tweaked(gpu, synth30, 30, 15000, tweak, max_windows=2)
+
+
+@pytest.mark.parametrize("mode", ["0", "half"])
+def test_gpu_join_global_memory_paths(gpu, synth30, mode, monkeypatch):
+    # windows too large for shared memory keep count tables / per-read state in global memory
+    monkeypatch.setenv("POMFRET_GPU_JOIN_SMEM", mode)
+    _run_tweaked(gpu, synth30, 30, 15000, lambda cfg: None)

@@ -143,6 +143,9 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
                                  uint32_t n_reads);
 int pomfret_gpu_batch_submit(pomfret_gpu_batch *b); /* async H2D of the staged records */
+/* Back to the state right after submit(): the staged records stay resident on the device and the stages can
+ * be run again (other thresholds, k, candidate counts on the same reads).  Waits for the batch's stream. */
+int pomfret_gpu_batch_rewind(pomfret_gpu_batch *b);
 
 /* ---- (b) MM/ML + CIGAR decode: fill_read_meth_record_from_bam_line + get_mod_poss_on_ref ---- */
 int pomfret_gpu_decode(pomfret_gpu_batch *b, uint8_t qual_lo, uint8_t qual_hi);

@@ -95,6 +95,7 @@ class GpuLib:
         lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
+        lib.pomfret_gpu_batch_rewind.argtypes = [vp]
         lib.pomfret_gpu_decode.argtypes = [vp, C.c_uint8, C.c_uint8]
         lib.pomfret_gpu_haptag.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp]
         lib.pomfret_gpu_pileup.argtypes = [vp, C.POINTER(Config)]
@@ -168,6 +169,9 @@ class Batch:
 
     def submit(self):
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_submit(self.h), "batch_submit")
+
+    def rewind(self):
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_rewind(self.h), "batch_rewind")
 
     def decode(self, lo, hi):
         self.gpu.check(self.gpu.lib.pomfret_gpu_decode(self.h, lo, hi), "decode")

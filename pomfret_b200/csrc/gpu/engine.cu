@@ -577,6 +577,19 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     return POMFRET_GPU_OK;
 }
 
+int pomfret_gpu_batch_rewind(pomfret_gpu_batch *b) {
+    if (!b) return POMFRET_GPU_ERR_ARG;
+    if (b->stage < ST_SUBMITTED) return POMFRET_GPU_ERR_STATE;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    const uint64_t h2d = b->tm.bytes_h2d;
+    memset(&b->tm, 0, sizeof(b->tm));
+    b->tm.bytes_h2d = h2d;
+    b->have_results = false;
+    b->stage = ST_SUBMITTED;
+    return POMFRET_GPU_OK;
+}
+
 static int launch_decode(pomfret_gpu_batch *b) {
     const size_t nr = b->h_reads.n;
     const size_t slots = (size_t)b->calls_total + 16;

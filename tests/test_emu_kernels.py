@@ -84,3 +84,28 @@ def test_emulated_join_global_memory_paths(emu_gpu, synth_small, mode, monkeypat
     # windows too large for shared memory keep tables / per-read state in global memory
     monkeypatch.setenv("POMFRET_GPU_JOIN_SMEM", mode)
     _run_cfg(emu_gpu, synth_small, 36, 2000, lambda cfg: None)
+
+
+def test_emulated_rewind_reruns_with_other_parameters(emu_gpu, synth_small):
+    # records stay resident: second pass with other thresholds and k must match the oracle for those
+    host = pb.load_host()
+    hb = host.bam_open(synth_small["bam"])
+    cfg = pb.make_config(36, readlen=2000)
+    wins = parity.load_windows(host, hb, synth_small["gaps"][:1], cfg)
+    ctx = emu_gpu.init()
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(emu_gpu, ctx, host, wins, cfg)
+    assert rc == 0
+    kw = dict(k=2, k_span=900, lo=80, hi=180)
+    cfg2, ocfg2 = pb.make_config(24, readlen=2000, **kw), ob.make_config(24, readlen=2000, **kw)
+    b.rewind()
+    b.decode(cfg2.lo, cfg2.hi)
+    b.pileup(cfg2)
+    b.join(cfg2)
+    res, tags, ids, rc = b.collect(check=False)
+    assert rc == 0
+    (w, n, chrom, s, e), (first, _) = wins[0], layout[0]
+    p = ob.port_window(host.window_descs(w), n, s, e, ocfg2)
+    assert not parity.compare_window(b, 0, first, n, res, tags, ids, p)
+    b.end()
+    emu_gpu.destroy(ctx)
+    host.bam_close(hb)

@@ -47,6 +47,8 @@ struct DecodeParams {
     uint8_t *tmp_mcat;
     uint32_t *r_ncalls, *r_status, *r_end;
     uint32_t *n_overflow;  // records that ran out of call slots (the engine re-runs them with more room)
+    uint32_t *next;        // work queue head (zeroed before the launch)
+    const uint32_t *order; // queue order: record indices, longest first (nullptr: batch order)
     uint32_t lo, hi;
 };
 
@@ -975,38 +977,46 @@ __device__ uint32_t decode_generic(const DecodeParams &P, const ReadRec &R, GenS
 // ---------------------------------------------------------------------------------------------
 static_assert(sizeof(DecodeWarpSmem) >= sizeof(GenSeg) * GEN_MAXSEG, "the general path reuses the warp's staging area");
 
+// Persistent warps: every warp takes the next record off a queue (longest records first), so neither the
+// spread of record lengths inside a CTA nor the last wave of the grid leaves warp slots idle.
 __global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams P) {
     __shared__ DecodeWarpSmem smem[DEC_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t ri = blockIdx.x * DEC_WARPS + warp;
-    if (ri >= P.n_reads) return;  // whole warp leaves together
-    const ReadRec R = P.reads[ri];
     DecodeWarpSmem &sm = smem[warp];
-    // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
-    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
-    uint32_t rlen = 0;
-    for (uint32_t i = lane; i < R.n_cigar; i += 32) {
-        uint32_t c = cigar[i], op = c & 15u;
-        if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) rlen += c >> 4;
-    }
-    rlen = warp_sum(rlen);
-    if (R.flags & 4u) rlen = 0;
-    if (rlen == 0) rlen = 1;
-    uint32_t n_calls = 0;
-    bool need_generic = false;
-    uint32_t status = decode_fast(P, R, sm, &n_calls, &need_generic);
-    need_generic = __any_sync(FULL_MASK, need_generic);
-    if (need_generic) {
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(P.next, 1u);
+        qi = __shfl_sync(FULL_MASK, qi, 0);
+        if (qi >= P.n_reads) return;  // whole warp leaves together
+        const uint32_t ri = P.order ? P.order[qi] : qi;
+        const ReadRec &R = P.reads[ri];  // read-only for the whole launch: fields are fetched where they are used
+        // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
+        const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
+        uint32_t rlen = 0;
+        for (uint32_t i = lane; i < R.n_cigar; i += 32) {
+            uint32_t c = cigar[i], op = c & 15u;
+            if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) rlen += c >> 4;
+        }
+        rlen = warp_sum(rlen);
+        if (R.flags & 4u) rlen = 0;
+        if (rlen == 0) rlen = 1;
+        uint32_t n_calls = 0;
+        bool need_generic = false;
+        uint32_t status = decode_fast(P, R, sm, &n_calls, &need_generic);
+        need_generic = __any_sync(FULL_MASK, need_generic);
+        if (need_generic) {
+            __syncwarp();
+            if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
+            status = __shfl_sync(FULL_MASK, status, 0);
+            n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
+        }
+        if (lane == 0) {
+            if (status & RS_OVERFLOW) atomicAdd(P.n_overflow, 1u);
+            P.r_ncalls[ri] = (status & RS_KEPT) || (status & RS_OVERFLOW) ? n_calls : 0;
+            P.r_status[ri] = status;
+            P.r_end[ri] = R.pos + rlen;
+        }
         __syncwarp();
-        if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
-        status = __shfl_sync(FULL_MASK, status, 0);
-        n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
-    }
-    if (lane == 0) {
-        if (status & RS_OVERFLOW) atomicAdd(P.n_overflow, 1u);
-        P.r_ncalls[ri] = (status & RS_KEPT) || (status & RS_OVERFLOW) ? n_calls : 0;
-        P.r_status[ri] = status;
-        P.r_end[ri] = R.pos + rlen;
     }
 }
 

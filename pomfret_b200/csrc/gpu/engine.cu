@@ -224,6 +224,7 @@ struct pomfret_gpu_batch {
     PinVec<WindowState> h_state;
     PinVec<uint32_t> h_u32;   // scratch for small D2H reads
     PinVec<uint32_t> h_cta;   // join launch order: window * 2 + direction
+    PinVec<uint32_t> h_order_len;  // record indices, longest first
     std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
     uint64_t calls_total = 0;
     uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
@@ -239,7 +240,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -256,7 +257,7 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len};
     }
 };
 
@@ -367,7 +368,7 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     for (DevBuf *d : all) d->release();
     b->arena.release();
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
-    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release();
+    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release(); b->h_order_len.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
@@ -572,6 +573,17 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
     if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
     if ((rc = up(b, b->d_read_win, b->h_read_win.data(), nr * 4))) return rc;
+    // queue order of the per-record kernels: longest records first (counting sort over 256-base buckets)
+    if ((rc = b->h_order_len.resize(nr ? nr : 1))) return rc;
+    {
+        constexpr uint32_t NB = 4096;
+        std::vector<uint32_t> cnt(NB + 1, 0);
+        for (size_t i = 0; i < nr; i++) cnt[NB - 1 - std::min<uint32_t>(b->h_reads[i].l_qseq >> 8, NB - 1)]++;
+        uint32_t acc = 0;
+        for (uint32_t k = 0; k <= NB; k++) { uint32_t c = cnt[k]; cnt[k] = acc; acc += c; }
+        for (size_t i = 0; i < nr; i++) b->h_order_len[cnt[NB - 1 - std::min<uint32_t>(b->h_reads[i].l_qseq >> 8, NB - 1)]++] = (uint32_t)i;
+    }
+    if ((rc = up(b, b->d_order_len, b->h_order_len.data(), nr * 4))) return rc;
     CK(cudaEventRecord(b->ev[1], b->stream));
     b->stage = ST_SUBMITTED;
     return POMFRET_GPU_OK;
@@ -612,9 +624,12 @@ static int launch_decode(pomfret_gpu_batch *b) {
     P.r_status = b->d_r_status.as<uint32_t>();
     P.r_end = b->d_r_end.as<uint32_t>();
     P.n_overflow = b->d_flags.as<uint32_t>();
+    P.next = b->d_flags.as<uint32_t>() + 1;
+    P.order = nr ? b->d_order_len.as<uint32_t>() : nullptr;
     P.lo = b->lo; P.hi = b->hi;
     if (nr) {
-        unsigned grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS);
+        // one CTA per 4 records, at most the resident set (8 CTAs per SM): the warps loop over a queue
+        unsigned grid = (unsigned)std::min<size_t>((nr + DEC_WARPS - 1) / DEC_WARPS, (size_t)b->sm_count * 8);
         POMFRET_LAUNCH(decode_kernel, grid, DEC_WARPS * 32, 0, b->stream, P);
         b->tm.launches++;
     }

@@ -251,7 +251,7 @@ def main():
     # keep several region chunks on the device at once.  The join kernel is latency bound (one read tagged per
     # iteration); a second batch in flight fills the SMs it leaves idle.  Every step still runs every stage
     # (rewind -> decode -> pileup -> methmers -> join -> collect) on all of its records.
-    nfl = max(1, min(args.in_flight, args.steps))
+    nfl = max(1, min(args.in_flight, args.steps))  # 1: the timed steps run one after the other
     fl_batches = [b]
     for i in range(1, nfl):
         bt = gpu.batch_begin(ctx, 100 + i, local_rank)

@@ -630,6 +630,9 @@ static int launch_decode(pomfret_gpu_batch *b) {
     if (nr) {
         // one CTA per 4 records, at most the resident set (8 CTAs per SM): the warps loop over a queue
         unsigned grid = (unsigned)std::min<size_t>((nr + DEC_WARPS - 1) / DEC_WARPS, (size_t)b->sm_count * 8);
+        if (const char *e = getenv("POMFRET_GPU_DECODE_QUEUE")) {  // measurement hook: "0" = one warp per record in batch order
+            if (!strcmp(e, "0")) { grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS); P.order = nullptr; }
+        }
         POMFRET_LAUNCH(decode_kernel, grid, DEC_WARPS * 32, 0, b->stream, P);
         b->tm.launches++;
     }
@@ -755,6 +758,7 @@ static void fill_methmer_params(pomfret_gpu_batch *b, MethmerParams &M) {
     }
     M.pool_total = b->d_pool_total.as<uint32_t>(); M.mmr_pool = b->d_mmr_pool.as<uint32_t>(); M.ent_pool = b->d_ent_pool.as<uint32_t>();
     M.pool_cap = b->pool_cap; M.n_slots = (uint32_t)b->h_reads.n; M.k = b->cfg.k;
+    M.order = b->d_order_len.as<uint32_t>();
 }
 
 int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
@@ -810,7 +814,7 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         (rc = b->d_tab.ensure(((size_t)tab_sites + 1) * row_words * 4)))
         return rc;
     fill_methmer_params(b, M);
-    unsigned grid = (unsigned)((nr * 2 + MMR_WARPS - 1) / MMR_WARPS);
+    unsigned grid = (unsigned)std::min<size_t>((nr * 2 + MMR_WARPS - 1) / MMR_WARPS, (size_t)b->sm_count * 16);
     if (grid) {
         POMFRET_LAUNCH(methmer_fill_kernel, grid, MMR_WARPS * 32, 0, b->stream, M);
         b->tm.launches++;

@@ -31,7 +31,8 @@ struct MethmerParams {
     const uint32_t *site_start[2];
     const uint8_t *site_len[2];
     uint32_t *mm_xl[2], *mm_xr[2], *mm_off[2], *mm_n[2], *mm_start[2];
-    uint32_t *pool_total;          // [0] methmer slots, [1] table sites, [2] largest site count of a window
+    uint32_t *pool_total;          // [0] methmer slots, [1] table sites, [2] largest site count of a window, [3] fill queue head
+    const uint32_t *order;         // fill queue order: slots by descending record length (nullptr: slot order)
     uint32_t *mmr_pool;            // keys
     uint32_t *ent_pool;            // scratch: (site index << 2 | symbol) per entry
     uint32_t pool_cap;
@@ -131,12 +132,24 @@ __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams 
 
 constexpr int MMR_WARPS = 4;
 
+// Persistent warps over a queue of (record, direction) items, longest records first (see decode_kernel).
+__device__ void methmer_fill_item(const MethmerParams &P, uint32_t slot, uint32_t d);
+
 __global__ void __launch_bounds__(MMR_WARPS * 32) methmer_fill_kernel(MethmerParams P) {
     const unsigned lane = lane_id();
-    const uint32_t item = blockIdx.x * MMR_WARPS + (threadIdx.x >> 5);
-    if (item >= P.n_slots * 2) return;
-    const uint32_t d = item >= P.n_slots ? 1u : 0u;
-    const uint32_t slot = item - d * P.n_slots;
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(P.pool_total + 3, 1u);
+        q = __shfl_sync(FULL_MASK, q, 0);
+        if (q >= P.n_slots * 2) return;
+        const uint32_t slot = P.order ? P.order[q >> 1] : q >> 1;
+        methmer_fill_item(P, slot, q & 1u);
+        __syncwarp();
+    }
+}
+
+__device__ void methmer_fill_item(const MethmerParams &P, uint32_t slot, uint32_t d) {
+    const unsigned lane = lane_id();
     const uint32_t w = P.read_win[slot];
     if (w == 0xffffffffu) return;  // record outside every window
     const WindowRec W = P.win[w];

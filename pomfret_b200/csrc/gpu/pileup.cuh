@@ -61,33 +61,50 @@ __global__ void __launch_bounds__(PILE_THREADS) pileup_tile_kernel(PileupParams 
     // Positions are handled relative to the window base in wrapping 32-bit arithmetic, compared as signed:
     // the reference's position arithmetic wraps too, and a call that a clipped record
     // maps left of the base stays ordered (negative) instead of turning into a huge offset.
-    for (uint32_t id = warp; id < n; id += n_warps) {
-        const uint32_t src = P.rs_src[W.first_read + id];
-        const uint32_t nc = P.r_ncalls[src];
-        if (nc == 0) continue;
-        const bool sorted = !(P.r_status[src] & RS_UNSORTED);
-        const uint32_t *cp = P.calls_pos + P.reads[src].calls_off;
-        const uint8_t *cc = P.calls_cat + P.reads[src].calls_off;
-        uint32_t a = 0;
-        if (sorted) {
-            // most records of the window miss this tile altogether: look at their first and last call
-            if ((int32_t)(cp[nc - 1] - wbase) < (int32_t)t0 || (int32_t)(cp[0] - wbase) >= (int32_t)(t0 + PILE_TILE)) continue;
-            // first call at or behind the tile start, then stream until the tile ends
-            uint32_t lo = 0, hi = nc;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)(cp[mid] - wbase) < (int32_t)t0) lo = mid + 1; else hi = mid; }
-            a = lo;
-        }
-        for (uint32_t j0 = a; j0 < nc; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            bool past = false;
-            if (j < nc) {
-                const uint32_t rel = cp[j] - wbase - t0;
-                const uint32_t cat = cc[j];
-                if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
-                past = (int32_t)rel >= (int32_t)PILE_TILE;
+    // Step 1, one record per lane: metadata, "does the record touch this tile" (most do not) and the index of
+    // its first call inside the tile — 32 independent chains of dependent loads at a time.  Step 2, one
+    // record per warp step: the calls are streamed with lane-consecutive loads into the shared counters.
+    for (uint32_t id0 = warp * 32; id0 < n; id0 += n_warps * 32) {
+        const uint32_t id = id0 + lane;
+        uint32_t nc = 0, coff = 0, a = 0;
+        bool hit = false, sorted = true;
+        if (id < n) {
+            const uint32_t src = P.rs_src[W.first_read + id];
+            nc = P.r_ncalls[src];
+            if (nc) {
+                sorted = !(P.r_status[src] & RS_UNSORTED);
+                coff = P.reads[src].calls_off;
+                const uint32_t *cp = P.calls_pos + coff;
+                hit = true;
+                if (sorted) {
+                    hit = !((int32_t)(cp[nc - 1] - wbase) < (int32_t)t0 || (int32_t)(cp[0] - wbase) >= (int32_t)(t0 + PILE_TILE));
+                    if (hit) {
+                        uint32_t lo = 0, hi = nc;
+                        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)(cp[mid] - wbase) < (int32_t)t0) lo = mid + 1; else hi = mid; }
+                        a = lo;
+                    }
+                }
             }
-            // sorted: once a lane is past the tile, so is everything behind it
-            if (sorted && __any_sync(FULL_MASK, past)) break;
+        }
+        for (unsigned todo = __ballot_sync(FULL_MASK, hit); todo; todo &= todo - 1u) {
+            const int L = __ffs((int)todo) - 1;
+            const uint32_t r_nc = __shfl_sync(FULL_MASK, nc, L), r_off = __shfl_sync(FULL_MASK, coff, L);
+            const uint32_t r_a = __shfl_sync(FULL_MASK, a, L);
+            const bool r_sorted = __shfl_sync(FULL_MASK, (int)sorted, L) != 0;
+            const uint32_t *cp = P.calls_pos + r_off;
+            const uint8_t *cc = P.calls_cat + r_off;
+            for (uint32_t j0 = r_a; j0 < r_nc; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool past = false;
+                if (j < r_nc) {
+                    const uint32_t rel = cp[j] - wbase - t0;
+                    const uint32_t cat = cc[j];
+                    if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
+                    past = (int32_t)rel >= (int32_t)PILE_TILE;
+                }
+                // sorted: once a lane is past the tile, so is everything behind it
+                if (r_sorted && __any_sync(FULL_MASK, past)) break;
+            }
         }
     }
     __syncthreads();

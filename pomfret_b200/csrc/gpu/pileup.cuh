@@ -50,6 +50,7 @@ struct PileupParams {
 __global__ void __launch_bounds__(PILE_THREADS) pileup_tile_kernel(PileupParams P) {
     POMFRET_DYN_SMEM(uint32_t, cnt);  // PILE_TILE packed counters
     __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_hits, s_hit_off[PILE_THREADS], s_hit_a[PILE_THREADS], s_hit_e[PILE_THREADS];
     const TileRec T = P.tiles[blockIdx.x];
     const WindowRec W = P.win[T.window];
     const uint32_t n = P.state[T.window].n;
@@ -61,51 +62,53 @@ __global__ void __launch_bounds__(PILE_THREADS) pileup_tile_kernel(PileupParams 
     // Positions are handled relative to the window base in wrapping 32-bit arithmetic, compared as signed:
     // the reference's position arithmetic wraps too, and a call that a clipped record
     // maps left of the base stays ordered (negative) instead of turning into a huge offset.
-    // Step 1, one record per lane: metadata, "does the record touch this tile" (most do not) and the index of
-    // its first call inside the tile — 32 independent chains of dependent loads at a time.  Step 2, one
-    // record per warp step: the calls are streamed with lane-consecutive loads into the shared counters.
-    for (uint32_t id0 = warp * 32; id0 < n; id0 += n_warps * 32) {
-        const uint32_t id = id0 + lane;
-        uint32_t nc = 0, coff = 0, a = 0;
-        bool hit = false, sorted = true;
+    // Step 1, one record per thread: metadata, "does the record touch this tile" (most do not) and the range
+    // of its calls inside the tile — up to 512 independent chains of dependent loads at a time; the records
+    // that touch the tile are listed in shared memory.  Step 2, one listed record per warp step: its calls are
+    // streamed with lane-consecutive loads (known trip count) into the shared counters.
+    for (uint32_t id0 = 0; id0 < n; id0 += PILE_THREADS) {
+        if (tid == 0) s_hits = 0;
+        __syncthreads();
+        const uint32_t id = id0 + tid;
         if (id < n) {
             const uint32_t src = P.rs_src[W.first_read + id];
-            nc = P.r_ncalls[src];
+            const uint32_t nc = P.r_ncalls[src];
             if (nc) {
-                sorted = !(P.r_status[src] & RS_UNSORTED);
-                coff = P.reads[src].calls_off;
+                const uint32_t coff = P.reads[src].calls_off;
                 const uint32_t *cp = P.calls_pos + coff;
-                hit = true;
-                if (sorted) {
+                uint32_t a = 0, e = nc;
+                bool hit = true;
+                if (!(P.r_status[src] & RS_UNSORTED)) {
                     hit = !((int32_t)(cp[nc - 1] - wbase) < (int32_t)t0 || (int32_t)(cp[0] - wbase) >= (int32_t)(t0 + PILE_TILE));
                     if (hit) {
                         uint32_t lo = 0, hi = nc;
                         while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)(cp[mid] - wbase) < (int32_t)t0) lo = mid + 1; else hi = mid; }
                         a = lo;
+                        hi = nc;
+                        while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((int32_t)(cp[mid] - wbase) < (int32_t)(t0 + PILE_TILE)) lo = mid + 1; else hi = mid; }
+                        e = lo;
+                        hit = e > a;
                     }
                 }
-            }
-        }
-        for (unsigned todo = __ballot_sync(FULL_MASK, hit); todo; todo &= todo - 1u) {
-            const int L = __ffs((int)todo) - 1;
-            const uint32_t r_nc = __shfl_sync(FULL_MASK, nc, L), r_off = __shfl_sync(FULL_MASK, coff, L);
-            const uint32_t r_a = __shfl_sync(FULL_MASK, a, L);
-            const bool r_sorted = __shfl_sync(FULL_MASK, (int)sorted, L) != 0;
-            const uint32_t *cp = P.calls_pos + r_off;
-            const uint8_t *cc = P.calls_cat + r_off;
-            for (uint32_t j0 = r_a; j0 < r_nc; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                bool past = false;
-                if (j < r_nc) {
-                    const uint32_t rel = cp[j] - wbase - t0;
-                    const uint32_t cat = cc[j];
-                    if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
-                    past = (int32_t)rel >= (int32_t)PILE_TILE;
+                if (hit) {
+                    const uint32_t k = atomicAdd(&s_hits, 1u);  // order is irrelevant: the counters only add
+                    s_hit_off[k] = coff; s_hit_a[k] = a; s_hit_e[k] = e;
                 }
-                // sorted: once a lane is past the tile, so is everything behind it
-                if (r_sorted && __any_sync(FULL_MASK, past)) break;
             }
         }
+        __syncthreads();
+        const uint32_t nh = s_hits;
+        for (uint32_t h = warp; h < nh; h += n_warps) {
+            const uint32_t *cp = P.calls_pos + s_hit_off[h];
+            const uint8_t *cc = P.calls_cat + s_hit_off[h];
+            const uint32_t e = s_hit_e[h];
+            for (uint32_t j = s_hit_a[h] + lane; j < e; j += 32) {
+                const uint32_t rel = cp[j] - wbase - t0;
+                const uint32_t cat = cc[j];
+                if (rel < PILE_TILE && cat < 2u) atomicAdd(&cnt[rel], cat == 0u ? 1u : 0x10000u);
+            }
+        }
+        __syncthreads();
     }
     __syncthreads();
     // selection + ordered compaction

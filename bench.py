@@ -313,7 +313,10 @@ def main():
             o += n
         chunk_descs.append((arr, tot))
 
+    e2e_prof = {"stage": 0.0, "device": 0.0}
+
     def produce(q):
+        t_p = time.perf_counter()
         for i, (bt, ws) in enumerate(zip(batches, chunks)):
             bt.reset()
             arr, tot = chunk_descs[i]
@@ -324,6 +327,7 @@ def main():
                 first += n
             bt.submit()
             q.put(i)
+        e2e_prof["stage"] += time.perf_counter() - t_p
 
     def e2e_step():
         q = queue.Queue()
@@ -331,11 +335,13 @@ def main():
         th.start()
         for _ in range(nb):
             i = q.get()
+            t_c = time.perf_counter()
             bt = batches[i]
             bt.decode(cfg.lo, cfg.hi)
             bt.pileup(cfg)
             bt.join(cfg)
             e2e_results[i] = bt.collect()
+            e2e_prof["device"] += time.perf_counter() - t_c
         th.join()
 
     h2d_e2e = d2h_e2e = 0
@@ -345,6 +351,8 @@ def main():
         e2e_step()
         barrier()
         dt = time.perf_counter() - t0
+        if it < args.warmup:
+            e2e_prof["stage"] = e2e_prof["device"] = 0.0
         if it >= args.warmup:
             e2e_times.append(dt)
             h2d_e2e = sum(bt.timing().bytes_h2d for bt in batches)
@@ -410,7 +418,9 @@ def main():
             "latency_ms_per_step": lat_mean * 1e3,
             "e2e": {"value": tot_reads / e2e_mean, "unit": "reads/s", "ms_per_step": e2e_mean * 1e3,
                     "bases_per_s": tot_bases / e2e_mean, "h2d_bytes_per_step": int(h2d_e2e),
-                    "d2h_bytes_per_step": int(d2h_e2e), "batches_per_step": nb},
+                    "d2h_bytes_per_step": int(d2h_e2e), "batches_per_step": nb,
+                    "host_stage_ms_per_step": 1e3 * e2e_prof["stage"] / args.steps,
+                    "device_calls_ms_per_step": 1e3 * e2e_prof["device"] / args.steps},
             "gpu_launches": int(launches) * K,
             "kernel_ms": kernels,
             "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"],

@@ -311,7 +311,11 @@ def main():
         for w, n, chrom, s, e in ws:
             C.memmove(C.byref(arr, o * C.sizeof(_ffi.ReadDesc)), host.window_descs(w), n * C.sizeof(_ffi.ReadDesc))
             o += n
-        chunk_descs.append((arr, tot))
+        import numpy as np
+        firsts = np.cumsum([0] + [n for _, n, _, _, _ in ws][:-1]).astype(np.uint32) if ws else np.zeros(0, np.uint32)
+        chunk_descs.append((arr, tot, np.array([s for _, _, _, s, _ in ws], dtype=np.uint32),
+                            np.array([e for _, _, _, _, e in ws], dtype=np.uint32), firsts,
+                            np.array([n for _, n, _, _, _ in ws], dtype=np.uint32)))
 
     e2e_prof = {"stage": 0.0, "device": 0.0}
 
@@ -319,12 +323,9 @@ def main():
         t_p = time.perf_counter()
         for i, (bt, ws) in enumerate(zip(batches, chunks)):
             bt.reset()
-            arr, tot = chunk_descs[i]
+            arr, tot, w_s, w_e, w_first, w_n = chunk_descs[i]
             bt.add_reads(arr, tot)
-            first = 0
-            for w, n, chrom, s, e in ws:
-                bt.add_window(s, e, first, n)
-                first += n
+            bt.add_windows(w_s, w_e, w_first, w_n)
             bt.submit()
             q.put(i)
         e2e_prof["stage"] += time.perf_counter() - t_p

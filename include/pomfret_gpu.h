@@ -142,6 +142,9 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
  * chrom:(ref_start-50000)-(ref_end+50000) in BAM order */
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,
                                  uint32_t n_reads);
+/* the same for n windows at once (parallel arrays) */
+int pomfret_gpu_batch_add_windows(pomfret_gpu_batch *b, const uint32_t *ref_start, const uint32_t *ref_end,
+                                  const uint32_t *first_read, const uint32_t *n_reads, uint32_t n);
 int pomfret_gpu_batch_submit(pomfret_gpu_batch *b); /* async H2D of the staged records */
 /* Back to the state right after submit(): the staged records stay resident on the device and the stages can
  * be run again (other thresholds, k, candidate counts on the same reads).  Waits for the batch's stream. */

@@ -94,6 +94,7 @@ class GpuLib:
         lib.pomfret_gpu_batch_add_read.argtypes = [vp, vp]
         lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        lib.pomfret_gpu_batch_add_windows.argtypes = [vp, vp, vp, vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
         lib.pomfret_gpu_batch_rewind.argtypes = [vp]
         lib.pomfret_gpu_decode.argtypes = [vp, C.c_uint8, C.c_uint8]
@@ -166,6 +167,14 @@ class Batch:
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_window(self.h, ref_start, ref_end, first_read, n_reads),
                        "batch_add_window")
         self.n_windows += 1
+
+    def add_windows(self, ref_start, ref_end, first_read, n_reads):
+        """parallel uint32 numpy arrays, one entry per window"""
+        n = len(ref_start)
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_windows(self.h, ref_start.ctypes.data, ref_end.ctypes.data,
+                                                                  first_read.ctypes.data, n_reads.ctypes.data, n),
+                       "batch_add_windows")
+        self.n_windows += n
 
     def submit(self):
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_submit(self.h), "batch_submit")

@@ -540,6 +540,14 @@ int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint3
     return b->h_win.push(W);
 }
 
+int pomfret_gpu_batch_add_windows(pomfret_gpu_batch *b, const uint32_t *ref_start, const uint32_t *ref_end,
+                                  const uint32_t *first_read, const uint32_t *n_reads, uint32_t n) {
+    if (!b || (n && (!ref_start || !ref_end || !first_read || !n_reads))) return POMFRET_GPU_ERR_ARG;
+    for (uint32_t i = 0; i < n; i++)
+        if (int rc = pomfret_gpu_batch_add_window(b, ref_start[i], ref_end[i], first_read[i], n_reads[i])) return rc;
+    return POMFRET_GPU_OK;
+}
+
 static int up(pomfret_gpu_batch *b, DevBuf &d, const void *src, size_t bytes) {
     if (int rc = d.ensure(bytes ? bytes : 16)) return rc;
     if (bytes) {

@@ -137,7 +137,7 @@ def main():
     ap.add_argument("--region-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_MB", "63.5")))
     ap.add_argument("--cov", type=int, default=30)
     ap.add_argument("--cpu-sample-windows", type=int, default=12)
-    ap.add_argument("--e2e-batches", type=int, default=4, help="region chunks per step on the end-to-end path")
+    ap.add_argument("--e2e-batches", type=int, default=3, help="region chunks per step on the end-to-end path")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight when measuring device-resident throughput")
     args = ap.parse_args()
     if args.warmup < 3:

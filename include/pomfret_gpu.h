@@ -133,6 +133,14 @@ int pomfret_gpu_device_count(void);
 const char *pomfret_gpu_version(void);
 
 /* ---- (a) staging ---- */
+/* Optional: pin and map a host buffer that holds alignment records (e.g. the buffer BGZF blocks are inflated
+ * into) for as long as it is registered.  add_reads() then leaves the payload of records that lie completely
+ * inside registered buffers where it is, and submit() lets the device gather it over PCIe: no host-side copy.
+ * Records elsewhere are copied into the library's pinned arena as before.  The buffer must not be freed,
+ * moved or modified between add_reads() and the completion of submit()'s transfers (collect(), rewind() or
+ * reset() of the batch). */
+int pomfret_gpu_host_register(pomfret_gpu_ctx *ctx, void *ptr, size_t bytes);
+int pomfret_gpu_host_unregister(pomfret_gpu_ctx *ctx, void *ptr);
 int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfret_gpu_batch **out);
 int pomfret_gpu_batch_reset(pomfret_gpu_batch *b);
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r);

@@ -90,6 +90,8 @@ class GpuLib:
         lib.pomfret_gpu_init.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int]
         lib.pomfret_gpu_destroy.argtypes = [vp]
         lib.pomfret_gpu_batch_begin.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        lib.pomfret_gpu_host_register.argtypes = [vp, vp, C.c_size_t]
+        lib.pomfret_gpu_host_unregister.argtypes = [vp, vp]
         lib.pomfret_gpu_batch_reset.argtypes = [vp]
         lib.pomfret_gpu_batch_add_read.argtypes = [vp, vp]
         lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
@@ -131,6 +133,12 @@ class GpuLib:
             rc = self.lib.pomfret_gpu_init(C.byref(ctx), None, 0, n_workers)
         self.check(rc, "pomfret_gpu_init")
         return ctx
+
+    def host_register(self, ctx, ptr, nbytes):
+        self.check(self.lib.pomfret_gpu_host_register(ctx, ptr, nbytes), "host_register")
+
+    def host_unregister(self, ctx, ptr):
+        self.check(self.lib.pomfret_gpu_host_unregister(ctx, ptr), "host_unregister")
 
     def destroy(self, ctx):
         self.lib.pomfret_gpu_destroy(ctx)
@@ -295,6 +303,8 @@ class HostLib:
         lib.pomfret_host_window_qname.argtypes = [vp, C.c_int]
         lib.pomfret_host_window_bases.restype = C.c_uint64
         lib.pomfret_host_window_bases.argtypes = [vp]
+        lib.pomfret_host_window_arena.restype = vp
+        lib.pomfret_host_window_arena.argtypes = [vp, C.POINTER(C.c_uint64)]
         lib.pomfret_host_window_free.argtypes = [vp]
 
     def bam_open(self, path):
@@ -325,6 +335,11 @@ class HostLib:
 
     def window_bases(self, w):
         return self.lib.pomfret_host_window_bases(w)
+
+    def window_arena(self, w):
+        n = C.c_uint64()
+        p = self.lib.pomfret_host_window_arena(w, C.byref(n))
+        return p, n.value
 
     def window_free(self, w):
         self.lib.pomfret_host_window_free(w)

@@ -27,6 +27,7 @@
 #include "methmer.cuh"
 #include "join.cuh"
 #include "haptag.cuh"
+#include "gather.cuh"
 #include "pomfret_gpu.h"
 #include "htslib/kfunc.h"
 
@@ -200,10 +201,13 @@ enum Stage { ST_EMPTY = 0, ST_SUBMITTED = 1, ST_DECODED = 2, ST_PILED = 3, ST_JO
 
 }  // namespace
 
+struct HostRegion { uintptr_t begin, end; uint64_t dev; };  // registered caller memory and its device-visible address
+
 struct pomfret_gpu_ctx {
     std::vector<int> devices;
     int n_workers = 1;
     std::mutex mu;
+    std::vector<HostRegion> regions;  // sorted by begin
 };
 
 struct pomfret_gpu_batch {
@@ -232,6 +236,8 @@ struct pomfret_gpu_batch {
     size_t blob_hint = 0;           // blob size of the previous batch: device buffer is ready before staging starts
     size_t blob_sent = 0;           // bytes of the blob already handed to the DMA engine while staging
     bool streaming = false, h2d_started = false;
+    bool direct_any = false, copied_any = false;  // records gathered by the device / copied by the host in this batch
+    PinVec<GatherSrc> h_gsrc;
     // device
     DevArena arena;
     DevBuf d_blob, d_reads, d_win, d_read_win, d_calls_pos, d_calls_cat, d_tmp_rank, d_tmp_mpos, d_tmp_mcat;
@@ -240,7 +246,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -257,7 +263,7 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc};
     }
 };
 
@@ -311,6 +317,43 @@ int pomfret_gpu_init(pomfret_gpu_ctx **out, const int *devices, int n_devices, i
 
 void pomfret_gpu_destroy(pomfret_gpu_ctx *ctx) { delete ctx; }
 
+int pomfret_gpu_host_register(pomfret_gpu_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ctx || !ptr || !bytes) return POMFRET_GPU_ERR_ARG;
+    CK(cudaSetDevice(ctx->devices[0]));
+    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    void *dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, ptr, 0) != cudaSuccess || !dev) { cudaHostUnregister(ptr); return POMFRET_GPU_ERR_CUDA; }
+    std::lock_guard<std::mutex> g(ctx->mu);
+    HostRegion r{(uintptr_t)ptr, (uintptr_t)ptr + bytes, (uint64_t)(uintptr_t)dev};
+    ctx->regions.insert(std::upper_bound(ctx->regions.begin(), ctx->regions.end(), r,
+                                         [](const HostRegion &a, const HostRegion &c) { return a.begin < c.begin; }), r);
+    return POMFRET_GPU_OK;
+}
+
+int pomfret_gpu_host_unregister(pomfret_gpu_ctx *ctx, void *ptr) {
+    if (!ctx || !ptr) return POMFRET_GPU_ERR_ARG;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        auto it = std::find_if(ctx->regions.begin(), ctx->regions.end(), [&](const HostRegion &r) { return r.begin == (uintptr_t)ptr; });
+        if (it == ctx->regions.end()) return POMFRET_GPU_ERR_ARG;
+        ctx->regions.erase(it);
+    }
+    CK(cudaHostUnregister(ptr));
+    return POMFRET_GPU_OK;
+}
+
+// device-visible address of [p, p+n) if it lies inside one registered region, else 0
+static uint64_t region_lookup(const std::vector<HostRegion> &regs, const void *p, size_t n, size_t *hint) {
+    const uintptr_t a = (uintptr_t)p;
+    if (*hint < regs.size() && a >= regs[*hint].begin && a + n <= regs[*hint].end) return regs[*hint].dev + (a - regs[*hint].begin);
+    auto it = std::upper_bound(regs.begin(), regs.end(), a, [](uintptr_t v, const HostRegion &r) { return v < r.begin; });
+    if (it == regs.begin()) return 0;
+    --it;
+    if (a + n > it->end) return 0;
+    *hint = (size_t)(it - regs.begin());
+    return it->dev + (a - it->begin);
+}
+
 int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfret_gpu_batch **out) {
     (void)worker;
     if (!ctx || !out) return POMFRET_GPU_ERR_ARG;
@@ -342,7 +385,8 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
 int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     if (!b) return POMFRET_GPU_ERR_ARG;
     b->h_blob.len = 0;
-    b->h_reads.clear(); b->h_win.clear(); b->h_read_win.clear();
+    b->h_reads.clear(); b->h_win.clear(); b->h_read_win.clear(); b->h_gsrc.clear();
+    b->direct_any = b->copied_any = false;
     b->h_end.clear();
     b->calls_total = 0;
     b->alg_decode_bytes = b->alg_haptag_bytes = 0;
@@ -368,7 +412,7 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     for (DevBuf *d : all) d->release();
     b->arena.release();
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
-    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release(); b->h_order_len.release();
+    b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release(); b->h_order_len.release(); b->h_gsrc.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
@@ -464,6 +508,7 @@ static void copy_read(uint8_t *blob, const ReadRec &R, const pomfret_gpu_read_de
 // known to be large enough; submit() sends whatever is left).
 static int stream_blob(pomfret_gpu_batch *b, bool force) {
     if (!b->streaming) return 0;
+    if (b->direct_any) { b->streaming = false; return 0; }  // mixed batch: submit() copies the host-staged part in one go
     if (b->h_blob.len + 2048 > b->d_blob.cap) { b->streaming = false; return 0; }  // larger than planned: submit() copies all
     const size_t ready = b->h_blob.len;
     if (ready <= b->blob_sent || (!force && ready - b->blob_sent < ((size_t)8 << 20))) return 0;
@@ -490,12 +535,51 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             return rc;
         }
     }
+    if (int rc = b->h_gsrc.resize(first + n)) return rc;
+    b->h_end.resize(first + n);
+    // records that lie completely inside registered caller buffers stay where they are: the device gathers them
+    {
+        std::vector<HostRegion> regs;
+        { std::lock_guard<std::mutex> g(b->ctx->mu); regs = b->ctx->regions; }
+        bool direct = !regs.empty();
+        size_t hint = 0;
+        for (uint32_t i = 0; i < n && direct; i++) {
+            const pomfret_gpu_read_desc &d = r[i];
+            GatherSrc &G = b->h_gsrc[first + i];
+            memset(&G, 0, sizeof(G));
+            const void *p[5] = {d.cigar, d.seq, d.mm, d.ml_len >= 0 ? d.ml : nullptr, d.md};
+            const size_t sz[5] = {(size_t)d.n_cigar * 4, ((size_t)d.l_qseq + 1) / 2, d.mm ? d.mm_len : 0,
+                                  d.ml_len > 0 ? (size_t)d.ml_len : 0, d.md ? d.md_len : 0};
+            for (int f = 0; f < 5; f++) {
+                if (!p[f] || !sz[f]) continue;
+                // (word-aligned reads may touch up to 3 bytes on either side: registered memory is pinned page-wise)
+                G.ptr[f] = region_lookup(regs, p[f], sz[f], &hint);
+                if (!G.ptr[f]) { direct = false; break; }
+            }
+        }
+        if (direct) {
+            const ReadRec *recs = b->h_reads.data() + first;
+            (void)recs;
+            for (uint32_t i = 0; i < n; i++) {
+                uint64_t rlen = 0;
+                for (uint32_t c = 0; c < r[i].n_cigar; c++) {
+                    const uint32_t op = r[i].cigar[c] & 15u;
+                    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += r[i].cigar[c] >> 4;
+                }
+                b->h_end[first + i] = (uint32_t)(r[i].pos + (rlen ? rlen : 1));
+            }
+            b->h_blob.len = len;  // layout only: nothing is written on the host
+            b->direct_any = true;
+            return POMFRET_GPU_OK;
+        }
+        for (uint32_t i = 0; i < n; i++) memset(&b->h_gsrc[first + i], 0, sizeof(GatherSrc));
+    }
+    b->copied_any = true;
     if (len + 2048 > b->h_blob.cap) {
         // growing the pinned arena moves it: no DMA may still be reading the old one
         if (b->blob_sent) { CK(cudaSetDevice(b->device)); CK(cudaStreamSynchronize(b->stream)); }
         if (int rc = b->h_blob.reserve(len + 2048)) return rc;
     }
-    b->h_end.resize(first + n);
     uint8_t *blob = b->h_blob.p;
     const ReadRec *recs = b->h_reads.data() + first;
     uint32_t *ends = b->h_end.data() + first;
@@ -564,21 +648,44 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     const size_t nr = b->h_reads.n, nw = b->h_win.n;
     int rc;
     // the blob keeps 1 KB of zeroed slack behind the last field
-    if (b->h_blob.len + 2048 > b->h_blob.cap) {
-        if (b->blob_sent) CK(cudaStreamSynchronize(b->stream));
-        if ((rc = b->h_blob.reserve(b->h_blob.len + 2048))) return rc;
-    }
-    memset(b->h_blob.p + b->h_blob.len, 0, 1024);
-    b->h_blob.len += 1024;
-    if ((rc = stream_blob(b, true))) return rc;
-    if (!b->h2d_started) { CK(cudaEventRecord(b->ev[0], b->stream)); b->h2d_started = true; }
-    if (!b->streaming) {
-        b->blob_sent = 0;
-        if ((rc = up(b, b->d_blob, b->h_blob.p, b->h_blob.len))) return rc;
+    if (b->copied_any) {
+        if (b->h_blob.len + 2048 > b->h_blob.cap) {
+            if (b->blob_sent) CK(cudaStreamSynchronize(b->stream));
+            if ((rc = b->h_blob.reserve(b->h_blob.len + 2048))) return rc;
+        }
+        memset(b->h_blob.p + b->h_blob.len, 0, 1024);
+        b->h_blob.len += 1024;
+        if ((rc = stream_blob(b, true))) return rc;
+        if (!b->h2d_started) { CK(cudaEventRecord(b->ev[0], b->stream)); b->h2d_started = true; }
+        if (!b->streaming) {
+            b->blob_sent = 0;
+            if ((rc = up(b, b->d_blob, b->h_blob.p, b->h_blob.len))) return rc;
+        }
+    } else {
+        // every record is gathered by the device: only the slack has to be prepared
+        if (!b->h2d_started) { CK(cudaEventRecord(b->ev[0], b->stream)); b->h2d_started = true; }
+        if ((rc = b->d_blob.ensure(b->h_blob.len + 2048))) return rc;
+        CK(cudaMemsetAsync(b->d_blob.as<uint8_t>() + b->h_blob.len, 0, 1024, b->stream));
+        b->h_blob.len += 1024;
     }
     b->blob_hint = std::max(b->h_blob.len, b->blob_hint - b->blob_hint / 16);  // follows the batch size, decays slowly
     b->h_blob.len -= 1024;
     if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
+    if (b->direct_any && nr) {
+        if ((rc = up(b, b->d_gsrc, b->h_gsrc.data(), nr * sizeof(GatherSrc)))) return rc;
+        GatherParams G;
+        G.reads = b->d_reads.as<ReadRec>(); G.src = b->d_gsrc.as<GatherSrc>(); G.blob = b->d_blob.as<uint8_t>(); G.n_reads = (uint32_t)nr;
+        POMFRET_LAUNCH(gather_kernel, (unsigned)((nr + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, b->stream, G);
+        b->tm.launches++;
+        for (size_t i = 0; i < nr; i++)
+            for (int f = 0; f < 5; f++)
+                if (b->h_gsrc[i].ptr[f]) {
+                    const ReadRec &R = b->h_reads[i];
+                    const uint64_t sz[5] = {(uint64_t)R.n_cigar * 4, ((uint64_t)R.l_qseq + 1) / 2, R.mm_len, R.ml_len, R.md_len};
+                    b->tm.bytes_h2d += sz[f];
+                }
+        CK(cudaGetLastError());
+    }
     if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
     if ((rc = up(b, b->d_read_win, b->h_read_win.data(), nr * 4))) return rc;
     // queue order of the per-record kernels: longest records first (counting sort over 256-base buckets)

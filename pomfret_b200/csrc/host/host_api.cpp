@@ -25,6 +25,12 @@ int pomfret_host_window_n(void *w) { return (int)((WindowReads *)w)->descs.size(
 const pomfret_gpu_read_desc *pomfret_host_window_descs(void *w) { return ((WindowReads *)w)->descs.data(); }
 const char *pomfret_host_window_qname(void *w, int i) { return ((WindowReads *)w)->qname((size_t)i); }
 uint64_t pomfret_host_window_bases(void *w) { return ((WindowReads *)w)->n_bases; }
+// the buffer that holds the window's record copies (what the descriptors point into)
+const uint8_t *pomfret_host_window_arena(void *w, uint64_t *n_bytes) {
+    WindowReads *r = (WindowReads *)w;
+    if (n_bytes) *n_bytes = r->arena.size();
+    return r->arena.data();
+}
 void pomfret_host_window_free(void *w) { delete (WindowReads *)w; }
 
 }  // extern "C"

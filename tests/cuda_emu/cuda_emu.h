@@ -221,6 +221,10 @@ cudaError_t cudaFree(void *p);
 cudaError_t cudaMallocHost(void **p, size_t n);
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned flags);
 cudaError_t cudaFreeHost(void *p);
+enum { cudaHostRegisterPortable = 1, cudaHostRegisterMapped = 2 };
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind k, cudaStream_t s = nullptr);
 cudaError_t cudaMemset(void *p, int v, size_t n);

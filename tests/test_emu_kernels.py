@@ -109,3 +109,26 @@ def test_emulated_rewind_reruns_with_other_parameters(emu_gpu, synth_small):
     b.end()
     emu_gpu.destroy(ctx)
     host.bam_close(hb)
+
+
+def test_emulated_gather_from_registered_buffers(emu_gpu, synth_small):
+    # the loader's record buffer is registered: add_reads() copies nothing, the gather kernel lays the blob out
+    host = pb.load_host()
+    hb = host.bam_open(synth_small["bam"])
+    cfg, ocfg = pb.make_config(36, readlen=2000), ob.make_config(36, readlen=2000)
+    wins = parity.load_windows(host, hb, synth_small["gaps"][:1], cfg)
+    ctx = emu_gpu.init()
+    ptr, nbytes = host.window_arena(wins[0][0])
+    emu_gpu.host_register(ctx, ptr, nbytes)
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(emu_gpu, ctx, host, wins, cfg)
+    assert rc == 0
+    t = b.timing()
+    assert t.launches == 9 or t.launches == 8  # one more than the copy path: the gather kernel
+    (w, n, chrom, s, e), (first, _) = wins[0], layout[0]
+    p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+    assert not parity.compare_window(b, 0, first, n, res, tags, ids, p)
+    assert t.bytes_h2d < 1.1 * nbytes  # gathered payload + descriptors, counted once
+    b.end()
+    emu_gpu.host_unregister(ctx, ptr)
+    emu_gpu.destroy(ctx)
+    host.bam_close(hb)

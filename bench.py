@@ -322,11 +322,18 @@ def main():
     def produce(q):
         t_p = time.perf_counter()
         for i, (bt, ws) in enumerate(zip(batches, chunks)):
+            ta = time.perf_counter()
             bt.reset()
+            tb = time.perf_counter()
             arr, tot, w_s, w_e, w_first, w_n = chunk_descs[i]
             bt.add_reads(arr, tot)
+            tc = time.perf_counter()
             bt.add_windows(w_s, w_e, w_first, w_n)
             bt.submit()
+            td = time.perf_counter()
+            e2e_prof["reset"] = e2e_prof.get("reset", 0.0) + tb - ta
+            e2e_prof["add_reads"] = e2e_prof.get("add_reads", 0.0) + tc - tb
+            e2e_prof["submit"] = e2e_prof.get("submit", 0.0) + td - tc
             q.put(i)
         e2e_prof["stage"] += time.perf_counter() - t_p
 
@@ -339,6 +346,7 @@ def main():
         bt.join(cfg)
         e2e_results[i] = bt.collect()
         e2e_prof["device"] = max(e2e_prof["device"], 0.0) + (time.perf_counter() - t_c) / nb
+        e2e_prof["transfer_ms_evt"] = e2e_prof.get("transfer_ms_evt", 0.0) + bt.timing().h2d_ms
 
     def e2e_step():
         # one producer (the gather copy saturates host memory bandwidth), one consumer per chunk: the device
@@ -364,7 +372,8 @@ def main():
             barrier()
             dt = time.perf_counter() - t0
             if it < args.warmup:
-                e2e_prof["stage"] = e2e_prof["device"] = 0.0
+                for k_ in list(e2e_prof):
+                    e2e_prof[k_] = 0.0
             else:
                 times.append(dt)
                 h2d = sum(bt.timing().bytes_h2d for bt in batches)
@@ -372,6 +381,9 @@ def main():
         # the chunked run must give what the single batch gave
         if [r.decision for r in res] != [r.decision for i in range(nb) for r in e2e_results[i][0]]:
             raise RuntimeError("chunked end-to-end run disagrees with the single-batch run")
+        if os.environ.get("POMFRET_BENCH_VERBOSE"):
+            sys.stderr.write("e2e profile per step (ms): %r\n" % {k_: round((1e3 if k_ != "transfer_ms_evt" else 1.0) * v_ / args.steps, 3)
+                                                                  for k_, v_ in e2e_prof.items()})
         return dict(times=times, h2d=h2d, d2h=d2h, stage=1e3 * e2e_prof["stage"] / args.steps,
                     device=1e3 * e2e_prof["device"] / args.steps)
 

@@ -560,14 +560,24 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
         if (direct) {
             const ReadRec *recs = b->h_reads.data() + first;
             (void)recs;
-            for (uint32_t i = 0; i < n; i++) {
+            // reference ends (tile planning on the host): the only payload the CPU looks at, a few hundred bytes per record
+            uint32_t *ends = b->h_end.data() + first;
+            auto scan = [&](size_t i) {
                 uint64_t rlen = 0;
                 for (uint32_t c = 0; c < r[i].n_cigar; c++) {
                     const uint32_t op = r[i].cigar[c] & 15u;
                     if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += r[i].cigar[c] >> 4;
                 }
-                b->h_end[first + i] = (uint32_t)(r[i].pos + (rlen ? rlen : 1));
+                ends[i] = (uint32_t)(r[i].pos + (rlen ? rlen : 1));
+            };
+            if (n >= 64 && !b->pool) {
+                unsigned hw = std::thread::hardware_concurrency();
+                int per = (int)(hw ? hw : 1) / std::max(1, b->ctx->n_workers);
+                if (const char *e = getenv("POMFRET_GPU_STAGE_THREADS")) per = atoi(e);
+                b->pool = new StagePool(std::max(0, std::min(per, 12) - 1));
             }
+            if (b->pool && n >= 64) b->pool->run((n + 63) / 64, [&](size_t g) { for (size_t i = g * 64; i < std::min<size_t>(n, g * 64 + 64); i++) scan(i); });
+            else for (uint32_t i = 0; i < n; i++) scan(i);
             b->h_blob.len = len;  // layout only: nothing is written on the host
             b->direct_any = true;
             return POMFRET_GPU_OK;

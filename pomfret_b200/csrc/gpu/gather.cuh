@@ -32,17 +32,34 @@ __device__ __forceinline__ void warp_gather_field(uint8_t *dst, uint64_t src_add
     const uint32_t n_src_words = (n + sh + 3u) >> 2;     // aligned words that hold the field
     const uint32_t n_out_words = ((n + 15u) & ~15u) >> 2;  // words written, padding included
     uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
-    for (uint32_t w0 = 0; w0 < n_out_words; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        uint32_t lo = w < n_src_words ? sw[w] : 0u;
-        uint32_t hi = __shfl_down_sync(FULL_MASK, lo, 1);
-        if (lane == 31) hi = w + 1 < n_src_words ? sw[w + 1] : 0u;
-        uint32_t v = sh ? __funnelshift_r(lo, hi, sh * 8u) : lo;
-        // bytes at and behind the end of the field are padding
-        const uint32_t b0 = w * 4u;
-        if (b0 >= n) v = 0u;
-        else if (n - b0 < 4u) v &= (1u << ((n - b0) * 8u)) - 1u;
-        if (w < n_out_words) dw[w] = v;
+    constexpr int U = 8;  // 8 x 128 bytes per warp in flight: reads over PCIe are latency bound
+    for (uint32_t w0 = 0; w0 < n_out_words; w0 += 32 * U) {
+        uint32_t lo[U], nx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t w = w0 + u * 32 + lane;
+            lo[u] = w < n_src_words ? sw[w] : 0u;
+        }
+        // the word behind lane 31's: first word of the next group of 32
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t first_next = u + 1 < U ? __shfl_sync(FULL_MASK, lo[u + 1 < U ? u + 1 : u], 0) : 0u;
+            nx[u] = __shfl_down_sync(FULL_MASK, lo[u], 1);
+            if (lane == 31) {
+                const uint32_t w = w0 + u * 32 + 32;
+                nx[u] = u + 1 < U ? first_next : (w < n_src_words ? sw[w] : 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t w = w0 + u * 32 + lane;
+            uint32_t v = sh ? __funnelshift_r(lo[u], nx[u], sh * 8u) : lo[u];
+            // bytes at and behind the end of the field are padding
+            const uint32_t b0 = w * 4u;
+            if (b0 >= n) v = 0u;
+            else if (n - b0 < 4u) v &= (1u << ((n - b0) * 8u)) - 1u;
+            if (w < n_out_words) dw[w] = v;
+        }
     }
 }
 

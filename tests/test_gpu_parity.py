@@ -143,3 +143,30 @@ def test_gpu_join_global_memory_paths(gpu, synth30, mode, monkeypatch):
     # windows too large for shared memory keep count tables / per-read state in global memory
     monkeypatch.setenv("POMFRET_GPU_JOIN_SMEM", mode)
     _run_tweaked(gpu, synth30, 30, 15000, lambda cfg: None)
+
+
+def test_gpu_gather_from_registered_buffers(gpu, synth30):
+    # registered loader buffers: no host copy, the gather kernel lays out the blob (unaligned sources, odd lengths)
+    host = pb.load_host()
+    hb = host.bam_open(synth30["bam"])
+    cfg, ocfg = pb.make_config(30), ob.make_config(30)
+    wins = parity.load_windows(host, hb, synth30["gaps"][:2], cfg)
+    ctx = gpu.init([0])
+    regs = []
+    for w, n, chrom, s, e in wins:
+        ptr, nbytes = host.window_arena(w)
+        if nbytes:
+            gpu.host_register(ctx, ptr, nbytes)
+            regs.append(ptr)
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(gpu, ctx, host, wins, cfg)
+    assert rc == 0, gpu.strerror(rc)
+    payload = sum(host.window_arena(w)[1] for w, _, _, _, _ in wins)
+    assert b.timing().bytes_h2d < 1.1 * payload
+    for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+        p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+        assert not parity.compare_window(b, wi, first, n, res, tags, ids, p), (chrom, s, e)
+    b.end()
+    for ptr in regs:
+        gpu.host_unregister(ctx, ptr)
+    gpu.destroy(ctx)
+    host.bam_close(hb)

@@ -150,7 +150,6 @@ class StagePool {
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
-    int helpers() const { return (int)th_.size(); }
     void run(size_t n, const std::function<void(size_t)> &fn) {
         if (th_.empty() || n < 2) { for (size_t i = 0; i < n; i++) fn(i); return; }
         {
@@ -558,8 +557,6 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             }
         }
         if (direct) {
-            const ReadRec *recs = b->h_reads.data() + first;
-            (void)recs;
             // reference ends (tile planning on the host): the only payload the CPU looks at, a few hundred bytes per record
             uint32_t *ends = b->h_end.data() + first;
             auto scan = [&](size_t i) {
@@ -1065,8 +1062,6 @@ int pomfret_gpu_batch_collect(pomfret_gpu_batch *b, pomfret_gpu_window_result *w
     if ((rc = b->h_state.resize(nw ? nw : 1))) return rc;
     b->host_tags_fwd.resize(nr + 1);
     b->host_rid.resize(nr + 1);
-    cudaEvent_t e0 = b->ev[0], e1 = b->ev[1];
-    (void)e0; (void)e1;
     if (nw) {
         CK(cudaMemcpyAsync(b->h_state.data(), b->d_state.p, nw * sizeof(WindowState), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaMemcpyAsync(b->host_tags_fwd.data(), b->d_tags[0].p, nr, cudaMemcpyDeviceToHost, b->stream));

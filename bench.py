@@ -153,6 +153,9 @@ def main():
     build.build_host()
 
     tmp = tempfile.mkdtemp(prefix="pomfret_bench_")
+    import atexit
+    import shutil
+    atexit.register(shutil.rmtree, tmp, True)
     cov = args.cov
     cfg = pb.make_config(cov)
     workload = "synthetic chr20-like %dx ONT reads (MM/ML+MD, haplotagged), %.0f Mb region, phased VCF; methphase -c %d" % (

@@ -23,42 +23,77 @@ struct GatherParams {
     uint32_t n_reads;
 };
 
-// dst is 16-byte aligned and owns align16(n) bytes; src has any alignment.  Source words are read 4-byte
-// aligned (lane-consecutive: 128-byte requests on the bus) and shifted into place.
+// 16 output bytes = bytes [sh, sh + 16) of the 32-byte window (a, b); sh = 4 * Q + r with Q a compile-time
+// word offset and r the byte offset inside a word
+template <int Q> __device__ __forceinline__ uint4 shift_window(const uint4 &a, const uint4 &b, uint32_t r8) {
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 o;
+    o.x = __funnelshift_r(w[Q + 0], w[Q + 1], r8);
+    o.y = __funnelshift_r(w[Q + 1], w[Q + 2], r8);
+    o.z = __funnelshift_r(w[Q + 2], w[Q + 3], r8);
+    o.w = __funnelshift_r(w[Q + 3], w[Q + 4], r8);
+    return o;
+}
+
+// dst is 16-byte aligned and owns align16(n) bytes; src has any alignment.  The source is read in 16-byte
+// aligned chunks, lane-consecutive (512-byte requests on the bus, GATHER_U of them in flight per warp), and
+// every output chunk is cut out of two neighbouring source chunks.
+constexpr int GATHER_U = 4;
+
 __device__ __forceinline__ void warp_gather_field(uint8_t *dst, uint64_t src_addr, uint32_t n) {
     const unsigned lane = lane_id();
-    const uint32_t sh = (uint32_t)(src_addr & 3u);
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src_addr - sh);
-    const uint32_t n_src_words = (n + sh + 3u) >> 2;     // aligned words that hold the field
-    const uint32_t n_out_words = ((n + 15u) & ~15u) >> 2;  // words written, padding included
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
-    constexpr int U = 8;  // 8 x 128 bytes per warp in flight: reads over PCIe are latency bound
-    for (uint32_t w0 = 0; w0 < n_out_words; w0 += 32 * U) {
-        uint32_t lo[U], nx[U];
+    const uint32_t sh = (uint32_t)(src_addr & 15u);
+    const uint4 *sc = reinterpret_cast<const uint4 *>(src_addr - sh);
+    const uint32_t n_src = (n + sh + 15u) >> 4;  // aligned source chunks that hold the field
+    const uint32_t n_out = (n + 15u) >> 4;       // chunks written, padding included
+    uint4 *dc = reinterpret_cast<uint4 *>(dst);
+    const uint32_t q = sh >> 2, r8 = (sh & 3u) * 8u;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (uint32_t c0 = 0; c0 < n_out; c0 += 32 * GATHER_U) {
+        uint4 cur[GATHER_U], nxt[GATHER_U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t w = w0 + u * 32 + lane;
-            lo[u] = w < n_src_words ? sw[w] : 0u;
+        for (int u = 0; u < GATHER_U; u++) {
+            const uint32_t c = c0 + u * 32 + lane;
+            cur[u] = c < n_src ? sc[c] : zero;
         }
-        // the word behind lane 31's: first word of the next group of 32
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t first_next = u + 1 < U ? __shfl_sync(FULL_MASK, lo[u + 1 < U ? u + 1 : u], 0) : 0u;
-            nx[u] = __shfl_down_sync(FULL_MASK, lo[u], 1);
-            if (lane == 31) {
-                const uint32_t w = w0 + u * 32 + 32;
-                nx[u] = u + 1 < U ? first_next : (w < n_src_words ? sw[w] : 0u);
+        for (int u = 0; u < GATHER_U; u++) {
+            // the chunk behind this lane's: the next lane's, or for lane 31 the first of the next group of 32
+            nxt[u].x = __shfl_down_sync(FULL_MASK, cur[u].x, 1); nxt[u].y = __shfl_down_sync(FULL_MASK, cur[u].y, 1);
+            nxt[u].z = __shfl_down_sync(FULL_MASK, cur[u].z, 1); nxt[u].w = __shfl_down_sync(FULL_MASK, cur[u].w, 1);
+            uint4 f = zero;
+            if (u + 1 < GATHER_U) {
+                const uint4 &g = cur[u + 1 < GATHER_U ? u + 1 : u];
+                f.x = __shfl_sync(FULL_MASK, g.x, 0); f.y = __shfl_sync(FULL_MASK, g.y, 0);
+                f.z = __shfl_sync(FULL_MASK, g.z, 0); f.w = __shfl_sync(FULL_MASK, g.w, 0);
+            } else if (lane == 31 && sh) {
+                const uint32_t c = c0 + GATHER_U * 32;
+                if (c < n_src) f = sc[c];
             }
+            if (lane == 31) nxt[u] = f;
         }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t w = w0 + u * 32 + lane;
-            uint32_t v = sh ? __funnelshift_r(lo[u], nx[u], sh * 8u) : lo[u];
+        for (int u = 0; u < GATHER_U; u++) {
+            const uint32_t c = c0 + u * 32 + lane;
+            uint4 o;
+            if (sh == 0) o = cur[u];
+            else if (q == 0) o = shift_window<0>(cur[u], nxt[u], r8);
+            else if (q == 1) o = shift_window<1>(cur[u], nxt[u], r8);
+            else if (q == 2) o = shift_window<2>(cur[u], nxt[u], r8);
+            else o = shift_window<3>(cur[u], nxt[u], r8);
             // bytes at and behind the end of the field are padding
-            const uint32_t b0 = w * 4u;
-            if (b0 >= n) v = 0u;
-            else if (n - b0 < 4u) v &= (1u << ((n - b0) * 8u)) - 1u;
-            if (w < n_out_words) dw[w] = v;
+            const uint32_t b0 = c * 16u;
+            if (b0 + 16u > n) {
+                uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t bw = b0 + 4u * i;
+                    if (bw >= n) w[i] = 0u;
+                    else if (n - bw < 4u) w[i] &= (1u << ((n - bw) * 8u)) - 1u;
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (c < n_out) dc[c] = o;
         }
     }
 }

@@ -233,15 +233,43 @@ def build_records(seed, n_random=60, max_len=9000, long_lens=(70000,)):
     return R
 
 
-def check_against_port(gpu, R, lo=100, hi=156):
+def pack_into_one_buffer(R, seed=0):
+    """Move every field of every record into one byte buffer at random (mis)alignments and point the
+    descriptors there: what a loader's record buffer looks like.  Returns (address, size) of the buffer."""
+    rng = np.random.default_rng(seed)
+    fields = []
+    total = 64
+    for d in R.descs:
+        for name, size in (("cigar", d.n_cigar * 4), ("seq", (d.l_qseq + 1) // 2), ("mm", d.mm_len if d.mm else 0),
+                           ("ml", d.ml_len if d.ml_len > 0 else 0), ("md", d.md_len if d.md else 0)):
+            if getattr(d, name) and size:
+                off = total + int(rng.integers(0, 16))
+                if name == "cigar":
+                    off = (off + 3) & ~3  # CIGAR words stay 4-byte aligned, as inside a BAM record
+                fields.append((d, name, size, off))
+                total = off + size
+    buf = np.zeros(total + 64, dtype=np.uint8)
+    base = buf.ctypes.data
+    for d, name, size, off in fields:
+        C.memmove(base + off, getattr(d, name), size)
+        setattr(d, name, base + off)
+    R.keep.append(buf)
+    return base, len(buf)
+
+
+def check_against_port(gpu, R, lo=100, hi=156, register=None):
     """Decode R on `gpu` (CUDA or emulated library) and with the oracle port; return the list of differences."""
     arr = R.array()
     n = len(R.descs)
     ctx = gpu.init()
+    if register:
+        gpu.host_register(ctx, register[0], register[1])
     b = gpu.batch_begin(ctx)
     b.add_reads(arr, n)
     b.submit()
     b.decode(lo, hi)
+    if register:
+        assert b.timing().launches == 2, "the records were expected to be gathered by the device"
     port = ob.port_lib()
     bad = []
     n_overflow = 0
@@ -266,6 +294,8 @@ def check_against_port(gpu, R, lo=100, hi=156):
             if not (np.array_equal(gpos, ppos) and np.array_equal(gcat, pcat)):
                 bad.append((R.names[i], i, "calls", len(gpos), len(ppos)))
     b.end()
+    if register:
+        gpu.host_unregister(ctx, register[0])
     gpu.destroy(ctx)
     if n_overflow > n // 10:
         bad.append(("too many call-slot overflows", n_overflow, n))

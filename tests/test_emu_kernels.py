@@ -132,3 +132,24 @@ def test_emulated_gather_from_registered_buffers(emu_gpu, synth_small):
     emu_gpu.host_unregister(ctx, ptr)
     emu_gpu.destroy(ctx)
     host.bam_close(hb)
+
+
+def test_emulated_long_reads_uncached_keys(emu_gpu, built, tmp_path):
+    # reads that span more than 256 methmer sites: their keys are scored straight from the pool
+    import conftest
+    data = conftest.run_synth(str(tmp_path / "long"), ["-c", "32", "-s", "41", "-C", "chrL:900000:0-600000", "--readlen", "70000",
+                                                        "--block", "250000", "--gap", "20000-30000"])
+    host = pb.load_host()
+    hb = host.bam_open(data["bam"])
+    cfg, ocfg = pb.make_config(32), ob.make_config(32)
+    wins = parity.load_windows(host, hb, data["gaps"][:1], cfg)
+    ctx = emu_gpu.init()
+    b, layout, res, tags, ids, rc = parity.run_gpu_batch(emu_gpu, ctx, host, wins, cfg)
+    assert rc == 0
+    (w, n, chrom, s, e), (first, _) = wins[0], layout[0]
+    p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+    assert max(len(b.mmrs(first + i, 0)[0]) for i in range(n)) > 256
+    assert not parity.compare_window(b, 0, first, n, res, tags, ids, p, deep=False)
+    b.end()
+    emu_gpu.destroy(ctx)
+    host.bam_close(hb)

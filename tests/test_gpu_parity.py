@@ -170,3 +170,11 @@ def test_gpu_gather_from_registered_buffers(gpu, synth30):
         gpu.host_unregister(ctx, ptr)
     gpu.destroy(ctx)
     host.bam_close(hb)
+
+
+def test_gpu_long_reads_uncached_keys(gpu, built, tmp_path):
+    # reads that span more than 256 methmer sites: their keys are scored straight from the pool
+    import conftest
+    data = conftest.run_synth(str(tmp_path / "long"), ["-c", "32", "-s", "41", "-C", "chrL:900000:0-600000", "--readlen", "70000",
+                                                        "--block", "250000", "--gap", "20000-30000"])
+    _run(gpu, data, 32, check_ref=False)

@@ -237,9 +237,6 @@ struct pomfret_gpu_batch {
     bool streaming = false, h2d_started = false;
     bool direct_any = false, copied_any = false;  // records gathered by the device / copied by the host in this batch
     PinVec<GatherSrc> h_gsrc;
-    struct RawSpan { const uint8_t *host; size_t bytes, dev_off; };
-    std::vector<RawSpan> raw_spans;  // dense stretches of registered caller memory that the copy engine moves as they are
-    size_t raw_len = 16;
     // device
     DevArena arena;
     DevBuf d_blob, d_reads, d_win, d_read_win, d_calls_pos, d_calls_cat, d_tmp_rank, d_tmp_mpos, d_tmp_mcat;
@@ -248,7 +245,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc, d_raw;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -265,7 +262,7 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_raw};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc};
     }
 };
 
@@ -389,8 +386,6 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     b->h_blob.len = 0;
     b->h_reads.clear(); b->h_win.clear(); b->h_read_win.clear(); b->h_gsrc.clear();
     b->direct_any = b->copied_any = false;
-    b->raw_spans.clear();
-    b->raw_len = 16;
     b->h_end.clear();
     b->calls_total = 0;
     b->alg_decode_bytes = b->alg_haptag_bytes = 0;
@@ -562,37 +557,6 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             }
         }
         if (direct) {
-            // If the call's fields sit densely in one stretch of the caller's buffer (a loader's record buffer),
-            // the copy engine moves the stretch as it is (DMA runs at full PCIe rate) and the gather kernel reads
-            // the device copy; scattered fields are read by the kernel straight from the mapped host memory.
-            uintptr_t lo = ~(uintptr_t)0, hi = 0;
-            size_t payload = 0;
-            for (uint32_t i = 0; i < n; i++) {
-                const pomfret_gpu_read_desc &d = r[i];
-                const void *p[5] = {d.cigar, d.seq, d.mm, d.ml_len >= 0 ? d.ml : nullptr, d.md};
-                const size_t sz[5] = {(size_t)d.n_cigar * 4, ((size_t)d.l_qseq + 1) / 2, d.mm ? d.mm_len : 0,
-                                      d.ml_len > 0 ? (size_t)d.ml_len : 0, d.md ? d.md_len : 0};
-                for (int f = 0; f < 5; f++) {
-                    if (!p[f] || !sz[f]) continue;
-                    lo = std::min(lo, (uintptr_t)p[f]);
-                    hi = std::max(hi, (uintptr_t)p[f] + sz[f]);
-                    payload += sz[f];
-                }
-            }
-            size_t hint2 = 0;
-            if (payload && hi - lo <= payload + payload / 4 + 65536 && region_lookup(regs, (const void *)lo, hi - lo, &hint2)) {
-                // same alignment class on the device as on the host: the gather kernel cuts 16-byte chunks
-                const size_t dev_off = ((b->raw_len + 15) & ~(size_t)15) + (lo & 15);
-                b->raw_spans.push_back({(const uint8_t *)lo, hi - lo, dev_off});
-                b->raw_len = dev_off + (hi - lo) + 16;
-                for (uint32_t i = 0; i < n; i++) {
-                    const pomfret_gpu_read_desc &d = r[i];
-                    const void *p[5] = {d.cigar, d.seq, d.mm, d.ml_len >= 0 ? d.ml : nullptr, d.md};
-                    GatherSrc &G = b->h_gsrc[first + i];
-                    for (int f = 0; f < 5; f++)
-                        if (G.ptr[f]) G.ptr[f] = GATHER_RAW | (uint64_t)(dev_off + ((uintptr_t)p[f] - lo));
-                }
-            }
             // reference ends (tile planning on the host): the only payload the CPU looks at, a few hundred bytes per record
             uint32_t *ends = b->h_end.data() + first;
             auto scan = [&](size_t i) {
@@ -716,12 +680,8 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     if ((rc = up(b, b->d_reads, b->h_reads.data(), nr * sizeof(ReadRec)))) return rc;
     if (b->direct_any && nr) {
         if ((rc = up(b, b->d_gsrc, b->h_gsrc.data(), nr * sizeof(GatherSrc)))) return rc;
-        if ((rc = b->d_raw.ensure(b->raw_len + 64))) return rc;
-        for (const pomfret_gpu_batch::RawSpan &sp : b->raw_spans)
-            CK(cudaMemcpyAsync(b->d_raw.as<uint8_t>() + sp.dev_off, sp.host, sp.bytes, cudaMemcpyHostToDevice, b->stream));
         GatherParams G;
         G.reads = b->d_reads.as<ReadRec>(); G.src = b->d_gsrc.as<GatherSrc>(); G.blob = b->d_blob.as<uint8_t>(); G.n_reads = (uint32_t)nr;
-        G.raw = b->d_raw.as<uint8_t>();
         POMFRET_LAUNCH(gather_kernel, (unsigned)((nr + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, b->stream, G);
         b->tm.launches++;
         for (size_t i = 0; i < nr; i++)

@@ -10,21 +10,16 @@
 
 namespace pomfret_gpu {
 
-constexpr int GATHER_WARPS = 4;
-
-constexpr uint64_t GATHER_RAW = 1ull << 63;  // the address is an offset into the batch's raw copy, not a mapped host address
+constexpr int GATHER_WARPS = 8;
 
 struct GatherSrc {
-    // where cigar, seq, mm, ml, md of a record are: a device-visible address of the caller's (mapped) memory,
-    // or GATHER_RAW | offset into the raw copy that the DMA engine made of the caller's buffer; 0: not gathered
-    uint64_t ptr[5];
+    uint64_t ptr[5];  // device-visible addresses of cigar, seq, mm, ml, md in the caller's memory; 0: not gathered
 };
 
 struct GatherParams {
     const ReadRec *reads;
     const GatherSrc *src;
     uint8_t *blob;
-    const uint8_t *raw;  // raw copy of the caller's record buffer (contiguous spans moved by the copy engine)
     uint32_t n_reads;
 };
 
@@ -107,10 +102,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_kernel(GatherParams 
     const uint32_t ri = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
     if (ri >= P.n_reads) return;
     const ReadRec &R = P.reads[ri];
-    GatherSrc S = P.src[ri];
-#pragma unroll
-    for (int f = 0; f < 5; f++)
-        if (S.ptr[f] & GATHER_RAW) S.ptr[f] = (uint64_t)(uintptr_t)P.raw + (S.ptr[f] & ~GATHER_RAW);
+    const GatherSrc &S = P.src[ri];
     if (S.ptr[0]) warp_gather_field(P.blob + (size_t)R.cigar_off * 16, S.ptr[0], R.n_cigar * 4u);
     if (S.ptr[1]) {
         warp_gather_field(P.blob + (size_t)R.seq_off * 16, S.ptr[1], (R.l_qseq + 1u) >> 1);

@@ -233,16 +233,13 @@ def build_records(seed, n_random=60, max_len=9000, long_lens=(70000,)):
     return R
 
 
-def pack_into_one_buffer(R, seed=0, hole=0):
+def pack_into_one_buffer(R, seed=0):
     """Move every field of every record into one byte buffer at random (mis)alignments and point the
-    descriptors there: what a loader's record buffer looks like.  `hole` leaves that many unused bytes in the
-    middle.  Returns (address, size) of the buffer."""
+    descriptors there: what a loader's record buffer looks like.  Returns (address, size) of the buffer."""
     rng = np.random.default_rng(seed)
     fields = []
     total = 64
-    for di, d in enumerate(R.descs):
-        if hole and di == len(R.descs) // 2:
-            total += hole  # unused stretch: the records no longer sit densely (no raw DMA copy, mapped reads instead)
+    for d in R.descs:
         for name, size in (("cigar", d.n_cigar * 4), ("seq", (d.l_qseq + 1) // 2), ("mm", d.mm_len if d.mm else 0),
                            ("ml", d.ml_len if d.ml_len > 0 else 0), ("md", d.md_len if d.md else 0)):
             if getattr(d, name) and size:

@@ -1,5 +1,5 @@
 // (b) Per-read decode kernel: MM/ML base-modification tags + CIGAR -> reference-coordinate 5mC
-// calls at CpG sites.  One warp per alignment record.
+// calls at CpG sites.  One warp per alignment record at a time (persistent warps over a queue, longest first).
 //
 // Replaces, for records that passed the host filters:
 //   bam_parse_basemod / bam_mods_at_next_pos as used at reference blockjoin.c:807,832-882
@@ -11,11 +11,14 @@
 // Data flow per warp (all global accesses are 128-bit or lane-consecutive):
 //   1. CIGAR pre-scan: reference span, first stopping op, fatal-op test.
 //   2. MM structure scan: ';' positions -> segment table; headers parsed by lane 0.
-//   3. Delta lists: one lane per comma parses its number out of a shared-memory staged chunk;
-//      warp prefix sums turn deltas into "index among canonical bases" targets.
-//   4. SEQ scan, 512 B per warp step: nibble match flags, popcount prefix scan, targets selected with
-//      a lane binary search + find-nth-set-bit; CpG context checked on SEQ; ML byte -> category.
-//      Reverse-strand records scan SEQ from its end so targets count from the read's own 5' end.
+//   3. Delta lists: 16 characters per lane, classified with SWAR byte masks; every comma's number is
+//      converted without a loop from a shared-memory staged chunk; warp prefix sums turn deltas into
+//      ranks ("index among the canonical bases").
+//   4. SEQ, pass 1: two 512 B tiles per warp step (next step prefetched): nibble match flags, popcounts,
+//      one packed warp scan; the rank of every 32-base chunk's first canonical base goes to shared memory.
+//      Pass 2, dense over the listed bases (32 per pass): binary search of the chunk holding the rank,
+//      select-nth inside the chunk, CpG context on SEQ, ML byte -> category, coalesced stores.
+//      Reverse-strand records scan SEQ from its end so ranks count from the read's own 5' end.
 //   5. CIGAR walk: M/I ops compacted (read-end, offset) into shared memory in chunks; each kept mod
 //      binary-searches the op that the reference's inclusive trigger loop would handle it under;
 //      positions de-duplicated with the reference's overwrite rule and written out.

@@ -10,11 +10,17 @@
 // The reference keeps, per site, a growing list of (key, count per haplotype); membership is all that
 // the list adds over a dense table, and "key present" == "some haplotype count is non-zero", so the
 // table here is dense: one 32-bit word per (site, key) holding both 16-bit counts, one word per site
-// for the two sums.  It lives in global memory (L1/L2 resident, a few hundred KB per window).
+// for the two sums.  It lives in the CTA's shared memory (about 100 KB for a 30x window at k = 3; windows
+// whose tables exceed an SM fall back to a global pool), next to the per-read methmer metadata, the scan
+// order, a tagged bitmap and the candidates' methmer keys.
 //
 // Score sums are order sensitive fp32 (blockjoin.c:3620-3636): values are produced in parallel, one
-// lane per methmer, then added strictly in methmer order by one lane per haplotype with IEEE
-// round-to-nearest adds and divides (no fast-math, no FMA contraction possible).
+// lane per methmer (IEEE divides), the non-zero ones compacted in methmer order and then added strictly
+// in that order with round-to-nearest adds (no fast-math, no FMA contraction possible).
+//
+// The loop is latency bound (one read tagged per iteration), so everything on its critical path is kept
+// short: candidates live in fixed slots, the next candidate and its keys are prefetched by a service warp
+// while the others score, two barriers per iteration.
 #ifndef POMFRET_GPU_JOIN_CUH
 #define POMFRET_GPU_JOIN_CUH
 #include "gpu_rt.h"

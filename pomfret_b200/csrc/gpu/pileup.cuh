@@ -6,10 +6,11 @@
 // for the forward and the backward direction.
 //
 // pileup_tile_kernel: one CTA per (window, position tile).  The tile's counters live in shared memory
-// as one packed 32-bit word per position (low half methylated, high half unmethylated).  Every warp
-// streams the calls of its share of the window's reads that fall into the tile (binary search of the
-// tile bounds in the read's sorted call list, then lane-consecutive loads) and adds into the counters
-// with shared-memory atomics; no-call entries are not needed for selection and are skipped.  The
+// as one packed 32-bit word per position (low half methylated, high half unmethylated).  One record per
+// thread first: does it touch the tile, and which of its (sorted) calls fall into it (two binary
+// searches); the records that do are listed in shared memory and then streamed one per warp step with
+// lane-consecutive loads into the counters (shared-memory atomics); no-call entries are not needed for
+// selection and are skipped.  The
 // strand-saturation bits of the reference counter never reach an output and are not materialised; its
 // count field is 12 bits wide (u16 >> 4), which is reproduced by masking with 0xfff.
 // sites_finalize_kernel: one CTA per window, concatenates the tile outputs in position order and

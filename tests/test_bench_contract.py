@@ -1,0 +1,37 @@
+"""bench.py contract pieces that run without a GPU: the reference arm (the unmodified reference binary on the
+host cores) prints one JSON line with the agreed keys; our arm refuses to run without a CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_bindings as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.exists(ob.REF_BIN), reason="oracle/_ref/pomfret not built")
+def test_reference_arm_prints_the_contract_line(built):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                        "--region-mb", "2"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "reads/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 3
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_our_arm_fails_loudly_without_a_device(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--region-mb", "1"], capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode != 0
+    assert not [l for l in p.stdout.splitlines() if l.startswith("{")]

@@ -1,11 +1,21 @@
 #!/usr/bin/env python
 """bench.py — methphase hot-path throughput (BASELINE.json metric: reads/s and bases/s, HBM GB/s vs peak).
 
-A "step" is one pass of the hot path (decode -> read sets -> pileup -> methmers -> greedy join) over one
-batch of synthetic windows.  `value` times the device stages with inputs resident in HBM; `e2e` times
-the same through the C ABI with host buffers (staging copy + H2D + kernels + D2H inside the timed region).
-`--impl reference` times the reference's own CPU implementation (oracle/_ref/pomfret methphase -t N) on
-the same synthetic BAM.
+A "step" is one pass of the hot path (decode -> read sets -> pileup -> methmers -> greedy join -> collect) over
+one batch of synthetic windows: the whole chr20 30x workload, 98 windows, ~21 k
+records, ~306 MB staged per GPU.
+
+  value / ms_per_step   K steps with the records resident in HBM, `--in-flight` batches (default 2) driven by as
+                        many host threads: the latency-bound join of one batch overlaps the other batch's kernels
+  latency_ms_per_step   one step alone on the device (launches, the pool-size round trip, D2H + Fisher included)
+  kernel_ms             CUDA-event time of every stage of that single step; roofline = decode_kernel
+  e2e                   the same step through the C ABI from a registered host buffer: descriptors, device gather
+                        over PCIe, kernels, D2H; `--e2e-batches` region chunks pipelined (producer + consumers)
+  e2e_host_copy         the same from unregistered host buffers (host gather copy into pinned memory + H2D)
+  cpu_baseline          the compiled reference's per-window call sequence on a bounded sample, 1 thread (N = 1 only)
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/pomfret methphase -t N) on the
+same synthetic BAM.  Under torchrun every rank owns its own region set (weak scaling, no data-path collective).
 """
 import argparse
 import ctypes as C

@@ -334,3 +334,50 @@ double refh_fisher_two_sided(int a, int b, int c, int d) {
 float refh_evaluate_separation1(const uint8_t *ref, const uint8_t *query, int n, int *join_dir) {
     return evaluate_separation1((uint8_t *)ref, (uint8_t *)query, n, join_dir, NULL);
 }
+
+/* ---- one hand-built record through the reference's fill_read_meth_record_from_bam_line (blockjoin.c:794-908)
+ * on top of the shim's bam_parse_basemod / bam_mods_at_next_pos: known-answer vectors for the MM/ML layer.
+ * mm == NULL: no MM tag; ml_len < 0: no ML tag; mn < 0: no MN tag.  Returns the function's return value. */
+int refh_fill_read_meth(uint32_t pos, int flag, const uint32_t *cigar, int n_cigar, const uint8_t *seq4, int l_qseq,
+                        const char *mm, const uint8_t *ml, int ml_len, int mn, int lo, int hi, uint32_t *out_pos,
+                        uint8_t *out_cat, int cap, int *n_out, int *has_implicit) {
+    bam1_t *b = bam_init1();
+    size_t mm_l = mm ? strlen(mm) : 0;
+    size_t need = 4 + (size_t)n_cigar * 4 + ((size_t)l_qseq + 1) / 2 + (size_t)l_qseq + 3 + mm_l + 1 + 8 + (ml_len > 0 ? ml_len : 0) + 16;
+    b->data = (uint8_t *)calloc(1, need);
+    b->m_data = (uint32_t)need;
+    uint8_t *p = b->data;
+    memcpy(p, "q\0\0\0", 4); p += 4;
+    b->core.l_qname = 4; b->core.l_extranul = 2;
+    memcpy(p, cigar, (size_t)n_cigar * 4); p += (size_t)n_cigar * 4;
+    memcpy(p, seq4, ((size_t)l_qseq + 1) / 2); p += ((size_t)l_qseq + 1) / 2;
+    memset(p, 0xff, (size_t)l_qseq); p += l_qseq;
+    if (mm) { *p++ = 'M'; *p++ = 'M'; *p++ = 'Z'; memcpy(p, mm, mm_l + 1); p += mm_l + 1; }
+    if (ml_len >= 0) {
+        *p++ = 'M'; *p++ = 'L'; *p++ = 'B'; *p++ = 'C';
+        uint32_t n = (uint32_t)ml_len;
+        memcpy(p, &n, 4); p += 4;
+        if (ml_len) memcpy(p, ml, (size_t)ml_len);
+        p += ml_len;
+    }
+    if (mn >= 0) { *p++ = 'M'; *p++ = 'N'; *p++ = 'I'; uint32_t v = (uint32_t)mn; memcpy(p, &v, 4); p += 4; }
+    b->l_data = (int)(p - b->data);
+    b->core.pos = (int32_t)pos; b->core.flag = (uint16_t)flag; b->core.n_cigar = (uint32_t)n_cigar; b->core.l_qseq = l_qseq;
+    b->core.qual = 60; b->core.tid = 0; b->core.mtid = -1; b->core.mpos = -1;
+    read_t h;
+    memset(&h, 0, sizeof(h));
+    init_mod_t(&h.meth, 16);
+    hts_base_mod_state *ms = hts_base_mod_state_alloc();
+    vu32_t poss; vu8_t quals;
+    kv_init(poss); kv_init(quals);
+    global_data_has_implicit = 0;
+    int stat = fill_read_meth_record_from_bam_line(&h, b, ms, &poss, &quals, (uint8_t)lo, (uint8_t)hi);
+    *n_out = (int)h.meth.calls.n;
+    for (int i = 0; i < (int)h.meth.calls.n && i < cap; i++) { out_pos[i] = h.meth.calls.a[i]; out_cat[i] = h.meth.quals.a[i]; }
+    if (has_implicit) *has_implicit = global_data_has_implicit;
+    kv_destroy(poss); kv_destroy(quals);
+    destroy_mod_t(&h.meth, 0);
+    hts_base_mod_state_free(ms);
+    bam_destroy1(b);
+    return stat;
+}

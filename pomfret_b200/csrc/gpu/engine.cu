@@ -109,7 +109,8 @@ struct PinBuf {
         size_t want = std::max(std::max(bytes + bytes / 2, cap * 2), min_cap);
         void *q = nullptr;
         if (cudaMallocHost(&q, want) != cudaSuccess) return POMFRET_GPU_ERR_NOMEM;
-        if (p) { memcpy(q, p, len); cudaFreeHost(p); }
+        // `len` is the laid-out size; records gathered by the device have no bytes here, so it may exceed cap
+        if (p) { memcpy(q, p, len < cap ? len : cap); cudaFreeHost(p); }
         p = (uint8_t *)q; cap = want;
         return 0;
     }
@@ -526,15 +527,16 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
     if (n == 0) return POMFRET_GPU_OK;
     const size_t first = b->h_reads.n;
     size_t len = b->h_blob.len;
+    const uint64_t calls0 = b->calls_total, dec0 = b->alg_decode_bytes, hap0 = b->alg_haptag_bytes;
+    auto rollback = [&]() {  // a failed call leaves the batch as it found it
+        b->h_reads.n = first; b->h_reads.b.len = first * sizeof(ReadRec);
+        b->h_read_win.n = first; b->h_read_win.b.len = first * 4;
+        b->calls_total = calls0; b->alg_decode_bytes = dec0; b->alg_haptag_bytes = hap0;
+    };
     for (uint32_t i = 0; i < n; i++) {
-        if (int rc = plan_read(b, r + i, &len)) {
-            // roll back the partially planned call
-            b->h_reads.n = first; b->h_reads.b.len = first * sizeof(ReadRec);
-            b->h_read_win.n = first; b->h_read_win.b.len = first * 4;
-            return rc;
-        }
+        if (int rc = plan_read(b, r + i, &len)) { rollback(); return rc; }
     }
-    if (int rc = b->h_gsrc.resize(first + n)) return rc;
+    if (int rc = b->h_gsrc.resize(first + n)) { rollback(); return rc; }
     b->h_end.resize(first + n);
     // records that lie completely inside registered caller buffers stay where they are: the device gathers them
     {
@@ -585,7 +587,7 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
     if (len + 2048 > b->h_blob.cap) {
         // growing the pinned arena moves it: no DMA may still be reading the old one
         if (b->blob_sent) { CK(cudaSetDevice(b->device)); CK(cudaStreamSynchronize(b->stream)); }
-        if (int rc = b->h_blob.reserve(len + 2048)) return rc;
+        if (int rc = b->h_blob.reserve(len + 2048)) { rollback(); return rc; }
     }
     uint8_t *blob = b->h_blob.p;
     const ReadRec *recs = b->h_reads.data() + first;

@@ -92,10 +92,10 @@ void describe_record(const bam1_t *b, int hp, pomfret_gpu_read_desc *d) {
 int for_each_window_record(BamReader &bam, const char *chrom, uint32_t ref_start, uint32_t ref_end, int readlen_threshold,
                            int min_mapq, const RawTagMap *raw_tags, const std::function<void(const bam1_t *, int hp)> &fn) {
     const int itvl_s = (int)ref_start, itvl_e = (int)ref_end;
-    char region[1024];
-    snprintf(region, sizeof(region), "%s:%d-%d", chrom, (itvl_s - kReadback) > 0 ? itvl_s - kReadback : 0,
-             itvl_e + kReadback);
-    hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, region);
+    // (the reference mallocs strlen(chrom) + 30 here, blockjoin.c:1057: any contig name fits)
+    const std::string region = std::string(chrom) + ":" + std::to_string((itvl_s - kReadback) > 0 ? itvl_s - kReadback : 0) + "-" +
+                               std::to_string(itvl_e + kReadback);
+    hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, region.c_str());
     if (!itr) return POMFRET_GPU_ERR_ARG;
     bam1_t *b = bam.rec;
     while (sam_itr_next(bam.fp, itr, b) >= 0) {

@@ -165,6 +165,42 @@ static int reserve(bam1_t *b, size_t want) {
     return 0;
 }
 
+/* Alignments with more than 65535 CIGAR operations are stored (SAM spec section 4.2.2) with the placeholder
+ * CIGAR `<l_qseq>S<ref_len>N` and the real operations in a CG:B,I tag.  htslib's bam_read1 moves them back
+ * into place and drops the tag, so callers always see the real CIGAR; this does the same.
+ * Returns 1 if the record was rewritten, 0 if it was left alone, -1 on error. */
+static int restore_long_cigar(bam1_t *b) {
+    bam1_core_t *c = &b->core;
+    if (c->n_cigar == 0 || c->tid < 0 || c->pos < 0) return 0;
+    uint32_t first;
+    memcpy(&first, b->data + c->l_qname, 4);
+    if (bam_cigar_op(first) != BAM_CSOFT_CLIP || (int32_t)bam_cigar_oplen(first) != c->l_qseq) return 0;
+    const uint8_t *tag = bam_aux_get(b, "CG");
+    if (!tag) return errno == ENOENT ? 0 : -1;
+    if (tag[0] != 'B' || (tag[1] != 'I' && tag[1] != 'i')) return 0;
+    const uint32_t n_real = ld32(tag + 2);
+    if (n_real < c->n_cigar || n_real >= (1u << 29)) return 0;
+    const size_t cig_at = c->l_qname, placeholder = (size_t)c->n_cigar * 4, real = (size_t)n_real * 4;
+    const size_t tag_at = (size_t)(tag - b->data) - 2, tag_len = 8 + real;  /* "CG" 'B' 'I' count + payload */
+    const size_t old_len = (size_t)b->l_data;
+    if (tag_at + tag_len > old_len) return -1;
+    /* new record = [.. cig_at) + real CIGAR + (cig_at + placeholder .. tag_at) + (tag_at + tag_len .. old_len) */
+    uint8_t *ops = (uint8_t *)malloc(real ? real : 1);
+    if (!ops) return -1;
+    memcpy(ops, b->data + tag_at + 8, real);
+    const size_t new_len = old_len - placeholder - 8;
+    if (reserve(b, new_len + 8) != 0) { free(ops); return -1; }
+    /* drop the tag first (it lies behind the CIGAR), then open the gap for the real operations */
+    memmove(b->data + tag_at, b->data + tag_at + tag_len, old_len - tag_at - tag_len);
+    const size_t after_cig = cig_at + placeholder, tail = old_len - tag_len - after_cig;
+    memmove(b->data + cig_at + real, b->data + after_cig, tail);
+    memcpy(b->data + cig_at, ops, real);
+    free(ops);
+    c->n_cigar = n_real;
+    b->l_data = (int)new_len;
+    return 1;
+}
+
 /* Returns bytes consumed (>=4) on success, -1 at EOF, < -1 on error. */
 int bam_read1(BGZF *fp, bam1_t *b) {
     uint8_t x[36];
@@ -198,6 +234,7 @@ int bam_read1(BGZF *fp, bam1_t *b) {
     b->l_data = (int)(payload + extranul);
     size_t need = (size_t)c->l_qname + ((size_t)c->n_cigar << 2) + (((size_t)c->l_qseq + 1) >> 1) + (size_t)c->l_qseq;
     if (need > (size_t)b->l_data) return -4;
+    if (restore_long_cigar(b) < 0) return -4;
     __atomic_fetch_add(&g_n_records, 1, __ATOMIC_RELAXED);
     __atomic_fetch_add(&g_n_bytes, (uint64_t)block_len + 4, __ATOMIC_RELAXED);
     return 4 + block_len;
@@ -208,13 +245,20 @@ int bam_write1(BGZF *fp, const bam1_t *b) {
     uint8_t x[36];
     uint32_t l_qname = c->l_qname - c->l_extranul;
     uint32_t block_len = (uint32_t)b->l_data - c->l_extranul + 32;
+    const int long_cigar = c->n_cigar > 0xffffu;  /* placeholder CIGAR (8 bytes) + "CGBI" + count (8 bytes) */
+    hts_pos_t ref_len = 0;
+    if (long_cigar) {
+        ref_len = bam_cigar2rlen((int)c->n_cigar, bam_get_cigar(b));
+        if (ref_len >= (1 << 28)) return -1;  /* does not fit one CIGAR operation: not representable in BAM */
+        block_len += 16;
+    }
     st32(x, block_len);
     st32(x + 4, (uint32_t)c->tid);
     st32(x + 8, (uint32_t)c->pos);
     x[12] = (uint8_t)l_qname;
     x[13] = c->qual;
     st16(x + 14, c->bin);
-    st16(x + 16, (uint16_t)c->n_cigar);
+    st16(x + 16, long_cigar ? 2 : (uint16_t)c->n_cigar);
     st16(x + 18, c->flag);
     st32(x + 20, (uint32_t)c->l_qseq);
     st32(x + 24, (uint32_t)c->mtid);
@@ -223,8 +267,22 @@ int bam_write1(BGZF *fp, const bam1_t *b) {
     if (bgzf_flush_try(fp, 4 + block_len) != 0) return -1;
     if (bgzf_write(fp, x, 36) != 36) return -1;
     if (bgzf_write(fp, b->data, l_qname) != (ssize_t)l_qname) return -1;
-    size_t rest = (size_t)b->l_data - c->l_qname;
-    if (bgzf_write(fp, b->data + c->l_qname, rest) != (ssize_t)rest) return -1;
+    if (!long_cigar) {
+        size_t rest = (size_t)b->l_data - c->l_qname;
+        if (bgzf_write(fp, b->data + c->l_qname, rest) != (ssize_t)rest) return -1;
+    } else {
+        uint8_t ph[8], tg[8] = {'C', 'G', 'B', 'I', 0, 0, 0, 0};
+        const size_t real = (size_t)c->n_cigar * 4;
+        const uint8_t *after = b->data + c->l_qname + real;
+        const size_t rest = (size_t)b->l_data - c->l_qname - real;
+        st32(ph, (uint32_t)c->l_qseq << 4 | BAM_CSOFT_CLIP);
+        st32(ph + 4, (uint32_t)ref_len << 4 | BAM_CREF_SKIP);
+        st32(tg + 4, c->n_cigar);
+        if (bgzf_write(fp, ph, 8) != 8) return -1;
+        if (bgzf_write(fp, after, rest) != (ssize_t)rest) return -1;
+        if (bgzf_write(fp, tg, 8) != 8) return -1;
+        if (bgzf_write(fp, b->data + c->l_qname, real) != (ssize_t)real) return -1;
+    }
     return (int)(4 + block_len);
 }
 

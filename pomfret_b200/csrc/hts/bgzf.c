@@ -95,6 +95,8 @@ static int read_block(BGZF *fp) {
     int rc = inflate(&zs, Z_FINISH);
     inflateEnd(&zs);
     if (rc != Z_STREAM_END || zs.total_out != isize) { fp->errcode |= 2; return -1; }
+    /* the footer's CRC32 covers the inflated block (htslib checks it too) */
+    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), fp->ublock, isize) != ld32(fp->cblock + clen)) { fp->errcode |= 2; return -1; }
     fp->block_address = addr;
     fp->next_address = addr + bsize + 1;
     fp->block_length = (int)isize;

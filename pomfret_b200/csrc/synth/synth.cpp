@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include <zlib.h>
 #include "htslib/sam.h"
@@ -63,6 +64,8 @@ const char kBases[4] = {'A', 'C', 'G', 'T'};
 struct Genome {
     uint64_t seed;
     int cpg_period;
+    // reference bases fixed from outside (REF alleles of an imported VCF), keyed by (contig << 40 | pos)
+    const std::unordered_map<uint64_t, char> *fixed = nullptr;
     uint64_t key(int contig, int64_t pos, uint64_t salt) const {
         return mix64(seed ^ mix64(((uint64_t)contig << 40) ^ (uint64_t)pos ^ (salt << 56)));
     }
@@ -70,6 +73,10 @@ struct Genome {
     int raw(int c, int64_t p) const { return (int)(key(c, p, 2) & 3); }
     // local function of (p, p-1, p-2): random base with accidental CG removed, designated CpGs forced
     char base(int c, int64_t p) const {
+        if (fixed && !fixed->empty()) {
+            auto it = fixed->find(((uint64_t)c << 40) | (uint64_t)p);
+            if (it != fixed->end()) return it->second;
+        }
         if (designated(c, p)) return 'C';
         if (designated(c, p - 1)) return 'G';
         int r = raw(c, p);
@@ -254,6 +261,8 @@ extern "C" void pomfret_synth_default_config(synth_config *c) {
     c->frac_noncpg_calls = 0.0;
     c->n_header_contigs_before = 0;
     c->frac_cpg_listed = 1.0;
+    c->de_cap = 0.0;
+    c->vcf_in = nullptr;
 }
 
 namespace {
@@ -321,6 +330,127 @@ void build_variants(const synth_config &cfg, const Genome &g, const ContigPlan &
         p += 8 + (int64_t)(-std::log(1.0 - rng.uni() * 0.999999) * cfg.var_period);
     }
     // every block needs at least two phased variants to define its span; shrink blocks to their variants
+}
+
+// ---- imported VCF (--vcf-in): header contigs, variants and phase sets of a real call set ----
+struct VcfRecord { int64_t pos; std::string ref, alt, gt; int64_t ps; };
+struct VcfImport {
+    std::vector<std::string> contig_names;
+    std::vector<uint32_t> contig_lens;
+    std::unordered_map<std::string, std::vector<VcfRecord>> recs;
+};
+
+bool read_vcf(const char *fn, VcfImport *out) {
+    gzFile f = gzopen(fn, "rb");
+    if (!f) return false;
+    std::string line;
+    char buf[1 << 16];
+    auto next_line = [&]() -> bool {
+        line.clear();
+        while (gzgets(f, buf, sizeof(buf))) {
+            line += buf;
+            if (!line.empty() && line.back() == '\n') { line.pop_back(); return true; }
+        }
+        return !line.empty();
+    };
+    while (next_line()) {
+        if (line.rfind("##contig=<", 0) == 0) {
+            size_t a = line.find("ID="), b = line.find("length=");
+            if (a == std::string::npos || b == std::string::npos) continue;
+            size_t ae = line.find_first_of(",>", a);
+            out->contig_names.push_back(line.substr(a + 3, ae - a - 3));
+            out->contig_lens.push_back((uint32_t)strtoul(line.c_str() + b + 7, nullptr, 10));
+            continue;
+        }
+        if (line.empty() || line[0] == '#') continue;
+        std::vector<std::string> col;
+        size_t p = 0;
+        while (col.size() < 10) {
+            size_t q = line.find('\t', p);
+            col.push_back(line.substr(p, q == std::string::npos ? std::string::npos : q - p));
+            if (q == std::string::npos) break;
+            p = q + 1;
+        }
+        if (col.size() < 10) continue;
+        VcfRecord r;
+        r.pos = atoll(col[1].c_str()) - 1;
+        r.ref = col[3]; r.alt = col[4];
+        r.ps = -1;
+        // FORMAT keys -> sample values
+        std::vector<std::string> keys, vals;
+        for (int which = 0; which < 2; which++) {
+            const std::string &src = col[8 + which];
+            std::vector<std::string> &dst = which ? vals : keys;
+            size_t a = 0;
+            for (;;) {
+                size_t b = src.find(':', a);
+                dst.push_back(src.substr(a, b == std::string::npos ? std::string::npos : b - a));
+                if (b == std::string::npos) break;
+                a = b + 1;
+            }
+        }
+        for (size_t i = 0; i < keys.size() && i < vals.size(); i++) {
+            if (keys[i] == "GT") r.gt = vals[i];
+            if (keys[i] == "PS" && vals[i] != ".") r.ps = atoll(vals[i].c_str());
+        }
+        out->recs[col[0]].push_back(r);
+    }
+    gzclose(f);
+    return true;
+}
+
+// blocks = phase sets (span of their phased records), variants = the simple records (SNV, anchored indels)
+void import_variants(const std::vector<VcfRecord> &recs, Rng &rng, std::vector<Block> &blocks, std::vector<Variant> &vars) {
+    std::vector<int64_t> ps_ids;
+    auto phased = [](const VcfRecord &r) { return r.ps >= 0 && r.gt.size() == 3 && r.gt[1] == '|' && r.gt[0] != r.gt[2]; };
+    for (const VcfRecord &r : recs) {
+        if (!phased(r)) continue;
+        size_t k = std::find(ps_ids.begin(), ps_ids.end(), r.ps) - ps_ids.begin();
+        // (whatshap names a phase set after the position of its first variant: the set starts there even if the
+        //  file at hand is a slice that begins later)
+        if (k == ps_ids.size()) { ps_ids.push_back(r.ps); blocks.push_back(Block{std::min(r.pos, r.ps - 1), r.pos + 1, (int)(rng.next() & 1)}); }
+        blocks[k].s = std::min(blocks[k].s, r.pos);
+        blocks[k].e = std::max(blocks[k].e, r.pos + 1);
+    }
+    std::vector<size_t> order(blocks.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return blocks[a].s < blocks[b].s; });
+    std::vector<Block> sorted;
+    std::vector<int> remap(blocks.size(), -1);
+    for (size_t i : order) {
+        if (!sorted.empty() && blocks[i].s < sorted.back().e) continue;  // interleaved phase sets: keep the first
+        remap[i] = (int)sorted.size();
+        sorted.push_back(blocks[i]);
+    }
+    int64_t prev_end = -100;
+    for (const VcfRecord &r : recs) {
+        if (r.alt.find(',') != std::string::npos || r.ref.empty() || r.alt.empty()) continue;
+        bool ok = true;
+        for (char c : r.ref + r.alt) if (c != 'A' && c != 'C' && c != 'G' && c != 'T') ok = false;
+        if (!ok) continue;
+        Variant v;
+        v.pos = r.pos;
+        if (r.ref.size() == 1 && r.alt.size() == 1) { v.type = 0; v.len = 1; }
+        else if (r.alt.size() == 1 && r.ref[0] == r.alt[0]) { v.type = 1; v.len = (int)r.ref.size() - 1; }
+        else if (r.ref.size() == 1 && r.ref[0] == r.alt[0]) { v.type = 2; v.len = (int)r.alt.size() - 1; }
+        else continue;
+        if (v.pos <= prev_end + 8) continue;  // alleles must not overlap
+        v.ref = r.ref; v.alt = r.alt;
+        v.block = -1;
+        v.alt_hap = (int)(rng.next() & 1);
+        const bool hom = r.gt.size() == 3 && r.gt[0] == '1' && r.gt[2] == '1';
+        const bool het = r.gt.size() == 3 && ((r.gt[0] == '0' && r.gt[2] == '1') || (r.gt[0] == '1' && r.gt[2] == '0'));
+        if (hom) v.kind = 1;
+        else if (het && phased(r)) {
+            size_t k = std::find(ps_ids.begin(), ps_ids.end(), r.ps) - ps_ids.begin();
+            if (remap[k] < 0) v.kind = 2;
+            else { v.kind = 0; v.block = remap[k]; v.alt_hap = (r.gt[0] == '1' ? 0 : 1) ^ sorted[(size_t)remap[k]].orient; }
+        } else if (het) v.kind = 2;
+        else continue;
+        vars.push_back(v);
+        prev_end = v.pos + (v.type == 1 ? v.len : 0);
+    }
+    blocks.swap(sorted);
 }
 
 struct ReadSim {
@@ -429,6 +559,7 @@ struct ReadSim {
         out.aux.clear();
         int64_t aligned = (int64_t)seq.size() - clipL - clipR;
         float de = aligned > 0 ? (float)n_err / (float)aligned : 0.f;
+        if (cfg.de_cap > 0 && de > (float)cfg.de_cap) de = (float)cfg.de_cap;
         if (rng.chance(cfg.frac_high_de)) de = 0.11f + 0.2f * (float)rng.uni();
         aux_put_int(out.aux, "NM", n_err);
         aux_put_float(out.aux, "de", de);
@@ -517,7 +648,10 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
                                    const int64_t *contig_lens, const int64_t *region_beg, const int64_t *region_end,
                                    int n_contigs, const char *prefix) {
     const synth_config &cfg = *cfgp;
-    Genome g{cfg.seed, cfg.cpg_period};
+    std::unordered_map<uint64_t, char> fixed_bases;
+    Genome g{cfg.seed, cfg.cpg_period, &fixed_bases};
+    VcfImport imported;
+    if (cfg.vcf_in && !read_vcf(cfg.vcf_in, &imported)) return -7;
     std::string fn_bam = std::string(prefix) + ".bam";
     std::string fn_vcf = std::string(prefix) + ".vcf.gz";
     std::string fn_truth = std::string(prefix) + ".truth.tsv";
@@ -530,14 +664,27 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
     hdr.n_targets = n_fill + n_contigs;
     std::vector<std::string> names;
     std::vector<uint32_t> lens;
+    if (cfg.vcf_in) {  // the header is the call set's contig list; -C picks contigs of it
+        n_fill = 0;
+        names = imported.contig_names;
+        lens = imported.contig_lens;
+        hdr.n_targets = (int)names.size();
+    }
     for (int i = 0; i < n_fill; i++) { names.push_back("fill" + std::to_string(i + 1)); lens.push_back(1000000); }
     for (int i = 0; i < n_contigs; i++) {
-        names.push_back(contig_names[i]);
-        lens.push_back((uint32_t)contig_lens[i]);
         ContigPlan p;
         p.name = contig_names[i];
         p.len = contig_lens[i];
         p.tid = n_fill + i;
+        if (cfg.vcf_in) {
+            size_t k = std::find(names.begin(), names.end(), p.name) - names.begin();
+            if (k == names.size()) return -8;
+            p.tid = (int)k;
+            p.len = lens[k];
+        } else {
+            names.push_back(contig_names[i]);
+            lens.push_back((uint32_t)contig_lens[i]);
+        }
         p.region_beg = region_beg ? std::max<int64_t>(0, region_beg[i]) : 0;
         p.region_end = region_end && region_end[i] > 0 ? std::min<int64_t>(region_end[i], p.len) : p.len;
         plan.push_back(p);
@@ -560,7 +707,7 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
     if (!out) return -1;
     if (bam_hdr_write(out, &hdr) != 0) return -2;
 
-    gzFile vcf = gzopen(fn_vcf.c_str(), "wb1");
+    gzFile vcf = gzopen(cfg.vcf_in ? "/dev/null" : fn_vcf.c_str(), "wb1");
     FILE *truth = fopen(fn_truth.c_str(), "w");
     if (!vcf || !truth) return -3;
     gzprintf(vcf, "##fileformat=VCFv4.2\n##source=pomfret-synth\n");
@@ -578,8 +725,14 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
         Rng rng(cfg.seed * 1000003ull + ci * 7919ull + 13);
         std::vector<Block> blocks;
         std::vector<Variant> vars;
-        build_blocks(cfg, ct, rng, blocks);
-        build_variants(cfg, g, ct, blocks, rng, vars);
+        if (cfg.vcf_in) {
+            import_variants(imported.recs[ct.name], rng, blocks, vars);
+            for (const Variant &v : vars)
+                for (size_t k = 0; k < v.ref.size(); k++) fixed_bases[((uint64_t)ct.tid << 40) | (uint64_t)(v.pos + (int64_t)k)] = v.ref[k];
+        } else {
+            build_blocks(cfg, ct, rng, blocks);
+            build_variants(cfg, g, ct, blocks, rng, vars);
+        }
 
         // VCF + truth
         {

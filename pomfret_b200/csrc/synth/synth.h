@@ -29,6 +29,9 @@ typedef struct synth_config {
     double frac_two_segments, frac_multicode, frac_noncpg_calls;
     int n_header_contigs_before; /* filler @SQ lines so target ids are not 0 */
     double frac_cpg_listed;      /* fraction of CpG cytosines that appear in the MM list (1 = all) */
+    double de_cap;               /* > 0: upper bound of the reported `de` tag (keeps very noisy reads past the filter) */
+    const char *vcf_in;          /* variants, phase sets and the header's contig list come from this VCF (plain or
+                                    gzip) instead of being simulated; no <prefix>.vcf.gz is written */
 } synth_config;
 
 void pomfret_synth_default_config(synth_config *c);

@@ -20,6 +20,12 @@ static void usage() {
             "  --implicit F  fraction of non-CpG C positions that also get a C+m call [0]\n"
             "  --listed F    fraction of CpG cytosines present in the MM list [1]\n"
             "  --err F       per-base error rate [0.01]\n"
+            "  --de-cap F    upper bound of the reported de tag [none]\n"
+            "  --frac-meth F / --frac-unmeth F  CpG sites methylated / unmethylated on both haplotypes [0.70 / 0.15];\n"
+            "                the rest is haplotype specific\n"
+            "  --ml-flip F   probability that a call shows the wrong state [0.08]\n"
+            "  --hp-drop F   fraction of reads inside a phase block that get no HP tag [0.1]\n"
+            "  --vcf-in FILE take variants, phase sets and the header's contig list from FILE; -C names a contig of it\n"
             "  --readlen F   mean read length [20000]\n"
             "  --gap A-B     phase-block gap length range [20000-150000]\n"
             "  --block F     median phase-block length [500000]\n");
@@ -47,6 +53,12 @@ int main(int argc, char **argv) {
         else if (a == "--implicit") cfg.frac_noncpg_calls = atof(need("--implicit"));
         else if (a == "--listed") cfg.frac_cpg_listed = atof(need("--listed"));
         else if (a == "--err") cfg.err_rate = atof(need("--err"));
+        else if (a == "--de-cap") cfg.de_cap = atof(need("--de-cap"));
+        else if (a == "--frac-meth") cfg.frac_meth = atof(need("--frac-meth"));
+        else if (a == "--frac-unmeth") cfg.frac_unmeth = atof(need("--frac-unmeth"));
+        else if (a == "--ml-flip") cfg.ml_flip = atof(need("--ml-flip"));
+        else if (a == "--vcf-in") cfg.vcf_in = need("--vcf-in");
+        else if (a == "--hp-drop") cfg.hp_drop = atof(need("--hp-drop"));
         else if (a == "--readlen") cfg.read_len_mean = atof(need("--readlen"));
         else if (a == "--block") cfg.block_len_median = atof(need("--block"));
         else if (a == "--gap") {

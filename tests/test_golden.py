@@ -20,7 +20,11 @@ MINE = os.path.join(os.path.dirname(HERE), "pomfret_b200", "bin", "pomfret")
 
 
 def _inputs(tmp_path, name):
-    return conftest.run_synth(str(tmp_path / "in"), MANIFEST[name]["synth"])
+    case = MANIFEST[name]
+    data = conftest.run_synth(str(tmp_path / "in"), [a.replace("{GOLD}", GOLD) for a in case["synth"]])
+    if "vcf" in case:  # a committed input call set (config 1: the example's variants.vcf.gz)
+        data["vcf"] = os.path.join(GOLD, case["vcf"])
+    return data
 
 
 def _run_front_end(tmp_path, name, gpu_lib):
@@ -59,8 +63,17 @@ def test_oracle_port_reproduces_golden_windows(built, tmp_path, name):
     host.bam_close(hb)
 
 
+def test_config1_replica_reproduces_the_bundled_example_output():
+    """The reference's committed quick-start output (example/output.mp.vcf) against what the compiled reference
+    writes for the replica of its input: identical up to the one record that is stale against the reference's own
+    current code; recorded by make_golden.py where /root/reference exists."""
+    case = MANIFEST["config1_quickstart"]
+    assert case["example_output_vcf_lines"] == 347 and case["example_output_vcf_diff_lines"] == [344]
+    assert [w["decision"] for w in case["windows"]] == [1]
+
+
 @pytest.mark.emu
-@pytest.mark.parametrize("name", ["small_methphase", "untagged_methphase"])  # the rest runs on the GPU (and in test_host_frontend.py)
+@pytest.mark.parametrize("name", ["small_methphase", "untagged_methphase", "config1_quickstart"])  # the rest runs on the GPU (and in test_host_frontend.py)
 def test_front_end_reproduces_golden_files_emulated(built, tmp_path, name):
     import build_emu
     _run_front_end(tmp_path, name, build_emu.build())

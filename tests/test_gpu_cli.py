@@ -44,3 +44,52 @@ def test_methphase_small_batches_and_many_workers(synth30, tmp_path):
     # chunking of windows into batches / workers must not change any output
     run_both(str(tmp_path), synth30, ["-t", "8", "-c", "30", "--windows-per-batch", "1", "--write-bam"], None,
              [".mp.gtf", ".mp.vcf", ".mp.bam"])
+
+
+def test_methphase_60x_files_identical(synth60, tmp_path):
+    # BASELINE.json config-3 depth
+    run_both(str(tmp_path), synth60, ["-t", "3", "-c", "60", "--write-bam", "--output-tsv"], None,
+             [".mp.gtf", ".mp.tsv", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_methphase_config1_quickstart(synth_config1, tmp_path):
+    # BASELINE.json config 1: `methphase -c 60 --write-bam` on the bundled call set
+    run_both(str(tmp_path), synth_config1, ["-c", "60", "--write-bam"], None, [".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_methphase_wgs5_one_thread_per_contig(synth_wgs5, tmp_path):
+    run_both(str(tmp_path), synth_wgs5, ["-t", "5", "-c", "30", "--write-bam"], None, [".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_methphase_long_cigar(synth_long_cigar, tmp_path):
+    run_both(str(tmp_path), synth_long_cigar, ["-c", "30", "--write-bam"], None, [".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_report_60x(synth60, tmp_path):
+    # BASELINE.json config 5 shape: report --chunk-size 50000 --chunk-stride 100000 at -c 60
+    res = run_both(str(tmp_path), synth60, ["-c", "60", "--chunk-size", "50000", "--chunk-stride", "100000"], None,
+                   [".report.tsv"], sub="report")
+    assert res["ref"][1] == res["mine"][1]
+
+
+def _n_devices():
+    import pomfret_b200 as pb
+    return pb.load_gpu().device_count()
+
+
+@pytest.mark.parametrize("gpus", ["2", "all"])
+def test_methphase_multi_gpu_files_identical(synth_wgs5, tmp_path, gpus):
+    """region sets sharded over several devices of one box: same files as the reference binary"""
+    if _n_devices() < 2:
+        pytest.skip("needs at least two CUDA devices")
+    n = _n_devices() if gpus == "all" else int(gpus)
+    run_both(str(tmp_path), synth_wgs5, ["-t", str(max(4, n)), "-c", "30", "--gpus", str(n), "--write-bam"], None,
+             [".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_methphase_untagged_multi_gpu(built, tmp_path):
+    if _n_devices() < 2:
+        pytest.skip("needs at least two CUDA devices")
+    data = conftest.run_synth(str(tmp_path / "unt"), ["-c", "30", "-s", "35", "-C", "chr1:248956422:1000000-1700000", "-C",
+                                                      "chr2:242193529:5000000-5600000", "--untagged"])
+    run_both(str(tmp_path), data, ["-u", "-t", "4", "-c", "30", "--gpus", "2"], None, [".mp.gtf", ".mp.vcf"])

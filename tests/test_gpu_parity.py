@@ -53,6 +53,37 @@ def test_gpu_matches_oracle_30x(gpu, synth30):
     assert len(d) >= 2
 
 
+def test_gpu_matches_oracle_60x(gpu, synth60):
+    # BASELINE.json config-3 depth (-c 60: cov_for_selection 7, runtime 14, 16 candidates, up to ~900 reads per window)
+    d = _run(gpu, synth60, 60)
+    assert sorted(set(d)) == [-1, 0, 1]
+
+
+def test_gpu_matches_oracle_config1_quickstart(gpu, synth_config1):
+    d = _run(gpu, synth_config1, 60)
+    assert d == [1]  # the bundled example's own answer: the second phase set is flipped ("trans")
+
+
+def test_gpu_matches_oracle_wgs5(gpu, synth_wgs5):
+    d = _run(gpu, synth_wgs5, 30)
+    assert len(d) == 7 and {c for c, _, _, _ in synth_wgs5["gaps"]} == {"chr1", "chr2", "chr20", "chrX"}
+
+
+def test_gpu_matches_oracle_long_cigar(gpu, synth_long_cigar):
+    # records with more than 65535 CIGAR operations (restored from the CG tag by the loader)
+    host = pb.load_host()
+    hb = host.bam_open(synth_long_cigar["bam"])
+    import ctypes as C
+    from pomfret_b200 import _ffi
+    c, s, e, _ = synth_long_cigar["gaps"][0]
+    w = host.window_load(hb, c, s, e, 15000, 10)
+    d = C.cast(host.window_descs(w), C.POINTER(_ffi.ReadDesc))
+    assert max(d[i].n_cigar for i in range(host.window_n(w))) > 65535
+    host.window_free(w)
+    host.bam_close(hb)
+    _run(gpu, synth_long_cigar, 30)
+
+
 def test_gpu_matches_oracle_short_reads(gpu, synth_small):
     _run(gpu, synth_small, 36, readlen=2000)
 
@@ -168,6 +199,42 @@ def test_gpu_gather_from_registered_buffers(gpu, synth30):
     b.end()
     for ptr in regs:
         gpu.host_unregister(ctx, ptr)
+    gpu.destroy(ctx)
+    host.bam_close(hb)
+
+
+def test_gpu_mixed_registered_and_unregistered_records(gpu, synth30):
+    """One batch whose records come partly from registered buffers (gathered by the device) and partly from plain
+    memory (copied by the host), in both orders, and again after a reset that follows a smaller batch: the pinned
+    arena then holds fewer bytes than the laid-out blob (ADVICE r1: PinBuf::reserve copied `len` bytes)."""
+    host = pb.load_host()
+    hb = host.bam_open(synth30["bam"])
+    cfg, ocfg = pb.make_config(30), ob.make_config(30)
+    wins = parity.load_windows(host, hb, synth30["gaps"][:3], cfg)
+    ctx = gpu.init([0])
+    b = gpu.batch_begin(ctx)
+    for registered in ([0], [1, 2], [0, 2]):
+        regs = []
+        for i in registered:
+            ptr, nbytes = host.window_arena(wins[i][0])
+            if nbytes:
+                gpu.host_register(ctx, ptr, nbytes)
+                regs.append(ptr)
+        b.reset()
+        layout = []
+        for w, n, chrom, s, e in wins:
+            first = b.add_reads(host.window_descs(w), n)
+            b.add_window(s, e, first, n)
+            layout.append((first, n))
+        b.submit(); b.decode(cfg.lo, cfg.hi); b.pileup(cfg); b.join(cfg)
+        res, tags, ids, rc = b.collect(check=False)
+        assert rc == 0, gpu.strerror(rc)
+        for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+            p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+            assert not parity.compare_window(b, wi, first, n, res, tags, ids, p, deep=False), (registered, chrom, s, e)
+        for ptr in regs:
+            gpu.host_unregister(ctx, ptr)
+    b.end()
     gpu.destroy(ctx)
     host.bam_close(hb)
 

@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — methphase hot-path throughput (BASELINE.json metric: reads/s and bases/s, HBM GB/s vs peak).
 
-A "step" is one pass of the hot path (decode -> read sets -> pileup -> methmers -> greedy join -> collect) over
-one batch of synthetic windows: the whole chr20 30x workload, 98 windows, ~21 k
-records, ~306 MB staged per GPU.
+Workload (BASELINE.json config 3 at the size one GPU and a few minutes allow): a synthetic 60x haplotagged sample
+over `--contigs` regions of the hg38 primary contigs (`--contig-mb` each, 20 kb ONT-like reads with MM/ML + MD,
+whatshap-style phased VCF).  Its phase-block windows are staged `--replicas` times as distinct records so that one
+batch has the record count of a few percent of a 60x genome (~0.6 M reads, ~8 GB in HBM, seconds of device work per
+timed region).  A "step" is one pass of the hot path (decode -> read sets -> pileup -> methmers -> greedy join ->
+collect) over that batch.
 
-  value / ms_per_step   K steps with the records resident in HBM, `--in-flight` batches (default 2) driven by as
-                        many host threads: the latency-bound join of one batch overlaps the other batch's kernels
+  value / ms_per_step   K steps, records resident in HBM, `--in-flight` batches (default 2) from as many host threads
   latency_ms_per_step   one step alone on the device (launches, the pool-size round trip, D2H + Fisher included)
-  kernel_ms             CUDA-event time of every stage of that single step; roofline = decode_kernel
-  e2e                   the same step through the C ABI from a registered host buffer: descriptors, device gather
-                        over PCIe, kernels, D2H; `--e2e-batches` region chunks pipelined (producer + consumers)
-  e2e_host_copy         the same from unregistered host buffers (host gather copy into pinned memory + H2D)
+  kernel_ms             CUDA-event time of every stage of one step; roofline = decode_kernel, roofline_pileup
+  e2e                   the same step through the C ABI from registered HOST buffers: descriptors, device gather over
+                        PCIe, kernels, D2H of decisions and tags; region chunks pipelined
+  cli_e2e               wall time of the drop-in CLI (`pomfret methphase`, BGZF inflate and writers included) next to the
+                        unmodified reference CLI on the same files — the like-for-like number; cli_report: `report`
+  untagged              config 4: the -u read haplotagger over an untagged 30x sample (roofline_haptag)
+  strong                N > 1: the same batch cut into one contiguous region set per rank (no data-path collective,
+                        host gather of decisions, checked against rank 0's own full run)
   cpu_baseline          the compiled reference's per-window call sequence on a bounded sample, 1 thread (N = 1 only)
 
-`--impl reference` times the reference's own CPU implementation (oracle/_ref/pomfret methphase -t N) on the
-same synthetic BAM.  Under torchrun every rank owns its own region set (weak scaling, no data-path collective).
+`--impl reference` times the unmodified reference CLI (oracle/_ref/pomfret methphase -t <cores>) on the same sample.
+Every rank works on the same sample (rank 0 generates it); weak scaling = every rank runs the whole batch.
 """
 import argparse
 import ctypes as C
@@ -31,6 +37,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+# hg38 primary contigs (the ##contig list of the reference's example VCF), longest first
+HG38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555), ("chr5", 181538259),
+        ("chr6", 170805979), ("chr7", 159345973), ("chrX", 156040895), ("chr8", 145138636), ("chr9", 138394717),
+        ("chr11", 135086622), ("chr10", 133797422), ("chr12", 133275309), ("chr13", 114364328), ("chr14", 107043718),
+        ("chr15", 101991189), ("chr16", 90338345), ("chr17", 83257441), ("chr18", 80373285), ("chr20", 64444167),
+        ("chr19", 58617616), ("chrY", 57227415), ("chr22", 50818468), ("chr21", 46709983)]
+
 
 def env_int(name, default):
     try:
@@ -40,14 +53,14 @@ def env_int(name, default):
 
 
 def measured_traffic(kernel, reads_per_launch):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
-    (profiles/traffic.json, written from the .ncu-rep by profiles/summarize_ncu.py); None if there is no capture
-    of a launch of this size."""
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/traffic.json, written from
+    the .ncu-rep by profiles/summarize_ncu.py), scaled by the record count when the capture is of a smaller launch of the
+    same workload; None if there is no capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p)).get(kernel)
-        if t and abs(t["reads_per_launch"] - reads_per_launch) <= 0.02 * reads_per_launch:
-            return t["dram_bytes"]
+        if t and t.get("workload") == "60x" and t["reads_per_launch"] > 0:
+            return int(t["dram_bytes"] * reads_per_launch / t["reads_per_launch"])
     except Exception:
         pass
     return None
@@ -98,44 +111,29 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_workload(tmp, region_mb, cov, seed, tagged=True):
-    """Synthetic chr20-like haplotagged BAM + phased VCF (the default 63.5 Mb is the
-    whole contig from 1 Mb to its end)."""
-    import conftest
-    beg = 1000000
-    end = min(64444167, beg + int(region_mb * 1e6))
-    args = ["-c", str(cov), "-s", str(seed), "-C", "chr20:64444167:%d-%d" % (beg, end), "-F", "19"]
+def synth_args(n_contigs, contig_mb, cov, seed, tagged=True):
+    args = ["-c", str(cov), "-s", str(seed)]
+    for name, length in HG38[:n_contigs]:
+        beg = 1000000
+        end = min(length, beg + int(contig_mb * 1e6))
+        args += ["-C", "%s:%d:%d-%d" % (name, length, beg, end)]
     if not tagged:
         args.append("--untagged")
-    return conftest.run_synth(os.path.join(tmp, "bench_s%d" % seed), args)
+    return args
 
 
-def run_reference(args, data, cov):
-    """The unmodified reference CLI built against the hts shim (oracle/_ref), all host threads it can use."""
-    import oracle_bindings as ob
-    if not os.path.exists(ob.REF_BIN):
-        return {"impl": "reference", "unavailable": "oracle/_ref/pomfret not built"}
-    ncpu = os.cpu_count() or 1
-    times = []
-    reads = bases = None
-    n_steps = args.warmup + args.steps
-    for it in range(n_steps):
-        out = os.path.join(os.path.dirname(data["bam"]), "ref_out")
-        t0 = time.perf_counter()
-        subprocess.run([ob.REF_BIN, "methphase", "-t", str(ncpu), "-c", str(cov), "-o", out, "--vcf", data["vcf"],
-                        data["bam"]], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-    return times
+def make_workload(tmp, tag, n_contigs, contig_mb, cov, seed, tagged=True):
+    import conftest
+    return conftest.run_synth(os.path.join(tmp, tag), synth_args(n_contigs, contig_mb, cov, seed, tagged))
 
 
-def count_units(host, hb, data, cfg):
-    import parity
-    wins = parity.load_windows(host, hb, data["gaps"], cfg)
-    reads = sum(n for _, n, _, _, _ in wins)
-    bases = sum(host.window_bases(w) for w, _, _, _, _ in wins)
-    return wins, reads, bases
+def wall(cmd, env=None):
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, text=True)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError("%s failed: %s" % (" ".join(cmd[:3]), p.stderr[-1500:]))
+    return dt
 
 
 def main():
@@ -144,11 +142,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--region-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_MB", "63.5")))
-    ap.add_argument("--cov", type=int, default=30)
-    ap.add_argument("--cpu-sample-windows", type=int, default=12)
-    ap.add_argument("--e2e-batches", type=int, default=3, help="region chunks per step on the end-to-end path")
+    ap.add_argument("--cov", type=int, default=60)
+    ap.add_argument("--contigs", type=int, default=env_int("POMFRET_BENCH_CONTIGS", 12))
+    ap.add_argument("--contig-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_CONTIG_MB", "2.5")))
+    ap.add_argument("--replicas", type=int, default=env_int("POMFRET_BENCH_REPLICAS", 16),
+                    help="times the sample's windows are staged (as distinct records) to form one WGS-scale batch")
+    ap.add_argument("--cpu-sample-windows", type=int, default=24)
+    ap.add_argument("--e2e-batches", type=int, default=4, help="region chunks per step on the end-to-end path")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight when measuring device-resident throughput")
+    ap.add_argument("--skip-cli", action="store_true", help="leave out the CLI wall-time comparisons (profiling runs)")
+    ap.add_argument("--skip-untagged", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -159,45 +162,57 @@ def main():
     import pomfret_b200 as pb
     import oracle_bindings as ob
     import parity
-    from pomfret_b200 import build
+    from pomfret_b200 import build, shard, _ffi
     build.build_host()
 
-    tmp = tempfile.mkdtemp(prefix="pomfret_bench_")
     import atexit
     import shutil
-    atexit.register(shutil.rmtree, tmp, True)
     cov = args.cov
     cfg = pb.make_config(cov)
-    workload = "synthetic chr20-like %dx ONT reads (MM/ML+MD, haplotagged), %.0f Mb region, phased VCF; methphase -c %d" % (
-        cov, args.region_mb, cov)
+    workload = ("synthetic %dx ONT-like reads (20 kb, MM/ML+MD, haplotagged) on %d hg38 contig regions of %.1f Mb, phased VCF; "
+                "methphase -c %d" % (cov, args.contigs, args.contig_mb, cov))
+    ncpu = os.cpu_count() or 1
 
     if args.impl == "reference":
         if rank != 0:
             return
-        data = make_workload(tmp, args.region_mb, cov, seed=100)
+        tmp = tempfile.mkdtemp(prefix="pomfret_bench_")
+        atexit.register(shutil.rmtree, tmp, True)
+        data = make_workload(tmp, "s60", args.contigs, args.contig_mb, cov, seed=100)
+        if not os.path.exists(ob.REF_BIN):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/pomfret not built"}))
+            return
         host = pb.load_host()
         hb = host.bam_open(data["bam"])
-        wins, reads, bases = count_units(host, hb, data, cfg)
-        times = run_reference(args, data, cov)
-        if isinstance(times, dict):
-            print(json.dumps(times))
-            return
+        wins = parity.load_windows(host, hb, data["gaps"], cfg)
+        reads = sum(n for _, n, _, _, _ in wins)
+        bases = sum(host.window_bases(w) for w, _, _, _, _ in wins)
+        n_gap_contigs = len({c for c, _, _, _ in data["gaps"]})
+        times = []
+        for it in range(args.warmup + args.steps):
+            dt = wall([ob.REF_BIN, "methphase", "-t", str(ncpu), "-c", str(cov), "-o", os.path.join(tmp, "ref_out"), "--vcf",
+                       data["vcf"], data["bam"]])
+            if it >= args.warmup:
+                times.append(dt)
         mean = sum(times) / len(times)
-        ncpu = os.cpu_count() or 1
         v = reads / mean
+        cores = max(1, min(ncpu, n_gap_contigs))
         line = {"impl": "reference", "metric": "methphase reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores", "data": "synthetic",
                 "bases_per_s": bases / mean,
-                "config": {"workload": workload, "windows": len(wins), "reads_per_step": reads, "bases_per_step": bases},
-                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": min(ncpu, 1), "kind": "reference",
-                                 "sample": "pomfret methphase -t %d on the whole workload (1 contig => 1 worker thread, "
-                                           "kt_for over contigs); includes BGZF inflate and per-window BAM open" % ncpu},
+                "config": {"workload": workload, "windows": len(wins), "reads_per_step": reads, "bases_per_step": bases,
+                           "replicas": 1},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                 "sample": "pomfret methphase -t %d on the un-replicated sample (%d contigs with gaps => %d worker "
+                                           "threads busy, kt_for over contigs); BGZF inflate, per-window BAM open and the "
+                                           "writers included" % (ncpu, n_gap_contigs, cores)},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
     # ---------------- our arm ----------------
+    import numpy as np
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -206,84 +221,126 @@ def main():
     gpu = pb.load_gpu()
     if gpu.device_count() < 1:
         raise RuntimeError("no CUDA device: pomfret_b200 has no CPU fallback")
-    # the staging helper threads of all ranks share the host's cores
-    os.environ.setdefault("POMFRET_GPU_STAGE_THREADS", str(max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))))
+    os.environ.setdefault("POMFRET_GPU_STAGE_THREADS", str(max(1, min(12, ncpu // max(world, 1)))))
     host = pb.load_host()
-    # weak scaling: every rank owns its own contiguous region set (different seed), no data-path collective
-    data = make_workload(tmp, args.region_mb, cov, seed=100 + rank)
-    hb = host.bam_open(data["bam"])
-    wins, reads, bases = count_units(host, hb, data, cfg)
-    ctx = gpu.init([local_rank])
-    b = gpu.batch_begin(ctx, 0, local_rank)
-
-    def stage():
-        b.reset()
-        for w, n, chrom, s, e in wins:
-            first = b.add_reads(host.window_descs(w), n)
-            b.add_window(s, e, first, n)
-
-    def device_pass():
-        b.decode(cfg.lo, cfg.hi)
-        b.pileup(cfg)
-        b.join(cfg)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one sample for all ranks: rank 0 generates, the others wait for it
+    tmp_holder = [None]
+    if rank == 0:
+        tmp_holder[0] = tempfile.mkdtemp(prefix="pomfret_bench_")
+        atexit.register(shutil.rmtree, tmp_holder[0], True)
+    if world > 1:
+        dist.broadcast_object_list(tmp_holder, src=0)
+    tmp = tmp_holder[0]
+    data = None
+    if rank == 0:
+        data = make_workload(tmp, "s60", args.contigs, args.contig_mb, cov, seed=100)
+    if world > 1:
+        box = [data]
+        dist.broadcast_object_list(box, src=0)
+        data = box[0]
+    hb = host.bam_open(data["bam"])
+    wins = parity.load_windows(host, hb, data["gaps"], cfg)
+    base_reads = sum(n for _, n, _, _, _ in wins)
+    base_bases = sum(host.window_bases(w) for w, _, _, _, _ in wins)
+    R = max(1, args.replicas)
+    # the batch: every window of the sample, R times (window order: replica-major)
+    batch_windows = [(r, i) for r in range(R) for i in range(len(wins))]
+    reads = base_reads * R
+    bases = base_bases * R
+    ctx = gpu.init([local_rank])
+
+    # the records of the sample in ONE host buffer registered with the engine (pinned + mapped), the way a loader keeps
+    # the buffers it inflates BGZF blocks into; every replica's descriptors point into it
+    sizes = [host.window_arena(w)[1] for w, _, _, _, _ in wins]
+    big = np.empty(sum((x + 63) & ~63 for x in sizes) + 8192, dtype=np.uint8)
+    big_base = (big.ctypes.data + 4095) & ~4095
+    win_descs = []
+    o = 0
+    dsz = C.sizeof(_ffi.ReadDesc)
+    for (w, n, _, _, _), nbytes in zip(wins, sizes):
+        ptr, _ = host.window_arena(w)
+        C.memmove(big_base + o, ptr, nbytes)
+        delta = (big_base + o) - ptr
+        arr = (_ffi.ReadDesc * max(n, 1))()
+        C.memmove(arr, host.window_descs(w), n * dsz)
+        for j in range(n):
+            d = arr[j]
+            for f in ("cigar", "seq", "mm", "ml", "md"):
+                v = getattr(d, f)
+                if v:
+                    setattr(d, f, v + delta)
+        win_descs.append(arr)
+        o += (nbytes + 63) & ~63
+    gpu.host_register(ctx, big_base, o + 4096)
+
+    def stage(bt, window_list):
+        # (descriptors point into the registered buffer: add_reads() lays the batch out, the device gathers the payloads)
+        bt.reset()
+        for _, i in window_list:
+            w, n, chrom, s, e = wins[i]
+            first = bt.add_reads(win_descs[i], n)
+            bt.add_window(s, e, first, n)
+
+    def device_pass(bt):
+        bt.decode(cfg.lo, cfg.hi)
+        bt.pileup(cfg)
+        bt.join(cfg)
+
     sampler = ClockSampler(local_rank)
-    # device-resident timing: stage + H2D outside, kernels inside
-    dev_times, kern_times, e2e_times, launches = [], [], [], 0
-    tsum = {}
+    b = gpu.batch_begin(ctx, 0, local_rank)
+    stage(b, batch_windows)
+    b.submit()
+    # ---- single-step latency and per-stage kernel times (records resident, one batch) ----
+    dev_times, tsum, launches = [], {}, 0
+    res = None
     for it in range(args.warmup + args.steps):
         if it == args.warmup:
             sampler.start()
-        stage()
-        b.submit()
+        if it:
+            b.rewind()
         barrier()
         t0 = time.perf_counter()
-        device_pass()
+        device_pass(b)
         res, tags, ids, rc = b.collect()
-        barrier()
+        torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tm = b.timing()
-        kern = tm.decode_ms + tm.readset_ms + tm.pileup_ms + tm.methmer_ms + tm.join_ms
         if it >= args.warmup:
-            dev_times.append(dt)          # whole device pass: launches, the pool-size round trip, D2H + Fisher in collect
-            kern_times.append(kern / 1e3)  # sum of the kernels' own CUDA-event intervals
+            dev_times.append(dt)
             launches = tm.launches
             for k in ("decode_ms", "readset_ms", "pileup_ms", "methmer_ms", "join_ms", "h2d_ms"):
                 tsum[k] = tsum.get(k, 0.0) + getattr(tm, k)
             tsum["decode_bytes"] = tm.decode_bytes
             tsum["pileup_bytes"] = tm.pileup_bytes
             tsum["h2d"] = tm.bytes_h2d
-            tsum["d2h"] = tm.bytes_d2h
-    # Throughput with the inputs resident in HBM: the K timed steps are issued by `--in-flight` host threads, each
-    # with its own batch (own stream, own resident copy of the step's records), the way the front end's workers
-    # keep several region chunks on the device at once.  The join kernel is latency bound (one read tagged per
-    # iteration); a second batch in flight fills the SMs it leaves idle.  Every step still runs every stage
-    # (rewind -> decode -> pileup -> methmers -> join -> collect) on all of its records.
-    nfl = max(1, min(args.in_flight, args.steps))  # 1: the timed steps run one after the other
+    full_decisions = [x.decision for x in res]
+    for r in range(1, R):  # replicas are independent copies of the same windows
+        if full_decisions[r * len(wins):(r + 1) * len(wins)] != full_decisions[:len(wins)]:
+            raise RuntimeError("replica %d of the window set disagrees with replica 0" % r)
+    # ---- throughput with the inputs resident in HBM: K steps from `--in-flight` host threads, one batch each ----
+    nfl = max(1, min(args.in_flight, args.steps))
     fl_batches = [b]
     for i in range(1, nfl):
         bt = gpu.batch_begin(ctx, 100 + i, local_rank)
-        for w, n, chrom, s, e in wins:
-            first = bt.add_reads(host.window_descs(w), n)
-            bt.add_window(s, e, first, n)
+        stage(bt, batch_windows)
         bt.submit()
         fl_batches.append(bt)
     fl_dec = [None] * nfl
 
     def fl_worker(j, n_steps):
         bt = fl_batches[j]
+        r = None
         for _ in range(n_steps):
             bt.rewind()
-            bt.decode(cfg.lo, cfg.hi)
-            bt.pileup(cfg)
-            bt.join(cfg)
+            device_pass(bt)
             r = bt.collect()
-        fl_dec[j] = [x.decision for x in r[0]]
+        fl_dec[j] = [x.decision for x in r[0]] if r else None
 
     def fl_run(total_steps):
         share = [total_steps // nfl + (1 if j < total_steps % nfl else 0) for j in range(nfl)]
@@ -300,136 +357,110 @@ def main():
     barrier()
     fl_mean = (time.perf_counter() - t0) / args.steps
     for dj in fl_dec:
-        if dj is not None and dj != [r.decision for r in res]:
+        if dj is not None and dj != full_decisions:
             raise RuntimeError("a batch in flight disagrees with the single-batch run")
     for bt in fl_batches[1:]:
         bt.end()
-    # end-to-end timing through the C ABI with host buffers.  The step's windows go through the engine as
-    # `--e2e-batches` region chunks, the way the front end's workers drive it: a producer thread stages and
-    # submits chunk i+1 (gather copy into pinned memory + H2D) while the device works on chunk i.
-    import numpy as np
-    nb = max(1, min(args.e2e_batches, len(wins)))
-    cuts = [round(i * len(wins) / nb) for i in range(nb + 1)]
-    chunks = [wins[cuts[i]:cuts[i + 1]] for i in range(nb)]
+
+    # ---- strong scaling over the same batch: one contiguous region set per rank, host gather of the decisions ----
+    strong = None
+    if world > 1:
+        win_list = [(wins[i][2], wins[i][3], wins[i][4]) for _, i in batch_windows]
+        a, z = shard.partition_windows(win_list, world, cov)[rank]
+        stage(b, batch_windows[a:z])
+        b.submit()
+        local = None
+        for it in range(args.warmup):
+            if it:
+                b.rewind()
+            device_pass(b)
+            local = b.collect()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            b.rewind()
+            device_pass(b)
+            local = b.collect()
+        barrier()
+        st_mean = (time.perf_counter() - t0) / args.steps
+        merged = shard.gather_results([x.decision for x in local[0]], rank, world, dist)
+        if merged != full_decisions:
+            raise RuntimeError("region-sharded run over %d ranks disagrees with the single-rank run of the same batch" % world)
+        strong = st_mean
+        stage(b, batch_windows)  # back to the full batch for what follows
+        b.submit()
+
+    # ---- end to end through the C ABI from registered host buffers (descriptors -> device gather over PCIe ->
+    #      kernels -> D2H of decisions + tags), `--e2e-batches` region chunks pipelined: producer + one consumer each ----
+    nb = max(1, min(args.e2e_batches, len(batch_windows)))
+    cuts = [round(i * len(batch_windows) / nb) for i in range(nb + 1)]
+    chunks = [batch_windows[cuts[i]:cuts[i + 1]] for i in range(nb)]
     batches = [b] + [gpu.batch_begin(ctx, i, local_rank) for i in range(1, nb)]
     e2e_results = [None] * nb
-    # the loader's descriptors of a chunk as one array (72-byte records pointing at the host copies of the BAM
-    # records): one add_reads() call per chunk
-    from pomfret_b200 import _ffi
     chunk_descs = []
     for ws in chunks:
-        tot = sum(n for _, n, _, _, _ in ws)
+        tot = sum(wins[i][1] for _, i in ws)
         arr = (_ffi.ReadDesc * max(tot, 1))()
-        o = 0
-        for w, n, chrom, s, e in ws:
-            C.memmove(C.byref(arr, o * C.sizeof(_ffi.ReadDesc)), host.window_descs(w), n * C.sizeof(_ffi.ReadDesc))
-            o += n
-        import numpy as np
-        firsts = np.cumsum([0] + [n for _, n, _, _, _ in ws][:-1]).astype(np.uint32) if ws else np.zeros(0, np.uint32)
-        chunk_descs.append((arr, tot, np.array([s for _, _, _, s, _ in ws], dtype=np.uint32),
-                            np.array([e for _, _, _, _, e in ws], dtype=np.uint32), firsts,
-                            np.array([n for _, n, _, _, _ in ws], dtype=np.uint32)))
-
+        k = 0
+        for _, i in ws:
+            n = wins[i][1]
+            C.memmove(C.byref(arr, k * dsz), win_descs[i], n * dsz)
+            k += n
+        ns = [wins[i][1] for _, i in ws]
+        firsts = np.cumsum([0] + ns[:-1]).astype(np.uint32) if ws else np.zeros(0, np.uint32)
+        chunk_descs.append((arr, tot, np.array([wins[i][3] for _, i in ws], dtype=np.uint32),
+                            np.array([wins[i][4] for _, i in ws], dtype=np.uint32), firsts, np.array(ns, dtype=np.uint32)))
     e2e_prof = {"stage": 0.0, "device": 0.0}
 
-    def produce(q):
+    def produce(evs):
         t_p = time.perf_counter()
-        for i, (bt, ws) in enumerate(zip(batches, chunks)):
-            ta = time.perf_counter()
+        for i, bt in enumerate(batches):
             bt.reset()
-            tb = time.perf_counter()
             arr, tot, w_s, w_e, w_first, w_n = chunk_descs[i]
             bt.add_reads(arr, tot)
-            tc = time.perf_counter()
             bt.add_windows(w_s, w_e, w_first, w_n)
             bt.submit()
-            td = time.perf_counter()
-            e2e_prof["reset"] = e2e_prof.get("reset", 0.0) + tb - ta
-            e2e_prof["add_reads"] = e2e_prof.get("add_reads", 0.0) + tc - tb
-            e2e_prof["submit"] = e2e_prof.get("submit", 0.0) + td - tc
-            q.put(i)
+            evs[i].set()
         e2e_prof["stage"] += time.perf_counter() - t_p
 
     def consume(i, ev):
         ev.wait()
         t_c = time.perf_counter()
         bt = batches[i]
-        bt.decode(cfg.lo, cfg.hi)
-        bt.pileup(cfg)
-        bt.join(cfg)
+        device_pass(bt)
         e2e_results[i] = bt.collect()
-        e2e_prof["device"] = max(e2e_prof["device"], 0.0) + (time.perf_counter() - t_c) / nb
-        e2e_prof["transfer_ms_evt"] = e2e_prof.get("transfer_ms_evt", 0.0) + bt.timing().h2d_ms
+        e2e_prof["device"] += (time.perf_counter() - t_c) / nb
 
     def e2e_step():
-        # one producer (the gather copy saturates host memory bandwidth), one consumer per chunk: the device
-        # stages of consecutive chunks overlap on their own streams
         evs = [threading.Event() for _ in range(nb)]
-
-        class Q:
-            def put(self, i):
-                evs[i].set()
-        ths = [threading.Thread(target=produce, args=(Q(),))] + [threading.Thread(target=consume, args=(i, evs[i])) for i in range(nb)]
+        ths = [threading.Thread(target=produce, args=(evs,))] + [threading.Thread(target=consume, args=(i, evs[i])) for i in range(nb)]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
 
-    def run_e2e():
-        times = []
-        h2d = d2h = 0
-        for it in range(args.warmup + args.steps):
-            barrier()
-            t0 = time.perf_counter()
-            e2e_step()
-            barrier()
-            dt = time.perf_counter() - t0
-            if it < args.warmup:
-                for k_ in list(e2e_prof):
-                    e2e_prof[k_] = 0.0
-            else:
-                times.append(dt)
-                h2d = sum(bt.timing().bytes_h2d for bt in batches)
-                d2h = sum(bt.timing().bytes_d2h for bt in batches)
-        # the chunked run must give what the single batch gave
-        if [r.decision for r in res] != [r.decision for i in range(nb) for r in e2e_results[i][0]]:
-            raise RuntimeError("chunked end-to-end run disagrees with the single-batch run")
-        if os.environ.get("POMFRET_BENCH_VERBOSE"):
-            sys.stderr.write("e2e profile per step (ms): %r\n" % {k_: round((1e3 if k_ != "transfer_ms_evt" else 1.0) * v_ / args.steps, 3)
-                                                                  for k_, v_ in e2e_prof.items()})
-        return dict(times=times, h2d=h2d, d2h=d2h, stage=1e3 * e2e_prof["stage"] / args.steps,
-                    device=1e3 * e2e_prof["device"] / args.steps)
-
-    # (1) host buffers as the loader left them: the engine gathers the payloads into its pinned arena (host copy)
-    e2e_copy = run_e2e()
-    # (2) the same records in one host buffer that is registered with the engine once (pinned + mapped, the way a
-    #     loader would keep its inflate buffers): no host copy, the device gathers the payloads over PCIe
-    sizes = [host.window_arena(w)[1] for w, _, _, _, _ in wins]
-    big = np.empty(sum((x + 63) & ~63 for x in sizes) + 8192, dtype=np.uint8)
-    big_base = (big.ctypes.data + 4095) & ~4095
-    deltas, o = {}, 0
-    for (w, _, _, _, _), nbytes in zip(wins, sizes):
-        ptr, _ = host.window_arena(w)
-        C.memmove(big_base + o, ptr, nbytes)
-        deltas[w] = (big_base + o) - ptr
-        o += (nbytes + 63) & ~63
-    for (arr, tot, *_), ws in zip(chunk_descs, chunks):
-        k = 0
-        for w, n, _, _, _ in ws:
-            dl = deltas[w]
-            for j in range(k, k + n):
-                d = arr[j]
-                for f in ("cigar", "seq", "mm", "ml", "md"):
-                    v = getattr(d, f)
-                    if v:
-                        setattr(d, f, v + dl)
-            k += n
-    gpu.host_register(ctx, big_base, o + 4096)
-    e2e_reg = run_e2e()
+    e2e_times = []
+    h2d_e2e = d2h_e2e = 0
+    n_e2e = max(3, min(args.steps, 10))  # (a step moves the whole batch over PCIe: ten of them are seconds of traffic)
+    for it in range(3 + n_e2e):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if it < 3:
+            for k_ in list(e2e_prof):
+                e2e_prof[k_] = 0.0
+        else:
+            e2e_times.append(dt)
+            h2d_e2e = sum(bt.timing().bytes_h2d for bt in batches)
+            d2h_e2e = sum(bt.timing().bytes_d2h for bt in batches)
+    if full_decisions != [r.decision for i in range(nb) for r in e2e_results[i][0]]:
+        raise RuntimeError("chunked end-to-end run disagrees with the single-batch run")
     gpu.host_unregister(ctx, big_base)
-    e2e_times = e2e_reg["times"]
-    h2d_e2e, d2h_e2e = e2e_reg["h2d"], e2e_reg["d2h"]
     sampler.stop_flag = True
+    for bt in batches[1:]:
+        bt.end()
 
     def maxr(x):
         if world > 1:
@@ -438,19 +469,87 @@ def main():
             return float(t.item())
         return x
 
-    def sumr(x):
-        if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            return float(t.item())
-        return float(x)
-
-    lat_mean = maxr(sum(dev_times) / len(dev_times))  # one step alone on the device
-    dev_mean = maxr(fl_mean)                          # per step with `nfl` batches in flight
+    lat_mean = maxr(sum(dev_times) / len(dev_times))
+    dev_mean = maxr(fl_mean)
     e2e_mean = maxr(sum(e2e_times) / len(e2e_times))
-    e2e_copy_mean = maxr(sum(e2e_copy["times"]) / len(e2e_copy["times"]))
-    tot_reads = sumr(reads)
-    tot_bases = sumr(bases)
+    strong_mean = maxr(strong) if strong is not None else None
+    tot_reads = float(reads) * world   # weak scaling: every rank runs the whole batch
+    tot_bases = float(bases) * world
+
+    # ---- config 4: the -u read haplotagger over an untagged 30x sample (rank 0) ----
+    untagged = None
+    if rank == 0 and not args.skip_untagged:
+        udata = make_workload(tmp, "u30", min(args.contigs, 6), min(args.contig_mb, 2.0), 30, seed=130, tagged=False)
+        lib = host.lib
+        lib.pomfret_host_contig_load.restype = C.c_void_p
+        lib.pomfret_host_contig_load.argtypes = [C.c_void_p, C.c_char_p]
+        lib.pomfret_host_load_variants.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        uhb = host.bam_open(udata["bam"])
+        ub = gpu.batch_begin(ctx, 50, local_rank)
+        u_reads = u_bases = 0
+        u_ms = u_bytes = 0.0
+        rep_u = 8
+        for name, _ in HG38[:min(args.contigs, 6)]:
+            w = lib.pomfret_host_contig_load(uhb, name.encode())
+            n = host.window_n(w)
+            cap = 1 << 18
+            vars_ = (pb.Variant * cap)()
+            vb = np.zeros(cap * 4, np.uint8)
+            nbv = C.c_int()
+            nk = lib.pomfret_host_load_variants(udata["vcf"].encode(), name.encode(), vars_, cap, vb.ctypes.data, cap * 4, C.byref(nbv))
+            if n == 0 or nk <= 0:
+                continue
+            known = np.frombuffer(vars_, dtype=np.uint8, count=nk * C.sizeof(pb.Variant)).copy()
+            var_pos = np.array([vars_[i].pos for i in range(nk)], dtype=np.uint32)
+            descs = host.window_descs(w)
+            starts = np.array([_ffi.ReadDesc.from_address(descs + i * dsz).pos for i in range(n)], dtype=np.uint32)
+            kf = np.searchsorted(var_pos, starts, side="left").astype(np.uint32)  # the i_left cursor of blockjoin.c:1716-1720
+            ub.reset()
+            for _ in range(rep_u):
+                ub.add_reads(descs, n)
+            ub.submit()
+            kfr = np.tile(kf, rep_u)
+            for it in range(3):
+                if it:
+                    ub.rewind()
+                ub.haptag(known, nk, vb[:nbv.value], kfr)
+                utags, ustat = ub.collect_haptags()
+            t = ub.timing()
+            u_ms += t.haptag_ms
+            u_bytes += t.haptag_bytes
+            u_reads += n * rep_u
+            u_bases += host.window_bases(w) * rep_u
+            host.window_free(w)
+        ub.end()
+        host.bam_close(uhb)
+        if u_ms > 0:
+            untagged = {"reads": u_reads, "bases": u_bases, "haptag_ms": u_ms, "bytes": u_bytes, "data": udata}
+
+    # ---- the drop-in CLI against the unmodified reference CLI on the same files (rank 0; uses all N devices) ----
+    cli = {}
+    if rank == 0 and not args.skip_cli and os.path.exists(ob.REF_BIN):
+        mine = os.path.join(ROOT, "pomfret_b200", "bin", "pomfret")
+        thr = str(max(2, min(ncpu, 16)))
+        env = dict(os.environ)
+        env.pop("POMFRET_GPU_STAGE_THREADS", None)
+        for key, sub, extra, d in (("cli_e2e", "methphase", ["-c", str(cov)], data),
+                                   ("cli_report", "report", ["-c", str(cov), "--chunk-size", "50000", "--chunk-stride", "100000"], data),
+                                   ("cli_untagged", "methphase", ["-u", "-c", "30"], untagged["data"] if untagged else None)):
+            if d is None:
+                continue
+            po, pr = os.path.join(tmp, key + "_ours"), os.path.join(tmp, key + "_ref")
+            common = extra + ["--vcf", d["vcf"], d["bam"]]
+            t_ours = min(wall([mine, sub, "-t", thr, "--gpus", str(world), "-o", po] + common, env) for _ in range(2))
+            t_ref = wall([ob.REF_BIN, sub, "-t", thr, "-o", pr] + common)
+            suffixes = [".report.tsv"] if sub == "report" else [".mp.gtf", ".mp.vcf"]
+            same = all(open(po + s_, "rb").read() == open(pr + s_, "rb").read() for s_ in suffixes)
+            if not same:
+                raise RuntimeError("%s: output files differ from the reference's" % key)
+            cli[key] = {"ours_s": t_ours, "reference_s": t_ref, "speedup": t_ref / t_ours, "threads": int(thr), "gpus": world,
+                        "outputs_identical": True,
+                        "what": "wall time of `pomfret %s %s` on the un-replicated sample files, BGZF inflate, index, "
+                                "VCF and writers included; both binaries read the files through the same single-threaded "
+                                "zlib shim" % (sub, " ".join(extra))}
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
@@ -459,39 +558,37 @@ def main():
     pile_ms = tsum["pileup_ms"] / K
     dec_gbs = tsum["decode_bytes"] / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
     pile_gbs = tsum["pileup_bytes"] / (pile_ms * 1e-3) / 1e9 if pile_ms > 0 else 0.0
-    kernels = {k: tsum[k] / K for k in ("decode_ms", "readset_ms", "pileup_ms", "methmer_ms", "join_ms", "h2d_ms")}
-    kernels["kernel_sum_ms"] = 1e3 * sum(kern_times) / len(kern_times)
+    kernels = {k: tsum[k] / K for k in ("decode_ms", "readset_ms", "pileup_ms", "methmer_ms", "join_ms")}
+    kernels["kernel_sum_ms"] = sum(kernels.values())
     # CPU baseline on a bounded sample of the same windows (rank 0, N = 1 only)
     cpu = None
     if world == 1 and os.path.exists(ob.REF_SO):
         ocfg = ob.make_config(cov)
         sample = data["gaps"][:args.cpu_sample_windows]
         t0 = time.perf_counter()
-        r_reads = 0
         for chrom, s, e, _ in sample:
-            r = ob.ref_window(data["bam"], chrom, s, e, ocfg)
-            r_reads += r["n_reads_loaded"]
+            ob.ref_window(data["bam"], chrom, s, e, ocfg)
         dtc = time.perf_counter() - t0
         n_in = sum(n for (_, n, _, _, _) in wins[:len(sample)])
         cpu = {"value": n_in / dtc, "unit": "reads/s", "cores": 1, "kind": "reference",
-               "sample": "first %d windows through the compiled reference's haplotag_region_given_bam call sequence "
-                         "(BAM open + inflate + decode + join), 1 thread" % len(sample)}
+               "sample": "first %d windows of the sample through the compiled reference's haplotag_region_given_bam call "
+                         "sequence (BAM open + inflate + decode + join), 1 thread, %.1f s" % (len(sample), dtc)}
     line = {"metric": "methphase reads/s", "value": tot_reads / dev_mean, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_mean * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer + f32 scores", "data": "synthetic",
             "bases_per_s": tot_bases / dev_mean,
-            "config": {"workload": workload, "windows_per_gpu": len(wins), "reads_per_step": tot_reads,
-                       "bases_per_step": tot_bases, "l2": "inputs (%.0f MB per GPU and batch) larger than L2" % (tsum["h2d"] / 1e6),
-                       "batches_in_flight": nfl},
+            "config": {"workload": workload, "windows": len(wins), "replicas": R, "windows_per_gpu": len(batch_windows),
+                       "reads_per_step": tot_reads, "bases_per_step": tot_bases, "reads_in_sample": base_reads,
+                       "l2": "inputs (%.0f MB per GPU and batch) larger than L2" % (tsum["h2d"] / 1e6),
+                       "batches_in_flight": nfl, "timed_region_s": dev_mean * K},
             "latency_ms_per_step": lat_mean * 1e3,
             "e2e": {"value": tot_reads / e2e_mean, "unit": "reads/s", "ms_per_step": e2e_mean * 1e3,
                     "bases_per_s": tot_bases / e2e_mean, "h2d_bytes_per_step": int(h2d_e2e),
-                    "d2h_bytes_per_step": int(d2h_e2e), "batches_per_step": nb,
-                    "host_buffers": "one registered (pinned, mapped) buffer per rank; payloads gathered by the device over PCIe",
-                    "host_stage_ms_per_step": e2e_reg["stage"], "device_calls_ms_per_step": e2e_reg["device"]},
-            "e2e_host_copy": {"value": tot_reads / e2e_copy_mean, "unit": "reads/s", "ms_per_step": 1e3 * e2e_copy_mean,
-                              "host_buffers": "unregistered: payloads copied into the engine's pinned arena by host threads",
-                              "host_stage_ms_per_step": e2e_copy["stage"], "h2d_bytes_per_step": int(e2e_copy["h2d"])},
+                    "d2h_bytes_per_step": int(d2h_e2e), "batches_per_step": nb, "steps": n_e2e,
+                    "host_buffers": "C ABI from one registered (pinned, mapped) host buffer per rank holding already inflated "
+                                    "BAM records; payloads gathered by the device over PCIe; BGZF inflate is NOT in this number "
+                                    "(cli_e2e has it)",
+                    "host_stage_ms_per_step": 1e3 * e2e_prof["stage"] / n_e2e, "device_calls_ms_per_step": 1e3 * e2e_prof["device"] / n_e2e},
             "gpu_launches": int(launches) * K,
             "kernel_ms": kernels,
             "roofline": {"kernel": "decode_kernel", "bound": "hbm", "achieved": dec_gbs, "peak": peaks["hbm_gbs"],
@@ -499,8 +596,24 @@ def main():
                          "traffic": measured_traffic("decode_kernel", reads), "algorithmic_bytes": int(tsum["decode_bytes"]),
                          "launch_ms": dec_ms, "peak_kind": peak_kind},
             "roofline_pileup": {"kernel": "pileup_tile_kernel+sites_finalize_kernel", "bound": "hbm", "achieved": pile_gbs,
-                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pile_gbs / peaks["hbm_gbs"]},
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": pile_gbs / peaks["hbm_gbs"],
+                                "algorithmic_bytes": int(tsum["pileup_bytes"]), "launch_ms": pile_ms},
+            "windows_per_s": len(batch_windows) * world / dev_mean,
             "clocks": sampler.summary()}
+    if strong_mean is not None:
+        line["strong"] = {"value": reads / strong_mean, "unit": "reads/s", "ms_per_step": strong_mean * 1e3,
+                          "what": "the same batch (%d windows) cut into %d contiguous region sets, one per rank; decisions "
+                                  "gathered on the host and equal to the single-rank run" % (len(batch_windows), world),
+                          "efficiency_vs_one_rank_latency": lat_mean / (strong_mean * world)}
+    if untagged:
+        hap_gbs = untagged["bytes"] / (untagged["haptag_ms"] * 1e-3) / 1e9
+        line["untagged"] = {"value": untagged["reads"] / (untagged["haptag_ms"] * 1e-3), "unit": "reads/s",
+                            "bases_per_s": untagged["bases"] / (untagged["haptag_ms"] * 1e-3), "haptag_ms": untagged["haptag_ms"],
+                            "what": "haptag_kernel over every primary record of an untagged 30x sample (config 4), records "
+                                    "resident, CUDA-event time"}
+        line["roofline_haptag"] = {"kernel": "haptag_kernel", "bound": "hbm", "achieved": hap_gbs, "peak": peaks["hbm_gbs"],
+                                   "unit": "GB/s", "frac": hap_gbs / peaks["hbm_gbs"], "algorithmic_bytes": int(untagged["bytes"])}
+    line.update(cli)
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

@@ -146,6 +146,11 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b);
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r);
 /* the same for an array of n descriptors (one call per window instead of one per record) */
 int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n);
+/* Decode-once form: same_as[i] >= 0 names an earlier read of this batch that is the same
+ * alignment record (it lies in two overlapping windows; the reference re-decodes it per window, blockjoin.c:1056).
+ * The new slot shares that read's staged payload, call slots and decode result; r[i] then only needs pos, l_qseq,
+ * n_cigar (checked) and hp.  same_as[i] < 0 (or same_as == NULL): an ordinary record. */
+int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as);
 /* reads [first_read, first_read+n_reads) are the records of the region query
  * chrom:(ref_start-50000)-(ref_end+50000) in BAM order */
 int pomfret_gpu_batch_add_window(pomfret_gpu_batch *b, uint32_t ref_start, uint32_t ref_end, uint32_t first_read,

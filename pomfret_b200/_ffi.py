@@ -95,6 +95,7 @@ class GpuLib:
         lib.pomfret_gpu_batch_reset.argtypes = [vp]
         lib.pomfret_gpu_batch_add_read.argtypes = [vp, vp]
         lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
+        lib.pomfret_gpu_batch_add_reads_shared.argtypes = [vp, vp, C.c_uint32, vp]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_add_windows.argtypes = [vp, vp, vp, vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
@@ -167,6 +168,15 @@ class Batch:
         """descs_ptr: address of an array of pomfret_gpu_read_desc"""
         base = descs_ptr if isinstance(descs_ptr, int) else C.cast(descs_ptr, C.c_void_p).value
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_reads(self.h, base, n), "batch_add_reads")
+        first = self.n_reads
+        self.n_reads += n
+        return first
+
+    def add_reads_shared(self, descs_ptr, n, same_as):
+        """same_as: int64 numpy array, >= 0 names the earlier batch read that is the same alignment record"""
+        base = descs_ptr if isinstance(descs_ptr, int) else C.cast(descs_ptr, C.c_void_p).value
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_reads_shared(self.h, base, n, same_as.ctypes.data if same_as is not None else None),
+                       "batch_add_reads_shared")
         first = self.n_reads
         self.n_reads += n
         return first

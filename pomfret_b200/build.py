@@ -101,10 +101,10 @@ def build_host(verbose=False):
     sy = os.path.join(BIN, "pomfret-synth")
     sy_srcs = [os.path.join(synth, "synth.cpp"), os.path.join(synth, "synth_main.cpp")]
     if not _newer(sy, sy_srcs + [os.path.join(synth, "synth.h")] + objs):
-        _run(cxx + inc + ["-o", sy] + sy_srcs + objs + ["-lz"], verbose)
+        _run(cxx + inc + ["-o", sy] + sy_srcs + objs + ["-lz", "-pthread"], verbose)
     sylib = os.path.join(LIB, "libpomfret_synth.so")
     if not _newer(sylib, sy_srcs[:1] + [os.path.join(synth, "synth.h")] + objs):
-        _run(cxx + ["-shared"] + inc + ["-o", sylib, sy_srcs[0]] + objs + ["-lz"], verbose)
+        _run(cxx + ["-shared"] + inc + ["-o", sylib, sy_srcs[0]] + objs + ["-lz", "-pthread"], verbose)
     return lib
 
 

@@ -42,6 +42,7 @@ constexpr int N_MODS_LIMIT = 10;      // reference N_MODS, blockjoin.c:34
 struct DecodeParams {
     const ReadRec *reads;
     uint32_t n_reads;
+    uint32_t n_queue;      // entries of `order` to decode (records shared between windows are decoded once)
     const uint8_t *blob;
     uint32_t *calls_pos;
     uint8_t *calls_cat;
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams 
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(P.next, 1u);
         qi = __shfl_sync(FULL_MASK, qi, 0);
-        if (qi >= P.n_reads) return;  // whole warp leaves together
+        if (qi >= P.n_queue) return;  // whole warp leaves together
         const uint32_t ri = P.order ? P.order[qi] : qi;
         const ReadRec &R = P.reads[ri];  // read-only for the whole launch: fields are fetched where they are used
         // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
@@ -1021,6 +1022,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams 
         }
         __syncwarp();
     }
+}
+
+// A record that lies in two windows occupies two slots of the batch but is decoded once: the later slot takes
+// the result (call count, status, reference end) of the earlier one; their ReadRec already share the call slots.
+__global__ void share_decoded_kernel(const uint32_t *dup_of, uint32_t n, uint32_t *r_ncalls, uint32_t *r_status, uint32_t *r_end) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = dup_of[i];
+    if (j == 0xffffffffu) return;
+    r_ncalls[i] = r_ncalls[j]; r_status[i] = r_status[j]; r_end[i] = r_end[j];
 }
 
 }  // namespace pomfret_gpu

@@ -230,6 +230,8 @@ struct pomfret_gpu_batch {
     PinVec<uint32_t> h_cta;   // join launch order: window * 2 + direction
     PinVec<uint32_t> h_order_len;  // record indices, longest first
     std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
+    std::vector<uint32_t> h_dup_of;  // per read: earlier batch read with the same payload (decoded once), or kNoDup
+    size_t n_dups = 0;
     uint64_t calls_total = 0;
     uint64_t alg_decode_bytes = 0, alg_haptag_bytes = 0;
     StagePool *pool = nullptr;      // gather-copy helpers (created on first bulk add)
@@ -246,7 +248,7 @@ struct pomfret_gpu_batch {
     DevBuf d_site_pos, d_site_start[2], d_site_len[2];
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
-    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc;
+    DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc, d_dup_of;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -263,11 +265,12 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_dup_of};
     }
 };
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+static const uint32_t kNoDup = 0xffffffffu;
 // dynamic shared memory of join_kernel: one CTA per SM may take kJoinSmemMax, two CTAs per SM kJoinSmemHalf each
 static const size_t kJoinSmemMax = (size_t)216 * 1024, kJoinSmemHalf = (size_t)108 * 1024;
 
@@ -388,6 +391,8 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     b->h_reads.clear(); b->h_win.clear(); b->h_read_win.clear(); b->h_gsrc.clear();
     b->direct_any = b->copied_any = false;
     b->h_end.clear();
+    b->h_dup_of.clear();
+    b->n_dups = 0;
     b->calls_total = 0;
     b->alg_decode_bytes = b->alg_haptag_bytes = 0;
     b->stage = ST_EMPTY;
@@ -424,7 +429,23 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
 
 // Phase 1 of staging (serial, no payload touched): lay the record's fields out in the blob and reserve
 // its call slots.  Every field starts on a 16-byte boundary and is zero padded to the next one.
-static int plan_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, size_t *len) {
+static int plan_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, size_t *len, int64_t same_as) {
+    if (same_as >= 0) {
+        // The same alignment record as an earlier read of this batch (it lies in two windows): the slot shares
+        // the payload, the call slots and the decode result of that read; only the haplotag is its own.
+        if ((uint64_t)same_as >= b->h_reads.n) return POMFRET_GPU_ERR_ARG;
+        uint32_t root = (uint32_t)same_as;
+        if (b->h_dup_of[root] != kNoDup) root = b->h_dup_of[root];
+        ReadRec R = b->h_reads[root];
+        if (R.pos != r->pos || R.l_qseq != r->l_qseq || R.n_cigar != r->n_cigar) return POMFRET_GPU_ERR_ARG;
+        R.hp = r->hp;
+        int rc;
+        if ((rc = b->h_reads.push(R))) return rc;
+        if ((rc = b->h_read_win.push(0xffffffffu))) return rc;
+        b->h_dup_of.push_back(root);
+        b->n_dups++;
+        return POMFRET_GPU_OK;
+    }
     if (r->l_qseq >= (1u << 28)) return POMFRET_GPU_ERR_UNSUPPORTED;  // decode.cuh: DEC_SAT
     ReadRec R;
     memset(&R, 0, sizeof(R));
@@ -453,6 +474,7 @@ static int plan_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, size_
     int rc;
     if ((rc = b->h_reads.push(R))) return rc;
     if ((rc = b->h_read_win.push(0xffffffffu))) return rc;
+    b->h_dup_of.push_back(kNoDup);
     return POMFRET_GPU_OK;
 }
 
@@ -522,20 +544,28 @@ static int stream_blob(pomfret_gpu_batch *b, bool force) {
 }
 
 int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n) {
+    return pomfret_gpu_batch_add_reads_shared(b, r, n, nullptr);
+}
+
+int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as) {
     if (!b || (n && !r)) return POMFRET_GPU_ERR_ARG;
     if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
     if (n == 0) return POMFRET_GPU_OK;
     const size_t first = b->h_reads.n;
     size_t len = b->h_blob.len;
     const uint64_t calls0 = b->calls_total, dec0 = b->alg_decode_bytes, hap0 = b->alg_haptag_bytes;
+    const size_t dups0 = b->n_dups;
     auto rollback = [&]() {  // a failed call leaves the batch as it found it
         b->h_reads.n = first; b->h_reads.b.len = first * sizeof(ReadRec);
         b->h_read_win.n = first; b->h_read_win.b.len = first * 4;
+        b->h_dup_of.resize(first);
+        b->n_dups = dups0;
         b->calls_total = calls0; b->alg_decode_bytes = dec0; b->alg_haptag_bytes = hap0;
     };
     for (uint32_t i = 0; i < n; i++) {
-        if (int rc = plan_read(b, r + i, &len)) { rollback(); return rc; }
+        if (int rc = plan_read(b, r + i, &len, same_as ? same_as[i] : -1)) { rollback(); return rc; }
     }
+    auto is_dup = [&](size_t i) { return b->h_dup_of[first + i] != kNoDup; };
     if (int rc = b->h_gsrc.resize(first + n)) { rollback(); return rc; }
     b->h_end.resize(first + n);
     // records that lie completely inside registered caller buffers stay where they are: the device gathers them
@@ -548,6 +578,7 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             const pomfret_gpu_read_desc &d = r[i];
             GatherSrc &G = b->h_gsrc[first + i];
             memset(&G, 0, sizeof(G));
+            if (is_dup(i)) continue;
             const void *p[5] = {d.cigar, d.seq, d.mm, d.ml_len >= 0 ? d.ml : nullptr, d.md};
             const size_t sz[5] = {(size_t)d.n_cigar * 4, ((size_t)d.l_qseq + 1) / 2, d.mm ? d.mm_len : 0,
                                   d.ml_len > 0 ? (size_t)d.ml_len : 0, d.md ? d.md_len : 0};
@@ -562,6 +593,7 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             // reference ends (tile planning on the host): the only payload the CPU looks at, a few hundred bytes per record
             uint32_t *ends = b->h_end.data() + first;
             auto scan = [&](size_t i) {
+                if (is_dup(i)) return;
                 uint64_t rlen = 0;
                 for (uint32_t c = 0; c < r[i].n_cigar; c++) {
                     const uint32_t op = r[i].cigar[c] & 15u;
@@ -577,6 +609,7 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
             }
             if (b->pool && n >= 64) b->pool->run((n + 63) / 64, [&](size_t g) { for (size_t i = g * 64; i < std::min<size_t>(n, g * 64 + 64); i++) scan(i); });
             else for (uint32_t i = 0; i < n; i++) scan(i);
+            if (b->n_dups != dups0) for (uint32_t i = 0; i < n; i++) if (is_dup(i)) ends[i] = b->h_end[b->h_dup_of[first + i]];
             b->h_blob.len = len;  // layout only: nothing is written on the host
             b->direct_any = true;
             return POMFRET_GPU_OK;
@@ -599,16 +632,26 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
         b->pool = new StagePool(std::max(0, std::min(per, 12) - 1));
     }
     // Groups of ~4 MB: the helpers copy one group while the DMA engine already moves the previous ones.
+    // (shared records own no bytes: `laid[i]` is where the first record at or behind i that does begins)
+    std::vector<size_t> laid;
+    if (b->n_dups != dups0) {
+        laid.resize(n);
+        size_t cur = len;
+        for (uint32_t i = n; i-- > 0;) { if (!is_dup(i)) cur = (size_t)recs[i].cigar_off * 16; laid[i] = cur; }
+    }
+    auto start_of = [&](uint32_t i) { return laid.empty() ? (size_t)recs[i].cigar_off * 16 : laid[i]; };
+    auto copy_one = [&](size_t i) { if (!is_dup(i)) copy_read(blob, recs[i], r + i, ends + i); };
     for (uint32_t g0 = 0; g0 < n;) {
         uint32_t g1 = g0;
-        const size_t from = (size_t)recs[g0].cigar_off * 16;
-        while (g1 < n && (g1 - g0 < 16 || (size_t)recs[g1].cigar_off * 16 - from < ((size_t)4 << 20))) g1++;
-        if (b->pool && g1 - g0 >= 16) b->pool->run(g1 - g0, [&](size_t i) { copy_read(blob, recs[g0 + i], r + g0 + i, ends + g0 + i); });
-        else for (uint32_t i = g0; i < g1; i++) copy_read(blob, recs[i], r + i, ends + i);
-        b->h_blob.len = g1 < n ? (size_t)recs[g1].cigar_off * 16 : len;
+        const size_t from = start_of(g0);
+        while (g1 < n && (g1 - g0 < 16 || start_of(g1) - from < ((size_t)4 << 20))) g1++;
+        if (b->pool && g1 - g0 >= 16) b->pool->run(g1 - g0, [&](size_t i) { copy_one(g0 + i); });
+        else for (uint32_t i = g0; i < g1; i++) copy_one(i);
+        b->h_blob.len = g1 < n ? start_of(g1) : len;
         if (int rc = stream_blob(b, false)) return rc;
         g0 = g1;
     }
+    if (b->n_dups != dups0) for (uint32_t i = 0; i < n; i++) if (is_dup(i)) ends[i] = b->h_end[b->h_dup_of[first + i]];
     return POMFRET_GPU_OK;
 }
 
@@ -698,16 +741,19 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
     if ((rc = up(b, b->d_win, b->h_win.data(), nw * sizeof(WindowRec)))) return rc;
     if ((rc = up(b, b->d_read_win, b->h_read_win.data(), nr * 4))) return rc;
     // queue order of the per-record kernels: longest records first (counting sort over 256-base buckets)
+    // (records shared with an earlier read come last: decode stops in front of them, the per-slot kernels go on)
     if ((rc = b->h_order_len.resize(nr ? nr : 1))) return rc;
     {
         constexpr uint32_t NB = 4096;
-        std::vector<uint32_t> cnt(NB + 1, 0);
-        for (size_t i = 0; i < nr; i++) cnt[NB - 1 - std::min<uint32_t>(b->h_reads[i].l_qseq >> 8, NB - 1)]++;
+        std::vector<uint32_t> cnt(2 * NB + 1, 0);
+        auto bucket = [&](size_t i) { return (b->h_dup_of[i] != kNoDup ? NB : 0u) + NB - 1 - std::min<uint32_t>(b->h_reads[i].l_qseq >> 8, NB - 1); };
+        for (size_t i = 0; i < nr; i++) cnt[bucket(i)]++;
         uint32_t acc = 0;
-        for (uint32_t k = 0; k <= NB; k++) { uint32_t c = cnt[k]; cnt[k] = acc; acc += c; }
-        for (size_t i = 0; i < nr; i++) b->h_order_len[cnt[NB - 1 - std::min<uint32_t>(b->h_reads[i].l_qseq >> 8, NB - 1)]++] = (uint32_t)i;
+        for (uint32_t k = 0; k <= 2 * NB; k++) { uint32_t c = cnt[k]; cnt[k] = acc; acc += c; }
+        for (size_t i = 0; i < nr; i++) b->h_order_len[cnt[bucket(i)]++] = (uint32_t)i;
     }
     if ((rc = up(b, b->d_order_len, b->h_order_len.data(), nr * 4))) return rc;
+    if (b->n_dups && (rc = up(b, b->d_dup_of, b->h_dup_of.data(), nr * 4))) return rc;
     CK(cudaEventRecord(b->ev[1], b->stream));
     b->stage = ST_SUBMITTED;
     return POMFRET_GPU_OK;
@@ -751,13 +797,20 @@ static int launch_decode(pomfret_gpu_batch *b) {
     P.next = b->d_flags.as<uint32_t>() + 1;
     P.order = nr ? b->d_order_len.as<uint32_t>() : nullptr;
     P.lo = b->lo; P.hi = b->hi;
-    if (nr) {
+    const size_t nq = nr - b->n_dups;  // the queue holds every distinct record once
+    P.n_queue = (uint32_t)nq;
+    if (nq) {
         // one CTA per 4 records, at most the resident set (8 CTAs per SM): the warps loop over a queue
-        unsigned grid = (unsigned)std::min<size_t>((nr + DEC_WARPS - 1) / DEC_WARPS, (size_t)b->sm_count * 8);
+        unsigned grid = (unsigned)std::min<size_t>((nq + DEC_WARPS - 1) / DEC_WARPS, (size_t)b->sm_count * 8);
         if (const char *e = getenv("POMFRET_GPU_DECODE_QUEUE")) {  // measurement hook: "0" = one warp per record in batch order
-            if (!strcmp(e, "0")) { grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS); P.order = nullptr; }
+            if (!strcmp(e, "0")) { grid = (unsigned)((nr + DEC_WARPS - 1) / DEC_WARPS); P.order = nullptr; P.n_queue = (uint32_t)nr; }
         }
         POMFRET_LAUNCH(decode_kernel, grid, DEC_WARPS * 32, 0, b->stream, P);
+        b->tm.launches++;
+    }
+    if (b->n_dups) {
+        POMFRET_LAUNCH(share_decoded_kernel, (unsigned)((nr + 255) / 256), 256, 0, b->stream, b->d_dup_of.as<uint32_t>(), (uint32_t)nr,
+                       P.r_ncalls, P.r_status, P.r_end);
         b->tm.launches++;
     }
     CK(cudaGetLastError());
@@ -916,6 +969,11 @@ int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
         uint64_t total = 0;
         for (size_t i = 0; i < nr; i++) {
             ReadRec &R = b->h_reads[i];
+            if (b->h_dup_of[i] != kNoDup) {  // shares the (already re-planned) slots of the earlier read
+                R.calls_cap = b->h_reads[b->h_dup_of[i]].calls_cap;
+                R.calls_off = b->h_reads[b->h_dup_of[i]].calls_off;
+                continue;
+            }
             if (st[i] & RS_OVERFLOW) R.calls_cap = R.calls_cap + R.l_qseq / 2 + 16;
             R.calls_off = (uint32_t)total;
             total += R.calls_cap;

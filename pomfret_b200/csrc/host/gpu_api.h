@@ -17,7 +17,11 @@ struct GpuApi {
     int (*batch_reset)(pomfret_gpu_batch *) = nullptr;
     int (*batch_add_read)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *) = nullptr;
     int (*batch_add_reads)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *, uint32_t) = nullptr;
+    int (*batch_add_reads_shared)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *, uint32_t, const int64_t *) = nullptr;
     int (*batch_add_window)(pomfret_gpu_batch *, uint32_t, uint32_t, uint32_t, uint32_t) = nullptr;
+    int (*batch_add_windows)(pomfret_gpu_batch *, const uint32_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t) = nullptr;
+    int (*host_register)(pomfret_gpu_ctx *, void *, size_t) = nullptr;
+    int (*host_unregister)(pomfret_gpu_ctx *, void *) = nullptr;
     int (*batch_submit)(pomfret_gpu_batch *) = nullptr;
     int (*decode)(pomfret_gpu_batch *, uint8_t, uint8_t) = nullptr;
     int (*haptag)(pomfret_gpu_batch *, const pomfret_gpu_variant *, uint32_t, const uint8_t *, uint32_t, const uint32_t *) = nullptr;

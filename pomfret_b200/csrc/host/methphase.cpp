@@ -2,6 +2,9 @@
 #include "methphase.h"
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,6 +58,9 @@ struct WindowJob {
     int i_ref;
     size_t i_win;
     uint32_t start, end;
+    // the region query of load_reads_given_interval (blockjoin.c:1053-1061) as the iterator sees it: [beg0, end0)
+    int64_t beg0() const { int64_t b = (int64_t)start - kReadback; if (b < 0) b = 0; b -= 1; return b < 0 ? 0 : b; }
+    int64_t end0() const { return (int64_t)end + kReadback; }
 };
 
 struct WindowOut {
@@ -62,55 +68,155 @@ struct WindowOut {
     std::vector<std::pair<std::string, int>> tags;  // kept reads in BAM order, only when decision >= 0
 };
 
-// One worker: its own BAM handle and its own batch on its own device/stream.
+// Record storage of one worker: slabs of page-aligned host memory registered with the engine once (pinned and
+// mapped).  The BAM reader inflates records straight into them and the device gathers the fields it needs over
+// PCIe: the host never copies a payload and base qualities never leave the host.
+struct RecordArena {
+    static constexpr size_t kSlab = (size_t)256 << 20, kMinFree = (size_t)32 << 20;
+    struct Slab { uint8_t *p; size_t cap, len; };
+    std::vector<Slab> slabs;
+    size_t cur = 0;
+    const GpuApi *api = nullptr;
+    pomfret_gpu_ctx *ctx = nullptr;
+    void rewind() { for (Slab &s : slabs) s.len = 0; cur = 0; }
+    // a place for one record of at most kMinFree bytes
+    uint8_t *room(size_t *cap) {
+        while (cur < slabs.size() && slabs[cur].cap - slabs[cur].len < kMinFree) cur++;
+        if (cur == slabs.size()) {
+            void *p = nullptr;
+            if (posix_memalign(&p, 4096, kSlab) != 0) return nullptr;
+            int rc = api->host_register(ctx, p, kSlab);
+            if (rc != 0) { fprintf(stderr, "[W::%s] host_register: %s (records will be copied instead)\n", "pomfret", api->strerror(rc)); }
+            slabs.push_back({(uint8_t *)p, kSlab, 0});
+        }
+        *cap = slabs[cur].cap - slabs[cur].len;
+        return slabs[cur].p + slabs[cur].len;
+    }
+    void commit(size_t n) { slabs[cur].len += (n + 63) & ~(size_t)63; }
+    void release() {
+        for (Slab &s : slabs) { api->host_unregister(ctx, s.p); free(s.p); }
+        slabs.clear();
+    }
+};
+
+// One worker: its own BAM handle, record arena and batch on its own device/stream.
 struct Worker {
     Engine *eng = nullptr;
     int id = 0, device = 0;
     BamReader bam;
     pomfret_gpu_batch *batch = nullptr;
+    RecordArena arena;
+    bam1_t view;   // record header over arena memory (POMFRET_BAM_EXTERNAL_DATA)
     RunStats stats;
     bool open(const std::string &fn_bam) {
         if (!bam.open(fn_bam)) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "load_reads_given_interval", fn_bam.c_str()); return false; }
         int rc = eng->api.batch_begin(eng->ctx, id, device, &batch);
         if (rc != 0) { fprintf(stderr, "[E::%s] batch_begin: %s\n", "pomfret", eng->api.strerror(rc)); return false; }
+        arena.api = &eng->api; arena.ctx = eng->ctx;
+        memset(&view, 0, sizeof(view));
+        view.id = POMFRET_BAM_EXTERNAL_DATA;
         return true;
     }
-    void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; }
+    void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; arena.release(); }
 
-    // haplotag_region_given_bam for a chunk of windows of one contig
+    // next record of the iterator, inflated in place into the arena; false at the end
+    bool next_record(hts_itr_t *itr) {
+        size_t cap = 0;
+        view.data = arena.room(&cap);
+        if (!view.data) { fprintf(stderr, "[E::%s] out of host memory\n", "pomfret"); exit(1); }
+        view.m_data = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+        view.l_data = 0;
+        const int rc = sam_itr_next(bam.fp, itr, &view);
+        if (rc < -1) { fprintf(stderr, "[E::%s] error while reading %s (truncated file, or a record larger than %zu MB)\n", "pomfret", bam.fn.c_str(), RecordArena::kMinFree >> 20); exit(1); }
+        return rc >= 0;
+    }
+
+    struct Rec { bam1_core_t core; uint8_t *data; int l_data; int hp; int64_t first_slot; };
+
+    // haplotag_region_given_bam for a chunk of windows of one contig.  Windows whose region queries overlap
+    // form a run that is read from the BAM once; a record that lies in several windows is staged and decoded
+    // once (the reference re-opens the file and re-decodes per window, blockjoin.c:1056).
     void run_chunk(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg,
                    const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
         const GpuApi &api = eng->api;
         double t0 = now_s();
-        // records go from the BAM reader straight into the batch's pinned arena (one copy); only names are kept
-        struct Win { std::vector<uint32_t> qname_off; std::string qnames; size_t n = 0;
-                     const char *qname(size_t i) const { return qnames.data() + qname_off[i]; } };
-        std::vector<Win> wins(jobs.size());
         int rc = api.batch_reset(batch);
         if (rc) die_gpu(api, rc, "batch_reset");
-        uint32_t first = 0;
-        std::vector<uint32_t> firsts;
-        for (size_t w = 0; w < jobs.size(); w++) {
-            Win &W = wins[w];
-            rc = for_each_window_record(bam, chrom.c_str(), jobs[w].start, jobs[w].end, cfg.readlen_threshold, cfg.min_mapq, raw_tags,
-                                        [&](const bam1_t *b, int hp) {
-                pomfret_gpu_read_desc d;
-                describe_record(b, hp, &d);
-                d.md = nullptr; d.md_len = 0;  // the window engine does not read MD
-                int rc2 = api.batch_add_read(batch, &d);
-                if (rc2) die_gpu(api, rc2, "batch_add_read");
-                W.qname_off.push_back((uint32_t)W.qnames.size());
-                W.qnames.append(bam_get_qname(b));
-                W.qnames.push_back('\0');
-                W.n++;
-                stats.n_bases += d.l_qseq;
-            });
-            if (rc) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[w].start, jobs[w].end); exit(1); }
-            if ((rc = api.batch_add_window(batch, jobs[w].start, jobs[w].end, first, (uint32_t)W.n))) die_gpu(api, rc, "batch_add_window");
-            firsts.push_back(first);
-            first += (uint32_t)W.n;
-            stats.n_reads += W.n;
+        arena.rewind();
+        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
+        std::vector<Rec> recs;
+        std::vector<std::vector<uint32_t>> win_recs(jobs.size());
+        for (size_t r0 = 0; r0 < jobs.size();) {
+            size_t r1 = r0 + 1;
+            int64_t run_end = jobs[r0].end0();
+            while (r1 < jobs.size() && jobs[r1].beg0() < run_end) { run_end = std::max(run_end, jobs[r1].end0()); r1++; }
+            hts_itr_t *itr = tid >= 0 ? sam_itr_queryi(bam.idx, tid, jobs[r0].beg0(), run_end) : nullptr;
+            if (!itr) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[r0].start, jobs[r0].end); exit(1); }
+            while (next_record(itr)) {
+                const bam1_t *b = &view;
+                const int flag = b->core.flag;
+                const uint32_t len = (uint32_t)b->core.l_qseq;
+                if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;      // blockjoin.c:1081-1084
+                if (b->core.qual < (uint32_t)cfg.min_mapq) continue;
+                if (len < 2 || len < (uint32_t)cfg.readlen_threshold) continue;
+                float de = -1;
+                if (uint8_t *t = bam_aux_get(b, "de")) de = (float)bam_aux2f(t);
+                if (de > kMinAlnDe) continue;
+                const int64_t pos = b->core.pos, endpos = bam_endpos(b);
+                bool used = false;
+                for (size_t w = r0; w < r1; w++) {
+                    if (!(pos < jobs[w].end0() && endpos > jobs[w].beg0())) continue;  // what this window's own query returns
+                    if (!used) {
+                        int hp;
+                        if (raw_tags) {
+                            auto it = raw_tags->find(bam_get_qname(b));
+                            hp = it != raw_tags->end() ? it->second : kHaptagUnphased;
+                        } else hp = hp_from_record(b);
+                        recs.push_back({b->core, b->data, b->l_data, hp, -1});
+                        arena.commit((size_t)b->l_data);
+                        used = true;
+                    }
+                    win_recs[w].push_back((uint32_t)recs.size() - 1);
+                }
+            }
+            hts_itr_destroy(itr);
+            r0 = r1;
         }
+        // slots in window order; the second and later uses of a record share the first one's payload and calls
+        std::vector<pomfret_gpu_read_desc> descs;
+        std::vector<int64_t> same_as;
+        std::vector<uint32_t> w_start, w_end, w_first, w_n;
+        bool any_shared = false;
+        for (size_t w = 0; w < jobs.size(); w++) {
+            w_start.push_back(jobs[w].start); w_end.push_back(jobs[w].end);
+            w_first.push_back((uint32_t)descs.size()); w_n.push_back((uint32_t)win_recs[w].size());
+            for (uint32_t ri : win_recs[w]) {
+                Rec &R = recs[ri];
+                pomfret_gpu_read_desc d;
+                if (R.first_slot < 0) {
+                    bam1_t tmp;
+                    memset(&tmp, 0, sizeof(tmp));
+                    tmp.core = R.core; tmp.data = R.data; tmp.l_data = R.l_data;
+                    describe_record(&tmp, R.hp, &d);
+                    d.md = nullptr; d.md_len = 0;  // the window engine does not read MD
+                    R.first_slot = (int64_t)descs.size();
+                    same_as.push_back(-1);
+                    stats.n_bases += d.l_qseq;
+                } else {
+                    memset(&d, 0, sizeof(d));
+                    d.pos = (uint32_t)R.core.pos; d.l_qseq = (uint32_t)R.core.l_qseq; d.n_cigar = R.core.n_cigar; d.hp = R.hp;
+                    d.mn = -1; d.ml_len = -1;
+                    same_as.push_back(R.first_slot);
+                    any_shared = true;
+                    stats.n_shared++;
+                }
+                descs.push_back(d);
+            }
+            stats.n_reads += win_recs[w].size();
+        }
+        if (!descs.empty() && (rc = api.batch_add_reads_shared(batch, descs.data(), (uint32_t)descs.size(), any_shared ? same_as.data() : nullptr)))
+            die_gpu(api, rc, "batch_add_reads");
+        if ((rc = api.batch_add_windows(batch, w_start.data(), w_end.data(), w_first.data(), w_n.data(), (uint32_t)jobs.size()))) die_gpu(api, rc, "batch_add_window");
         stats.n_windows += jobs.size();
         double t1 = now_s();
         stats.t_load += t1 - t0;
@@ -118,20 +224,22 @@ struct Worker {
         if ((rc = api.decode(batch, (uint8_t)cfg.lo, (uint8_t)cfg.hi))) die_gpu(api, rc, "decode");
         if ((rc = api.pileup(batch, &cfg))) die_gpu(api, rc, "pileup");
         if ((rc = api.join(batch, &cfg))) die_gpu(api, rc, "join");
+        const size_t n_slots = descs.size();
         std::vector<pomfret_gpu_window_result> res(jobs.size() ? jobs.size() : 1);
-        std::vector<uint8_t> tags(first ? first : 1);
-        std::vector<int32_t> ids(first ? first : 1);
+        std::vector<uint8_t> tags(n_slots ? n_slots : 1);
+        std::vector<int32_t> ids(n_slots ? n_slots : 1);
         if ((rc = api.batch_collect(batch, res.data(), tags.data(), ids.data()))) die_gpu(api, rc, "batch_collect");
         stats.t_gpu += now_s() - t1;
         outs->assign(jobs.size(), WindowOut());
         for (size_t w = 0; w < jobs.size(); w++) {
-            const size_t n = wins[w].n;
+            const size_t n = win_recs[w].size();
+            auto qname = [&](size_t i) { return (const char *)recs[win_recs[w][i]].data; };
             // duplicated read names among the loaded records are fatal (blockjoin.c:1143-1155)
             std::unordered_set<std::string> seen;
             for (size_t i = 0; i < n; i++) {
-                if (ids[firsts[w] + i] < 0) continue;
-                if (!seen.insert(wins[w].qname(i)).second) {
-                    fprintf(stderr, "[E::%s] duplicated read name seen from reading bam: %s\n", "load_reads_given_interval", wins[w].qname(i));
+                if (ids[w_first[w] + i] < 0) continue;
+                if (!seen.insert(qname(i)).second) {
+                    fprintf(stderr, "[E::%s] duplicated read name seen from reading bam: %s\n", "load_reads_given_interval", qname(i));
                     exit(1);
                 }
             }
@@ -143,31 +251,31 @@ struct Worker {
                     res[w].join_fwd, res[w].join_bwd);
             if (o.decision >= 0)
                 for (size_t i = 0; i < n; i++)
-                    if (ids[firsts[w] + i] >= 0) o.tags.emplace_back(wins[w].qname(i), (int)tags[firsts[w] + i]);
+                    if (ids[w_first[w] + i] >= 0) o.tags.emplace_back(qname(i), (int)tags[w_first[w] + i]);
         }
     }
 
-    // pre_haplotagging_read_in_one_ref (blockjoin.c:1841-1898): every primary record of the contig
+    // pre_haplotagging_read_in_one_ref (blockjoin.c:1841-1898): every primary record of the contig, in BAM order
+    // into `raw` (first alignment of a name wins, :1880-1889)
     void haptag_contig(const std::string &chrom, const KnownVariants &kv, TagMap *raw) {
         const GpuApi &api = eng->api;
         double t0 = now_s();
         hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, chrom.c_str());
         if (!itr) return;
-        struct Pending { std::string qname; };
-        std::vector<std::string> names;
+        std::vector<const char *> names;
         std::vector<uint32_t> known_first;
-        std::vector<std::vector<uint8_t>> payload;  // record copies of the current batch
         std::vector<pomfret_gpu_read_desc> descs;
         uint32_t prev_i_left = 0;
         size_t bytes = 0;
         int n_new[4] = {0, 0, 0, 0};
+        arena.rewind();
         auto flush = [&]() {
             if (names.empty()) return;
             std::vector<uint8_t> tags(names.size(), (uint8_t)kHaptagUnphased);
             if (!kv.vars.empty()) {
                 int rc = api.batch_reset(batch);
                 if (rc) die_gpu(api, rc, "batch_reset");
-                for (const pomfret_gpu_read_desc &d : descs) if ((rc = api.batch_add_read(batch, &d))) die_gpu(api, rc, "batch_add_read");
+                if ((rc = api.batch_add_reads(batch, descs.data(), (uint32_t)descs.size()))) die_gpu(api, rc, "batch_add_reads");
                 if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
                 if ((rc = api.haptag(batch, kv.vars.data(), (uint32_t)kv.vars.size(), kv.bases.data(), (uint32_t)kv.bases.size(), known_first.data())))
                     die_gpu(api, rc, "haptag");
@@ -178,14 +286,16 @@ struct Worker {
                 auto ins = raw->emplace(names[i], (int)tags[i]);  // first alignment wins (blockjoin.c:1880-1889)
                 if (ins.second) n_new[tags[i] == 0 ? 0 : tags[i] == 1 ? 1 : 2]++; else n_new[3]++;
             }
-            names.clear(); known_first.clear(); payload.clear(); descs.clear(); bytes = 0;
+            names.clear(); known_first.clear(); descs.clear(); bytes = 0;
+            arena.rewind();
         };
-        bam1_t *b = bam.rec;
-        while (sam_itr_next(bam.fp, itr, b) >= 0) {
+        while (next_record(itr)) {
+            const bam1_t *b = &view;
             const int flag = b->core.flag;
             if ((flag & 4) || (flag & 256) || (flag & 2048)) continue;
             if (!bam_aux_get(b, "MD")) die_gpu(api, POMFRET_GPU_ERR_MISSING_MD, "haptag");
-            names.emplace_back(bam_get_qname(b));
+            names.push_back(bam_get_qname(b));
+            arena.commit((size_t)b->l_data);
             stats.n_haptag_reads++;
             stats.n_haptag_bases += (uint64_t)b->core.l_qseq;
             if (!kv.vars.empty()) {
@@ -195,16 +305,13 @@ struct Worker {
                 while (i < kv.vars.size() && kv.vars[i].pos < start_pos) i++;
                 prev_i_left = i == 0 ? 0 : i - 1;
                 known_first.push_back(i);
-                payload.emplace_back(b->data, b->data + b->l_data);
-                bam1_t tmp = *b;
-                tmp.data = payload.back().data();
                 pomfret_gpu_read_desc d;
-                describe_record(&tmp, kHaptagUnphased, &d);
+                describe_record(b, kHaptagUnphased, &d);
                 d.mm = nullptr; d.mm_len = 0; d.ml = nullptr; d.ml_len = -1;  // the haplotagger needs CIGAR, SEQ and MD only
                 descs.push_back(d);
-                bytes += (size_t)b->l_data;
             }
-            if (names.size() >= 16384 || bytes >= ((size_t)512 << 20)) flush();
+            bytes += (size_t)b->l_data;
+            if (names.size() >= 32768 || bytes >= ((size_t)768 << 20)) flush();
         }
         flush();
         hts_itr_destroy(itr);
@@ -246,46 +353,74 @@ void check_limits(const pomfret_gpu_config &c) {
     }
 }
 
-// Run all windows of all contigs; chunks of consecutive windows are independent jobs.
+// Run all windows of all contigs.  The ordered (contig, window) list is cut into chunks of consecutive windows
+// (one batch each) and the chunk list into one contiguous region set per device, balanced by the estimated
+// number of records; a worker serves its device's set first and helps the others when it
+// runs dry.  Nothing is exchanged between devices: the host gathers one decision per window and one tag per read.
 void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const std::vector<pomfret_gpu_config> &cfg_per_ref,
                  std::vector<std::vector<WindowOut>> *results, RunStats *stats) {
-    struct Chunk { int i_ref; std::vector<WindowJob> jobs; };
+    struct Chunk { int i_ref; std::vector<WindowJob> jobs; uint64_t cost; };
     std::vector<Chunk> chunks;
     const int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 8;
     results->assign(ps.st.ref_names.size(), {});
+    uint64_t total_cost = 0;
     for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
         const Ranges &rg = ps.st.ranges[r];
         (*results)[r].assign(rg.n, WindowOut());
         for (size_t i = 0; i < rg.n; i += (size_t)per) {
             Chunk c;
             c.i_ref = (int)r;
-            for (size_t j = i; j < rg.n && j < i + (size_t)per; j++) c.jobs.push_back({(int)r, j, rg.starts[j], rg.ends[j]});
+            c.cost = 0;
+            for (size_t j = i; j < rg.n && j < i + (size_t)per; j++) {
+                c.jobs.push_back({(int)r, j, rg.starts[j], rg.ends[j]});
+                c.cost += (uint64_t)(rg.ends[j] - rg.starts[j]) + 2 * kReadback;  // ~ records fetched for the window
+            }
+            total_cost += c.cost;
             chunks.push_back(std::move(c));
         }
     }
+    const int n_dev = std::max(1, eng.n_dev);
+    std::vector<size_t> set_begin((size_t)n_dev + 1, chunks.size());
+    {
+        uint64_t acc = 0;
+        size_t c = 0;
+        for (int d = 0; d < n_dev; d++) {
+            set_begin[(size_t)d] = c;
+            const uint64_t target = total_cost * (uint64_t)(d + 1) / (uint64_t)n_dev;
+            while (c < chunks.size() && (acc < target || d == n_dev - 1)) acc += chunks[c++].cost;
+        }
+        set_begin[(size_t)n_dev] = chunks.size();
+    }
+    std::vector<std::atomic<size_t>> cursor((size_t)n_dev);
+    for (int d = 0; d < n_dev; d++) cursor[(size_t)d].store(set_begin[(size_t)d]);
     const int n_workers = std::max(1, std::min<int>(opt.threads, (int)chunks.size()));
-    std::atomic<size_t> next(0);
     std::mutex mu;
     auto body = [&](int wid) {
         Worker wk;
-        wk.eng = &eng; wk.id = wid; wk.device = wid % eng.n_dev;
+        wk.eng = &eng; wk.id = wid; wk.device = wid % n_dev;
         const double tw0 = now_s();
         if (!wk.open(opt.fn_bam)) exit(1);
         const double tw1 = now_s();
-        for (;;) {
-            size_t c = next.fetch_add(1);
-            if (c >= chunks.size()) break;
-            const Chunk &ch = chunks[c];
-            std::vector<WindowOut> outs;
-            wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
-            for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
+        size_t n_own = 0, n_helped = 0;
+        for (int k = 0; k < n_dev; k++) {
+            const size_t d = (size_t)((wk.device + k) % n_dev);  // own region set first, then the others'
+            for (;;) {
+                const size_t c = cursor[d].fetch_add(1);
+                if (c >= set_begin[d + 1]) break;
+                const Chunk &ch = chunks[c];
+                std::vector<WindowOut> outs;
+                wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
+                for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
+                (k == 0 ? n_own : n_helped)++;
+            }
         }
         const double tw2 = now_s();
         wk.close();
-        fprintf(stderr, "[T::worker %d] open %.2fs, chunks %.2fs (load %.2fs, gpu %.2fs), close %.2fs\n", wid, tw1 - tw0, tw2 - tw1,
-                wk.stats.t_load, wk.stats.t_gpu, now_s() - tw2);
+        fprintf(stderr, "[T::worker %d] device %d: %zu chunks of its region set, %zu of others; open %.2fs, chunks %.2fs (load %.2fs, gpu %.2fs), close %.2fs\n",
+                wid, wk.device, n_own, n_helped, tw1 - tw0, tw2 - tw1, wk.stats.t_load, wk.stats.t_gpu, now_s() - tw2);
         std::lock_guard<std::mutex> lock(mu);
         stats->n_windows += wk.stats.n_windows; stats->n_reads += wk.stats.n_reads; stats->n_bases += wk.stats.n_bases;
+        stats->n_shared += wk.stats.n_shared;
         stats->t_load += wk.stats.t_load; stats->t_gpu += wk.stats.t_gpu;
     };
     std::vector<std::thread> th;
@@ -294,21 +429,55 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
     for (auto &t : th) t.join();
 }
 
-// load_intervals_from_file with the -u pre-pass hooked in (blockjoin.c:4446-4468)
+// load_intervals_from_file with the -u pre-pass hooked in (blockjoin.c:4446-4468).  The reference tags one
+// contig after the other on the main thread; here the contigs are handed to workers (one device each) as the
+// VCF reader finishes them, every contig into its own table, and the tables are merged in contig order with
+// first-insert-wins (blockjoin.c:1880-1889) — what the sequential run produces.
 bool load_all_intervals(Engine &eng, const Options &opt, PhaseState *ps, RunStats *stats) {
     std::string fatal;
     const std::string fn_interval = !opt.fn_tsv.empty() ? opt.fn_tsv : !opt.fn_gtf.empty() ? opt.fn_gtf : opt.fn_vcf;
     const IntervalFormat fmt = !opt.fn_tsv.empty() ? IntervalFormat::TSV : !opt.fn_gtf.empty() ? IntervalFormat::GTF : IntervalFormat::VCF;
     if (opt.bam_needs_haplotagging) {
-        Worker wk;
-        wk.eng = &eng; wk.id = 0; wk.device = 0;
-        if (!wk.open(opt.fn_bam)) return false;
+        struct Task { std::string chrom; KnownVariants kv; TagMap tags; };
+        std::deque<Task> tasks;  // stable addresses
+        std::mutex mu;
+        std::condition_variable cv;
+        size_t next_task = 0;
+        bool done_reading = false;
+        const int n_workers = std::max(1, opt.threads);
+        std::vector<std::thread> th;
+        auto body = [&](int wid) {
+            Worker wk;
+            wk.eng = &eng; wk.id = wid; wk.device = wid % std::max(1, eng.n_dev);
+            bool opened = false;
+            for (;;) {
+                Task *t = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return next_task < tasks.size() || done_reading; });
+                    if (next_task >= tasks.size()) break;
+                    t = &tasks[next_task++];
+                }
+                if (!opened) { if (!wk.open(opt.fn_bam)) exit(1); opened = true; }
+                wk.haptag_contig(t->chrom, t->kv, &t->tags);
+            }
+            if (opened) wk.close();
+            std::lock_guard<std::mutex> lk(mu);
+            stats->n_haptag_reads += wk.stats.n_haptag_reads; stats->n_haptag_bases += wk.stats.n_haptag_bases; stats->t_haptag += wk.stats.t_haptag;
+        };
+        for (int t = 0; t < n_workers; t++) th.emplace_back(body, t);
         ps->stores_raw_tag = true;
         bool ok = load_intervals(opt.fn_vcf, IntervalFormat::VCF, &ps->st,
-                                 [&](const std::string &chrom, KnownVariants &kv, bool) { wk.haptag_contig(chrom, kv, &ps->qname2haptag_raw); },
+                                 [&](const std::string &chrom, KnownVariants &kv, bool) {
+                                     { std::lock_guard<std::mutex> lk(mu); tasks.push_back(Task{chrom, kv, TagMap()}); }
+                                     cv.notify_one();
+                                 },
                                  &fatal);
-        wk.close();
-        stats->n_haptag_reads += wk.stats.n_haptag_reads; stats->n_haptag_bases += wk.stats.n_haptag_bases; stats->t_haptag += wk.stats.t_haptag;
+        { std::lock_guard<std::mutex> lk(mu); done_reading = true; }
+        cv.notify_all();
+        for (auto &t : th) t.join();
+        for (Task &t : tasks)
+            for (auto &kv : t.tags) ps->qname2haptag_raw.emplace(kv.first, kv.second);
         if (!ok) { fprintf(stderr, "[E::%s] failed to open file for phase blocks: %s\n", "load_intervals_from_file", opt.fn_vcf.c_str()); exit(1); }
         if (!fatal.empty()) { fprintf(stderr, "%s\n", fatal.c_str()); exit(1); }
         size_t n_loaded = 0;

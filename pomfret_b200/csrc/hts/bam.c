@@ -156,6 +156,7 @@ void bam_destroy1(bam1_t *b) {
 
 static int reserve(bam1_t *b, size_t want) {
     if (want <= b->m_data) return 0;
+    if (b->id == POMFRET_BAM_EXTERNAL_DATA) return -1; /* caller-owned buffer: never reallocated */
     size_t m = b->m_data ? b->m_data : 256;
     while (m < want) m += m >> 1;
     uint8_t *d = (uint8_t *)realloc(b->data, m);

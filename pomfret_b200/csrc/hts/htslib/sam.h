@@ -76,6 +76,10 @@ typedef struct bam1_t {
     uint32_t m_data;
 } bam1_t;
 
+/* shim extension (not htslib API): with b->id set to this value, b->data / b->m_data describe a buffer owned by
+ * the caller (a loader's record arena); bam_read1 fills it in place and fails instead of reallocating it */
+#define POMFRET_BAM_EXTERNAL_DATA 0x504f4d4645584255ull
+
 #define bam_is_rev(b) (((b)->core.flag & BAM_FREVERSE) != 0)
 #define bam_get_qname(b) ((char *)(b)->data)
 #define bam_get_cigar(b) ((uint32_t *)((b)->data + (b)->core.l_qname))
@@ -113,6 +117,11 @@ hts_pos_t bam_cigar2rlen(int n_cigar, const uint32_t *cigar);
 
 hts_idx_t *sam_index_load(htsFile *fp, const char *fn);
 int sam_index_build3(const char *fn, const char *fnidx, int min_shift, int nthreads);
+/* shim extension (not htslib API): BAI construction from a writer's own virtual offsets, see index.c */
+typedef struct pomfret_bai_builder pomfret_bai_builder;
+pomfret_bai_builder *pomfret_bai_new(int n_ref);
+int pomfret_bai_add(pomfret_bai_builder *b, int tid, hts_pos_t beg, hts_pos_t end, int unmapped, uint64_t off0, uint64_t off1);
+int pomfret_bai_finish(pomfret_bai_builder *b, const char *fnidx);
 hts_itr_t *sam_itr_querys(const hts_idx_t *idx, sam_hdr_t *hdr, const char *region);
 hts_itr_t *sam_itr_queryi(const hts_idx_t *idx, int tid, hts_pos_t beg, hts_pos_t end);
 int sam_itr_next(htsFile *htsfp, hts_itr_t *itr, bam1_t *r);

@@ -308,56 +308,62 @@ static void w32(FILE *f, uint32_t v) {
 }
 static void w64(FILE *f, uint64_t v) { w32(f, (uint32_t)v); w32(f, (uint32_t)(v >> 32)); }
 
-int sam_index_build3(const char *fn, const char *fnidx, int min_shift, int nthreads) {
-    (void)nthreads;
-    if (min_shift != 0) return -1; /* BAI only */
-    htsFile *fp = hts_open(fn, "r");
-    if (!fp) return -2;
-    sam_hdr_t *h = sam_hdr_read(fp);
-    if (!h) { hts_close(fp); return -1; }
-    int n_ref = h->n_targets;
-    bref_t *refs = (bref_t *)calloc(n_ref > 0 ? n_ref : 1, sizeof(bref_t));
-    bam1_t *b = bam_init1();
-    BGZF *bg = fp->fp.bgzf;
-    uint64_t n_no_coor = 0;
-    uint64_t off0 = (uint64_t)bgzf_tell(bg);
-    int rc, ret = 0, last_tid = -1;
-    hts_pos_t last_pos = -1;
-    while ((rc = bam_read1(bg, b)) >= 0) {
-        uint64_t off1 = (uint64_t)bgzf_tell(bg);
-        int tid = b->core.tid;
-        if (tid < 0) { n_no_coor++; off0 = off1; continue; }
-        if (tid >= n_ref || tid < last_tid || (tid == last_tid && b->core.pos < last_pos)) { ret = -1; break; }
-        last_tid = tid;
-        last_pos = b->core.pos;
-        bref_t *r = &refs[tid];
-        if (!r->seen) { r->seen = 1; r->off_beg = off0; }
-        r->off_end = off1;
-        if (b->core.flag & BAM_FUNMAP) r->n_unmapped++; else r->n_mapped++;
-        hts_pos_t beg = b->core.pos, end = bam_endpos(b);
-        bbin_t *bb = get_bin(r, (uint32_t)reg2bin(beg, end));
-        if (bb->n > 0 && bb->a[bb->n - 1].end == off0) bb->a[bb->n - 1].end = off1;
-        else {
-            if (bb->n == bb->m) { bb->m = bb->m ? bb->m * 2 : 4; bb->a = (chunk_t *)realloc(bb->a, sizeof(chunk_t) * bb->m); }
-            bb->a[bb->n].beg = off0;
-            bb->a[bb->n].end = off1;
-            bb->n++;
-        }
-        int w0 = (int)(beg >> 14), w1 = (int)((end - 1) >> 14);
-        if (w1 + 1 > r->m_lin) {
-            int m = r->m_lin ? r->m_lin : 64;
-            while (m < w1 + 1) m *= 2;
-            r->lin = (uint64_t *)realloc(r->lin, sizeof(uint64_t) * m);
-            memset(r->lin + r->m_lin, 0, sizeof(uint64_t) * (m - r->m_lin));
-            r->m_lin = m;
-        }
-        for (int w = w0; w <= w1; w++) if (r->lin[w] == 0) r->lin[w] = off0;
-        if (w1 + 1 > r->n_lin) r->n_lin = w1 + 1;
-        off0 = off1;
+/* Incremental builder: one call per record in file order with the virtual offsets in front of and behind it.
+ * sam_index_build3() feeds it from a finished file; a writer that knows its own offsets (the synthetic data
+ * generator) feeds it directly and saves the second pass over the file. */
+struct pomfret_bai_builder {
+    int n_ref;
+    bref_t *refs;
+    uint64_t n_no_coor;
+    int last_tid;
+    hts_pos_t last_pos;
+};
+
+pomfret_bai_builder *pomfret_bai_new(int n_ref) {
+    pomfret_bai_builder *bb = (pomfret_bai_builder *)calloc(1, sizeof(*bb));
+    bb->n_ref = n_ref;
+    bb->refs = (bref_t *)calloc(n_ref > 0 ? n_ref : 1, sizeof(bref_t));
+    bb->last_tid = -1;
+    bb->last_pos = -1;
+    return bb;
+}
+
+int pomfret_bai_add(pomfret_bai_builder *B, int tid, hts_pos_t beg, hts_pos_t end, int unmapped, uint64_t off0, uint64_t off1) {
+    if (tid < 0) { B->n_no_coor++; return 0; }
+    if (tid >= B->n_ref || tid < B->last_tid || (tid == B->last_tid && beg < B->last_pos)) return -1;
+    B->last_tid = tid;
+    B->last_pos = beg;
+    bref_t *r = &B->refs[tid];
+    if (!r->seen) { r->seen = 1; r->off_beg = off0; }
+    r->off_end = off1;
+    if (unmapped) r->n_unmapped++; else r->n_mapped++;
+    bbin_t *bb = get_bin(r, (uint32_t)reg2bin(beg, end));
+    if (bb->n > 0 && bb->a[bb->n - 1].end == off0) bb->a[bb->n - 1].end = off1;
+    else {
+        if (bb->n == bb->m) { bb->m = bb->m ? bb->m * 2 : 4; bb->a = (chunk_t *)realloc(bb->a, sizeof(chunk_t) * bb->m); }
+        bb->a[bb->n].beg = off0;
+        bb->a[bb->n].end = off1;
+        bb->n++;
     }
-    if (rc < -1) ret = -1;
-    bam_destroy1(b);
-    if (ret == 0) {
+    int w0 = (int)(beg >> 14), w1 = (int)((end - 1) >> 14);
+    if (w1 + 1 > r->m_lin) {
+        int m = r->m_lin ? r->m_lin : 64;
+        while (m < w1 + 1) m *= 2;
+        r->lin = (uint64_t *)realloc(r->lin, sizeof(uint64_t) * m);
+        memset(r->lin + r->m_lin, 0, sizeof(uint64_t) * (m - r->m_lin));
+        r->m_lin = m;
+    }
+    for (int w = w0; w <= w1; w++) if (r->lin[w] == 0) r->lin[w] = off0;
+    if (w1 + 1 > r->n_lin) r->n_lin = w1 + 1;
+    return 0;
+}
+
+/* writes the index (fnidx may be NULL: just discard) and frees the builder */
+int pomfret_bai_finish(pomfret_bai_builder *B, const char *fnidx) {
+    int ret = 0;
+    bref_t *refs = B->refs;
+    const int n_ref = B->n_ref;
+    if (fnidx) {
         FILE *f = fopen(fnidx, "wb");
         if (!f) ret = -4;
         else {
@@ -383,7 +389,7 @@ int sam_index_build3(const char *fn, const char *fnidx, int min_shift, int nthre
                 w32(f, (uint32_t)r->n_lin);
                 for (int w = 0; w < r->n_lin; w++) w64(f, r->lin[w]);
             }
-            w64(f, n_no_coor);
+            w64(f, B->n_no_coor);
             if (fclose(f) != 0) ret = -4;
         }
     }
@@ -393,6 +399,31 @@ int sam_index_build3(const char *fn, const char *fnidx, int min_shift, int nthre
         free(refs[i].lin);
     }
     free(refs);
+    free(B);
+    return ret;
+}
+
+int sam_index_build3(const char *fn, const char *fnidx, int min_shift, int nthreads) {
+    (void)nthreads;
+    if (min_shift != 0) return -1; /* BAI only */
+    htsFile *fp = hts_open(fn, "r");
+    if (!fp) return -2;
+    sam_hdr_t *h = sam_hdr_read(fp);
+    if (!h) { hts_close(fp); return -1; }
+    pomfret_bai_builder *B = pomfret_bai_new(h->n_targets);
+    bam1_t *b = bam_init1();
+    BGZF *bg = fp->fp.bgzf;
+    uint64_t off0 = (uint64_t)bgzf_tell(bg);
+    int rc, ret = 0;
+    while ((rc = bam_read1(bg, b)) >= 0) {
+        uint64_t off1 = (uint64_t)bgzf_tell(bg);
+        if (pomfret_bai_add(B, b->core.tid, b->core.pos, bam_endpos(b), (b->core.flag & BAM_FUNMAP) != 0, off0, off1) != 0) { ret = -1; break; }
+        off0 = off1;
+    }
+    if (rc < -1) ret = -1;
+    bam_destroy1(b);
+    int rs = pomfret_bai_finish(B, ret == 0 ? fnidx : NULL);
+    if (ret == 0) ret = rs;
     sam_hdr_destroy(h);
     hts_close(fp);
     return ret;

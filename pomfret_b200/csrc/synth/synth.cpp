@@ -21,7 +21,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 #include <zlib.h>
@@ -718,13 +721,29 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
     gzprintf(vcf, "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n");
     fprintf(truth, "#chrom\tgap_start\tgap_end\ttruth\n");
 
-    bam1_t *b = bam_init1();
-    uint64_t serial = 0, n_written = 0, n_bases = 0;
-    for (size_t ci = 0; ci < plan.size(); ci++) {
-        const ContigPlan &ct = plan[ci];
-        Rng rng(cfg.seed * 1000003ull + ci * 7919ull + 13);
+    // Planning pass (sequential, cheap): blocks, variants, VCF and truth lines of every contig, and how many read
+    // serial numbers each contig consumes (read names and per-read streams derive from one running counter).
+    // The reads themselves are then simulated by one thread per contig into BGZF part files that are
+    // concatenated in contig order: the records are exactly those a sequential run would write.
+    struct ContigJob {
         std::vector<Block> blocks;
         std::vector<Variant> vars;
+        Rng rng{0};           // stream state where the read loop starts
+        uint64_t serial0 = 0; // first serial number of the contig
+        std::string part;     // BGZF part file
+        uint64_t n_written = 0, n_bases = 0;
+        int rc = 0;
+        struct IdxRec { int64_t beg, end; uint64_t off0, off1; };  // offsets inside the part file
+        std::vector<IdxRec> idx;
+    };
+    std::vector<ContigJob> jobs(plan.size());
+    uint64_t serial = 0;
+    for (size_t ci = 0; ci < plan.size(); ci++) {
+        const ContigPlan &ct = plan[ci];
+        ContigJob &J = jobs[ci];
+        Rng rng(cfg.seed * 1000003ull + ci * 7919ull + 13);
+        std::vector<Block> &blocks = J.blocks;
+        std::vector<Variant> &vars = J.vars;
         if (cfg.vcf_in) {
             import_variants(imported.recs[ct.name], rng, blocks, vars);
             for (const Variant &v : vars)
@@ -765,9 +784,33 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
                 }
             }
         }
+        J.rng = rng;
+        J.serial0 = serial;
+        J.part = fn_bam + ".part" + std::to_string(ci);
+        // dry run of the read loop's own draws (start spacing, length): how many serial numbers it takes
+        const double mean_gap = cfg.read_len_mean / cfg.coverage;
+        const double mu = std::log(cfg.read_len_mean) - 0.5 * cfg.read_len_sigma * cfg.read_len_sigma;
+        double pos = (double)ct.region_beg - cfg.read_len_mean;
+        for (;;) {
+            pos += -std::log(1.0 - rng.uni() * 0.999999999) * mean_gap;
+            if (pos >= (double)ct.region_end) break;
+            (void)std::exp(mu + cfg.read_len_sigma * rng.normal());
+            serial++;
+        }
+    }
+    if (bgzf_close(out) != 0) return -5;  // header part (ends with the BGZF end-of-file marker)
+    gzclose(vcf);
+    fclose(truth);
 
-        // reads
-        ReadSim sim{cfg, g, ct, vars, blocks};
+    auto simulate = [&](size_t ci) {
+        const ContigPlan &ct = plan[ci];
+        ContigJob &J = jobs[ci];
+        BGZF *po = bgzf_open(J.part.c_str(), mode);
+        if (!po) { J.rc = -1; return; }
+        bam1_t *b = bam_init1();
+        ReadSim sim{cfg, g, ct, J.vars, J.blocks};
+        Rng rng = J.rng;
+        uint64_t ser = J.serial0;
         double mean_gap = cfg.read_len_mean / cfg.coverage;
         double mu = std::log(cfg.read_len_mean) - 0.5 * cfg.read_len_sigma * cfg.read_len_sigma;
         double pos = (double)ct.region_beg - cfg.read_len_mean;  // lead-in so that depth is flat at region_beg
@@ -777,24 +820,84 @@ extern "C" int pomfret_synth_write(const synth_config *cfgp, const char *const *
             if (pos >= (double)ct.region_end) break;
             int64_t len = (int64_t)std::exp(mu + cfg.read_len_sigma * rng.normal());
             if (len < cfg.read_len_min) len = cfg.read_len_min;
-            serial++;
+            ser++;
             if (pos < 0 || pos < (double)ct.region_beg - 3 * cfg.read_len_mean) continue;
             int64_t start = (int64_t)pos;
             if (start < 0) continue;
-            Rng rr(cfg.seed ^ mix64(serial * 0x51ull + ci));
-            if (!sim.make(rr, start, len, serial, rec)) continue;
+            Rng rr(cfg.seed ^ mix64(ser * 0x51ull + ci));
+            if (!sim.make(rr, start, len, ser, rec)) continue;
             to_bam1(rec, cfg.qual_mode, rr, b);
-            if (bam_write1(out, b) < 0) return -4;
-            n_written++;
-            n_bases += rec.seq.size();
+            // (what bam_write1 does first: a record starts a new block if it does not fit the current one)
+            if (bgzf_flush_try(po, 4 + 32 + (ssize_t)b->l_data - b->core.l_extranul + (b->core.n_cigar > 0xffffu ? 16 : 0)) != 0) { J.rc = -4; break; }
+            const uint64_t off0 = (uint64_t)bgzf_tell(po);
+            if (bam_write1(po, b) < 0) { J.rc = -4; break; }
+            J.idx.push_back({b->core.pos, bam_endpos(b), off0, (uint64_t)bgzf_tell(po)});
+            J.n_written++;
+            J.n_bases += rec.seq.size();
         }
+        bam_destroy1(b);
+        if (bgzf_close(po) != 0 && !J.rc) J.rc = -5;
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        size_t n_thr = std::max<size_t>(1, std::min<size_t>(plan.size(), hw ? hw : 1));
+        if (const char *e = getenv("POMFRET_SYNTH_THREADS")) n_thr = std::max<size_t>(1, std::min<size_t>(plan.size(), (size_t)atoi(e)));
+        std::atomic<size_t> next(0);
+        auto body = [&]() { for (size_t ci; (ci = next.fetch_add(1)) < plan.size();) simulate(ci); };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < n_thr; t++) th.emplace_back(body);
+        body();
+        for (auto &t : th) t.join();
     }
-    bam_destroy1(b);
-    if (bgzf_close(out) != 0) return -5;
-    gzclose(vcf);
-    fclose(truth);
+    // concatenate: header blocks, then every part, each without its end-of-file marker; one marker at the very end
+    uint64_t n_written = 0, n_bases = 0;
+    pomfret_bai_builder *bai = nullptr;
+    {
+        const size_t kEof = 28;
+        FILE *fo = fopen(fn_bam.c_str(), "r+b");
+        if (!fo) return -5;
+        bai = pomfret_bai_new(hdr.n_targets);
+        fseeko(fo, 0, SEEK_END);
+        off_t hdr_end = ftello(fo) - (off_t)kEof;
+        uint8_t eof_block[28];
+        fseeko(fo, hdr_end, SEEK_SET);
+        if (fread(eof_block, 1, kEof, fo) != kEof) { fclose(fo); return -5; }
+        fseeko(fo, hdr_end, SEEK_SET);
+        std::vector<uint8_t> buf((size_t)8 << 20);
+        for (ContigJob &J : jobs) {
+            if (J.rc) { fclose(fo); return J.rc; }
+            FILE *fi = fopen(J.part.c_str(), "rb");
+            if (!fi) { fclose(fo); return -5; }
+            fseeko(fi, 0, SEEK_END);
+            off_t left = ftello(fi) - (off_t)kEof;
+            fseeko(fi, 0, SEEK_SET);
+            const uint64_t shift = (uint64_t)ftello(fo) << 16;  // virtual offset = compressed offset << 16 | offset in block
+            // a reader names the position behind a record that ends its block as the start of the next block:
+            // that is the next record's own start (for the last record: where the part's end-of-file marker sat)
+            for (size_t i = 0; i < J.idx.size(); i++)
+                J.idx[i].off1 = i + 1 < J.idx.size() ? J.idx[i + 1].off0 : (uint64_t)left << 16;
+            const int tid = plan[(size_t)(&J - jobs.data())].tid;
+            for (const ContigJob::IdxRec &r : J.idx)
+                if (pomfret_bai_add(bai, tid, r.beg, r.end, 0, r.off0 + shift, r.off1 + shift) != 0) { fclose(fi); fclose(fo); return -6; }
+
+            while (left > 0) {
+                size_t n = fread(buf.data(), 1, (size_t)std::min<off_t>(left, (off_t)buf.size()), fi);
+                if (n == 0 || fwrite(buf.data(), 1, n, fo) != n) { fclose(fi); fclose(fo); return -5; }
+                left -= (off_t)n;
+            }
+            fclose(fi);
+            remove(J.part.c_str());
+            n_written += J.n_written;
+            n_bases += J.n_bases;
+        }
+        if (fwrite(eof_block, 1, kEof, fo) != kEof) { fclose(fo); return -5; }
+        off_t total = ftello(fo);
+        fclose(fo);
+        if (truncate(fn_bam.c_str(), total) != 0) return -5;
+    }
     std::string fn_bai = fn_bam + ".bai";
-    int rc = sam_index_build3(fn_bam.c_str(), fn_bai.c_str(), 0, 1);
+    int rc = getenv("POMFRET_SYNTH_REINDEX") ? (pomfret_bai_finish(bai, nullptr), sam_index_build3(fn_bam.c_str(), fn_bai.c_str(), 0, 1))
+                                             : pomfret_bai_finish(bai, fn_bai.c_str());
     if (rc != 0) return -6;
     fprintf(stderr, "[pomfret-synth] wrote %llu reads, %llu bases to %s\n", (unsigned long long)n_written,
             (unsigned long long)n_bases, fn_bam.c_str());

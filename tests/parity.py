@@ -99,3 +99,35 @@ def compare_window(b, wi, first, n, res, tags, ids, p, deep=True):
     if not np.array_equal(ft, p["tags_final"]):
         bad.append(("final_tags",))
     return bad
+
+
+def run_gpu_batch_shared(gpu, ctx, host, wins, cfg):
+    """The windows of `wins` in one batch through the decode-once entry point: a record that an earlier window of
+    the batch already staged (same position, length, CIGAR size and name) is added as a reference to that read."""
+    import ctypes as C
+    from pomfret_b200 import _ffi
+    dsz = C.sizeof(_ffi.ReadDesc)
+    b = gpu.batch_begin(ctx)
+    seen = {}
+    layout, n_shared = [], 0
+    for w, n, chrom, s, e in wins:
+        same = np.full(max(n, 1), -1, dtype=np.int64)
+        names = host.window_qnames(w)
+        base = host.window_descs(w)
+        for i in range(n):
+            d = _ffi.ReadDesc.from_address(base + i * dsz)
+            key = (names[i], d.pos, d.l_qseq, d.n_cigar)
+            if key in seen:
+                same[i] = seen[key]
+                n_shared += 1
+            else:
+                seen[key] = b.n_reads + i
+        first = b.add_reads_shared(base, n, same)
+        b.add_window(s, e, first, n)
+        layout.append((first, n))
+    b.submit()
+    b.decode(cfg.lo, cfg.hi)
+    b.pileup(cfg)
+    b.join(cfg)
+    res, tags, ids, rc = b.collect(check=False)
+    return b, layout, res, tags, ids, rc, n_shared

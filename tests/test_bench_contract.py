@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(not os.path.exists(ob.REF_BIN), reason="oracle/_ref/pomfret not built")
 def test_reference_arm_prints_the_contract_line(built):
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
-                        "--region-mb", "2"], capture_output=True, text=True, timeout=900)
+                        "--contigs", "2", "--contig-mb", "0.8"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -31,7 +31,7 @@ def test_our_arm_fails_loudly_without_a_device(built):
     import torch
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--region-mb", "1"], capture_output=True,
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--contigs", "1", "--contig-mb", "0.5"], capture_output=True,
                        text=True, timeout=900)
     assert p.returncode != 0
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]

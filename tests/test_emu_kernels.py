@@ -39,6 +39,33 @@ def test_emulated_kernels_match_oracle(emu_gpu, synth_small):
     _run(emu_gpu, synth_small, 36, 2000)
 
 
+def _overlapping_windows(data, shift):
+    """the gaps of the data set plus shifted copies: neighbouring windows then share most of their records"""
+    out = []
+    for c, s, e, t in data["gaps"]:
+        out += [(c, s, e, t), (c, s + shift, e + shift, t)]
+    return out
+
+
+def test_emulated_shared_records_decode_once(emu_gpu, synth_small):
+    # decode-once entry point (SURVEY.md §8(f) row 2): overlapping windows, shared slots, same answers as the oracle
+    host = pb.load_host()
+    hb = host.bam_open(synth_small["bam"])
+    cfg, ocfg = pb.make_config(36, readlen=2000), ob.make_config(36, readlen=2000)
+    wins = parity.load_windows(host, hb, _overlapping_windows(synth_small, 3000)[:2], cfg)
+    ctx = emu_gpu.init()
+    b, layout, res, tags, ids, rc, n_shared = parity.run_gpu_batch_shared(emu_gpu, ctx, host, wins, cfg)
+    assert rc == 0 and n_shared > 100
+    for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+        p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+        bad = parity.compare_window(b, wi, first, n, res, tags, ids, p)
+        assert not bad, (chrom, s, e, bad[:10])
+        host.window_free(w)
+    b.end()
+    emu_gpu.destroy(ctx)
+    host.bam_close(hb)
+
+
 def test_emulated_kernels_implicit_mode(emu_gpu, synth_implicit):
     _run(emu_gpu, synth_implicit, 34, 1500)
 

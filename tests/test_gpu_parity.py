@@ -239,6 +239,33 @@ def test_gpu_mixed_registered_and_unregistered_records(gpu, synth30):
     host.bam_close(hb)
 
 
+def test_gpu_shared_records_decode_once(gpu, synth60, synth_sparse_implicit):
+    """decode-once entry point: overlapping windows whose common records are staged and
+    decoded once; every window still equals the oracle's answer for it; the call-slot overflow re-run keeps the sharing"""
+    host = pb.load_host()
+    for data, cov, readlen, shift in ((synth60, 60, 15000, 30000), (synth_sparse_implicit, 34, 1500, 2000)):
+        hb = host.bam_open(data["bam"])
+        cfg, ocfg = pb.make_config(cov, readlen=readlen), ob.make_config(cov, readlen=readlen)
+        gaps = []
+        for c, s, e, t in data["gaps"][:2]:
+            gaps += [(c, s, e, t), (c, s + shift, e + shift, t), (c, s + 2 * shift, e + 2 * shift, t)]
+        wins = parity.load_windows(host, hb, gaps, cfg)
+        ctx = gpu.init([0])
+        b, layout, res, tags, ids, rc, n_shared = parity.run_gpu_batch_shared(gpu, ctx, host, wins, cfg)
+        assert rc == 0, gpu.strerror(rc)
+        assert n_shared > sum(n for _, n, _, _, _ in wins) // 3
+        b0, layout0, res0, tags0, ids0, rc0 = parity.run_gpu_batch(gpu, ctx, host, wins, cfg)
+        assert b.timing().decode_bytes < 0.75 * b0.timing().decode_bytes  # shared records are decoded once
+        for wi, ((w, n, chrom, s, e), (first, _)) in enumerate(zip(wins, layout)):
+            p = ob.port_window(host.window_descs(w), n, s, e, ocfg)
+            bad = parity.compare_window(b, wi, first, n, res, tags, ids, p)
+            assert not bad, (chrom, s, e, bad[:10])
+            host.window_free(w)
+        b.end(); b0.end()
+        gpu.destroy(ctx)
+        host.bam_close(hb)
+
+
 def test_gpu_long_reads_uncached_keys(gpu, built, tmp_path):
     # reads that span more than 256 methmer sites: their keys are scored straight from the pool
     import conftest

@@ -314,6 +314,10 @@ int pomfret_gpu_init(pomfret_gpu_ctx **out, const int *devices, int n_devices, i
         }
     } else for (int i = 0; i < n; i++) c->devices.push_back(i);
     c->n_workers = n_workers > 0 ? n_workers : 1;
+    // create the contexts now (a front end calls init from a start-up thread while it opens its inputs)
+    for (int d : c->devices) {
+        if (cudaSetDevice(d) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) { delete c; return POMFRET_GPU_ERR_CUDA; }
+    }
     *out = c;
     return POMFRET_GPU_OK;
 }
@@ -373,14 +377,24 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
     CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
     {
-        cudaDeviceProp prop;
-        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.multiProcessorCount > 0) b->sm_count = prop.multiProcessorCount;
-    }
+        // (device attributes and kernel attributes are per device, not per batch: looked up once per process;
+        //  cudaGetDeviceProperties alone costs tens of milliseconds and serialises the workers that start together)
+        static std::mutex mu;
+        static std::vector<int> sm_of;
+        std::lock_guard<std::mutex> g(mu);
+        if ((int)sm_of.size() <= device) sm_of.resize((size_t)device + 1, 0);
+        if (!sm_of[(size_t)device]) {
+            int n_sm = 0;
 #ifndef POMFRET_CUDA_EMU
-    CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
-    CK(cudaFuncSetAttribute(join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
-    CK(cudaFuncSetAttribute(join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+            if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) n_sm = 0;
+            CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
+            CK(cudaFuncSetAttribute(join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+            CK(cudaFuncSetAttribute(join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
 #endif
+            sm_of[(size_t)device] = n_sm > 0 ? n_sm : 148;
+        }
+        b->sm_count = sm_of[(size_t)device];
+    }
     *out = b;
     return POMFRET_GPU_OK;
 }

@@ -4,6 +4,8 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <dirent.h>
+#include <future>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -40,6 +42,7 @@ struct Engine {
     pomfret_gpu_ctx *ctx = nullptr;
     int n_dev = 0;
     bool start(int want_gpus, int n_workers) {
+        const double t0 = now_s();
         std::string err;
         if (!api.load(&err)) { fprintf(stderr, "[E::%s] %s\n", "pomfret", err.c_str()); return false; }
         int n = api.device_count();
@@ -49,9 +52,30 @@ struct Engine {
         for (int i = 0; i < n_dev; i++) devs.push_back(i);
         int rc = api.init(&ctx, devs.data(), n_dev, n_workers);
         if (rc != 0) { fprintf(stderr, "[E::%s] pomfret_gpu_init: %s\n", "pomfret", api.strerror(rc)); return false; }
+        fprintf(stderr, "[T::%s] engine ready after %.2fs (%d devices)\n", "pomfret", now_s() - t0, n_dev);
         return true;
     }
-    ~Engine() { if (ctx) api.destroy(ctx); }
+    // CUDA start-up (driver, contexts: about half a second on a B200 box) runs beside the host work that does not
+    // need the device: interval loading, BAM/index opening and the inflate of every worker's first chunk
+    std::shared_future<bool> ready;
+    void start_async(int want_gpus, int n_workers) {
+        ready = std::async(std::launch::async, [this, want_gpus, n_workers] { return start(want_gpus, n_workers); }).share();
+    }
+    bool wait() { return ready.valid() ? ready.get() : ctx != nullptr; }
+    // devices the engine will report, without waiting for it: --gpus, else what CUDA_VISIBLE_DEVICES / the driver list
+    int expected_devices(int want_gpus) {
+        if (ready.valid() && ready.wait_for(std::chrono::seconds(0)) == std::future_status::ready) return ready.get() ? n_dev : 1;
+        int n = 0;
+        if (const char *v = getenv("CUDA_VISIBLE_DEVICES")) {
+            if (*v) { n = 1; for (const char *p = v; *p; p++) if (*p == ',') n++; }
+        } else if (DIR *d = opendir("/proc/driver/nvidia/gpus")) {
+            while (struct dirent *e = readdir(d)) if (e->d_name[0] != '.') n++;
+            closedir(d);
+        }
+        if (n <= 0) n = 1;
+        return want_gpus > 0 && want_gpus < n ? want_gpus : n;
+    }
+    ~Engine() { if (ready.valid()) ready.wait(); if (ctx) api.destroy(ctx); }
 };
 
 struct WindowJob {
@@ -68,11 +92,13 @@ struct WindowOut {
     std::vector<std::pair<std::string, int>> tags;  // kept reads in BAM order, only when decision >= 0
 };
 
-// Record storage of one worker: slabs of page-aligned host memory registered with the engine once (pinned and
-// mapped).  The BAM reader inflates records straight into them and the device gathers the fields it needs over
-// PCIe: the host never copies a payload and base qualities never leave the host.
+// Record storage of one worker: slabs of host memory the BAM reader inflates records straight into.  add_reads()
+// copies the fields the device needs (a third of a record: base qualities stay behind) into the engine's pinned
+// arena.  (Registering the slabs instead — pomfret_gpu_host_register, no copy — pins three times the bytes, and
+// pinning costs more than the copy until a run is long enough to reuse the slabs many times: POMFRET_PIN_RECORDS=1.)
 struct RecordArena {
-    static constexpr size_t kSlab = (size_t)256 << 20, kMinFree = (size_t)32 << 20;
+    static constexpr size_t kSlab = (size_t)64 << 20, kMinFree = (size_t)24 << 20;
+    bool pin = getenv("POMFRET_PIN_RECORDS") != nullptr;
     struct Slab { uint8_t *p; size_t cap, len; };
     std::vector<Slab> slabs;
     size_t cur = 0;
@@ -81,12 +107,15 @@ struct RecordArena {
     void rewind() { for (Slab &s : slabs) s.len = 0; cur = 0; }
     // a place for one record of at most kMinFree bytes
     uint8_t *room(size_t *cap) {
+        if (pin && !api) pin = false;  // (the engine is still starting: these slabs stay unpinned)
         while (cur < slabs.size() && slabs[cur].cap - slabs[cur].len < kMinFree) cur++;
         if (cur == slabs.size()) {
             void *p = nullptr;
             if (posix_memalign(&p, 4096, kSlab) != 0) return nullptr;
-            int rc = api->host_register(ctx, p, kSlab);
-            if (rc != 0) { fprintf(stderr, "[W::%s] host_register: %s (records will be copied instead)\n", "pomfret", api->strerror(rc)); }
+            if (pin) {
+                int rc = api->host_register(ctx, p, kSlab);
+                if (rc != 0) { fprintf(stderr, "[W::%s] host_register: %s (records will be copied instead)\n", "pomfret", api->strerror(rc)); pin = false; }
+            }
             slabs.push_back({(uint8_t *)p, kSlab, 0});
         }
         *cap = slabs[cur].cap - slabs[cur].len;
@@ -94,7 +123,7 @@ struct RecordArena {
     }
     void commit(size_t n) { slabs[cur].len += (n + 63) & ~(size_t)63; }
     void release() {
-        for (Slab &s : slabs) { api->host_unregister(ctx, s.p); free(s.p); }
+        for (Slab &s : slabs) { if (pin) api->host_unregister(ctx, s.p); free(s.p); }
         slabs.clear();
     }
 };
@@ -110,12 +139,17 @@ struct Worker {
     RunStats stats;
     bool open(const std::string &fn_bam) {
         if (!bam.open(fn_bam)) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "load_reads_given_interval", fn_bam.c_str()); return false; }
-        int rc = eng->api.batch_begin(eng->ctx, id, device, &batch);
-        if (rc != 0) { fprintf(stderr, "[E::%s] batch_begin: %s\n", "pomfret", eng->api.strerror(rc)); return false; }
-        arena.api = &eng->api; arena.ctx = eng->ctx;
         memset(&view, 0, sizeof(view));
         view.id = POMFRET_BAM_EXTERNAL_DATA;
         return true;
+    }
+    // the device side of the worker: waits for the engine's start-up if that is still under way
+    void need_batch() {
+        if (batch) return;
+        if (!eng->wait()) exit(1);
+        arena.api = &eng->api; arena.ctx = eng->ctx;
+        int rc = eng->api.batch_begin(eng->ctx, id, device % std::max(1, eng->n_dev), &batch);
+        if (rc != 0) { fprintf(stderr, "[E::%s] batch_begin: %s\n", "pomfret", eng->api.strerror(rc)); exit(1); }
     }
     void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; arena.release(); }
 
@@ -140,8 +174,7 @@ struct Worker {
                    const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
         const GpuApi &api = eng->api;
         double t0 = now_s();
-        int rc = api.batch_reset(batch);
-        if (rc) die_gpu(api, rc, "batch_reset");
+        int rc;
         arena.rewind();
         const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
         std::vector<Rec> recs;
@@ -214,6 +247,8 @@ struct Worker {
             }
             stats.n_reads += win_recs[w].size();
         }
+        need_batch();
+        if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
         if (!descs.empty() && (rc = api.batch_add_reads_shared(batch, descs.data(), (uint32_t)descs.size(), any_shared ? same_as.data() : nullptr)))
             die_gpu(api, rc, "batch_add_reads");
         if ((rc = api.batch_add_windows(batch, w_start.data(), w_end.data(), w_first.data(), w_n.data(), (uint32_t)jobs.size()))) die_gpu(api, rc, "batch_add_window");
@@ -260,6 +295,7 @@ struct Worker {
     void haptag_contig(const std::string &chrom, const KnownVariants &kv, TagMap *raw) {
         const GpuApi &api = eng->api;
         double t0 = now_s();
+        need_batch();
         hts_itr_t *itr = sam_itr_querys(bam.idx, bam.hdr, chrom.c_str());
         if (!itr) return;
         std::vector<const char *> names;
@@ -361,7 +397,12 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
                  std::vector<std::vector<WindowOut>> *results, RunStats *stats) {
     struct Chunk { int i_ref; std::vector<WindowJob> jobs; uint64_t cost; };
     std::vector<Chunk> chunks;
-    const int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 8;
+    // windows per batch: the option is the upper bound; a run with few windows is cut finer so that every worker
+    // has something to inflate (the batches are then small, but a batch costs microseconds of launches)
+    size_t n_windows_total = 0;
+    for (const Ranges &rg : ps.st.ranges) n_windows_total += rg.n;
+    int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 8;
+    per = (int)std::max<size_t>(1, std::min<size_t>((size_t)per, n_windows_total / (2 * (size_t)std::max(1, opt.threads)) + 1));
     results->assign(ps.st.ref_names.size(), {});
     uint64_t total_cost = 0;
     for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
@@ -379,7 +420,9 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
             chunks.push_back(std::move(c));
         }
     }
-    const int n_dev = std::max(1, eng.n_dev);
+    // (the engine may still be starting: the region sets are cut for the expected number of devices, and a worker's
+    //  device index is taken modulo the real count once it is known)
+    const int n_dev = std::max(1, eng.expected_devices(opt.gpus));
     std::vector<size_t> set_begin((size_t)n_dev + 1, chunks.size());
     {
         uint64_t acc = 0;
@@ -448,7 +491,7 @@ bool load_all_intervals(Engine &eng, const Options &opt, PhaseState *ps, RunStat
         std::vector<std::thread> th;
         auto body = [&](int wid) {
             Worker wk;
-            wk.eng = &eng; wk.id = wid; wk.device = wid % std::max(1, eng.n_dev);
+            wk.eng = &eng; wk.id = wid; wk.device = wid;  // (taken modulo the device count when the batch is created)
             bool opened = false;
             for (;;) {
                 Task *t = nullptr;
@@ -550,7 +593,7 @@ int run_methphase(const Options &opt, RunStats *stats) {
     const double T = now_s();
     if (!files_exist(opt)) return 1;
     Engine eng;
-    if (!eng.start(opt.gpus, opt.threads)) return 1;
+    eng.start_async(opt.gpus, opt.threads);
     PhaseState ps;
     if (!load_all_intervals(eng, opt, &ps, stats)) return 1;
     size_t n_loaded = 0;
@@ -639,7 +682,7 @@ int run_report(const Options &opt, RunStats *stats) {
     FILE *fp_out = fopen(fn_out.c_str(), "w");
     if (!fp_out) { fprintf(stderr, "[E::%s] failed to open output file\n", "main_methreport"); exit(1); }
     Engine eng;
-    if (!eng.start(opt.gpus, opt.threads)) return 1;
+    eng.start_async(opt.gpus, opt.threads);
     PhaseState ps;
     Options o2 = opt;
     o2.fn_tsv.clear(); o2.fn_gtf.clear();  // report always derives its blocks from the vcf (blockjoin.c:4958)

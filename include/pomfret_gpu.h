@@ -123,6 +123,7 @@ typedef struct pomfret_gpu_window_result {
 #define POMFRET_GPU_READ_MM_ERROR 8u      /* malformed MM/ML: record has no modifications */
 #define POMFRET_GPU_READ_SLOWPATH 16u     /* decoded by the single-lane general path */
 #define POMFRET_GPU_READ_UNSORTED 32u     /* internal: calls not strictly ascending */
+#define POMFRET_GPU_READ_LEAN 128u        /* decoded by the lean path (whole-record tables in shared memory) */
 #define POMFRET_GPU_READ_OVERFLOW 64u     /* internal: ran out of call slots; pileup() re-runs the record with more room */
 
 /* ---- context ---- */

@@ -32,7 +32,7 @@
 namespace pomfret_gpu {
 
 constexpr int DEC_WARPS = 4;
-constexpr int DEC_MAXSEG = 16;
+constexpr int DEC_MAXSEG = 12;
 constexpr int DEC_MI_CAP = 256;       // M/I ops staged per chunk
 constexpr int DEC_MM_CHUNK = 512;     // MM bytes staged per step
 constexpr int DEC_T = 2;              // SEQ tiles (512 B = 1024 bases each) per scan step
@@ -54,6 +54,7 @@ struct DecodeParams {
     uint32_t *next;        // work queue head (zeroed before the launch)
     const uint32_t *order; // queue order: record indices, longest first (nullptr: batch order)
     uint32_t lo, hi;
+    uint32_t no_lean;      // test / measurement hook: every record takes the streaming path
 };
 
 struct SegInfo {
@@ -69,13 +70,27 @@ struct SegInfo {
     uint8_t pad[2];
 };
 
+// Whole-record tables of the lean path (records of at most 65535 bases and LEAN_MI M/I operations: every position
+// fits 16 bits, so both tables of a record stay in shared memory and nothing goes through scratch arrays).
+constexpr int LEAN_CH = 2048;         // 16-byte SEQ chunks of a record: 65536 bases
+constexpr int LEAN_MI = 512;          // M/I operations in front of the first stopping operation
+constexpr int LEAN_MAXLEN = 65535;
+constexpr int16_t LEAN_DROP = (int16_t)0x8000;
+
 struct DecodeWarpSmem {
     __align__(16) uint8_t mmbuf[DEC_MM_CHUNK + 16];
     union {
-        uint32_t first[DEC_FC + 1];   // SEQ scan: rank of the first canonical base of every 32-base chunk of the section
-        struct {                      // CIGAR walk (afterwards): staged M/I ops
-            uint32_t mi_end[DEC_MI_CAP];
-            int32_t mi_off[DEC_MI_CAP];
+        struct {                          // lean path
+            uint16_t l_first[LEAN_CH + 8];    // rank of the first canonical base of every chunk in scan order; [n_ch] = total
+            uint16_t l_end[LEAN_MI];          // read offset behind every M/I operation
+            int16_t l_off[LEAN_MI];           // reference offset of the bases of an M operation, LEAN_DROP for I
+        };
+        union {                           // streaming path (any record size)
+            uint32_t first[DEC_FC + 1];   // SEQ scan: rank of the first canonical base of every 32-base chunk of the section
+            struct {                      // CIGAR walk (afterwards): staged M/I ops
+                uint32_t mi_end[DEC_MI_CAP];
+                int32_t mi_off[DEC_MI_CAP];
+            };
         };
     };
     SegInfo seg[DEC_MAXSEG];
@@ -111,6 +126,37 @@ __device__ __forceinline__ uint32_t nib_eq_flags(uint32_t w, uint32_t pat) {
     x |= x >> 2;
     return ~x & 0x11111111u;
 }
+// prmt.b32 with its hardware selector semantics: nibble i of `sel` (low 16 bits) picks byte (nibble & 7) of {hi:lo};
+// bit 3 of the nibble replicates that byte's sign bit instead.
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t lo, uint32_t hi, uint32_t sel) {
+#ifdef POMFRET_CUDA_EMU
+    const uint64_t src = ((uint64_t)hi << 32) | lo;
+    uint32_t out = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (sel >> (4 * i)) & 15u;
+        uint32_t byte = (uint32_t)(src >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        out |= byte << (8 * i);
+    }
+    return out;
+#else
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
+#endif
+}
+// Number of nibbles of a 16-byte SEQ chunk equal to the base code C (2) or G (4), without a popcount: the SEQ
+// nibbles themselves are used as byte selectors into a table that holds 1 at the wanted code's index (codes with
+// bit 3 replicate the sign of a table byte, which is 0), four nibbles per instruction; the 0/1 bytes of the eight
+// results add up in byte lanes.
+__device__ __forceinline__ uint32_t count_code_in_chunk(const uint4 &v, uint32_t tab_lo, uint32_t tab_hi) {
+    uint32_t acc = prmt_raw(tab_lo, tab_hi, v.x) + prmt_raw(tab_lo, tab_hi, v.x >> 16);
+    acc += prmt_raw(tab_lo, tab_hi, v.y) + prmt_raw(tab_lo, tab_hi, v.y >> 16);
+    acc += prmt_raw(tab_lo, tab_hi, v.z) + prmt_raw(tab_lo, tab_hi, v.z >> 16);
+    acc += prmt_raw(tab_lo, tab_hi, v.w) + prmt_raw(tab_lo, tab_hi, v.w >> 16);
+    return (acc * 0x01010101u) >> 24;
+}
+
 // base index (0..7) of the n-th (0-based, base order) flagged base of a flags word
 __device__ __forceinline__ uint32_t select_base_in_word(uint32_t f, uint32_t n) {
     uint32_t g = ((f & 0x01010101u) << 4) | ((f >> 4) & 0x01010101u);  // bit 4b <-> base b
@@ -176,13 +222,9 @@ __device__ int mm_scan_segments(const uint8_t *mm, uint32_t mm_len, DecodeWarpSm
         uint32_t off = base + lane * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (off < mm_len) v = *reinterpret_cast<const uint4 *>(mm + off);  // blob segments are padded to 16 B
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t semi = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-            if (off + i < mm_len && c == ';') semi |= 1u << i;
-        }
+        uint32_t semi = pack4(byte_eq_mask4(v.x, 0x3b3b3b3bu)) | pack4(byte_eq_mask4(v.y, 0x3b3b3b3bu)) << 4 |
+                        pack4(byte_eq_mask4(v.z, 0x3b3b3b3bu)) << 8 | pack4(byte_eq_mask4(v.w, 0x3b3b3b3bu)) << 12;
+        semi &= off < mm_len ? (mm_len - off >= 16u ? 0xffffu : (1u << (mm_len - off)) - 1u) : 0u;  // characters of the string only
         uint32_t cnt = __popc(semi);
         uint32_t incl = warp_inclusive_sum(cnt);
         uint32_t excl = incl - cnt;
@@ -344,6 +386,92 @@ __device__ bool mm_parse_list(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm,
     g.total = total;
     __syncwarp();
     return !bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Delta list of one segment, lean form: the commas of a staged 512-byte piece are first listed (their offsets,
+// compacted through a warp scan), then handled one per lane: digit run length from the staged non-digit masks,
+// up to four digits converted without a loop, ranks by a plain warp scan.  Values are clamped to 65536 (the lean
+// path only serves records of at most 65535 bases, so a larger skip is "beyond SEQ" either way).
+// mode 0: count the deltas only (the list's ML bytes must be skipped, nothing else is needed);
+// mode 1: count and sum; mode 2: also write the ranks.  `scratch` is 600 bytes of the warp's shared memory.
+// Returns false (uniform) if the list is malformed or holds something unusual: the streaming path decides.
+// ---------------------------------------------------------------------------------------------
+__device__ bool mm_parse_list_lean(const uint8_t *mm, SegInfo &g, DecodeWarpSmem &sm, uint16_t *scratch, int mode, uint32_t *rank_out,
+                                   uint32_t rank_cap) {
+    const unsigned lane = lane_id();
+    const uint32_t lb = g.list_begin, le = g.list_end;  // list chars are [lb, le), le is ';'
+    uint16_t *cpos = scratch;        // [256] offsets of the piece's commas
+    uint16_t *ndm = scratch + 256;   // [34] non-digit masks of the 33 staged 16-byte groups
+    uint32_t n_delta = 0, total = 0;
+    bool bad = false;
+    const uint32_t *mmbuf32 = reinterpret_cast<const uint32_t *>(sm.mmbuf);
+    for (uint32_t base = lb & ~15u; base < le; base += DEC_MM_CHUNK) {
+        const uint32_t off = base + lane * 16;
+        const uint4 v = *reinterpret_cast<const uint4 *>(mm + off);  // bytes past the string are blob padding / later fields, never used
+        const uint32_t comma16 = pack4(byte_eq_mask4(v.x, 0x2c2c2c2cu)) | pack4(byte_eq_mask4(v.y, 0x2c2c2c2cu)) << 4 |
+                                 pack4(byte_eq_mask4(v.z, 0x2c2c2c2cu)) << 8 | pack4(byte_eq_mask4(v.w, 0x2c2c2c2cu)) << 12;
+        const uint32_t nd16 = pack4(nondigit_mask4(v.x)) | pack4(nondigit_mask4(v.y)) << 4 | pack4(nondigit_mask4(v.z)) << 8 |
+                              pack4(nondigit_mask4(v.w)) << 12;
+        const uint32_t lo_i = lb > off ? (lb - off < 16u ? lb - off : 16u) : 0u;
+        const uint32_t hi_i = le > off ? (le - off < 16u ? le - off : 16u) : 0u;
+        const uint32_t below_hi = (1u << hi_i) - 1u;
+        const uint32_t range = hi_i > lo_i ? below_hi & ~((1u << lo_i) - 1u) : 0u;  // positions inside the list
+        if (nd16 & ~comma16 & range) bad = true;  // neither digit nor comma
+        const uint32_t commas = comma16 & range;
+        const uint32_t cnt = (uint32_t)__popc(commas);
+        const uint32_t incl_c = warp_inclusive_sum(cnt);
+        const uint32_t n_here = __shfl_sync(FULL_MASK, incl_c, 31);
+        if (mode == 0) { n_delta += n_here; continue; }
+        // stage the piece (+16 bytes behind it), the non-digit masks (a run also ends where the list ends) and the comma offsets
+        *reinterpret_cast<uint4 *>(sm.mmbuf + lane * 16) = v;
+        ndm[lane] = (uint16_t)(nd16 | ~below_hi);
+        if (lane == 0) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(mm + base + DEC_MM_CHUNK);
+            *reinterpret_cast<uint4 *>(sm.mmbuf + DEC_MM_CHUNK) = x;
+            const uint32_t e_nd = pack4(nondigit_mask4(x.x)) | pack4(nondigit_mask4(x.y)) << 4 | pack4(nondigit_mask4(x.z)) << 8 |
+                                  pack4(nondigit_mask4(x.w)) << 12;
+            const uint32_t e_off = base + DEC_MM_CHUNK;
+            const uint32_t e_hi = le > e_off ? (le - e_off < 16u ? le - e_off : 16u) : 0u;
+            ndm[32] = (uint16_t)(e_nd | ~((1u << e_hi) - 1u));
+            ndm[33] = 0xffffu;
+        }
+        {
+            uint32_t o = incl_c - cnt;
+            for (uint32_t cm = commas; cm; cm &= cm - 1u) cpos[o++] = (uint16_t)(lane * 16u + (uint32_t)__ffs((int)cm) - 1u);
+        }
+        __syncwarp();
+        for (uint32_t j0 = 0; j0 < n_here; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            uint32_t val1 = 0;  // delta + 1
+            if (j < n_here) {
+                const uint32_t q = (uint32_t)cpos[j] + 1u;  // first digit, 1..512
+                const uint32_t m32 = (uint32_t)ndm[q >> 4] | ((uint32_t)ndm[(q >> 4) + 1] << 16);
+                const uint32_t run = m32 >> (q & 15u);
+                const uint32_t L = run ? (uint32_t)__ffs((int)run) - 1u : 17u;  // digits that follow the comma
+                if (L == 0u || L > 9u) bad = true;
+                const uint32_t x = __funnelshift_r(mmbuf32[q >> 2], mmbuf32[(q >> 2) + 1], (q & 3u) * 8u);
+                if (L <= 4u) {
+                    const uint32_t mask = L >= 4u ? 0xffffffffu : (1u << (8u * L)) - 1u;
+                    const uint32_t y = ((x & mask) - (0x30303030u & mask)) << (8u * (4u - L));  // last digit in the top byte
+                    val1 = (y >> 24) + ((y >> 16) & 0xffu) * 10u + ((y >> 8) & 0xffu) * 100u + (y & 0xffu) * 1000u + 1u;
+                } else val1 = 65536u;  // >= 10000 canonical bases skipped: never inside a record of this path
+            }
+            const uint32_t incl_s = warp_inclusive_sum(val1);
+            if (mode == 2 && j < n_here) {
+                const uint32_t k = n_delta + j, rk = total + incl_s - 1u;
+                if (k < rank_cap) rank_out[k] = rk < DEC_SAT ? rk : DEC_SAT;
+            }
+            total += __shfl_sync(FULL_MASK, incl_s, 31);
+            if (total > DEC_SAT) total = DEC_SAT;
+        }
+        n_delta += n_here;
+        __syncwarp();
+    }
+    g.n_delta = n_delta;
+    g.total = total;
+    __syncwarp();
+    return !__any_sync(FULL_MASK, bad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -715,6 +843,309 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
 }
 
 // ---------------------------------------------------------------------------------------------
+// The lean path: records of at most LEAN_MAXLEN bases with fewer than LEAN_MI M/I operations in front of the
+// first stopping operation, one C+m stream, no implicit calls — i.e. ordinary reads.  Both per-record tables
+// (canonical-base ranks per 16-byte SEQ chunk, M/I operations) stay in shared memory as 16-bit values for the
+// whole record, so every listed base is carried from its MM rank to its reference position in one pass:
+// rank -> SEQ chunk (branch-free search) -> offset in the read -> CpG test -> ML category -> M/I operation
+// (branch-free search) -> reference position -> ordered, de-duplicated store.  Nothing goes through the scratch
+// arrays except the ranks themselves.  Returns false when the record needs the streaming / general path
+// (nothing final has been written then).
+// ---------------------------------------------------------------------------------------------
+__device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpSmem &sm, uint32_t *status_out,
+                            uint32_t *n_calls_out, uint32_t *rlen_out) {
+    const unsigned lane = lane_id();
+    if (!(R.flags & RF_HAS_MM) || (R.flags & RF_MALFORMED)) return false;
+    const uint32_t len = R.l_qseq, n_cigar = R.n_cigar;
+    if (len < 2 || len > (uint32_t)LEAN_MAXLEN || n_cigar == 0) return false;
+    const uint8_t *blob = P.blob;
+    const uint32_t *cigar = reinterpret_cast<const uint32_t *>(blob + (size_t)R.cigar_off * 16);
+    const uint8_t *seq = blob + (size_t)R.seq_off * 16;
+    const uint8_t *mm = blob + (size_t)R.mm_off * 16;
+    const uint8_t *ml = blob + (size_t)R.ml_off * 16;
+    const bool rev = (R.flags & 16u) != 0;
+    const bool has_ml = (R.flags & RF_HAS_ML) != 0;
+    uint32_t *rank = P.tmp_rank + R.calls_off;
+    uint32_t *opos = P.calls_pos + R.calls_off;
+    uint8_t *ocat = P.calls_cat + R.calls_off;
+    const uint32_t cap = R.calls_cap;
+
+    // ---- MM structure and delta lists (ranks of the C+m list -> rank[]) ----
+    const int n_seg = mm_scan_segments(mm, R.mm_len, sm);
+    if (n_seg <= 0) return false;
+    int rel = -1, n_rel = 0;
+    bool other_canon = false;
+    for (int s = 0; s < n_seg; s++) {
+        const SegInfo &g = sm.seg[s];
+        if (g.canon == 2 && g.m_idx >= 0) { n_rel += g.m_count; rel = s; }
+        else if (g.canon != 2 && g.n_codes) other_canon = true;
+    }
+    if (n_rel != 1 || (rev && other_canon)) return false;
+    uint32_t ml_need = 0, need_c = 0;
+    for (int s = 0; s < n_seg; s++) {
+        SegInfo &g = sm.seg[s];
+        // (a list other than the C+m one only matters for its length, and on reversed alignments for its sum)
+        const int mode = s == rel ? 2 : (rev && g.n_codes ? 1 : 0);
+        if (!mm_parse_list_lean(mm, g, sm, sm.l_first, mode, rank, cap)) return false;
+        if (lane == 0) sm.seg[s].ml_base = ml_need;
+        ml_need += g.n_delta * g.n_codes;
+        if (has_ml && ml_need > R.ml_len) return false;
+        if (g.canon == 2 && g.n_codes && g.total > need_c) need_c = g.total;
+    }
+    if (has_ml && ml_need != R.ml_len) return false;
+    __syncwarp();
+    const uint32_t n_targets = sm.seg[rel].n_delta;
+    if (n_targets == 0 || n_targets > cap) return false;
+    const uint32_t ml_base = sm.seg[rel].ml_base, stride = sm.seg[rel].n_codes, m_idx = (uint32_t)sm.seg[rel].m_idx;
+
+    // ---- tables start out as "greater than any position" ----
+    {
+        const uint4 ones = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        uint4 *f4 = reinterpret_cast<uint4 *>(sm.l_first);
+        for (uint32_t i = lane; i < (LEAN_CH + 8) / 8; i += 32) f4[i] = ones;
+        uint4 *e4 = reinterpret_cast<uint4 *>(sm.l_end);
+        for (uint32_t i = lane; i < LEAN_MI / 8; i += 32) e4[i] = ones;
+    }
+    __syncwarp();
+
+    // ---- CIGAR, four operations per lane: reference span, M/I table up to the first stopping operation ----
+    uint32_t clip = 0, j0 = 0;
+    {
+        const uint32_t c0 = cigar[0];
+        if ((c0 & 15u) == 4u) { clip = c0 >> 4; j0 = 1; }
+    }
+    uint32_t rlen = 0, n_mi = 0, i_read = clip;
+    int32_t offset = 0;
+    bool stopped = false, fatal = false, bad = false;
+    const uint4 *cig4 = reinterpret_cast<const uint4 *>(cigar);
+    for (uint32_t base = 0; base < n_cigar; base += 128) {
+        const uint32_t idx0 = base + lane * 4;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (idx0 < n_cigar) v = cig4[idx0 >> 2];  // the field is zero padded to 16 bytes
+        const uint32_t c[4] = {v.x, v.y, v.z, v.w};
+        uint32_t my_stop = 4, my_stop_op = 0;
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {
+            const uint32_t op = c[i] & 15u;
+            const bool valid = idx0 + i < n_cigar;
+            if (valid && ((0x18du >> op) & 1u)) rlen += c[i] >> 4;  // M, D, N, =, X consume the reference
+            if (valid && idx0 + i >= j0 && op >= 3u) { my_stop = (uint32_t)i; my_stop_op = op; }
+        }
+        if (stopped) continue;
+        const unsigned stops = __ballot_sync(FULL_MASK, my_stop < 4u);
+        const int stop_lane = stops ? __ffs((int)stops) - 1 : 32;
+        const uint32_t lim = (int)lane < stop_lane ? 4u : ((int)lane == stop_lane ? my_stop : 0u);
+        uint32_t adv = 0, cnt = 0, l_adv[4];
+        int32_t doff = 0, l_doff[4];
+        bool l_mi[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t op = c[i] & 15u, L = c[i] >> 4;
+            const bool act = (uint32_t)i < lim && idx0 + i < n_cigar && idx0 + i >= j0;
+            l_doff[i] = doff;
+            l_mi[i] = act && op <= 1u;
+            if (l_mi[i]) { adv += L; cnt++; if (L > 0xffffu) bad = true; }
+            l_adv[i] = adv;
+            if (act) doff += op == 2u ? (int32_t)L : (op == 1u ? -(int32_t)L : 0);
+        }
+        const uint32_t packed = adv | (cnt << 24);  // per lane: adv <= 4 * 65535, over the warp < 2^24 (else `bad`)
+        const uint32_t incl = warp_inclusive_sum(packed);
+        const int32_t incl_d = warp_inclusive_sum(doff);
+        const uint32_t ex_adv = (incl - packed) & 0xffffffu, ex_cnt = (incl - packed) >> 24;
+        const int32_t ex_d = incl_d - doff;
+        uint32_t slot = n_mi + ex_cnt;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (l_mi[i]) {
+                const uint32_t e = i_read + ex_adv + l_adv[i];
+                const int32_t o = offset + ex_d + l_doff[i];
+                const bool is_m = (c[i] & 15u) == 0u;
+                if (e > 0xffffu || (is_m && (o < -32767 || o > 32767))) bad = true;
+                if (slot < (uint32_t)LEAN_MI) { sm.l_end[slot] = (uint16_t)e; sm.l_off[slot] = is_m ? (int16_t)o : LEAN_DROP; }
+                slot++;
+            }
+        }
+        const uint32_t tot = __shfl_sync(FULL_MASK, incl, 31);
+        n_mi += tot >> 24;
+        i_read += tot & 0xffffffu;
+        offset += __shfl_sync(FULL_MASK, incl_d, 31);
+        if (stops) {
+            stopped = true;
+            fatal = __shfl_sync(FULL_MASK, my_stop_op, stop_lane) >= 5u;
+        }
+    }
+    rlen = warp_sum(rlen);
+    if (__any_sync(FULL_MASK, bad) || fatal || n_mi >= (uint32_t)LEAN_MI) return false;  // (a fatal operation is reported by the streaming path)
+    *rlen_out = rlen;
+    __syncwarp();
+
+    // ---- SEQ pass: canonical bases per chunk -> l_first[] (scan order: from the read's own 5' end) ----
+    // Super-tiles of 2 KB (128 chunks, 4096 bases): every lane owns four consecutive chunks, so one warp scan and
+    // one 8-byte store serve 128 chunks.  Reversed alignments walk SEQ from its end (chunk g <-> scan index
+    // n_ch - 1 - g): ranks then count from the read's own 5' end, as the MM list does.
+    const uint32_t n_bytes = (len + 1) >> 1;
+    const uint32_t n_st = (n_bytes + 2047u) >> 11;
+    const uint32_t n_ch = n_st * 128u;
+    const uint32_t tab_lo = rev ? 0u : 0x00010000u, tab_hi = rev ? 0x00000001u : 0u;  // count G (4) on reversed alignments, C (2) otherwise
+    uint32_t total = 0;
+    {
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        uint4 cur[4];
+        auto load_st = [&](uint32_t st) {  // scan-order super-tile st: this lane's four chunks, in memory order
+            const uint32_t g0 = rev ? (n_st - 1u - st) * 128u + 4u * (31u - lane) : st * 128u + 4u * lane;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t byte_off = (g0 + (uint32_t)i) * 16u;
+                cur[i] = st < n_st && byte_off < n_bytes ? *reinterpret_cast<const uint4 *>(seq + byte_off) : zero;
+            }
+        };
+        load_st(0);
+        for (uint32_t st = 0; st < n_st; st++) {
+            const uint32_t K0 = count_code_in_chunk(cur[0], tab_lo, tab_hi), K1 = count_code_in_chunk(cur[1], tab_lo, tab_hi),
+                           K2 = count_code_in_chunk(cur[2], tab_lo, tab_hi), K3 = count_code_in_chunk(cur[3], tab_lo, tab_hi);
+            const uint32_t C[4] = {rev ? K3 : K0, rev ? K2 : K1, rev ? K1 : K2, rev ? K0 : K3};  // scan order inside the lane
+            load_st(st + 1);  // in flight during the scan
+            const uint32_t mine = C[0] + C[1] + C[2] + C[3];
+            const uint32_t incl = warp_inclusive_sum(mine);
+            const uint32_t f0 = total + incl - mine, f1 = f0 + C[0], f2 = f1 + C[1], f3 = f2 + C[2];
+            *reinterpret_cast<uint2 *>(&sm.l_first[st * 128u + 4u * lane]) = make_uint2(f0 | (f1 << 16), f2 | (f3 << 16));
+            total += __shfl_sync(FULL_MASK, incl, 31);
+        }
+    }
+    if (lane == 0) sm.l_first[n_ch] = (uint16_t)total;
+    if (rev && total < need_c) return false;  // "MM tag refers to bases beyond sequence length": reported by the streaming path
+    __syncwarp();
+
+    // ---- listed bases, 32 per step, in list order (descending SEQ offsets on reversed alignments) ----
+    const uint32_t pat = (rev ? 4u : 2u) * 0x11111111u;
+    const int cg = rev ? -1 : 0;
+    const uint32_t qs = R.pos, i_ref = qs - clip;
+    uint32_t n_out = 0, last_pos = 0, n_mods = 0, n_behind_clip = 0;
+    bool have_last = false, unsorted = false, implicit = false;
+    // Two rows of 32 listed bases per step: the rows are resolved with straight-line, predicated code (two independent
+    // chains of dependent shared-memory loads in flight per lane), then stored row by row, in list order.
+    const uint32_t last_chunk_off = (n_bytes - 1u) & ~15u;
+    const uint32_t want_nb = rev ? 2u : 4u;
+    for (uint32_t k0 = 0; k0 < n_targets; k0 += 64) {
+        bool r_found[2], r_ok[2], r_emit[2];
+        uint32_t r_pos[2], r_cat[2], r_p[2];
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            const uint32_t k = k0 + (uint32_t)row * 32u + lane;
+            const uint32_t kk = k < n_targets ? k : n_targets - 1u;
+            const uint32_t rr = rank[kk];
+            const bool found = k < n_targets && rr < total;  // ranks ascend: the bases that lie beyond SEQ form the tail of the list
+            const uint32_t r = found ? rr : 0u;
+            // chunk (scan order) that holds rank r: last c with l_first[c] <= r; unused entries are 0xffff
+            // (the cursor is a pointer so that every step is load-with-immediate-offset, compare, predicated add)
+            const uint16_t *fq = sm.l_first;
+#pragma unroll
+            for (uint32_t st = LEAN_CH / 2; st >= 1; st >>= 1)
+                if (fq[st] <= r) fq += st;
+            const uint32_t c = (uint32_t)(fq - sm.l_first);
+            const uint32_t f0 = fq[0], cnt = fq[1] - f0;
+            const uint32_t chunk = rev ? n_ch - 1u - c : c;
+            uint32_t n = rev ? cnt - 1u - (r - f0) : r - f0;  // index in base order inside the chunk
+            const uint32_t coff = chunk * 16u < last_chunk_off ? chunk * 16u : last_chunk_off;
+            const uint4 v = *reinterpret_cast<const uint4 *>(seq + coff);
+            const uint32_t g0 = nib_eq_flags(v.x, pat), g1 = nib_eq_flags(v.y, pat), g2 = nib_eq_flags(v.z, pat),
+                           g3 = nib_eq_flags(v.w, pat);
+            const uint32_t c0 = (uint32_t)__popc(g0), c1 = c0 + (uint32_t)__popc(g1), c2 = c1 + (uint32_t)__popc(g2);
+            const uint32_t wj = (n >= c0 ? 1u : 0u) + (n >= c1 ? 1u : 0u) + (n >= c2 ? 1u : 0u);
+            const uint32_t f = wj == 0u ? g0 : (wj == 1u ? g1 : (wj == 2u ? g2 : g3));
+            n -= wj == 0u ? 0u : (wj == 1u ? c0 : (wj == 2u ? c1 : c2));
+            const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
+            // blockjoin.c:846-858: C must be followed by G; on reversed alignments SEQ shows the G, preceded by C
+            const bool inner = found && p > 0 && p < len - 1;
+            // the neighbouring base: inside the 16-byte chunk at hand (nibble i of a word holds base i ^ 1) unless the base
+            // is the chunk's first / last one
+            const uint32_t b = (p & 31u) + (rev ? 0xffffffffu : 1u);  // neighbour's index inside the chunk: -1 .. 32
+            uint32_t nb;
+            if (b < 32u) {
+                const uint32_t w = b < 16u ? (b < 8u ? v.x : v.y) : (b < 24u ? v.z : v.w);
+                nb = (w >> ((((b & 7u) ^ 1u)) << 2)) & 0xfu;
+            } else nb = inner ? seq_nib(seq, rev ? p - 1u : p + 1u) : 0u;
+            const bool ok = inner && nb == want_nb;
+            if (inner && !ok) implicit = true;
+            const uint32_t q = has_ml ? ml[ml_base + kk * stride + m_idx] : 255u;
+            r_cat[row] = q < P.lo ? 1u : (q >= P.hi ? 0u : 2u);  // blockjoin.c:876-878
+            // the operation whose inclusive trigger loop (blockjoin.c:663-665) handles the base: first one ending at or behind it
+            const uint16_t *eq = sm.l_end - 1;
+#pragma unroll
+            for (uint32_t st = LEAN_MI / 2; st >= 1; st >>= 1)
+                if (eq[st] < p) eq += st;
+            const uint32_t j = (uint32_t)(eq + 1 - sm.l_end);
+            const int32_t o = sm.l_off[j < (uint32_t)LEAN_MI ? j : 0u];
+            const bool at_clip = j0 && p == clip;  // a base right at the clip edge (blockjoin.c:640-652)
+            const bool mapped = (p > clip || !j0) && j < n_mi && o != (int32_t)LEAN_DROP;
+            r_found[row] = found;
+            r_ok[row] = ok;
+            r_p[row] = p;
+            r_emit[row] = ok && (at_clip || mapped);
+            r_pos[row] = at_clip ? qs + (uint32_t)cg : i_ref + p + (uint32_t)cg + (uint32_t)o;
+        }
+        bool done = false;
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            const bool emit = r_emit[row];
+            const uint32_t pos = r_pos[row], cat = r_cat[row];
+            const unsigned okm = __ballot_sync(FULL_MASK, r_ok[row]);
+            n_mods += (uint32_t)__popc(okm);
+            n_behind_clip += (uint32_t)__popc(__ballot_sync(FULL_MASK, r_ok[row] && r_p[row] > clip));
+            // ordered, de-duplicated store (blockjoin.c:704-709: of the bases that land on one position the one latest in
+            // the read sets the category).  Forward: ascending from slot 0; reversed: descending from the top slot.
+            const unsigned em = __ballot_sync(FULL_MASK, emit);
+            const unsigned below = em & ((1u << lane) - 1u);
+            const int prev_lane = below ? 31 - __clz((int)below) : -1;
+            uint32_t prev_pos = __shfl_sync(FULL_MASK, pos, prev_lane < 0 ? 0 : prev_lane);
+            const bool has_prev = prev_lane >= 0 || have_last;
+            if (prev_lane < 0) prev_pos = last_pos;
+            const bool head = emit && !(has_prev && prev_pos == pos);
+            if (head && has_prev && (rev ? pos > prev_pos : pos < prev_pos)) unsorted = true;
+            const unsigned hm = __ballot_sync(FULL_MASK, head);
+            const uint32_t run_idx = n_out + (uint32_t)__popc(hm & ((2u << lane) - 1u)) - 1u;  // a continuation of the carried run: n_out - 1
+            if (!rev) {
+                const unsigned above = em & ~((2u << lane) - 1u);
+                const int next_lane = above ? __ffs((int)above) - 1 : -1;
+                const uint32_t next_pos = __shfl_sync(FULL_MASK, pos, next_lane < 0 ? 0 : next_lane);
+                const bool last_of_run = emit && (next_lane < 0 || next_pos != pos);
+                if (head) opos[run_idx] = pos;
+                if (last_of_run) ocat[run_idx] = (uint8_t)cat;
+            } else if (head) {
+                opos[cap - 1u - run_idx] = pos;
+                ocat[cap - 1u - run_idx] = (uint8_t)cat;
+            }
+            n_out += (uint32_t)__popc(hm);
+            if (em) {
+                last_pos = __shfl_sync(FULL_MASK, pos, 31 - __clz((int)em));
+                have_last = true;
+            }
+            if (__ballot_sync(FULL_MASK, r_found[row]) != FULL_MASK) done = true;
+        }
+        if (done) break;
+    }
+    if (__any_sync(FULL_MASK, implicit)) return false;            // implicit canonical calls: general path
+    if (n_mods == 0) { *status_out = RS_LEAN; *n_calls_out = 0; return true; }  // get_mod_poss_on_ref returns 0: record dropped
+    if (j0 && n_behind_clip == 0) return false;                     // every listed base inside the clip: lingering-trigger quirk, streaming path
+    __syncwarp();
+    if (rev && n_out && cap - n_out) {  // slide the calls down to the front of the record's slots
+        const uint32_t shift = cap - n_out;
+        for (uint32_t i0 = 0; i0 < n_out; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t a = 0;
+            uint8_t b = 0;
+            if (i < n_out) { a = opos[i + shift]; b = ocat[i + shift]; }
+            __syncwarp();
+            if (i < n_out) { opos[i] = a; ocat[i] = b; }
+            __syncwarp();
+        }
+    }
+    *n_calls_out = n_out;
+    *status_out = RS_KEPT | RS_LEAN | (__any_sync(FULL_MASK, unsorted) ? RS_UNSORTED : 0u);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // General sequential path (lane 0): any number of C+m streams, more than N_MODS streams, implicit
 // canonical calls.  Follows the reference statement by statement.
 // ---------------------------------------------------------------------------------------------
@@ -994,25 +1425,31 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams 
         if (qi >= P.n_queue) return;  // whole warp leaves together
         const uint32_t ri = P.order ? P.order[qi] : qi;
         const ReadRec &R = P.reads[ri];  // read-only for the whole launch: fields are fetched where they are used
-        // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
-        const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
-        uint32_t rlen = 0;
-        for (uint32_t i = lane; i < R.n_cigar; i += 32) {
-            uint32_t c = cigar[i], op = c & 15u;
-            if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) rlen += c >> 4;
-        }
-        rlen = warp_sum(rlen);
-        if (R.flags & 4u) rlen = 0;
-        if (rlen == 0) rlen = 1;
-        uint32_t n_calls = 0;
-        bool need_generic = false;
-        uint32_t status = decode_fast(P, R, sm, &n_calls, &need_generic);
-        need_generic = __any_sync(FULL_MASK, need_generic);
-        if (need_generic) {
+        uint32_t n_calls = 0, status = 0, rlen = 0;
+        if (!P.no_lean && decode_lean(P, R, sm, &status, &n_calls, &rlen)) {
+            if (R.flags & 4u) rlen = 0;
+            if (rlen == 0) rlen = 1;
+        } else {
             __syncwarp();
-            if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
-            status = __shfl_sync(FULL_MASK, status, 0);
-            n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
+            // reference span of the alignment (bam_endpos): M, D, N, =, X consume the reference
+            const uint32_t *cigar = reinterpret_cast<const uint32_t *>(P.blob + (size_t)R.cigar_off * 16);
+            rlen = 0;
+            for (uint32_t i = lane; i < R.n_cigar; i += 32) {
+                uint32_t c = cigar[i], op = c & 15u;
+                if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) rlen += c >> 4;
+            }
+            rlen = warp_sum(rlen);
+            if (R.flags & 4u) rlen = 0;
+            if (rlen == 0) rlen = 1;
+            bool need_generic = false;
+            status = decode_fast(P, R, sm, &n_calls, &need_generic);
+            need_generic = __any_sync(FULL_MASK, need_generic);
+            if (need_generic) {
+                __syncwarp();
+                if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
+                status = __shfl_sync(FULL_MASK, status, 0);
+                n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
+            }
         }
         if (lane == 0) {
             if (status & RS_OVERFLOW) atomicAdd(P.n_overflow, 1u);

@@ -811,6 +811,8 @@ static int launch_decode(pomfret_gpu_batch *b) {
     P.next = b->d_flags.as<uint32_t>() + 1;
     P.order = nr ? b->d_order_len.as<uint32_t>() : nullptr;
     P.lo = b->lo; P.hi = b->hi;
+    P.no_lean = 0;
+    if (const char *e = getenv("POMFRET_GPU_DECODE_LEAN")) P.no_lean = !strcmp(e, "0");  // test hook: streaming path for every record
     const size_t nq = nr - b->n_dups;  // the queue holds every distinct record once
     P.n_queue = (uint32_t)nq;
     if (nq) {
@@ -1219,7 +1221,7 @@ int pomfret_gpu_debug_read_info(pomfret_gpu_batch *b, uint32_t read, uint32_t *s
     if (b->stage < ST_DECODED) return POMFRET_GPU_ERR_STATE;
     int rc;
     uint32_t v;
-    if (status) { if ((rc = dl(b, &v, b->d_r_status.as<uint32_t>() + read, 4))) return rc; *status = v & 127u; }
+    if (status) { if ((rc = dl(b, &v, b->d_r_status.as<uint32_t>() + read, 4))) return rc; *status = v & 255u; }
     if (n_calls) { if ((rc = dl(b, &v, b->d_r_ncalls.as<uint32_t>() + read, 4))) return rc; *n_calls = v; }
     if (end_pos) { if ((rc = dl(b, &v, b->d_r_end.as<uint32_t>() + read, 4))) return rc; *end_pos = v; }
     return 0;

@@ -54,6 +54,7 @@ struct WindowState {
 constexpr uint32_t RS_KEPT = 1u, RS_HAS_IMPLICIT = 2u, RS_FATAL_CIGAR = 4u, RS_MM_ERROR = 8u, RS_SLOWPATH = 16u;
 constexpr uint32_t RS_UNSORTED = 32u;  // calls are not strictly increasing (internal)
 constexpr uint32_t RS_OVERFLOW = 64u;  // call slots exhausted (internal: engine retries with more room)
+constexpr uint32_t RS_LEAN = 128u;     // decoded by the lean path (whole-record tables in shared memory)
 
 constexpr int kMaxK = 4;               // dense count tables cover methmer keys of up to kMaxK symbols
 

@@ -361,7 +361,7 @@ _host = None
 
 def load_gpu(path=None):
     """Load libpomfret_gpu.so (the nvcc sm_100a build).  `path` is for tests that load another build."""
-    path = path or os.path.join(LIB_DIR, "libpomfret_gpu.so")
+    path = path or os.environ.get("POMFRET_GPU_LIB") or os.path.join(LIB_DIR, "libpomfret_gpu.so")
     if path not in _gpu:
         _gpu[path] = GpuLib(path)
     return _gpu[path]

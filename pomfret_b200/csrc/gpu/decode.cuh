@@ -1070,7 +1070,7 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             const uint32_t q = has_ml ? ml[ml_base + kk * stride + m_idx] : 255u;
             r_cat[row] = q < P.lo ? 1u : (q >= P.hi ? 0u : 2u);  // blockjoin.c:876-878
             // the operation whose inclusive trigger loop (blockjoin.c:663-665) handles the base: first one ending at or behind it
-            const uint16_t *eq = sm.l_end - 1;
+            const uint16_t *eq = &sm.l_end[0] - 1;  // (eq[st] is l_end[j + st - 1])
 #pragma unroll
             for (uint32_t st = LEAN_MI / 2; st >= 1; st >>= 1)
                 if (eq[st] < p) eq += st;

@@ -213,7 +213,9 @@ struct pomfret_gpu_ctx {
 struct pomfret_gpu_batch {
     pomfret_gpu_ctx *ctx = nullptr;
     int device = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: second join launch (large-table windows)
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t side[3] = {};     // join launch groups beside the first one
+    cudaEvent_t ev_side[3] = {};
     cudaEvent_t ev[10] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int sm_count = 148;
@@ -269,6 +271,7 @@ struct pomfret_gpu_batch {
     }
 };
 
+static const int kSideStreams = 3;
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 static const uint32_t kNoDup = 0xffffffffu;
 // dynamic shared memory of join_kernel: one CTA per SM may take kJoinSmemMax, two CTAs per SM kJoinSmemHalf each
@@ -373,6 +376,10 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
     b->h_blob.min_cap = (size_t)64 << 20;
     CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&b->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < kSideStreams; i++) {
+        CK(cudaStreamCreateWithFlags(&b->side[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming));
+    }
     for (auto &e : b->ev) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
@@ -388,8 +395,9 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
 #ifndef POMFRET_CUDA_EMU
             if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) n_sm = 0;
             CK(cudaFuncSetAttribute(pileup_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PILE_TILE * 4)));
-            CK(cudaFuncSetAttribute(join_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
-            CK(cudaFuncSetAttribute(join_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+            CK(cudaFuncSetAttribute(join_kernel<true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+            CK(cudaFuncSetAttribute(join_kernel<true, uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
+            CK(cudaFuncSetAttribute(join_kernel<false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kJoinSmemMax));
 #endif
             sm_of[(size_t)device] = n_sm > 0 ? n_sm : 148;
         }
@@ -436,6 +444,7 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream2) cudaStreamDestroy(b->stream2);
+    for (int i = 0; i < kSideStreams; i++) { if (b->ev_side[i]) cudaEventDestroy(b->ev_side[i]); if (b->side[i]) cudaStreamDestroy(b->side[i]); }
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b->pool;
     delete b;
@@ -1041,63 +1050,86 @@ int pomfret_gpu_join(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg) {
     }
     J.mmr_pool = b->d_mmr_pool.as<uint32_t>(); J.tab = b->d_tab.as<uint32_t>();
     J.n_cand = cfg->n_candidates_per_iter; J.cov_run = cfg->cov_for_runtime; J.k = cfg->k;
-    // Shared-memory plan.  Every CTA carries the per-read state of the largest window and the look-ahead key
-    // cache; the count tables of a window go to shared memory if they fit.  With more CTAs than SMs the windows
-    // are split into two launches on two streams: those whose tables fit beside a second CTA on the same SM
-    // (or fit nowhere: they use the global pool) and those that need most of an SM for themselves.
+    // Shared-memory plan.  Every CTA carries the per-read state of the largest window and the look-ahead key cache;
+    // the count tables of a window go to shared memory if they fit: with 8-bit counts (16-bit entries) when fewer
+    // than 256 reads touch any site of the window (WindowState::max_cov, the usual case up to ~200x), else with
+    // 16-bit counts.  Windows are sorted into launch groups by what a CTA needs, so that small windows run three
+    // to an SM and only the largest take an SM for themselves; the groups go to their own streams.  A window
+    // whose tables exceed an SM keeps them in the global pool (16-bit counts).
     // one warp per candidate slot (n_cand + 1) plus one that serves the look-ahead slot while the others score
     const unsigned join_threads = 32u * (unsigned)std::min(JOIN_WARPS, std::max(4, J.n_cand + 2));
+    const int join_warps = (int)join_threads / 32;
     uint32_t max_reads = 0;
     for (size_t w = 0; w < nw; w++) max_reads = std::max(max_reads, b->h_win[w].n_reads);
     J.meta_cap = max_reads <= 4096 ? max_reads : 0;
+    J.stage_cap = join_stage_cap(J.n_cand);
     const uint32_t stride = join_row_stride(cfg->k);
-    size_t small_limit = nw * 2 <= (size_t)b->sm_count ? kJoinSmemMax : kJoinSmemHalf;
-    size_t big_limit = kJoinSmemMax;
+    // (three CTAs of 16 warps fill the register file at the kernel's 40 registers per thread: no tier beyond three per SM)
+    constexpr int kTiers = 3;
+    size_t tier_limit[kTiers] = {kJoinSmemMax / POMFRET_JOIN_MIN_CTAS - 1024, kJoinSmemHalf, kJoinSmemMax};
+    bool allow_u8 = true;
+    if (nw * 2 <= (size_t)b->sm_count) tier_limit[0] = tier_limit[1] = kJoinSmemMax;  // every CTA gets an SM anyway
     if (const char *e = getenv("POMFRET_GPU_JOIN_SMEM")) {
         // test hook: "0" keeps per-read state and count tables in global memory (the paths very large windows
-        // take), "half" forbids the one-CTA-per-SM launch
-        if (!strcmp(e, "0")) { J.meta_cap = 0; small_limit = big_limit = 0; }
-        else if (!strcmp(e, "half")) big_limit = small_limit;
+        // take), "half" forbids the one-CTA-per-SM launch, "u16" forbids the 8-bit tables
+        if (!strcmp(e, "0")) { J.meta_cap = 0; for (size_t &t : tier_limit) t = 0; }
+        else if (!strcmp(e, "half")) tier_limit[2] = tier_limit[1];
+        else if (!strcmp(e, "u16")) allow_u8 = false;
     }
-    if (int rc = b->h_cta.resize(nw * 2 + 1)) return rc;
-    size_t n_a = 0, n_b = 0;
-    uint32_t tab_a = 0, tab_b = 0;
-    bool a_all_fit = true;
-    std::vector<uint32_t> big;
+    // group index: variant (0: 8-bit counts, 1: 16-bit counts) * kTiers + tier; 2 * kTiers: global tables
+    constexpr int kGroups = 2 * kTiers + 1;
+    std::vector<uint32_t> members[kGroups];
+    uint32_t group_entries[kGroups] = {};
     for (size_t w = 0; w < nw; w++) {
         const WindowState &S = b->h_state[w];
         if (S.n == 0 || S.n_sites == 0 || S.status != 0) continue;  // nothing to propagate: no CTA
-        const uint32_t words = S.n_sites * stride;
-        const size_t need = join_smem_bytes(words + 1, J.meta_cap, J.n_cand, (int)join_threads / 32);
-        if (need > small_limit && need <= big_limit) { big.push_back((uint32_t)w); tab_b = std::max(tab_b, words); }
-        else {
-            if (need <= small_limit) tab_a = std::max(tab_a, words);
-            else a_all_fit = false;  // larger than a whole SM's shared memory: this window keeps its tables in the global pool
-            b->h_cta[n_a++] = (uint32_t)w * 2; b->h_cta[n_a++] = (uint32_t)w * 2 + 1;
-        }
+        const uint32_t entries = S.n_sites * stride;
+        int g = 2 * kTiers;
+        for (int variant = allow_u8 && S.max_cov < 256u ? 0 : 1; variant < 2 && g == 2 * kTiers; variant++)
+            for (int t = 0; t < kTiers; t++)
+                if (join_smem_bytes(entries + 1, variant ? 4 : 2, J.meta_cap, J.n_cand, join_warps) <= tier_limit[t]) { g = variant * kTiers + t; break; }
+        members[g].push_back((uint32_t)w);
+        group_entries[g] = std::max(group_entries[g], entries);
     }
-    for (uint32_t w : big) { b->h_cta[n_a + n_b++] = w * 2; b->h_cta[n_a + n_b++] = w * 2 + 1; }
-    if (int rc = up(b, b->d_cta, b->h_cta.data(), (n_a + n_b) * 4)) return rc;
+    if (int rc = b->h_cta.resize(nw * 2 + 1)) return rc;
+    size_t n_cta = 0, group_first[kGroups];
+    for (int g = 0; g < kGroups; g++) {
+        group_first[g] = n_cta;
+        for (uint32_t w : members[g]) { b->h_cta[n_cta++] = w * 2; b->h_cta[n_cta++] = w * 2 + 1; }
+    }
+    if (int rc = up(b, b->d_cta, b->h_cta.data(), n_cta * 4)) return rc;
     CK(cudaEventRecord(b->ev[8], b->stream));
-    if (n_b) {
-        CK(cudaEventRecord(b->ev_fork, b->stream));
-        CK(cudaStreamWaitEvent(b->stream2, b->ev_fork, 0));
-        JoinParams JB = J;
-        JB.cta_map = b->d_cta.as<uint32_t>() + n_a;
-        JB.smem_tab_words = tab_b;
-        POMFRET_LAUNCH(join_kernel<true>, (unsigned)n_b, join_threads, join_smem_bytes(tab_b + 1, J.meta_cap, J.n_cand, (int)join_threads / 32), b->stream2, JB);
+    CK(cudaEventRecord(b->ev_fork, b->stream));
+    int n_side = 0;
+    for (int g = 0; g < kGroups; g++) {
+        if (members[g].empty()) continue;
+        // the first non-empty group stays on the batch's stream, the others fork to side streams
+        cudaStream_t st = b->stream;
+        if (n_side > 0) {
+            st = b->side[(n_side - 1) % kSideStreams];
+            CK(cudaStreamWaitEvent(st, b->ev_fork, 0));
+        }
+        JoinParams JG = J;
+        JG.cta_map = b->d_cta.as<uint32_t>() + group_first[g];
+        const unsigned grid = (unsigned)members[g].size() * 2u;
+        if (g == 2 * kTiers) {
+            JG.smem_tab_words = 0;
+            const size_t smem = join_smem_bytes(1, 4, J.meta_cap, J.n_cand, join_warps);
+            POMFRET_LAUNCH((join_kernel<false, uint32_t>), grid, join_threads, smem, st, JG);
+        } else if (g < kTiers) {
+            JG.smem_tab_words = group_entries[g];
+            const size_t smem = join_smem_bytes(group_entries[g] + 1, 2, J.meta_cap, J.n_cand, join_warps);
+            POMFRET_LAUNCH((join_kernel<true, uint16_t>), grid, join_threads, smem, st, JG);
+        } else {
+            JG.smem_tab_words = group_entries[g];
+            const size_t smem = join_smem_bytes(group_entries[g] + 1, 4, J.meta_cap, J.n_cand, join_warps);
+            POMFRET_LAUNCH((join_kernel<true, uint32_t>), grid, join_threads, smem, st, JG);
+        }
         b->tm.launches++;
-        CK(cudaEventRecord(b->ev_join, b->stream2));
+        if (n_side > 0) CK(cudaEventRecord(b->ev_side[(n_side - 1) % kSideStreams], st));
+        n_side++;
     }
-    if (n_a) {
-        J.cta_map = b->d_cta.as<uint32_t>();
-        J.smem_tab_words = tab_a;
-        const size_t smem_a = join_smem_bytes(tab_a + 1, J.meta_cap, J.n_cand, (int)join_threads / 32);
-        if (a_all_fit) POMFRET_LAUNCH(join_kernel<true>, (unsigned)n_a, join_threads, smem_a, b->stream, J);
-        else POMFRET_LAUNCH(join_kernel<false>, (unsigned)n_a, join_threads, smem_a, b->stream, J);
-        b->tm.launches++;
-    }
-    if (n_b) CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+    for (int i = 0; i < std::min(n_side - 1, kSideStreams); i++) CK(cudaStreamWaitEvent(b->stream, b->ev_side[i], 0));
     CK(cudaEventRecord(b->ev[9], b->stream));
     CK(cudaGetLastError());
     b->stage = ST_JOINED;

@@ -28,7 +28,10 @@
 
 namespace pomfret_gpu {
 
-constexpr int JOIN_THREADS = 512;
+#ifndef POMFRET_JOIN_THREADS
+#define POMFRET_JOIN_THREADS 512
+#endif
+constexpr int JOIN_THREADS = POMFRET_JOIN_THREADS;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
 constexpr int JOIN_MAX_CAND = 128;
 constexpr int JOIN_U = 8;                 // methmer sub-chunks (32 each) whose loads are issued together
@@ -53,6 +56,7 @@ struct JoinParams {
     const uint32_t *cta_map;  // blockIdx.x -> window * 2 + direction
     uint32_t smem_tab_words;  // shared-memory words reserved for the count tables
     uint32_t meta_cap;        // reads whose per-read state fits the shared-memory arrays
+    uint32_t stage_cap;       // score terms a candidate slot can stage before its warp has to fold them into the running sums
 };
 
 // Count tables: per site one row of 3^k key words (lo16 = haplotype 0 count, hi16 = haplotype 1 count)
@@ -65,22 +69,57 @@ __device__ __forceinline__ uint32_t compact_key(uint32_t key) {  // k <= 4
     return ((key >> 6) & 3u) * 27u + ((key >> 4) & 3u) * 9u + ((key >> 2) & 3u) * 3u + (key & 3u);
 }
 // dynamic shared memory of join_kernel for the given capacities (bytes)
-__host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_words, uint32_t meta_cap, int n_cand, int n_warps) {
-    return (size_t)tab_words * 4 + (size_t)n_warps * JOIN_STAGE * 8 + (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 +
-           (size_t)((meta_cap + 31) / 32) * 4 + (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
+// Score terms staged per candidate slot.  Measured on the 60x batch (profiles/r02_join_variants.txt): the kernel is
+// issue bound once two or three CTAs share an SM, so shared memory is better spent on a third CTA than on rows that
+// hold every term of a read: 12 KB for all slots (a row that runs full is folded early by its own warp).
+#ifndef POMFRET_JOIN_STAGE_KB
+#define POMFRET_JOIN_STAGE_KB 12
+#endif
+#ifndef POMFRET_JOIN_MIN_CTAS
+#define POMFRET_JOIN_MIN_CTAS 3
+#endif
+__host__ __device__ __forceinline__ uint32_t join_stage_cap(int n_cand) {
+    const uint32_t fit = (uint32_t)(POMFRET_JOIN_STAGE_KB * 1024) / ((uint32_t)(n_cand + 1) * 8u);
+    const uint32_t cap = fit > (uint32_t)JOIN_CHUNK + 1u ? (uint32_t)JOIN_CHUNK : (fit > 34u ? fit - 2u : 32u);
+    return cap & ~1u;  // even, so that the row stride cap + 1 (in 8-byte terms) is odd: lanes of the summing warp hit distinct banks
 }
+__host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_entries, uint32_t entry_bytes, uint32_t meta_cap, int n_cand, int n_warps) {
+    (void)n_warps;
+    return (((size_t)tab_entries * entry_bytes + 7) & ~(size_t)7) + (size_t)(n_cand + 1) * (join_stage_cap(n_cand) + 1) * 8 +
+           (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 + (size_t)((meta_cap + 31) / 32) * 4 +
+           (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
+}
+
+// A table entry holds the counts of both haplotypes: 16 + 16 bits in a 32-bit word, or 8 + 8 bits in a 16-bit word for
+// windows in which fewer than 256 reads touch any one site (WindowState::max_cov): half the shared memory per CTA,
+// twice the CTAs per SM.  Insertions by the extension loop go to distinct entries (one read, one methmer per site) and are
+// plain read-modify-writes; the seeding phase adds from several warps at once and uses atomics on the enclosing word.
+template <typename TabT> struct JoinTab;
+template <> struct JoinTab<uint32_t> {
+    static constexpr uint32_t kShift = 16, kMask = 0xffffu;
+    static __device__ __forceinline__ void atomic_add(uint32_t *p, uint32_t inc) { atomicAdd(p, inc); }
+};
+template <> struct JoinTab<uint16_t> {
+    static constexpr uint32_t kShift = 8, kMask = 0xffu;
+    static __device__ __forceinline__ void atomic_add(uint16_t *p, uint32_t inc) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        atomicAdd(reinterpret_cast<uint32_t *>(a & ~(uintptr_t)3), inc << ((a & 2u) * 8u));  // (no count reaches 256: no carry)
+    }
+};
 
 // Range growth of update_available_methmer_range (blockjoin.c:3669-3691), warp-parallel: the left edge
 // walks down from `mn` while the site's coverage reaches cov, the right edge walks up from `mx`.
-__device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride, uint32_t n_keys, uint32_t n_sites, int cov,
+template <typename TabT>
+__device__ __forceinline__ void grow_range(const TabT *tab, uint32_t stride, uint32_t n_keys, uint32_t n_sites, int cov,
                                            uint32_t &mn, uint32_t &mx) {
+    constexpr uint32_t kShift = JoinTab<TabT>::kShift, kMask = JoinTab<TabT>::kMask;
     const int lane = (int)lane_id();
     for (int i0 = (int)mn;; i0 -= 32) {
         const int i = i0 - lane;
         bool ok = false;
         if (i >= 0) {
             const uint32_t sm = tab[(size_t)i * stride + n_keys];
-            ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
+            ok = (int)((sm & kMask) + (sm >> kShift)) >= cov;
         }
         const unsigned bad = ~__ballot_sync(FULL_MASK, ok);  // first lane that stops the walk (or ran past site 0)
         const int f = bad ? __ffs((int)bad) - 1 : 32;
@@ -92,7 +131,7 @@ __device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride,
         bool ok = false;
         if (i < (int)n_sites) {
             const uint32_t sm = tab[(size_t)i * stride + n_keys];
-            ok = (int)((sm & 0xffffu) + (sm >> 16)) >= cov;
+            ok = (int)((sm & kMask) + (sm >> kShift)) >= cov;
         }
         const unsigned bad = ~__ballot_sync(FULL_MASK, ok);
         const int f = bad ? __ffs((int)bad) - 1 : 32;
@@ -103,7 +142,8 @@ __device__ __forceinline__ void grow_range(const uint32_t *tab, uint32_t stride,
 
 // kTabSmem: every window of the launch keeps its count tables in shared memory (the compiler then emits
 // shared-memory loads/stores for them); otherwise windows that do not fit use the global pool.
-template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_kernel(JoinParams P) {
+template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_THREADS, POMFRET_JOIN_MIN_CTAS) join_kernel(JoinParams P) {
+    constexpr uint32_t kShift = JoinTab<TabT>::kShift, kMask = JoinTab<TabT>::kMask;
     __shared__ int s_i_last, s_failed, s_done, s_fill, s_cursor, s_next_id;
     __shared__ int s_newest[2], s_nocc[2];
     __shared__ uint32_t s_min, s_max, s_seq;
@@ -111,8 +151,11 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
     // still look for the best candidate and the one that already recycles its slot)
     __shared__ uint32_t s_sid[2][JOIN_MAX_CAND + 1];    // read id
     __shared__ uint32_t s_sseq[2][JOIN_MAX_CAND + 1];   // position in scan order (monotone counter), SLOT_FREE if empty
-    __shared__ float s_score[JOIN_MAX_CAND + 1];
     __shared__ int s_tag[JOIN_MAX_CAND + 1];
+    __shared__ uint32_t s_nz[JOIN_MAX_CAND + 1];      // score terms staged in the slot's row
+    __shared__ float2 s_pre[JOIN_MAX_CAND + 1];       // ordered sums of the terms that were folded before (rows that ran full)
+    __shared__ int2 s_ll[JOIN_MAX_CAND + 1];          // the two score_h_l counters of the slot
+    __shared__ int s_best;
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
 
@@ -137,9 +180,10 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
     const int n_cand = P.n_cand;
 
     // ---- shared-memory carve-up ----
-    uint32_t *s_tab = dyn;
-    float2 *s_stage = reinterpret_cast<float2 *>(s_tab + (P.smem_tab_words + (P.smem_tab_words & 1u)));  // [nwarps][JOIN_STAGE]
-    uint32_t *s_moff = reinterpret_cast<uint32_t *>(s_stage + (size_t)nwarps * JOIN_STAGE);  // per read: offset of its keys in the pool
+    TabT *s_tab = reinterpret_cast<TabT *>(dyn);
+    float2 *s_stage = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(dyn) + (((size_t)P.smem_tab_words * sizeof(TabT) + 7) & ~(size_t)7));  // [nwarps][JOIN_STAGE]
+    const uint32_t stage_cap = P.stage_cap, stage_stride = P.stage_cap + 1u;  // [n_cand + 1][stage_stride]
+    uint32_t *s_moff = reinterpret_cast<uint32_t *>(s_stage + (size_t)(P.n_cand + 1) * stage_stride);  // per read: offset of its keys in the pool
     uint32_t *s_mn = s_moff + P.meta_cap;                      // per read: number of methmers
     uint32_t *s_mst = s_mn + P.meta_cap;                       // per read: site index of the first one
     uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
@@ -147,7 +191,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
     uint8_t *s_keys = reinterpret_cast<uint8_t *>(s_tagged + (P.meta_cap + 31) / 32);   // [n_cand + 1][JOIN_CHUNK]
     const bool tab_in_smem = kTabSmem || (size_t)n_sites * stride <= P.smem_tab_words;
     const bool meta_in_smem = n <= P.meta_cap;
-    uint32_t *tab = kTabSmem ? s_tab : (tab_in_smem ? s_tab : P.tab + (size_t)S.tab_base[d] * stride);
+    TabT *tab = kTabSmem ? s_tab : (tab_in_smem ? s_tab : reinterpret_cast<TabT *>(P.tab) + (size_t)S.tab_base[d] * stride);
 
     // ---- wipe the tables (insert_ref_reads_methmer_counts, :3780-3789), load the per-read state ----
     for (size_t i = tid, words = (size_t)n_sites * stride; i < words; i += nthreads) tab[i] = 0;
@@ -195,11 +239,11 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         const int hap = P.rs_hp[first + id];
         if (hap == 0 || hap == 1) {
             const uint32_t nm = g_n[id], st = g_start[id], off = g_off[id];
-            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
+            const uint32_t inc = hap == 0 ? 1u : 1u << kShift;
             for (uint32_t i0 = lane; i0 < nm; i0 += 32) {
-                uint32_t *row = tab + (size_t)(st + i0) * stride;
-                atomicAdd(&row[compact_key(pool[off + i0])], inc);
-                atomicAdd(&row[n_keys], inc);
+                TabT *row = tab + (size_t)(st + i0) * stride;
+                JoinTab<TabT>::atomic_add(&row[compact_key(pool[off + i0])], inc);
+                JoinTab<TabT>::atomic_add(&row[n_keys], inc);
             }
         }
     }
@@ -322,11 +366,12 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         const bool full = nocc == n_slots;
         uint32_t rmin = s_min, rmax = s_max;
         if (grow) {
-            grow_range(tab, stride, n_keys, n_sites, P.cov_run, rmin, rmax);
+            grow_range<TabT>(tab, stride, n_keys, n_sites, P.cov_run, rmin, rmax);
             if (tid == 0) { s_min = rmin; s_max = rmax; }  // others may still read the old pair: growing again is harmless
         }
         PF_MARK(0);  // grow
-        // ---- score the candidates, one warp per slot (use_mmr_count_predict_tag_for_one_read, :3594-3656) ----
+        // ---- score terms of the candidates, one warp per slot (use_mmr_count_predict_tag_for_one_read, :3594-3656):
+        //      lookups and divisions in parallel, the non-zero terms compacted in methmer order into the slot's row ----
         for (int c = (int)warp; c < n_slots; c += (int)nwarps) {
             if (s_sseq[cur][c] == SLOT_FREE || (full && c == newest)) { if (lane == 0) s_tag[c] = -2; continue; }  // empty / look-ahead
             const uint32_t id = s_sid[cur][c];
@@ -334,12 +379,13 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
             const bool cached = nm <= JOIN_CHUNK;
             const uint8_t *ck = s_keys + (size_t)c * JOIN_CHUNK;
-            float sc0 = 0.f, sc1 = 0.f;  // every lane carries both ordered sums
+            float sc0 = 0.f, sc1 = 0.f;  // ordered sums of terms folded early (only when the row runs full)
             int l0 = 0, l1 = 0;
             // only methmers whose site lies in the available range [rmin, rmax) are looked up (:3499-3502)
             const uint32_t i_lo = rmin > st ? rmin - st : 0u;
             const uint32_t i_hi = rmax > st ? (rmax - st < nm ? rmax - st : nm) : 0u;
-            float2 *stage = s_stage + (size_t)warp * JOIN_STAGE;
+            float2 *stage = s_stage + (size_t)c * stage_stride;
+            uint32_t nz = 0;  // non-zero terms staged (adding +0.0f is exact, so zero terms are dropped)
             for (uint32_t base = i_lo; base < i_hi; base += JOIN_STAGE) {
                 // up to four sub-chunks of 32 methmers at a time: their lookups and divisions overlap
                 uint32_t key[4], cnt[4], sums[4];
@@ -352,7 +398,7 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                 for (int u = 0; u < 4; u++) {
                     cnt[u] = 0; sums[u] = 0;
                     if (key[u] != 0xffffffffu) {
-                        const uint32_t *row = tab + (size_t)(st + base + u * 32 + lane) * stride;
+                        const TabT *row = tab + (size_t)(st + base + u * 32 + lane) * stride;
                         cnt[u] = row[key[u]];
                         sums[u] = row[n_keys];
                     }
@@ -363,8 +409,8 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                 for (int u = 0; u < 4; u++) {
                     v0[u] = v1[u] = 0.f; p0[u] = p1[u] = false;
                     if (base + u * 32 < i_hi) {  // uniform
-                        const uint32_t sum0 = sums[u] & 0xffffu, sum1 = sums[u] >> 16;
-                        const uint32_t c0 = cnt[u] & 0xffffu, c1 = cnt[u] >> 16;
+                        const uint32_t sum0 = sums[u] & kMask, sum1 = sums[u] >> kShift;
+                        const uint32_t c0 = cnt[u] & kMask, c1 = cnt[u] >> kShift;
                         p0[u] = cnt[u] != 0 && sum0 != 0;  // key present at this site and the haplotype has counts
                         p1[u] = cnt[u] != 0 && sum1 != 0;
                         // (zero operands are replaced by 1 so that the division always takes its fast path)
@@ -374,7 +420,6 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                         v1[u] = p1[u] && c1 ? q1 : 0.f;
                     }
                 }
-                uint32_t nz = 0;  // non-zero terms staged (adding +0.0f is exact, so zero terms are dropped)
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (base + u * 32 >= i_hi) break;
@@ -383,36 +428,28 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
                     l1 += (int)p1[u] + (int)(v1[u] > 0.f);
                     const bool nzv = v0[u] > 0.f || v1[u] > 0.f;
                     const unsigned zz = __ballot_sync(FULL_MASK, nzv);
+                    if (nz + (uint32_t)__popc(zz) > stage_cap) {
+                        // the row is full (a read with more methmers than a row holds): fold what is staged into the running
+                        // sums, strictly in order (every lane walks the row: broadcast reads)
+                        __syncwarp();
+                        for (uint32_t t = 0; t < nz; t++) { const float2 r = stage[t]; sc0 = __fadd_rn(sc0, r.x); sc1 = __fadd_rn(sc1, r.y); }
+                        __syncwarp();
+                        nz = 0;
+                    }
                     if (nzv) stage[nz + __popc(zz & ((1u << lane) - 1u))] = make_float2(v0[u], v1[u]);
                     nz += __popc(zz);
                 }
-                __syncwarp();
-                // strictly in methmer order, IEEE round-to-nearest (blockjoin.c:3620-3636); every lane walks the
-                // staged terms (broadcast reads), eight loads in flight ahead of the two add chains
-                for (uint32_t t0 = 0; t0 < nz; t0 += 8) {
-                    float2 r[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) r[j] = stage[t0 + j < JOIN_STAGE ? t0 + j : JOIN_STAGE - 1];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        if (t0 + j < nz) { sc0 = __fadd_rn(sc0, r[j].x); sc1 = __fadd_rn(sc1, r[j].y); }
-                    }
-                }
-                __syncwarp();
             }
             l0 = (int)__reduce_add_sync(FULL_MASK, (unsigned)l0);
             l1 = (int)__reduce_add_sync(FULL_MASK, (unsigned)l1);
             if (lane == 0) {
-                float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
-                int tag;
-                float sc;
-                if (diff < 3.0f && (l0 < 3 || l1 < 3)) { tag = -1; sc = 0.f; }
-                else { tag = sc0 > sc1 ? 0 : 1; sc = diff; }
-                s_score[c] = sc;
-                s_tag[c] = tag;
+                s_nz[c] = nz;
+                s_pre[c] = make_float2(sc0, sc1);
+                s_ll[c] = int2{l0, l1};
+                s_tag[c] = -3;  // terms ready, sums pending
             }
         }
-        PF_MARK(1);  // own scoring
+        PF_MARK(1);  // own terms
         if (warp == nwarps - 1) {
             // look-ahead service, off the critical path: keys of the entry placed last iteration, then the read
             // that will take the next freed slot
@@ -425,25 +462,50 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
         }
         __syncthreads();
         PF_MARK(2);  // wait for the slowest scorer / the look-ahead service
-        // ---- stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760);
-        //      every warp finds it on its own: scores are >= 0, so their bit patterns order like unsigned ints ----
-        int best = -1;
-        {
+        // ---- ordered sums, one LANE per candidate (warp 0): the additions of blockjoin.c:3620-3636 are a serial chain per
+        //      candidate and haplotype, so a whole warp per candidate would spend an issue slot per addition; one warp walks
+        //      all rows at once (row stride odd in 8-byte units: no bank conflicts).  Then the best candidate:
+        //      stable ascending sort + scan from the top == max score, ties to the later candidate (:3729-3760); scores are
+        //      >= 0, so their bit patterns order like unsigned ints ----
+        if (warp == 0) {
             uint32_t bs = 0, bq = 0;
             int bc = -1;
-            for (int c = (int)lane; c < n_slots; c += 32) {
-                const int t = s_tag[c];
-                if (t == 0 || t == 1) {
-                    const uint32_t sb = __float_as_uint(s_score[c]), sq = s_sseq[cur][c];
-                    if (bc < 0 || sb > bs || (sb == bs && sq > bq)) { bs = sb; bq = sq; bc = c; }
+            for (int g0 = 0; g0 < n_slots; g0 += 32) {
+                const int c = g0 + (int)lane;
+                const bool act = c < n_slots && s_tag[c] == -3;
+                const uint32_t nz = act ? s_nz[c] : 0u;
+                const uint32_t mx = __reduce_max_sync(FULL_MASK, nz);
+                const float2 *row = s_stage + (size_t)(c < n_slots ? c : 0) * stage_stride;
+                float sc0 = 0.f, sc1 = 0.f;
+                if (act) { const float2 pre = s_pre[c]; sc0 = pre.x; sc1 = pre.y; }
+                for (uint32_t t0 = 0; t0 < mx; t0 += 8) {
+                    float2 r[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) r[j] = row[t0 + j < stage_cap ? t0 + j : stage_cap - 1u];
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (t0 + j < nz) { sc0 = __fadd_rn(sc0, r[j].x); sc1 = __fadd_rn(sc1, r[j].y); }
+                }
+                if (act) {
+                    const int2 ll = s_ll[c];
+                    const float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
+                    if (!(diff < 3.0f && (ll.x < 3 || ll.y < 3))) {
+                        const uint32_t sb = __float_as_uint(diff), sq = s_sseq[cur][c];
+                        s_tag[c] = sc0 > sc1 ? 0 : 1;
+                        if (bc < 0 || sb > bs || (sb == bs && sq > bq)) { bs = sb; bq = sq; bc = c; }
+                    } else s_tag[c] = -1;
                 }
             }
             const uint32_t top = __reduce_max_sync(FULL_MASK, bc >= 0 ? bs : 0u);
             const bool cand = bc >= 0 && bs == top;
             const uint32_t topq = __reduce_max_sync(FULL_MASK, cand ? bq + 1u : 0u);
             const unsigned who = __ballot_sync(FULL_MASK, cand && bq + 1u == topq);
-            if (who) best = __shfl_sync(FULL_MASK, bc, __ffs((int)who) - 1);
+            int best_w0 = -1;
+            if (who) best_w0 = __shfl_sync(FULL_MASK, bc, __ffs((int)who) - 1);
+            if (lane == 0) s_best = best_w0;
         }
+        __syncthreads();
+        const int best = s_best;
         const uint32_t best_id = best >= 0 ? s_sid[cur][best] : 0u;
         const int hap = best >= 0 ? s_tag[best] : -1;
         PF_MARK(3);  // best
@@ -453,9 +515,9 @@ template <bool kTabSmem> __global__ void __launch_bounds__(JOIN_THREADS) join_ke
             const uint32_t off = meta_in_smem ? s_moff[best_id] : g_off[best_id];
             const bool cached = nm <= JOIN_CHUNK;
             const uint8_t *ck = s_keys + (size_t)best * JOIN_CHUNK;
-            const uint32_t inc = hap == 0 ? 1u : 0x10000u;
+            const TabT inc = (TabT)(hap == 0 ? 1u : 1u << kShift);
             for (uint32_t i0 = tid; i0 < nm; i0 += nthreads) {
-                uint32_t *row = tab + (size_t)(st + i0) * stride;
+                TabT *row = tab + (size_t)(st + i0) * stride;
                 row[cached ? (uint32_t)ck[i0] : compact_key(pool[off + i0])] += inc;
                 row[n_keys] += inc;
             }

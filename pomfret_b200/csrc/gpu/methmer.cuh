@@ -66,9 +66,13 @@ __device__ inline int search_left(const uint32_t *a, uint32_t l, uint32_t v, uin
     return stat;
 }
 
+constexpr uint32_t MMR_COV_SITES = 4096;  // windows with more sites report their read count as the coverage bound
+
 __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams P) {
     __shared__ uint32_t s_warp[33];
     __shared__ uint32_t s_base;
+    __shared__ int s_diff[2][MMR_COV_SITES + 1];  // per direction: +1 where a read's site range begins, -1 behind its end
+    __shared__ int s_maxcov;
     const uint32_t w = blockIdx.x;
     const WindowRec W = P.win[w];
     WindowState &S = P.state[w];
@@ -76,6 +80,10 @@ __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams 
     const bool active = n > 0 && n_sites > 0 && S.status == 0;
     uint32_t running = 0;
     const uint32_t n_items = active ? n * 2 : 0;
+    const bool count_cov = active && n_sites <= MMR_COV_SITES;
+    if (count_cov) for (uint32_t i = threadIdx.x; i <= n_sites; i += RS_THREADS) { s_diff[0][i] = 0; s_diff[1][i] = 0; }
+    if (threadIdx.x == 0) s_maxcov = 0;
+    __syncthreads();
     for (uint32_t base = 0; base < n_items; base += RS_THREADS) {
         uint32_t it = base + threadIdx.x;
         uint32_t cap = 0, slot = 0, d = 0;
@@ -103,7 +111,13 @@ __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams 
                 }
             }
             if (none || xr <= xl) { xl = 0; xr = 0; cap = 0; }
-            else cap = (xr - xl) + 2u * (uint32_t)P.k + 2u;
+            else {
+                cap = (xr - xl) + 2u * (uint32_t)P.k + 2u;
+                if (count_cov) {  // (methmers are counted at consecutive sites from the first complete one: at most `cap` of them)
+                    const uint32_t xe = xl + cap < n_sites ? xl + cap : n_sites;
+                    atomicAdd(&s_diff[d][xl], 1); atomicAdd(&s_diff[d][xe], -1);
+                }
+            }
             P.mm_xl[d][slot] = xl;
             P.mm_xr[d][slot] = xr;
         }
@@ -112,7 +126,23 @@ __global__ void __launch_bounds__(RS_THREADS) methmer_size_kernel(MethmerParams 
         if (it < n_items) P.mm_off[d][slot] = running + ex;  // window-local for now
         running += tot;
     }
+    // the largest number of reads over one site (either direction): every count of the join tables stays below it
+    if (count_cov) {
+        __syncthreads();
+        const uint32_t per = (n_sites + RS_THREADS - 1) / RS_THREADS;
+        for (int d = 0; d < 2; d++) {
+            const uint32_t a = threadIdx.x * per, z = a + per < n_sites ? a + per : n_sites;
+            int sum = 0;
+            for (uint32_t i = a; i < z; i++) sum += s_diff[d][i];
+            uint32_t tot;
+            int run = (int)block_exclusive_scan((uint32_t)sum, &tot, s_warp), mx = 0;  // (two's complement sums)
+            for (uint32_t i = a; i < z; i++) { run += s_diff[d][i]; mx = run > mx ? run : mx; }
+            atomicMax(&s_maxcov, mx);
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
+        S.max_cov = count_cov ? (uint32_t)s_maxcov : n;
         s_base = atomicAdd(&P.pool_total[0], running);
         S.mmr_base[0] = s_base;
         S.mmr_base[1] = s_base;

@@ -47,7 +47,7 @@ struct WindowState {
     uint32_t tab_base[2];   // offset (in sites) of the window's count tables
     int32_t table[2][4];    // evaluate_separation1 2x2 tables, [direction][ref*2+query]
     uint32_t n_order[2];
-    uint32_t pad;
+    uint32_t max_cov;       // upper bound of the reads that touch one methmer site (bounds every count of the join tables)
 };
 
 // status bits of a decoded read (mirror POMFRET_GPU_READ_* in pomfret_gpu.h)

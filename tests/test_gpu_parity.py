@@ -169,7 +169,7 @@ def test_gpu_join_candidate_counts(gpu, synth30, synth_small, n_cand):
     _run_tweaked(gpu, synth30, 30, 15000, tweak, max_windows=2)
 
 
-@pytest.mark.parametrize("mode", ["0", "half"])
+@pytest.mark.parametrize("mode", ["0", "half", "u16"])
 def test_gpu_join_global_memory_paths(gpu, synth30, mode, monkeypatch):
     # windows too large for shared memory keep count tables / per-read state in global memory
     monkeypatch.setenv("POMFRET_GPU_JOIN_SMEM", mode)

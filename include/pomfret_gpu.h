@@ -147,6 +147,66 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b);
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r);
 /* the same for an array of n descriptors (one call per window instead of one per record) */
 int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n);
+/* ---- (a') compressed ingest: BGZF inflate + BAM record slicing on the device ----
+ * Replaces, for the engine's inputs, what the reference does through htslib per window: sam_itr_next / bam_read1 /
+ * bgzf_read at blockjoin.c:1070 (windows), :1863 (-u pre-pass); the record filters of :1081-1084 run on the device too.
+ * The caller ships the BGZF blocks of the index chunks of its region queries exactly as they lie in the file and
+ * never inflates or parses a record. */
+typedef struct pomfret_gpu_bgzf_block {
+    uint64_t comp_off;   /* offset of the block (its gzip header) in the compressed buffer */
+    uint32_t csize;      /* whole block: BSIZE + 1 */
+    uint32_t isize;      /* ISIZE of the block's footer */
+    uint64_t out_off;    /* where the block inflates to: the blocks of a stream back to back */
+} pomfret_gpu_bgzf_block;
+typedef struct pomfret_gpu_bgzf_stream {  /* one chunk of the index: consecutive blocks that hold whole records */
+    uint64_t out_off;    /* out_off of the stream's first block */
+    uint64_t out_bytes;  /* inflated bytes up to the end of the chunk's last record */
+    uint32_t ubeg;       /* offset of the chunk's first record inside the first block */
+    int32_t tid;         /* a record of another target ends the stream ... */
+    uint32_t end0;       /* ... and so does one that starts at or behind this position (the query's end, 0-based exclusive) */
+    uint32_t first_block, n_blocks;
+    uint32_t reserved;
+} pomfret_gpu_bgzf_stream;
+typedef struct pomfret_gpu_ingest_filter {  /* blockjoin.c:1081-1084; all zero = primary records only (blockjoin.c:1862) */
+    uint32_t min_mapq;
+    uint32_t min_len;        /* readlen_threshold */
+    uint32_t min_len_floor;  /* 2: "len < 2" of the window loader */
+    uint32_t check_de;
+    float max_de;            /* MIN_ALN_DE 0.1 */
+} pomfret_gpu_ingest_filter;
+typedef struct pomfret_gpu_sliced_record {  /* one alignment record as the slicing kernel saw it; addresses are DEVICE addresses */
+    uint32_t pos, end_pos, l_qseq, n_cigar;   /* n_cigar / cigar: the real operations, also for CG-tag records */
+    uint16_t flag;
+    uint8_t mapq, tags_malformed;
+    int32_t hp, mn;                           /* as in pomfret_gpu_read_desc (hp: 254 if absent) */
+    uint32_t mm_len;
+    int32_t ml_len;
+    uint32_t md_len;
+    uint32_t stream;
+    uint8_t keep;                             /* passed the filters */
+    uint8_t bad;                              /* malformed record (fields run past its end) */
+    uint8_t has_mm, hp_irregular;             /* MM/Mm present; HP:0 ("irregular HP tag", blockjoin.c:916) */
+    uint8_t l_qname;                          /* with the NUL */
+    uint8_t pad[3];
+    uint64_t cigar, seq, mm, ml, md;          /* 0 if absent */
+    uint64_t qname_dev;
+    char qname[48];                           /* NUL terminated prefix; the whole name if l_qname <= 48 */
+} pomfret_gpu_sliced_record;
+/* pinned host buffer of the batch for the compressed blocks (valid until the next reset): the loader reads the file into it */
+int pomfret_gpu_batch_ingest_buffer(pomfret_gpu_batch *b, size_t bytes, void **out);
+/* H2D of the blocks, inflate (ISIZE + CRC-32 checked), record walk and slicing; *n_records = records found in the streams,
+ * in stream order and file order inside a stream.  `comp` is the buffer of ingest_buffer() or any host memory. */
+int pomfret_gpu_batch_ingest_bgzf(pomfret_gpu_batch *b, const void *comp, size_t comp_bytes, const pomfret_gpu_bgzf_block *blocks,
+                                  uint32_t n_blocks, const pomfret_gpu_bgzf_stream *streams, uint32_t n_streams,
+                                  const pomfret_gpu_ingest_filter *flt, uint32_t *n_records);
+int pomfret_gpu_batch_ingest_records(pomfret_gpu_batch *b, pomfret_gpu_sliced_record *out, uint32_t cap);
+/* add_reads_shared() for records of the ingest: the pointers of r[] are the device addresses of a sliced record and
+ * r[i].reserved carries its end_pos; the payload is copied out of the inflated stream on the device. */
+int pomfret_gpu_batch_add_reads_device(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as);
+/* parity getters: the inflated bytes of one stream; a record's whole name */
+int pomfret_gpu_debug_get_inflated(pomfret_gpu_batch *b, uint32_t stream, uint8_t *dst, size_t cap, size_t *n);
+int pomfret_gpu_batch_ingest_qname(pomfret_gpu_batch *b, uint32_t record, char *dst, uint32_t cap);
+
 /* Decode-once form: same_as[i] >= 0 names an earlier read of this batch that is the same
  * alignment record (it lies in two overlapping windows; the reference re-decodes it per window, blockjoin.c:1056).
  * The new slot shares that read's staged payload, call slots and decode result; r[i] then only needs pos, l_qseq,
@@ -191,6 +251,8 @@ typedef struct pomfret_gpu_timing {
     uint64_t bytes_h2d, bytes_d2h;
     uint64_t decode_bytes, pileup_bytes, methmer_bytes, haptag_bytes; /* algorithmic bytes, SURVEY.md §8(d) */
     uint32_t launches;
+    float inflate_ms, slice_ms;               /* compressed ingest: inflate_kernel; walk + scan + slice kernels */
+    uint64_t inflate_in_bytes, inflate_out_bytes;
 } pomfret_gpu_timing;
 int pomfret_gpu_batch_timing(pomfret_gpu_batch *b, pomfret_gpu_timing *out);
 

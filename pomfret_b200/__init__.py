@@ -10,8 +10,8 @@ The product is native code:
 This Python package is only a thin ctypes binding used by the tests and by ``bench.py``; there is no
 Python (or CPU) implementation of the path — loading fails loudly if the CUDA library is missing.
 """
-from ._ffi import (Config, ReadDesc, WindowResult, Timing, Variant, GpuLib, HostLib, load_gpu, load_host,
+from ._ffi import (Config, ReadDesc, WindowResult, Timing, Variant, BgzfBlock, BgzfStream, IngestFilter, SlicedRecord, GpuLib, HostLib, load_gpu, load_host,
                    make_config, PACKAGE_DIR, LIB_DIR)
 
-__all__ = ["Config", "ReadDesc", "WindowResult", "Timing", "Variant", "GpuLib", "HostLib", "load_gpu",
+__all__ = ["Config", "ReadDesc", "WindowResult", "Timing", "Variant", "BgzfBlock", "BgzfStream", "IngestFilter", "SlicedRecord", "GpuLib", "HostLib", "load_gpu",
            "load_host", "make_config", "PACKAGE_DIR", "LIB_DIR"]

@@ -43,12 +43,41 @@ class WindowResult(C.Structure):
                 ("which_way_bwd", C.c_int32), ("status", C.c_int32)]
 
 
+class BgzfBlock(C.Structure):
+    """pomfret_gpu_bgzf_block"""
+    _fields_ = [("comp_off", C.c_uint64), ("csize", C.c_uint32), ("isize", C.c_uint32), ("out_off", C.c_uint64)]
+
+
+class BgzfStream(C.Structure):
+    """pomfret_gpu_bgzf_stream"""
+    _fields_ = [("out_off", C.c_uint64), ("out_bytes", C.c_uint64), ("ubeg", C.c_uint32), ("tid", C.c_int32), ("end0", C.c_uint32),
+                ("first_block", C.c_uint32), ("n_blocks", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class IngestFilter(C.Structure):
+    """pomfret_gpu_ingest_filter"""
+    _fields_ = [("min_mapq", C.c_uint32), ("min_len", C.c_uint32), ("min_len_floor", C.c_uint32), ("check_de", C.c_uint32),
+                ("max_de", C.c_float)]
+
+
+class SlicedRecord(C.Structure):
+    """pomfret_gpu_sliced_record"""
+    _fields_ = [("pos", C.c_uint32), ("end_pos", C.c_uint32), ("l_qseq", C.c_uint32), ("n_cigar", C.c_uint32), ("flag", C.c_uint16),
+                ("mapq", C.c_uint8), ("tags_malformed", C.c_uint8), ("hp", C.c_int32), ("mn", C.c_int32), ("mm_len", C.c_uint32),
+                ("ml_len", C.c_int32), ("md_len", C.c_uint32), ("stream", C.c_uint32), ("keep", C.c_uint8), ("bad", C.c_uint8),
+                ("has_mm", C.c_uint8), ("hp_irregular", C.c_uint8), ("l_qname", C.c_uint8), ("pad", C.c_uint8 * 3),
+                ("cigar", C.c_uint64), ("seq", C.c_uint64), ("mm", C.c_uint64), ("ml", C.c_uint64), ("md", C.c_uint64),
+                ("qname_dev", C.c_uint64), ("qname", C.c_char * 48)]
+
+
 class Timing(C.Structure):
     """pomfret_gpu_timing"""
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "decode_ms", "haptag_ms", "readset_ms", "pileup_ms",
                                          "methmer_ms", "join_ms", "d2h_ms")] + \
                [(n, C.c_uint64) for n in ("bytes_h2d", "bytes_d2h", "decode_bytes", "pileup_bytes",
-                                          "methmer_bytes", "haptag_bytes")] + [("launches", C.c_uint32)]
+                                          "methmer_bytes", "haptag_bytes")] + [("launches", C.c_uint32)] + \
+               [("inflate_ms", C.c_float), ("slice_ms", C.c_float), ("inflate_in_bytes", C.c_uint64),
+                ("inflate_out_bytes", C.c_uint64)]
 
 
 def make_config(cov, k=3, k_span=5000, lo=100, hi=156, readlen=15000, mapq=10, report=False):
@@ -96,6 +125,12 @@ class GpuLib:
         lib.pomfret_gpu_batch_add_read.argtypes = [vp, vp]
         lib.pomfret_gpu_batch_add_reads.argtypes = [vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_add_reads_shared.argtypes = [vp, vp, C.c_uint32, vp]
+        lib.pomfret_gpu_batch_add_reads_device.argtypes = [vp, vp, C.c_uint32, vp]
+        lib.pomfret_gpu_batch_ingest_buffer.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+        lib.pomfret_gpu_batch_ingest_bgzf.argtypes = [vp, vp, C.c_size_t, vp, C.c_uint32, vp, C.c_uint32, vp, u32p]
+        lib.pomfret_gpu_batch_ingest_records.argtypes = [vp, vp, C.c_uint32]
+        lib.pomfret_gpu_debug_get_inflated.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+        lib.pomfret_gpu_batch_ingest_qname.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_add_windows.argtypes = [vp, vp, vp, vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
@@ -177,6 +212,33 @@ class Batch:
         base = descs_ptr if isinstance(descs_ptr, int) else C.cast(descs_ptr, C.c_void_p).value
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_reads_shared(self.h, base, n, same_as.ctypes.data if same_as is not None else None),
                        "batch_add_reads_shared")
+        first = self.n_reads
+        self.n_reads += n
+        return first
+
+    def ingest_bgzf(self, comp_ptr, comp_bytes, blocks_ptr, n_blocks, streams_ptr, n_streams, flt=None, check=True):
+        """compressed ingest; returns (rc, records) with records a ctypes array of SlicedRecord"""
+        n = C.c_uint32()
+        rc = self.gpu.lib.pomfret_gpu_batch_ingest_bgzf(self.h, comp_ptr, comp_bytes, blocks_ptr, n_blocks, streams_ptr, n_streams,
+                                                        C.byref(flt) if flt is not None else None, C.byref(n))
+        if check:
+            self.gpu.check(rc, "ingest_bgzf")
+        recs = (SlicedRecord * max(n.value, 1))()
+        if rc == 0:
+            self.gpu.check(self.gpu.lib.pomfret_gpu_batch_ingest_records(self.h, recs, n.value), "ingest_records")
+        return rc, recs, n.value
+
+    def inflated(self, stream, cap=1 << 28):
+        n = C.c_size_t()
+        self.gpu.check(self.gpu.lib.pomfret_gpu_debug_get_inflated(self.h, stream, None, 0, C.byref(n)), "debug_get_inflated")
+        buf = np.zeros(max(n.value, 1), dtype=np.uint8)
+        self.gpu.check(self.gpu.lib.pomfret_gpu_debug_get_inflated(self.h, stream, buf.ctypes.data, n.value, C.byref(n)), "debug_get_inflated")
+        return buf[:n.value]
+
+    def add_reads_device(self, descs_ptr, n, same_as=None):
+        base = descs_ptr if isinstance(descs_ptr, int) else C.cast(descs_ptr, C.c_void_p).value
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_add_reads_device(self.h, base, n, same_as.ctypes.data if same_as is not None else None),
+                       "batch_add_reads_device")
         first = self.n_reads
         self.n_reads += n
         return first
@@ -316,6 +378,34 @@ class HostLib:
         lib.pomfret_host_window_arena.restype = vp
         lib.pomfret_host_window_arena.argtypes = [vp, C.POINTER(C.c_uint64)]
         lib.pomfret_host_window_free.argtypes = [vp]
+
+    def ingest_plan(self, bam, chrom, regions):
+        """regions: list of (beg0, end0).  Returns a dict with the compressed bytes and the block / stream tables."""
+        lib = self.lib
+        vp = C.c_void_p
+        lib.pomfret_host_ingest_plan.restype = vp
+        lib.pomfret_host_ingest_plan.argtypes = [vp, C.c_char_p, vp, C.c_int]
+        for f, rt in (("comp", vp), ("blocks", vp), ("streams", vp)):
+            getattr(lib, "pomfret_host_ingest_" + f).restype = rt
+        lib.pomfret_host_ingest_comp.argtypes = [vp, C.POINTER(C.c_uint64)]
+        lib.pomfret_host_ingest_blocks.argtypes = [vp, C.POINTER(C.c_uint32)]
+        lib.pomfret_host_ingest_streams.argtypes = [vp, C.POINTER(C.c_uint32)]
+        lib.pomfret_host_ingest_stream_run.restype = C.c_uint32
+        lib.pomfret_host_ingest_stream_run.argtypes = [vp, C.c_uint32]
+        lib.pomfret_host_ingest_free.argtypes = [vp]
+        arr = np.array(regions, dtype=np.int64).reshape(-1)
+        h = lib.pomfret_host_ingest_plan(bam, chrom.encode(), arr.ctypes.data, len(regions))
+        if not h:
+            raise RuntimeError("ingest plan failed")
+        n64, nb, ns = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        comp = lib.pomfret_host_ingest_comp(h, C.byref(n64))
+        blocks = lib.pomfret_host_ingest_blocks(h, C.byref(nb))
+        streams = lib.pomfret_host_ingest_streams(h, C.byref(ns))
+        return dict(handle=h, comp=comp, comp_bytes=n64.value, blocks=blocks, n_blocks=nb.value, streams=streams, n_streams=ns.value,
+                    stream_run=[lib.pomfret_host_ingest_stream_run(h, s) for s in range(ns.value)])
+
+    def ingest_free(self, plan):
+        self.lib.pomfret_host_ingest_free(plan["handle"])
 
     def bam_open(self, path):
         h = self.lib.pomfret_host_bam_open(path.encode())

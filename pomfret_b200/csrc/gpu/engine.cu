@@ -28,6 +28,7 @@
 #include "join.cuh"
 #include "haptag.cuh"
 #include "gather.cuh"
+#include "ingest.cuh"
 #include "pomfret_gpu.h"
 #include "htslib/kfunc.h"
 
@@ -232,6 +233,13 @@ struct pomfret_gpu_batch {
     PinVec<uint32_t> h_cta;   // join launch order: window * 2 + direction
     PinVec<uint32_t> h_order_len;  // record indices, longest first
     std::vector<uint32_t> h_end;  // per read: reference end computed on the host (tile planning only)
+    // compressed ingest
+    PinBuf h_comp;                   // BGZF blocks as they lie in the file
+    PinVec<uint32_t> h_ing;          // block and stream tables on their way to the device
+    std::vector<pomfret_gpu_bgzf_stream> ing_streams;
+    uint32_t ing_records = 0;
+    bool ing_timed = false, device_reads = false;
+    cudaEvent_t ev_ing[4] = {};
     std::vector<uint32_t> h_dup_of;  // per read: earlier batch read with the same payload (decoded once), or kNoDup
     size_t n_dups = 0;
     uint64_t calls_total = 0;
@@ -251,6 +259,7 @@ struct pomfret_gpu_batch {
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
     DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc, d_dup_of;
+    DevBuf d_comp, d_inflated, d_ing_tab, d_ing_small, d_rec_off, d_rec_stream, d_sliced;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -267,7 +276,8 @@ struct pomfret_gpu_batch {
                      &d_mm_xl[1], &d_mm_xr[0], &d_mm_xr[1], &d_mm_off[0], &d_mm_off[1], &d_mm_n[0],
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
-                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_dup_of};
+                     &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_dup_of,
+                     &d_comp, &d_inflated, &d_ing_tab, &d_ing_small, &d_rec_off, &d_rec_stream, &d_sliced};
     }
 };
 
@@ -381,6 +391,7 @@ int pomfret_gpu_batch_begin(pomfret_gpu_ctx *ctx, int worker, int device, pomfre
         CK(cudaEventCreateWithFlags(&b->ev_side[i], cudaEventDisableTiming));
     }
     for (auto &e : b->ev) CK(cudaEventCreate(&e));
+    for (auto &e : b->ev_ing) CK(cudaEventCreate(&e));
     CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
     {
@@ -415,6 +426,7 @@ int pomfret_gpu_batch_reset(pomfret_gpu_batch *b) {
     b->h_end.clear();
     b->h_dup_of.clear();
     b->n_dups = 0;
+    b->ing_records = 0; b->ing_streams.clear(); b->ing_timed = false; b->device_reads = false;
     b->calls_total = 0;
     b->alg_decode_bytes = b->alg_haptag_bytes = 0;
     b->stage = ST_EMPTY;
@@ -441,6 +453,8 @@ void pomfret_gpu_batch_end(pomfret_gpu_batch *b) {
     b->h_blob.release(); b->h_reads.release(); b->h_win.release(); b->h_read_win.release();
     b->h_win_base.release(); b->h_win_tile_first.release(); b->h_tiles.release(); b->h_state.release(); b->h_u32.release(); b->h_cta.release(); b->h_order_len.release(); b->h_gsrc.release();
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : b->ev_ing) if (e) cudaEventDestroy(e);
+    b->h_comp.release(); b->h_ing.release();
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_join) cudaEventDestroy(b->ev_join);
     if (b->stream2) cudaStreamDestroy(b->stream2);
@@ -570,8 +584,20 @@ int pomfret_gpu_batch_add_reads(pomfret_gpu_batch *b, const pomfret_gpu_read_des
     return pomfret_gpu_batch_add_reads_shared(b, r, n, nullptr);
 }
 
+static int add_reads_impl(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as, bool device_ptrs);
+
 int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as) {
+    return add_reads_impl(b, r, n, same_as, false);
+}
+
+}  // extern "C"
+
+// device_ptrs: the records come from the compressed ingest; the pointers are device addresses inside the inflated
+// streams of this batch (the host must not touch them) and r[i].reserved holds the record's reference end
+static int add_reads_impl(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as, bool device_ptrs) {
     if (!b || (n && !r)) return POMFRET_GPU_ERR_ARG;
+    if (device_ptrs && (b->copied_any || (b->direct_any && !b->device_reads))) return POMFRET_GPU_ERR_STATE;  // one kind of source per batch
+    if (!device_ptrs && b->device_reads) return POMFRET_GPU_ERR_STATE;
     if (b->stage != ST_EMPTY) return POMFRET_GPU_ERR_STATE;
     if (n == 0) return POMFRET_GPU_OK;
     const size_t first = b->h_reads.n;
@@ -594,8 +620,8 @@ int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_r
     // records that lie completely inside registered caller buffers stay where they are: the device gathers them
     {
         std::vector<HostRegion> regs;
-        { std::lock_guard<std::mutex> g(b->ctx->mu); regs = b->ctx->regions; }
-        bool direct = !regs.empty();
+        if (!device_ptrs) { std::lock_guard<std::mutex> g(b->ctx->mu); regs = b->ctx->regions; }
+        bool direct = device_ptrs || !regs.empty();
         size_t hint = 0;
         for (uint32_t i = 0; i < n && direct; i++) {
             const pomfret_gpu_read_desc &d = r[i];
@@ -608,7 +634,7 @@ int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_r
             for (int f = 0; f < 5; f++) {
                 if (!p[f] || !sz[f]) continue;
                 // (word-aligned reads may touch up to 3 bytes on either side: registered memory is pinned page-wise)
-                G.ptr[f] = region_lookup(regs, p[f], sz[f], &hint);
+                G.ptr[f] = device_ptrs ? (uint64_t)(uintptr_t)p[f] : region_lookup(regs, p[f], sz[f], &hint);
                 if (!G.ptr[f]) { direct = false; break; }
             }
         }
@@ -617,6 +643,7 @@ int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_r
             uint32_t *ends = b->h_end.data() + first;
             auto scan = [&](size_t i) {
                 if (is_dup(i)) return;
+                if (device_ptrs) { ends[i] = r[i].reserved; return; }
                 uint64_t rlen = 0;
                 for (uint32_t c = 0; c < r[i].n_cigar; c++) {
                     const uint32_t op = r[i].cigar[c] & 15u;
@@ -635,6 +662,7 @@ int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_r
             if (b->n_dups != dups0) for (uint32_t i = 0; i < n; i++) if (is_dup(i)) ends[i] = b->h_end[b->h_dup_of[first + i]];
             b->h_blob.len = len;  // layout only: nothing is written on the host
             b->direct_any = true;
+            if (device_ptrs) b->device_reads = true;
             return POMFRET_GPU_OK;
         }
         for (uint32_t i = 0; i < n; i++) memset(&b->h_gsrc[first + i], 0, sizeof(GatherSrc));
@@ -677,6 +705,8 @@ int pomfret_gpu_batch_add_reads_shared(pomfret_gpu_batch *b, const pomfret_gpu_r
     if (b->n_dups != dups0) for (uint32_t i = 0; i < n; i++) if (is_dup(i)) ends[i] = b->h_end[b->h_dup_of[first + i]];
     return POMFRET_GPU_OK;
 }
+
+extern "C" {
 
 int pomfret_gpu_batch_add_read(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r) {
     if (!r) return POMFRET_GPU_ERR_ARG;
@@ -752,7 +782,7 @@ int pomfret_gpu_batch_submit(pomfret_gpu_batch *b) {
         G.reads = b->d_reads.as<ReadRec>(); G.src = b->d_gsrc.as<GatherSrc>(); G.blob = b->d_blob.as<uint8_t>(); G.n_reads = (uint32_t)nr;
         POMFRET_LAUNCH(gather_kernel, (unsigned)((nr + GATHER_WARPS - 1) / GATHER_WARPS), GATHER_WARPS * 32, 0, b->stream, G);
         b->tm.launches++;
-        for (size_t i = 0; i < nr; i++)
+        for (size_t i = 0; i < nr && !b->device_reads; i++)  // (ingested records crossed the bus compressed: counted there)
             for (int f = 0; f < 5; f++)
                 if (b->h_gsrc[i].ptr[f]) {
                     const ReadRec &R = b->h_reads[i];
@@ -1337,3 +1367,4 @@ int pomfret_gpu_debug_get_tag_order(pomfret_gpu_batch *b, uint32_t window, int d
 }  // extern "C"
 
 #include "engine_haptag.inc"
+#include "engine_ingest.inc"

@@ -1,0 +1,450 @@
+// (a) Compressed ingest: BGZF inflate and BAM record slicing on the device.
+//
+// The host ships the BGZF blocks of the index chunks of a region query as they lie in the file (a quarter of the
+// bytes of the inflated records); it never inflates or parses a record.  Replaces, for that path, what
+// sam_itr_next / bam_read1 / bgzf_read do for load_reads_given_interval (reference blockjoin.c:1056-1084) and for
+// pre_haplotagging_read_in_one_ref (:1853-1866):
+//
+//   inflate_kernel      one thread per BGZF block (RFC 1951: stored, fixed and dynamic Huffman blocks; 9-bit /
+//                       6-bit first-level tables in local memory, canonical bit-by-bit decode behind them),
+//                       ISIZE and CRC-32 (slicing-by-4) checked against the block footer.  Blocks of a stream are
+//                       inflated back to back, so records that span blocks are contiguous.
+//   walk_kernel         one thread per stream (an index chunk: whole records only): follows the block_size chain,
+//                       stops at the first record of another target or at / behind the region end; counts, then
+//                       writes the record offsets (two passes around a scan).
+//   slice_kernel        one warp per record: core fields, the record filters of blockjoin.c:1081-1084 (flag, MAPQ,
+//                       length, `de`), bam_endpos, the aux walk for MM/Mm, ML/Ml, MN, MD, HP, de, CG (long CIGARs,
+//                       SAM spec 4.2.2) -> one pomfret_gpu_sliced_record per record with device addresses of its fields.
+// The host then decides which windows a record belongs to and hands the records to add_reads_device(): the gather
+// kernel copies the fields out of the inflated stream into the aligned batch blob, device to device.
+#ifndef POMFRET_GPU_INGEST_CUH
+#define POMFRET_GPU_INGEST_CUH
+#include "gpu_rt.h"
+#include "types.h"
+#include "pomfret_gpu.h"
+
+namespace pomfret_gpu {
+
+struct InflateParams {
+    const uint8_t *comp;                   // the compressed blocks as they lie in the file
+    const pomfret_gpu_bgzf_block *blocks;  // comp_off, csize (whole block), isize, out_off
+    uint32_t n_blocks;
+    uint8_t *out;
+    const uint32_t *crc_tab;               // [4][256] slicing-by-4 tables of the reflected polynomial 0xEDB88320
+    int32_t *status;                       // per block: 0 or an error code
+    int32_t *n_bad;
+    int check_crc;
+};
+
+// ---- bit reader over the deflate payload of one block ----
+struct BitReader {
+    const uint8_t *p, *end;
+    uint64_t buf;
+    int n;
+    __device__ __forceinline__ void refill() {
+        while (n <= 56 && p < end) { buf |= (uint64_t)(*p++) << n; n += 8; }
+    }
+    __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)buf & ((1u << k) - 1u); }
+    __device__ __forceinline__ void drop(int k) { buf >>= k; n -= k; }
+    __device__ __forceinline__ uint32_t take(int k) { uint32_t v = peek(k); drop(k); return v; }
+};
+
+constexpr int INF_LIT_BITS = 9, INF_DIST_BITS = 6;
+
+// Canonical Huffman code of `n` symbols with the given lengths: counts per length, symbols in code order, and a
+// first-level table of `bits` bits (entry: symbol | length << 12; 0: longer code or unused).  Returns false for an
+// over-subscribed set of lengths.
+__device__ bool build_code(const uint8_t *lens, int n, uint16_t *count /*[16]*/, uint16_t *symbol, uint16_t *lut, int bits) {
+    for (int i = 0; i < 16; i++) count[i] = 0;
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    int left = 1;
+    for (int l = 1; l < 16; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+    uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; l++) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+    for (int i = 0; i < n; i++) if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+    for (int i = 0; i < (1 << bits); i++) lut[i] = 0;
+    // codes in canonical order: length by length, symbols ascending; the table is indexed by the bit-reversed code
+    uint32_t code = 0, idx = 0;
+    for (int l = 1; l <= bits; l++) {
+        for (int k = 0; k < count[l]; k++, code++, idx++) {
+            const uint32_t rev = __brev(code) >> (32 - l);
+            const uint16_t e = (uint16_t)(symbol[idx] | (l << 12));
+            for (uint32_t j = rev; j < (1u << bits); j += 1u << l) lut[j] = e;
+        }
+        code <<= 1;
+    }
+    return true;
+}
+
+// one symbol: first-level table, else the canonical walk (RFC 1951 3.2.2) from the first length behind the table
+__device__ __forceinline__ int decode_symbol(BitReader &br, const uint16_t *count, const uint16_t *symbol, const uint16_t *lut, int bits) {
+    const uint16_t e = lut[br.peek(bits)];
+    if (e) { br.drop(e >> 12); return e & 0xfff; }
+    int code = 0, first = 0, index = 0;
+    uint64_t b = br.buf;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)(b & 1u);
+        b >>= 1;
+        const int c = count[l];
+        if (code - c < first) { br.drop(l); return symbol[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ uint32_t crc32_update(const uint32_t *tab, uint32_t crc, const uint8_t *p, uint32_t n) {
+    crc = ~crc;
+    while (n && ((uintptr_t)p & 3u)) { crc = tab[(crc ^ *p++) & 0xffu] ^ (crc >> 8); n--; }
+    for (; n >= 4; n -= 4, p += 4) {
+        crc ^= *reinterpret_cast<const uint32_t *>(p);
+        crc = tab[3 * 256 + (crc & 0xffu)] ^ tab[2 * 256 + ((crc >> 8) & 0xffu)] ^ tab[256 + ((crc >> 16) & 0xffu)] ^ tab[crc >> 24];
+    }
+    while (n--) crc = tab[(crc ^ *p++) & 0xffu] ^ (crc >> 8);
+    return ~crc;
+}
+
+constexpr int INFLATE_THREADS = 32;  // one warp per CTA: the blocks of a launch spread over all SMs
+
+__global__ void __launch_bounds__(INFLATE_THREADS) inflate_kernel(InflateParams P) {
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= P.n_blocks) return;
+    const pomfret_gpu_bgzf_block B = P.blocks[bi];
+    const uint8_t *blk = P.comp + B.comp_off;
+    int err = 0;
+    // ---- BGZF header (RFC 1952 member with a BC extra subfield) ----
+    uint32_t xlen = 0;
+    if (B.csize < 28 || blk[0] != 0x1f || blk[1] != 0x8b || blk[2] != 8 || !(blk[3] & 4)) err = 1;
+    else xlen = (uint32_t)blk[10] | ((uint32_t)blk[11] << 8);
+    if (!err && 12 + xlen + 8 > B.csize) err = 1;
+    uint8_t *out = P.out + B.out_off;
+    const uint32_t isize = B.isize;
+    uint32_t o = 0;
+    if (!err) {
+        BitReader br;
+        br.p = blk + 12 + xlen;
+        br.end = blk + B.csize - 8;
+        br.buf = 0; br.n = 0;
+        uint16_t lcount[16], dcount[16], lsym[288], dsym[32], llut[1 << INF_LIT_BITS], dlut[1 << INF_DIST_BITS];
+        uint8_t lens[320];
+        bool last = false;
+        while (!last && !err) {
+            br.refill();
+            last = br.take(1) != 0;
+            const uint32_t type = br.take(2);
+            if (type == 0) {  // stored
+                br.drop(br.n & 7);
+                br.refill();
+                const uint32_t len = br.take(16), nlen = br.take(16);
+                if ((len ^ 0xffffu) != nlen) { err = 2; break; }
+                // give the whole bytes of the bit buffer back
+                br.p -= br.n >> 3; br.buf = 0; br.n = 0;
+                if (br.p + len > br.end || o + len > isize) { err = 2; break; }
+                for (uint32_t i = 0; i < len; i++) out[o + i] = br.p[i];
+                o += len; br.p += len;
+                continue;
+            }
+            if (type == 3) { err = 2; break; }
+            if (type == 1) {  // fixed code
+                for (int i = 0; i < 144; i++) lens[i] = 8;
+                for (int i = 144; i < 256; i++) lens[i] = 9;
+                for (int i = 256; i < 280; i++) lens[i] = 7;
+                for (int i = 280; i < 288; i++) lens[i] = 8;
+                build_code(lens, 288, lcount, lsym, llut, INF_LIT_BITS);
+                for (int i = 0; i < 30; i++) lens[i] = 5;
+                build_code(lens, 30, dcount, dsym, dlut, INF_DIST_BITS);
+            } else {  // dynamic code
+                br.refill();
+                const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+                if (nlen > 286 || ndist > 30) { err = 3; break; }
+                const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                for (int i = 0; i < 19; i++) lens[i] = 0;
+                for (int i = 0; i < ncode; i++) { br.refill(); lens[order[i]] = (uint8_t)br.take(3); }
+                uint16_t ccount[16], csym[19], clut[1 << 7];
+                if (!build_code(lens, 19, ccount, csym, clut, 7)) { err = 3; break; }
+                int idx = 0;
+                while (idx < nlen + ndist) {
+                    br.refill();
+                    int sym = decode_symbol(br, ccount, csym, clut, 7);
+                    if (sym < 0) { err = 3; break; }
+                    if (sym < 16) lens[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (idx == 0) { err = 3; break; } val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
+                        else if (sym == 17) rep = 3 + (int)br.take(3);
+                        else rep = 11 + (int)br.take(7);
+                        if (idx + rep > nlen + ndist) { err = 3; break; }
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                }
+                if (err) break;
+                if (lens[256] == 0) { err = 3; break; }
+                uint8_t dl[32];
+                for (int i = 0; i < ndist; i++) dl[i] = lens[nlen + i];
+                if (!build_code(lens, nlen, lcount, lsym, llut, INF_LIT_BITS)) { err = 3; break; }
+                if (!build_code(dl, ndist, dcount, dsym, dlut, INF_DIST_BITS)) { err = 3; break; }
+            }
+            // ---- symbols ----
+            for (;;) {
+                br.refill();
+                int sym = decode_symbol(br, lcount, lsym, llut, INF_LIT_BITS);
+                if (sym < 0) { err = 4; break; }
+                if (sym < 256) {
+                    if (o >= isize) { err = 5; break; }
+                    out[o++] = (uint8_t)sym;
+                    continue;
+                }
+                if (sym == 256) break;
+                sym -= 257;
+                if (sym >= 29) { err = 4; break; }
+                // length / distance bases and extra bits (RFC 1951 3.2.5)
+                const uint32_t lext = sym < 8 ? 0u : (sym == 28 ? 0u : (uint32_t)(sym - 4) >> 2);
+                const uint32_t lbase = sym < 8 ? 3u + (uint32_t)sym : (sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext));
+                const uint32_t len = lbase + br.take((int)lext);
+                br.refill();
+                int ds = decode_symbol(br, dcount, dsym, dlut, INF_DIST_BITS);
+                if (ds < 0 || ds >= 30) { err = 4; break; }
+                const uint32_t dext = ds < 4 ? 0u : (uint32_t)(ds - 2) >> 1;
+                const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext);
+                const uint32_t dist = dbase + br.take((int)dext);
+                if (dist > o || o + len > isize) { err = 5; break; }
+                for (uint32_t i = 0; i < len; i++, o++) out[o] = out[o - dist];
+            }
+        }
+        if (!err && o != isize) err = 6;  // ISIZE of the footer
+        if (!err && P.check_crc) {
+            const uint8_t *f = blk + B.csize - 8;
+            const uint32_t want = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+            if (crc32_update(P.crc_tab, 0u, out, isize) != want) err = 7;
+        }
+    }
+    P.status[bi] = err;
+    if (err) atomicAdd(P.n_bad, 1);
+}
+
+// ---- record walk ----
+struct WalkParams {
+    const pomfret_gpu_bgzf_stream *streams;  // out_off, ubeg, out_bytes (end of the last record), tid, end0
+    uint32_t n_streams;
+    const uint8_t *out;
+    uint32_t *count;        // per stream: records
+    const uint32_t *first;  // per stream: index of its first record (exclusive scan of count), fill pass only
+    uint64_t *rec_off;      // fill pass: offset of every record in `out`
+    uint32_t *rec_stream;
+    int32_t *n_bad;
+    int fill;
+};
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+__global__ void walk_kernel(WalkParams P) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_streams) return;
+    const pomfret_gpu_bgzf_stream S = P.streams[s];
+    uint64_t off = S.out_off + S.ubeg;
+    const uint64_t end = S.out_off + S.out_bytes;
+    uint32_t n = 0;
+    const uint32_t base = P.fill ? P.first[s] : 0u;
+    while (off + 36 <= end) {
+        const uint8_t *r = P.out + off;
+        const uint32_t block_size = ld_u32(r);
+        if (block_size < 32 || off + 4 + block_size > end) { atomicAdd(P.n_bad, 1); break; }  // the chunk does not hold whole records
+        const int32_t tid = (int32_t)ld_u32(r + 4), pos = (int32_t)ld_u32(r + 8);
+        if (tid != S.tid || pos >= (int32_t)S.end0) break;  // sam_itr_next: the query is over (records are coordinate sorted)
+        if (P.fill) { P.rec_off[base + n] = off; P.rec_stream[base + n] = s; }
+        n++;
+        off += 4 + (uint64_t)block_size;
+    }
+    if (!P.fill) P.count[s] = n;
+}
+
+// exclusive scan of the per-stream counts (one CTA; streams are few thousand at most)
+__global__ void scan_counts_kernel(const uint32_t *count, uint32_t *first, uint32_t n, uint32_t *total) {
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_w[33];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? count[i] : 0u;
+        const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+        uint32_t incl = warp_inclusive_sum(v);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < (blockDim.x >> 5) ? s_w[lane] : 0u;
+            uint32_t wi = warp_inclusive_sum(w);
+            s_w[lane] = wi - w;
+            if (lane == 31) s_w[32] = wi;
+        }
+        __syncthreads();
+        if (i < n) first[i] = s_carry + s_w[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+// ---- record slicing ----
+struct SliceParams {
+    const uint8_t *out;
+    const uint64_t *rec_off;
+    const uint32_t *rec_stream;
+    uint32_t n_records;
+    pomfret_gpu_sliced_record *rec;
+    pomfret_gpu_ingest_filter flt;
+};
+
+constexpr int SLICE_WARPS = 4;
+
+__global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) {
+    const uint32_t ri = blockIdx.x * SLICE_WARPS + (threadIdx.x >> 5);
+    if (ri >= P.n_records) return;
+    const unsigned lane = lane_id();
+    const uint8_t *r = P.out + P.rec_off[ri];
+    const uint32_t block_size = ld_u32(r);
+    const uint8_t *endp = r + 4 + block_size;
+    const uint32_t l_qname = r[12], mapq = r[13];
+    uint32_t n_cigar = (uint32_t)r[16] | ((uint32_t)r[17] << 8);
+    const uint32_t flag = (uint32_t)r[18] | ((uint32_t)r[19] << 8);
+    const uint32_t l_qseq = ld_u32(r + 20);
+    const int32_t pos = (int32_t)ld_u32(r + 8);
+    const uint8_t *qname = r + 36;
+    const uint8_t *cigar = qname + l_qname;
+    const uint8_t *seq = cigar + (size_t)n_cigar * 4;
+    const uint8_t *aux = seq + ((size_t)l_qseq + 1) / 2 + l_qseq;
+    pomfret_gpu_sliced_record R;
+    bool bad = aux > endp;  // fields run past the record
+    // ---- aux walk (every lane walks the same tags; only the length of a string is found by the lanes together) ----
+    const uint8_t *mm = nullptr, *mm_lc = nullptr, *ml = nullptr, *ml_lc = nullptr, *mn = nullptr, *md = nullptr, *hp = nullptr,
+                  *de = nullptr, *cg = nullptr;
+    uint32_t mm_len = 0, mm_lc_len = 0, md_len = 0;
+    for (const uint8_t *p = aux; !bad && p + 3 <= endp;) {
+        const uint32_t t0 = p[0], t1 = p[1], ty = p[2];
+        const uint8_t *val = p + 2;  // points at the type byte, like bam_aux_get
+        const uint8_t *q = p + 3;
+        uint32_t zlen = 0;
+        switch (ty) {
+        case 'A': case 'c': case 'C': q += 1; break;
+        case 's': case 'S': q += 2; break;
+        case 'i': case 'I': case 'f': q += 4; break;
+        case 'd': q += 8; break;
+        case 'Z': case 'H': {
+            // first NUL at or behind q, 32 bytes per step
+            for (;;) {
+                const uint8_t *c = q + zlen + lane;
+                const unsigned z = __ballot_sync(FULL_MASK, c >= endp || *c == 0);
+                if (z) { zlen += (uint32_t)__ffs((int)z) - 1u; break; }
+                zlen += 32;
+            }
+            if (q + zlen >= endp) bad = true;
+            q += zlen + 1;
+            break;
+        }
+        case 'B': {
+            if (q + 5 > endp) { bad = true; break; }
+            const uint32_t sub = q[0], cnt = ld_u32(q + 1);
+            const uint32_t es = (sub == 'c' || sub == 'C') ? 1u : (sub == 's' || sub == 'S') ? 2u : (sub == 'i' || sub == 'I' || sub == 'f') ? 4u : 0u;
+            if (!es) { bad = true; break; }
+            q += 5 + (size_t)cnt * es;
+            break;
+        }
+        default: bad = true; break;
+        }
+        if (bad || q > endp) { bad = true; break; }
+        // (bam_aux_get returns the first tag of a name)
+        if (t0 == 'M' && t1 == 'M' && !mm) { mm = val; mm_len = zlen; }
+        else if (t0 == 'M' && t1 == 'm' && !mm_lc) { mm_lc = val; mm_lc_len = zlen; }
+        else if (t0 == 'M' && t1 == 'L' && !ml) ml = val;
+        else if (t0 == 'M' && t1 == 'l' && !ml_lc) ml_lc = val;
+        else if (t0 == 'M' && t1 == 'N' && !mn) mn = val;
+        else if (t0 == 'M' && t1 == 'D' && !md) { md = val; md_len = zlen; }
+        else if (t0 == 'H' && t1 == 'P' && !hp) hp = val;
+        else if (t0 == 'd' && t1 == 'e' && !de) de = val;
+        else if (t0 == 'C' && t1 == 'G' && !cg) cg = val;
+        p = q;
+    }
+    auto aux2i = [](const uint8_t *v, bool *ok) -> int64_t {  // bam_aux2i
+        *ok = true;
+        switch (v[0]) {
+        case 'c': return (int8_t)v[1];
+        case 'C': return v[1];
+        case 's': return (int16_t)((uint32_t)v[1] | ((uint32_t)v[2] << 8));
+        case 'S': return (uint32_t)v[1] | ((uint32_t)v[2] << 8);
+        case 'i': return (int32_t)ld_u32(v + 1);
+        case 'I': return ld_u32(v + 1);
+        default: *ok = false; return 0;
+        }
+    };
+    // ---- long CIGAR in the CG tag (what htslib's bam_read1 restores): placeholder <l_qseq>S<n>N ----
+    if (!bad && cg && n_cigar >= 1 && cg[0] == 'B' && (cg[1] == 'I' || cg[1] == 'i')) {
+        const uint32_t first = ld_u32(cigar), n_real = ld_u32(cg + 2);
+        if ((first & 15u) == 4u && (first >> 4) == l_qseq && n_real >= n_cigar && n_real < (1u << 29) && pos >= 0) {
+            cigar = cg + 6;
+            n_cigar = n_real;
+        }
+    }
+    // ---- bam_endpos ----
+    uint32_t rlen = 0;
+    if (!bad)
+        for (uint32_t i = lane; i < n_cigar; i += 32) {
+            const uint32_t c = ld_u32(cigar + (size_t)i * 4), op = c & 15u;
+            if ((0x18du >> op) & 1u) rlen += c >> 4;
+        }
+    rlen = warp_sum(rlen);
+    if (flag & 4u) rlen = 0;
+    if (rlen == 0) rlen = 1;
+    if (lane != 0) return;
+    // ---- record filters (blockjoin.c:1081-1084 / :1862) ----
+    float de_v = -1.f;
+    if (de) {  // bam_aux2f
+        bool ok;
+        if (de[0] == 'f') { uint32_t u = ld_u32(de + 1); de_v = __uint_as_float(u); }
+        else if (de[0] == 'd') { uint64_t u = (uint64_t)ld_u32(de + 1) | ((uint64_t)ld_u32(de + 5) << 32); de_v = (float)__longlong_as_double((long long)u); }
+        else { const int64_t iv = aux2i(de, &ok); de_v = ok ? (float)iv : 0.f; }
+    }
+    bool keep = !bad && !(flag & (4u | 256u | 2048u));
+    if (keep && mapq < P.flt.min_mapq) keep = false;
+    if (keep && (l_qseq < P.flt.min_len_floor || l_qseq < P.flt.min_len)) keep = false;
+    if (keep && P.flt.check_de && de_v > P.flt.max_de) keep = false;
+    // ---- what describe_record() derives ----
+    memset(&R, 0, sizeof(R));
+    R.pos = (uint32_t)pos; R.end_pos = (uint32_t)pos + rlen; R.l_qseq = l_qseq; R.n_cigar = n_cigar;
+    R.flag = (uint16_t)flag; R.mapq = (uint8_t)mapq;
+    R.stream = P.rec_stream[ri];
+    R.mn = -1; R.ml_len = -1; R.hp = 254; R.hp_irregular = 0;
+    R.cigar = (uint64_t)(uintptr_t)cigar; R.seq = (uint64_t)(uintptr_t)seq;
+    R.qname_dev = (uint64_t)(uintptr_t)qname; R.l_qname = (uint8_t)l_qname;
+    for (uint32_t i = 0; i < sizeof(R.qname) - 1 && i + 1 < l_qname; i++) R.qname[i] = (char)qname[i];
+    const uint8_t *m = mm ? mm : mm_lc;
+    if (m) {
+        if (m[0] != 'Z') { R.tags_malformed = 1; R.mm = (uint64_t)(uintptr_t)(m + 1); R.mm_len = 0; R.has_mm = 1; }
+        else { R.mm = (uint64_t)(uintptr_t)(m + 1); R.mm_len = mm ? mm_len : mm_lc_len; R.has_mm = 1; }
+    }
+    if (mn) {
+        bool ok;
+        const int64_t v = aux2i(mn, &ok);
+        if (v != (int64_t)l_qseq && l_qseq) R.tags_malformed = 1;
+        R.mn = v >= 0 && v <= 0x7fffffff ? (int32_t)v : -1;
+    }
+    const uint8_t *l = ml ? ml : ml_lc;
+    if (l) {
+        if (l[0] != 'B' || l[1] != 'C') R.tags_malformed = 1;
+        else { R.ml = (uint64_t)(uintptr_t)(l + 6); R.ml_len = (int32_t)ld_u32(l + 2); }
+    }
+    if (md && md[0] == 'Z') { R.md = (uint64_t)(uintptr_t)(md + 1); R.md_len = md_len; }
+    if (hp) {  // get_hp_from_aln, blockjoin.c:910-923
+        bool ok;
+        const int64_t v = aux2i(hp, &ok);
+        if (v == 0) R.hp_irregular = 1; else R.hp = (int32_t)(v - 1);
+    }
+    R.keep = keep ? 1 : 0;
+    R.bad = bad ? 1 : 0;
+    P.rec[ri] = R;
+}
+
+}  // namespace pomfret_gpu
+#endif

@@ -47,7 +47,9 @@ bool GpuApi::load(std::string *err) {
     BIND(batch_reset, "pomfret_gpu_batch_reset") BIND(batch_add_read, "pomfret_gpu_batch_add_read")
     BIND(batch_add_reads, "pomfret_gpu_batch_add_reads") BIND(batch_add_reads_shared, "pomfret_gpu_batch_add_reads_shared")
     BIND(batch_add_windows, "pomfret_gpu_batch_add_windows") BIND(host_register, "pomfret_gpu_host_register")
-    BIND(host_unregister, "pomfret_gpu_host_unregister") BIND(batch_add_window, "pomfret_gpu_batch_add_window") BIND(batch_submit, "pomfret_gpu_batch_submit")
+    BIND(host_unregister, "pomfret_gpu_host_unregister") BIND(batch_add_reads_device, "pomfret_gpu_batch_add_reads_device")
+    BIND(batch_ingest_buffer, "pomfret_gpu_batch_ingest_buffer") BIND(batch_ingest_bgzf, "pomfret_gpu_batch_ingest_bgzf")
+    BIND(batch_ingest_records, "pomfret_gpu_batch_ingest_records") BIND(batch_ingest_qname, "pomfret_gpu_batch_ingest_qname") BIND(batch_add_window, "pomfret_gpu_batch_add_window") BIND(batch_submit, "pomfret_gpu_batch_submit")
     BIND(decode, "pomfret_gpu_decode") BIND(haptag, "pomfret_gpu_haptag") BIND(pileup, "pomfret_gpu_pileup")
     BIND(join, "pomfret_gpu_join") BIND(batch_collect, "pomfret_gpu_batch_collect")
     BIND(batch_collect_haptags, "pomfret_gpu_batch_collect_haptags") BIND(batch_end, "pomfret_gpu_batch_end")

@@ -20,6 +20,12 @@ struct GpuApi {
     int (*batch_add_reads_shared)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *, uint32_t, const int64_t *) = nullptr;
     int (*batch_add_window)(pomfret_gpu_batch *, uint32_t, uint32_t, uint32_t, uint32_t) = nullptr;
     int (*batch_add_windows)(pomfret_gpu_batch *, const uint32_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t) = nullptr;
+    int (*batch_add_reads_device)(pomfret_gpu_batch *, const pomfret_gpu_read_desc *, uint32_t, const int64_t *) = nullptr;
+    int (*batch_ingest_buffer)(pomfret_gpu_batch *, size_t, void **) = nullptr;
+    int (*batch_ingest_bgzf)(pomfret_gpu_batch *, const void *, size_t, const pomfret_gpu_bgzf_block *, uint32_t, const pomfret_gpu_bgzf_stream *,
+                             uint32_t, const pomfret_gpu_ingest_filter *, uint32_t *) = nullptr;
+    int (*batch_ingest_records)(pomfret_gpu_batch *, pomfret_gpu_sliced_record *, uint32_t) = nullptr;
+    int (*batch_ingest_qname)(pomfret_gpu_batch *, uint32_t, char *, uint32_t) = nullptr;
     int (*host_register)(pomfret_gpu_ctx *, void *, size_t) = nullptr;
     int (*host_unregister)(pomfret_gpu_ctx *, void *) = nullptr;
     int (*batch_submit)(pomfret_gpu_batch *) = nullptr;

@@ -128,3 +128,41 @@ void *pomfret_host_contig_load(void *bam, const char *chrom) {
 }
 
 }  // extern "C"
+
+// ---- compressed ingest: the block / stream tables of region queries, for the tests and bench.py ----
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "ingest.h"
+extern "C" {
+
+struct HostIngest {
+    IngestPlan plan;
+    std::vector<uint8_t> comp;
+};
+
+// regions: n x (beg0, end0) on `chrom`, one run each; the compressed blocks are read into the handle's own buffer
+void *pomfret_host_ingest_plan(void *bam, const char *chrom, const int64_t *regions, int n) {
+    BamReader &b = *(BamReader *)bam;
+    const int tid = sam_hdr_name2tid(b.hdr, chrom);
+    if (tid < 0) return nullptr;
+    int fd = open(b.fn.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) return nullptr;
+    HostIngest *h = new HostIngest();
+    bool ok = true;
+    for (int i = 0; i < n && ok; i++) ok = ingest_plan_region(b.idx, tid, regions[2 * i], regions[2 * i + 1], (uint32_t)i, (uint64_t)st.st_size, &h->plan);
+    h->comp.assign(h->plan.comp_bytes + 64, 0);
+    std::string err;
+    if (ok) ok = ingest_read(fd, &h->plan, h->comp.data(), &err);
+    close(fd);
+    if (!ok) { delete h; return nullptr; }
+    return h;
+}
+const uint8_t *pomfret_host_ingest_comp(void *h, uint64_t *n) { HostIngest *p = (HostIngest *)h; *n = p->plan.comp_bytes; return p->comp.data(); }
+const pomfret_gpu_bgzf_block *pomfret_host_ingest_blocks(void *h, uint32_t *n) { HostIngest *p = (HostIngest *)h; *n = (uint32_t)p->plan.blocks.size(); return p->plan.blocks.data(); }
+const pomfret_gpu_bgzf_stream *pomfret_host_ingest_streams(void *h, uint32_t *n) { HostIngest *p = (HostIngest *)h; *n = (uint32_t)p->plan.streams.size(); return p->plan.streams.data(); }
+uint32_t pomfret_host_ingest_stream_run(void *h, uint32_t s) { return ((HostIngest *)h)->plan.stream_run[s]; }
+void pomfret_host_ingest_free(void *h) { delete (HostIngest *)h; }
+
+}  // extern "C"

@@ -16,6 +16,10 @@
 #include "gpu_api.h"
 #include "intervals.h"
 #include "loader.h"
+#include "ingest.h"
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace pomfret {
 
@@ -57,6 +61,8 @@ struct Engine {
     }
     // CUDA start-up (driver, contexts: about half a second on a B200 box) runs beside the host work that does not
     // need the device: interval loading, BAM/index opening and the inflate of every worker's first chunk
+    // compressed ingest (BGZF inflate + record slicing on the device) unless POMFRET_HOST_INFLATE is set
+    bool gpu_ingest = getenv("POMFRET_HOST_INFLATE") == nullptr;
     std::shared_future<bool> ready;
     void start_async(int want_gpus, int n_workers) {
         ready = std::async(std::launch::async, [this, want_gpus, n_workers] { return start(want_gpus, n_workers); }).share();
@@ -151,7 +157,7 @@ struct Worker {
         int rc = eng->api.batch_begin(eng->ctx, id, device % std::max(1, eng->n_dev), &batch);
         if (rc != 0) { fprintf(stderr, "[E::%s] batch_begin: %s\n", "pomfret", eng->api.strerror(rc)); exit(1); }
     }
-    void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; arena.release(); }
+    void close() { if (batch) eng->api.batch_end(batch); batch = nullptr; arena.release(); if (fd >= 0) ::close(fd); fd = -1; }
 
     // next record of the iterator, inflated in place into the arena; false at the end
     bool next_record(hts_itr_t *itr) {
@@ -165,26 +171,41 @@ struct Worker {
         return rc >= 0;
     }
 
-    struct Rec { bam1_core_t core; uint8_t *data; int l_data; int hp; int64_t first_slot; };
+    // one alignment record of a chunk, however it was loaded: its descriptor (host pointers into the arena, or device
+    // addresses inside the inflated streams) and its name
+    struct Rec { pomfret_gpu_read_desc desc; const char *qname; int64_t first_slot; };
+    std::vector<Rec> recs;
+    std::vector<std::vector<uint32_t>> win_recs;
+    std::vector<char> names;   // device path: the names of the chunk's records
+    int fd = -1;               // device path: the BAM file for pread()
+    uint64_t file_size = 0;
+    IngestPlan plan;
 
-    // haplotag_region_given_bam for a chunk of windows of one contig.  Windows whose region queries overlap
-    // form a run that is read from the BAM once; a record that lies in several windows is staged and decoded
-    // once (the reference re-opens the file and re-decodes per window, blockjoin.c:1056).
-    void run_chunk(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg,
-                   const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
-        const GpuApi &api = eng->api;
-        double t0 = now_s();
-        int rc;
-        arena.rewind();
-        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
-        std::vector<Rec> recs;
-        std::vector<std::vector<uint32_t>> win_recs(jobs.size());
+    // runs of windows whose region queries overlap: [r0, r1) index ranges into jobs
+    static std::vector<std::pair<size_t, size_t>> runs_of(const std::vector<WindowJob> &jobs) {
+        std::vector<std::pair<size_t, size_t>> runs;
         for (size_t r0 = 0; r0 < jobs.size();) {
             size_t r1 = r0 + 1;
             int64_t run_end = jobs[r0].end0();
             while (r1 < jobs.size() && jobs[r1].beg0() < run_end) { run_end = std::max(run_end, jobs[r1].end0()); r1++; }
-            hts_itr_t *itr = tid >= 0 ? sam_itr_queryi(bam.idx, tid, jobs[r0].beg0(), run_end) : nullptr;
-            if (!itr) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[r0].start, jobs[r0].end); exit(1); }
+            runs.emplace_back(r0, r1);
+            r0 = r1;
+        }
+        return runs;
+    }
+    static int64_t run_end0(const std::vector<WindowJob> &jobs, const std::pair<size_t, size_t> &run) {
+        int64_t e = 0;
+        for (size_t w = run.first; w < run.second; w++) e = std::max(e, jobs[w].end0());
+        return e;
+    }
+
+    // host loader: the shim inflates every run once, records land in the arena
+    void load_chunk_host(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg, const RawTagMap *raw_tags) {
+        arena.rewind();
+        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
+        for (const auto &run : runs_of(jobs)) {
+            hts_itr_t *itr = tid >= 0 ? sam_itr_queryi(bam.idx, tid, jobs[run.first].beg0(), run_end0(jobs, run)) : nullptr;
+            if (!itr) { fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[run.first].start, jobs[run.first].end); exit(1); }
             while (next_record(itr)) {
                 const bam1_t *b = &view;
                 const int flag = b->core.flag;
@@ -197,7 +218,7 @@ struct Worker {
                 if (de > kMinAlnDe) continue;
                 const int64_t pos = b->core.pos, endpos = bam_endpos(b);
                 bool used = false;
-                for (size_t w = r0; w < r1; w++) {
+                for (size_t w = run.first; w < run.second; w++) {
                     if (!(pos < jobs[w].end0() && endpos > jobs[w].beg0())) continue;  // what this window's own query returns
                     if (!used) {
                         int hp;
@@ -205,7 +226,12 @@ struct Worker {
                             auto it = raw_tags->find(bam_get_qname(b));
                             hp = it != raw_tags->end() ? it->second : kHaptagUnphased;
                         } else hp = hp_from_record(b);
-                        recs.push_back({b->core, b->data, b->l_data, hp, -1});
+                        Rec R;
+                        describe_record(b, hp, &R.desc);
+                        R.desc.md = nullptr; R.desc.md_len = 0;  // the window engine does not read MD
+                        R.qname = bam_get_qname(b);
+                        R.first_slot = -1;
+                        recs.push_back(R);
                         arena.commit((size_t)b->l_data);
                         used = true;
                     }
@@ -213,8 +239,106 @@ struct Worker {
                 }
             }
             hts_itr_destroy(itr);
-            r0 = r1;
         }
+    }
+
+    // device loader (compressed ingest): the BGZF blocks of every run's index chunks go to the device as they lie in
+    // the file; inflate, record walk, filters and tag lookup happen there; the host gets one header per record back
+    void load_chunk_device(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg, const RawTagMap *raw_tags) {
+        const GpuApi &api = eng->api;
+        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
+        if (fd < 0) {
+            fd = ::open(bam.fn.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "load_reads_given_interval", bam.fn.c_str()); exit(1); }
+            file_size = (uint64_t)st.st_size;
+        }
+        plan.clear();
+        const auto runs = runs_of(jobs);
+        for (size_t r = 0; r < runs.size(); r++)
+            if (tid < 0 || !ingest_plan_region(bam.idx, tid, jobs[runs[r].first].beg0(), run_end0(jobs, runs[r]), (uint32_t)r, file_size, &plan)) {
+                fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[runs[r].first].start, jobs[runs[r].first].end);
+                exit(1);
+            }
+        need_batch();
+        int rc;
+        if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+        void *comp = nullptr;
+        if ((rc = api.batch_ingest_buffer(batch, plan.comp_bytes + 64, &comp))) die_gpu(api, rc, "ingest_buffer");
+        std::string err;
+        if (!ingest_read(fd, &plan, (uint8_t *)comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
+        pomfret_gpu_ingest_filter flt;
+        memset(&flt, 0, sizeof(flt));
+        flt.min_mapq = (uint32_t)std::max(0, cfg.min_mapq);
+        flt.min_len = (uint32_t)std::max(0, cfg.readlen_threshold);
+        flt.min_len_floor = 2; flt.check_de = 1; flt.max_de = kMinAlnDe;
+        uint32_t n_rec = 0;
+        if ((rc = api.batch_ingest_bgzf(batch, comp, plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
+                                        (uint32_t)plan.streams.size(), &flt, &n_rec)))
+            die_gpu(api, rc, "ingest_bgzf");
+        std::vector<pomfret_gpu_sliced_record> sl(n_rec ? n_rec : 1);
+        if ((rc = api.batch_ingest_records(batch, sl.data(), n_rec))) die_gpu(api, rc, "ingest_records");
+        stats.n_ingest_bytes += plan.comp_bytes;
+        names.clear();
+        names.reserve((size_t)n_rec * 40);
+        std::vector<size_t> name_off;
+        for (uint32_t i = 0; i < n_rec; i++) {
+            const pomfret_gpu_sliced_record &S = sl[i];
+            if (S.bad) { fprintf(stderr, "[E::%s] malformed alignment record in %s\n", "pomfret", bam.fn.c_str()); exit(1); }
+            if (!S.keep) continue;
+            const auto &run = runs[plan.stream_run[S.stream]];
+            bool used = false;
+            for (size_t w = run.first; w < run.second; w++) {
+                if (!((int64_t)S.pos < jobs[w].end0() && (int64_t)S.end_pos > jobs[w].beg0())) continue;
+                if (!used) {
+                    // the whole name (records with names longer than the inline prefix are fetched one by one)
+                    name_off.push_back(names.size());
+                    if (S.l_qname <= sizeof(S.qname)) names.insert(names.end(), S.qname, S.qname + strlen(S.qname) + 1);
+                    else {
+                        char buf[256];
+                        if ((rc = api.batch_ingest_qname(batch, i, buf, sizeof(buf)))) die_gpu(api, rc, "ingest_qname");
+                        names.insert(names.end(), buf, buf + strlen(buf) + 1);
+                    }
+                    const char *qn = names.data() + name_off.back();
+                    int hp = S.hp;
+                    if (raw_tags) {
+                        auto it = raw_tags->find(qn);
+                        hp = it != raw_tags->end() ? it->second : kHaptagUnphased;
+                    } else if (S.hp_irregular)
+                        fprintf(stderr, "[W::%s] irregular HP tag? qn=%s qs=%d\n", "get_hp_from_aln", qn, (int)S.pos);
+                    Rec R;
+                    pomfret_gpu_read_desc &d = R.desc;
+                    memset(&d, 0, sizeof(d));
+                    d.pos = S.pos; d.l_qseq = S.l_qseq; d.n_cigar = S.n_cigar; d.flag = S.flag; d.mapq = S.mapq;
+                    d.tags_malformed = S.tags_malformed; d.hp = hp; d.mn = S.mn;
+                    d.cigar = (const uint32_t *)(uintptr_t)S.cigar; d.seq = (const uint8_t *)(uintptr_t)S.seq;
+                    d.mm = S.has_mm ? (const char *)(uintptr_t)S.mm : nullptr; d.mm_len = S.mm_len;
+                    d.ml = (const uint8_t *)(uintptr_t)S.ml; d.ml_len = S.ml_len;
+                    d.reserved = S.end_pos;
+                    R.qname = nullptr;  // set below: `names` may still move
+                    R.first_slot = -1;
+                    recs.push_back(R);
+                    used = true;
+                }
+                win_recs[w].push_back((uint32_t)recs.size() - 1);
+            }
+        }
+        for (size_t i = 0; i < recs.size(); i++) recs[i].qname = names.data() + name_off[i];
+    }
+
+    // haplotag_region_given_bam for a chunk of windows of one contig.  Windows whose region queries overlap
+    // form a run that is read from the BAM once; a record that lies in several windows is staged and decoded
+    // once (the reference re-opens the file and re-decodes per window, blockjoin.c:1056).
+    void run_chunk(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg,
+                   const RawTagMap *raw_tags, std::vector<WindowOut> *outs) {
+        const GpuApi &api = eng->api;
+        double t0 = now_s();
+        int rc;
+        recs.clear();
+        win_recs.assign(jobs.size(), {});
+        const bool on_device = eng->gpu_ingest;
+        if (on_device) load_chunk_device(chrom, jobs, cfg, raw_tags);
+        else load_chunk_host(chrom, jobs, cfg, raw_tags);
         // slots in window order; the second and later uses of a record share the first one's payload and calls
         std::vector<pomfret_gpu_read_desc> descs;
         std::vector<int64_t> same_as;
@@ -225,32 +349,33 @@ struct Worker {
             w_first.push_back((uint32_t)descs.size()); w_n.push_back((uint32_t)win_recs[w].size());
             for (uint32_t ri : win_recs[w]) {
                 Rec &R = recs[ri];
-                pomfret_gpu_read_desc d;
                 if (R.first_slot < 0) {
-                    bam1_t tmp;
-                    memset(&tmp, 0, sizeof(tmp));
-                    tmp.core = R.core; tmp.data = R.data; tmp.l_data = R.l_data;
-                    describe_record(&tmp, R.hp, &d);
-                    d.md = nullptr; d.md_len = 0;  // the window engine does not read MD
                     R.first_slot = (int64_t)descs.size();
                     same_as.push_back(-1);
-                    stats.n_bases += d.l_qseq;
+                    stats.n_bases += R.desc.l_qseq;
+                    descs.push_back(R.desc);
                 } else {
+                    pomfret_gpu_read_desc d;
                     memset(&d, 0, sizeof(d));
-                    d.pos = (uint32_t)R.core.pos; d.l_qseq = (uint32_t)R.core.l_qseq; d.n_cigar = R.core.n_cigar; d.hp = R.hp;
+                    d.pos = R.desc.pos; d.l_qseq = R.desc.l_qseq; d.n_cigar = R.desc.n_cigar; d.hp = R.desc.hp;
                     d.mn = -1; d.ml_len = -1;
                     same_as.push_back(R.first_slot);
                     any_shared = true;
                     stats.n_shared++;
+                    descs.push_back(d);
                 }
-                descs.push_back(d);
             }
             stats.n_reads += win_recs[w].size();
         }
-        need_batch();
-        if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
-        if (!descs.empty() && (rc = api.batch_add_reads_shared(batch, descs.data(), (uint32_t)descs.size(), any_shared ? same_as.data() : nullptr)))
-            die_gpu(api, rc, "batch_add_reads");
+        if (!on_device) {
+            need_batch();
+            if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+        }
+        if (!descs.empty()) {
+            rc = on_device ? api.batch_add_reads_device(batch, descs.data(), (uint32_t)descs.size(), any_shared ? same_as.data() : nullptr)
+                           : api.batch_add_reads_shared(batch, descs.data(), (uint32_t)descs.size(), any_shared ? same_as.data() : nullptr);
+            if (rc) die_gpu(api, rc, "batch_add_reads");
+        }
         if ((rc = api.batch_add_windows(batch, w_start.data(), w_end.data(), w_first.data(), w_n.data(), (uint32_t)jobs.size()))) die_gpu(api, rc, "batch_add_window");
         stats.n_windows += jobs.size();
         double t1 = now_s();
@@ -268,7 +393,7 @@ struct Worker {
         outs->assign(jobs.size(), WindowOut());
         for (size_t w = 0; w < jobs.size(); w++) {
             const size_t n = win_recs[w].size();
-            auto qname = [&](size_t i) { return (const char *)recs[win_recs[w][i]].data; };
+            auto qname = [&](size_t i) { return recs[win_recs[w][i]].qname; };
             // duplicated read names among the loaded records are fatal (blockjoin.c:1143-1155)
             std::unordered_set<std::string> seen;
             for (size_t i = 0; i < n; i++) {
@@ -463,7 +588,7 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
                 wid, wk.device, n_own, n_helped, tw1 - tw0, tw2 - tw1, wk.stats.t_load, wk.stats.t_gpu, now_s() - tw2);
         std::lock_guard<std::mutex> lock(mu);
         stats->n_windows += wk.stats.n_windows; stats->n_reads += wk.stats.n_reads; stats->n_bases += wk.stats.n_bases;
-        stats->n_shared += wk.stats.n_shared;
+        stats->n_shared += wk.stats.n_shared; stats->n_ingest_bytes += wk.stats.n_ingest_bytes;
         stats->t_load += wk.stats.t_load; stats->t_gpu += wk.stats.t_gpu;
     };
     std::vector<std::thread> th;

@@ -14,6 +14,7 @@ namespace pomfret {
 
 struct RunStats {
     uint64_t n_windows = 0, n_reads = 0, n_bases = 0;      // window slots / bases of the distinct records behind them
+    uint64_t n_ingest_bytes = 0;                           // compressed bytes shipped to the device (compressed ingest)
     uint64_t n_shared = 0;                                 // slots that reuse a record staged and decoded for an earlier window
     uint64_t n_haptag_reads = 0, n_haptag_bases = 0;       // records fed to the -u haplotagger
     double t_load = 0, t_gpu = 0, t_haptag = 0, t_total = 0;

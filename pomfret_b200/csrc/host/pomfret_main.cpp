@@ -42,6 +42,9 @@ int main(int argc, char **argv) {
         fprintf(stderr, "[M::%s] windows %llu, reads %llu, bases %llu; haplotagged reads %llu; load %.2fs, gpu %.2fs, haptag %.2fs\n", "main",
                 (unsigned long long)stats.n_windows, (unsigned long long)stats.n_reads, (unsigned long long)stats.n_bases,
                 (unsigned long long)stats.n_haptag_reads, stats.t_load, stats.t_gpu, stats.t_haptag);
+    if (stats.n_shared || stats.n_ingest_bytes)
+        fprintf(stderr, "[M::%s] %llu window slots reuse a record decoded for another window; %.1f MB of BGZF blocks inflated on the device\n", "main",
+                (unsigned long long)stats.n_shared, stats.n_ingest_bytes / 1e6);
     fprintf(stderr, "[M::%s] used: %.1fs, peak RSS %.1fGiB\n", "main", get_T() - T, get_U());
     return ret;
 }

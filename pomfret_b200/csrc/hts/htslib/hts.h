@@ -42,6 +42,8 @@ htsFile *hts_open(const char *fn, const char *mode);
 int hts_close(htsFile *fp);
 void hts_idx_destroy(hts_idx_t *idx);
 void hts_itr_destroy(hts_itr_t *itr);
+/* shim extension (not htslib API): the (begin, end) virtual-offset pairs of the file chunks of a region iterator */
+int pomfret_itr_chunks(const hts_itr_t *itr, const uint64_t **pairs);
 
 /* shim extension: number of records / uncompressed bytes pulled through
  * iterators by this process (used by the throughput harness). */

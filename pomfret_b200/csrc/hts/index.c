@@ -227,6 +227,14 @@ hts_itr_t *sam_itr_querys(const hts_idx_t *idx, sam_hdr_t *hdr, const char *regi
     return sam_itr_queryi(idx, tid, beg, end);
 }
 
+/* shim extension: the file chunks an iterator would walk, as (begin, end) virtual offsets in file order
+ * (a loader that ships the BGZF blocks to the device instead of inflating them here) */
+int pomfret_itr_chunks(const hts_itr_t *itr, const uint64_t **pairs) {
+    if (!itr || itr->whole_file) return -1;
+    *pairs = (const uint64_t *)itr->chunks;
+    return itr->n_chunks;
+}
+
 int sam_itr_next(htsFile *htsfp, hts_itr_t *itr, bam1_t *r) {
     if (!itr || !htsfp) return -2;
     BGZF *fp = htsfp->fp.bgzf;

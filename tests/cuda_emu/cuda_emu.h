@@ -171,6 +171,7 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
 }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -93,3 +93,16 @@ def test_methphase_untagged_multi_gpu(built, tmp_path):
     data = conftest.run_synth(str(tmp_path / "unt"), ["-c", "30", "-s", "35", "-C", "chr1:248956422:1000000-1700000", "-C",
                                                       "chr2:242193529:5000000-5600000", "--untagged"])
     run_both(str(tmp_path), data, ["-u", "-t", "4", "-c", "30", "--gpus", "2"], None, [".mp.gtf", ".mp.vcf"])
+
+
+def test_methphase_host_inflate_loader(synth30, tmp_path, monkeypatch):
+    # the host loader (shim inflate into the record arena) stays available: same files
+    monkeypatch.setenv("POMFRET_HOST_INFLATE", "1")
+    run_both(str(tmp_path), synth30, ["-t", "4", "-c", "30", "--write-bam"], None, [".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"])
+
+
+def test_methphase_pinned_record_slabs(synth30, tmp_path, monkeypatch):
+    # host loader with registered (pinned, mapped) record slabs: payloads gathered by the device over PCIe
+    monkeypatch.setenv("POMFRET_HOST_INFLATE", "1")
+    monkeypatch.setenv("POMFRET_PIN_RECORDS", "1")
+    run_both(str(tmp_path), synth30, ["-t", "3", "-c", "30"], None, [".mp.gtf", ".mp.vcf"])

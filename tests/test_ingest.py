@@ -1,0 +1,209 @@
+"""Compressed ingest: BGZF inflate + BAM record slicing on the device.
+  * inflate_kernel against zlib, byte for byte, on the blocks of real region queries at deflate levels 0 (stored
+    blocks), 1, 6 and 9 (dynamic codes), and on hand-made members with fixed Huffman codes; corrupted blocks are
+    reported (CRC-32 / ISIZE);
+  * walk + slice kernels against the host loader: the records sam_itr_next returns for the same query, field by field;
+  * the whole hot path fed by add_reads_device() against the oracle port, window by window.
+The CPU run steps the kernels on the SIMT emulator; the `gpu` tests run the same checks on the CUDA library."""
+import ctypes as C
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import conftest
+import oracle_bindings as ob
+import parity
+import pomfret_b200 as pb
+from pomfret_b200 import _ffi
+
+READBACK = 50000
+
+
+def region_of(s, e):
+    beg = max(s - READBACK, 0) - 1
+    return (max(beg, 0), e + READBACK)
+
+
+def zlib_inflate_blocks(plan):
+    """reference answer: every BGZF block of the plan through zlib, concatenated per stream"""
+    comp = np.ctypeslib.as_array(C.cast(plan["comp"], C.POINTER(C.c_uint8)), shape=(plan["comp_bytes"],))
+    blocks = C.cast(plan["blocks"], C.POINTER(_ffi.BgzfBlock))
+    streams = C.cast(plan["streams"], C.POINTER(_ffi.BgzfStream))
+    out = []
+    for s in range(plan["n_streams"]):
+        S = streams[s]
+        data = b""
+        for bi in range(S.first_block, S.first_block + S.n_blocks):
+            B = blocks[bi]
+            raw = bytes(comp[B.comp_off:B.comp_off + B.csize])
+            xlen = struct.unpack_from("<H", raw, 10)[0]
+            data += zlib.decompress(raw[12 + xlen:-8], -15)
+        out.append(data[:S.out_bytes])
+    return out
+
+
+def check_ingest(gpu, data, cov, readlen, max_windows=2, full_pipeline=True):
+    host = pb.load_host()
+    hb = host.bam_open(data["bam"])
+    cfg, ocfg = pb.make_config(cov, readlen=readlen), ob.make_config(cov, readlen=readlen)
+    gaps = data["gaps"][:max_windows]
+    chrom = gaps[0][0]
+    gaps = [g for g in gaps if g[0] == chrom]
+    regions = [region_of(s, e) for _, s, e, _ in gaps]
+    plan = host.ingest_plan(hb, chrom, regions)
+    assert plan["n_streams"] >= len(gaps) and plan["n_blocks"] >= plan["n_streams"]
+    ctx = gpu.init()
+    b = gpu.batch_begin(ctx)
+    flt = _ffi.IngestFilter(cfg.min_mapq, cfg.readlen_threshold, 2, 1, 0.1)
+    rc, recs, n = b.ingest_bgzf(plan["comp"], plan["comp_bytes"], plan["blocks"], plan["n_blocks"], plan["streams"], plan["n_streams"], flt)
+    # (1) inflate, byte for byte
+    for s, want in enumerate(zlib_inflate_blocks(plan)):
+        got = bytes(b.inflated(s))
+        assert got == want, "stream %d differs from zlib" % s
+    # (2) records of every query against the host loader (the shim's iterator + filters)
+    wins = parity.load_windows(host, hb, gaps, cfg)
+    dsz = C.sizeof(_ffi.ReadDesc)
+    per_run = {}
+    for i in range(n):
+        R = recs[i]
+        assert not R.bad
+        per_run.setdefault(plan["stream_run"][R.stream], []).append(R)
+    descs_all, layout = [], []
+    for wi, ((w, nw, _, s, e), (beg0, end0)) in enumerate(zip(wins, regions)):
+        mine = [R for R in per_run.get(wi, []) if R.keep and R.pos < end0 and R.end_pos > beg0]
+        base = host.window_descs(w)
+        names = host.window_qnames(w)
+        assert len(mine) == nw, (wi, len(mine), nw)
+        arr = (_ffi.ReadDesc * max(nw, 1))()
+        for k, R in enumerate(mine):
+            d = _ffi.ReadDesc.from_address(base + k * dsz)
+            assert (R.pos, R.l_qseq, R.n_cigar, R.flag, R.mapq, R.tags_malformed, R.hp, R.mn, R.mm_len, R.ml_len) == \
+                   (d.pos, d.l_qseq, d.n_cigar, d.flag, d.mapq, d.tags_malformed, d.hp, d.mn, d.mm_len, d.ml_len), (wi, k)
+            assert R.qname.decode() == names[k]
+            a = arr[k]
+            a.pos, a.l_qseq, a.n_cigar, a.flag, a.mapq = R.pos, R.l_qseq, R.n_cigar, R.flag, R.mapq
+            a.tags_malformed, a.hp, a.mn = R.tags_malformed, R.hp, R.mn
+            a.cigar, a.seq = R.cigar, R.seq
+            a.mm = R.mm if R.has_mm else None
+            a.mm_len, a.ml, a.ml_len = R.mm_len, R.ml, R.ml_len
+            a.md, a.md_len, a.reserved = None, 0, R.end_pos
+        descs_all.append(arr)
+    if full_pipeline:
+        # (3) the hot path on the ingested records against the oracle
+        for (w, nw, _, s, e), arr in zip(wins, descs_all):
+            first = b.add_reads_device(arr, nw)
+            b.add_window(s, e, first, nw)
+            layout.append((first, nw))
+        b.submit(); b.decode(cfg.lo, cfg.hi); b.pileup(cfg); b.join(cfg)
+        res, tags, ids, rc = b.collect(check=False)
+        assert rc == 0
+        for wi, ((w, nw, chrom_, s, e), (first, _)) in enumerate(zip(wins, layout)):
+            p = ob.port_window(host.window_descs(w), nw, s, e, ocfg)
+            bad = parity.compare_window(b, wi, first, nw, res, tags, ids, p)
+            assert not bad, (chrom_, s, e, bad[:8])
+    for w, *_ in wins:
+        host.window_free(w)
+    b.end()
+    gpu.destroy(ctx)
+    host.ingest_free(plan)
+    host.bam_close(hb)
+    return n
+
+
+def bgzf_member(payload, deflated):
+    """a BGZF block around an already deflated payload"""
+    bsize = 12 + 6 + len(deflated) + 8 - 1
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + deflated +
+            struct.pack("<II", zlib.crc32(payload) & 0xffffffff, len(payload)))
+
+
+def check_handmade_members(gpu):
+    """fixed-Huffman members (zlib strategy Z_FIXED), a stored member, an empty member; then a flipped byte"""
+    rng = np.random.default_rng(3)
+    payloads = [bytes(rng.integers(0, 4, size=5000, dtype=np.uint8)), b"A" * 70 + bytes(range(256)) * 20, b"", b"x"]
+    members = []
+    for i, p in enumerate(payloads):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 9, zlib.Z_FIXED if i % 2 == 0 else zlib.Z_DEFAULT_STRATEGY)
+        members.append(bgzf_member(p, co.compress(p) + co.flush()))
+    stored = bytes(rng.integers(0, 256, size=300, dtype=np.uint8))
+    co = zlib.compressobj(0, zlib.DEFLATED, -15)
+    members.append(bgzf_member(stored, co.compress(stored) + co.flush()))
+    payloads.append(stored)
+    comp = np.frombuffer(b"".join(members), dtype=np.uint8).copy()
+    blocks = (_ffi.BgzfBlock * len(members))()
+    streams = (_ffi.BgzfStream * len(members))()
+    co_, oo = 0, 0
+    for i, (m, p) in enumerate(zip(members, payloads)):
+        blocks[i] = _ffi.BgzfBlock(co_, len(m), len(p), oo)
+        streams[i] = _ffi.BgzfStream(oo, len(p), len(p), 0, 0, i, 1, 0)  # ubeg = end: no records to walk
+        co_ += len(m)
+        oo += (len(p) + 15) & ~15
+    ctx = gpu.init()
+    b = gpu.batch_begin(ctx)
+    rc, recs, n = b.ingest_bgzf(comp.ctypes.data, len(comp), blocks, len(members), streams, len(members))
+    assert rc == 0 and n == 0
+    for i, p in enumerate(payloads):
+        assert bytes(b.inflated(i)) == p, i
+    # one flipped payload byte: CRC-32 (or the code itself) must catch it
+    bad = comp.copy()
+    bad[40] ^= 0x10
+    b.reset()
+    rc, _, _ = b.ingest_bgzf(bad.ctypes.data, len(bad), blocks, len(members), streams, len(members), check=False)
+    assert rc != 0
+    b.end()
+    gpu.destroy(ctx)
+
+
+@pytest.fixture(scope="module")
+def emu_gpu(built):
+    import build_emu
+    return pb.load_gpu(build_emu.build())
+
+
+@pytest.mark.emu
+def test_ingest_emulated(emu_gpu, synth_small):
+    assert check_ingest(emu_gpu, synth_small, 36, 2000, max_windows=1) > 500
+
+
+@pytest.mark.emu
+def test_inflate_handmade_members_emulated(emu_gpu):
+    check_handmade_members(emu_gpu)
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("level", [0, 6])
+def test_ingest_deflate_levels_emulated(emu_gpu, built, tmp_path, level):
+    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "30", "-s", "12", "-C", "chrT:300000:0-160000", "--readlen", "3000", "--block", "60000",
+                                                     "--gap", "8000-10000", "-l", str(level), "--qual"])
+    check_ingest(emu_gpu, data, 30, 1500, max_windows=1, full_pipeline=False)
+
+
+@pytest.mark.gpu
+def test_ingest_gpu_30x(built, synth30):
+    assert check_ingest(pb.load_gpu(), synth30, 30, 15000, max_windows=4) > 300
+
+
+@pytest.mark.gpu
+def test_ingest_gpu_60x(built, synth60):
+    check_ingest(pb.load_gpu(), synth60, 60, 15000, max_windows=5)
+
+
+@pytest.mark.gpu
+def test_ingest_gpu_long_cigar(built, synth_long_cigar):
+    # CG-tag records: the slicing kernel hands out the real CIGAR
+    check_ingest(pb.load_gpu(), synth_long_cigar, 30, 15000, max_windows=1)
+
+
+@pytest.mark.gpu
+def test_inflate_handmade_members_gpu(built):
+    check_handmade_members(pb.load_gpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_ingest_deflate_levels_gpu(built, tmp_path, level):
+    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "30", "-s", "12", "-C", "chr20:64444167:3000000-3600000", "--block", "200000",
+                                                     "--gap", "20000-40000", "-l", str(level), "--qual"])
+    check_ingest(pb.load_gpu(), data, 30, 15000, max_windows=2)

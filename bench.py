@@ -127,12 +127,16 @@ def make_workload(tmp, tag, n_contigs, contig_mb, cov, seed, tagged=True):
     return conftest.run_synth(os.path.join(tmp, tag), synth_args(n_contigs, contig_mb, cov, seed, tagged))
 
 
-def wall(cmd, env=None):
+def wall(cmd, env=None, want_startup=False):
     t0 = time.perf_counter()
     p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, text=True)
     dt = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError("%s failed: %s" % (" ".join(cmd[:3]), p.stderr[-1500:]))
+    if want_startup:  # the front end reports how long the CUDA driver / context start-up took
+        import re
+        m = re.search(r"engine ready after ([0-9.]+)s", p.stderr)
+        return dt, float(m.group(1)) if m else None
     return dt
 
 
@@ -143,9 +147,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cov", type=int, default=60)
-    ap.add_argument("--contigs", type=int, default=env_int("POMFRET_BENCH_CONTIGS", 12))
-    ap.add_argument("--contig-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_CONTIG_MB", "2.5")))
-    ap.add_argument("--replicas", type=int, default=env_int("POMFRET_BENCH_REPLICAS", 16),
+    ap.add_argument("--contigs", type=int, default=env_int("POMFRET_BENCH_CONTIGS", 16))
+    ap.add_argument("--contig-mb", type=float, default=float(os.environ.get("POMFRET_BENCH_CONTIG_MB", "5")))
+    ap.add_argument("--replicas", type=int, default=env_int("POMFRET_BENCH_REPLICAS", 6),
                     help="times the sample's windows are staged (as distinct records) to form one WGS-scale batch")
     ap.add_argument("--cpu-sample-windows", type=int, default=24)
     ap.add_argument("--e2e-batches", type=int, default=4, help="region chunks per step on the end-to-end path")
@@ -525,6 +529,30 @@ def main():
         if u_ms > 0:
             untagged = {"reads": u_reads, "bases": u_bases, "haptag_ms": u_ms, "bytes": u_bytes, "data": udata}
 
+    # ---- compressed ingest (what the front end does instead of host inflate): BGZF blocks of the sample's region queries
+    #      from host memory -> inflate_kernel -> record walk + slicing, per contig (rank 0) ----
+    ingest = None
+    if rank == 0:
+        ib = gpu.batch_begin(ctx, 60, local_rank)
+        flt = _ffi.IngestFilter(cfg.min_mapq, cfg.readlen_threshold, 2, 1, 0.1)
+        tot = {"in": 0, "out": 0, "inflate_ms": 0.0, "slice_ms": 0.0, "records": 0, "blocks": 0, "wall": 0.0}
+        for chrom in sorted({g[0] for g in data["gaps"]}):
+            regions = [(max(max(s_ - 50000, 0) - 1, 0), e_ + 50000) for c_, s_, e_, _ in data["gaps"] if c_ == chrom]
+            plan = host.ingest_plan(hb, chrom, regions)
+            for it in range(2):
+                ib.reset()
+                t0 = time.perf_counter()
+                rc_, recs_, n_ = ib.ingest_bgzf(plan["comp"], plan["comp_bytes"], plan["blocks"], plan["n_blocks"], plan["streams"],
+                                                plan["n_streams"], flt)
+                dt_ = time.perf_counter() - t0
+            t = ib.timing()
+            tot["in"] += t.inflate_in_bytes; tot["out"] += t.inflate_out_bytes; tot["inflate_ms"] += t.inflate_ms
+            tot["slice_ms"] += t.slice_ms; tot["records"] += n_; tot["blocks"] += plan["n_blocks"]; tot["wall"] += dt_
+            host.ingest_free(plan)
+        ib.end()
+        if tot["inflate_ms"] > 0:
+            ingest = tot
+
     # ---- the drop-in CLI against the unmodified reference CLI on the same files (rank 0; uses all N devices) ----
     cli = {}
     if rank == 0 and not args.skip_cli and os.path.exists(ob.REF_BIN):
@@ -539,17 +567,20 @@ def main():
                 continue
             po, pr = os.path.join(tmp, key + "_ours"), os.path.join(tmp, key + "_ref")
             common = extra + ["--vcf", d["vcf"], d["bam"]]
-            t_ours = min(wall([mine, sub, "-t", thr, "--gpus", str(world), "-o", po] + common, env) for _ in range(2))
+            t_ours, t_start = min(wall([mine, sub, "-t", thr, "--gpus", str(world), "-o", po] + common, env, True) for _ in range(2))
             t_ref = wall([ob.REF_BIN, sub, "-t", thr, "-o", pr] + common)
             suffixes = [".report.tsv"] if sub == "report" else [".mp.gtf", ".mp.vcf"]
             same = all(open(po + s_, "rb").read() == open(pr + s_, "rb").read() for s_ in suffixes)
             if not same:
                 raise RuntimeError("%s: output files differ from the reference's" % key)
             cli[key] = {"ours_s": t_ours, "reference_s": t_ref, "speedup": t_ref / t_ours, "threads": int(thr), "gpus": world,
-                        "outputs_identical": True,
-                        "what": "wall time of `pomfret %s %s` on the un-replicated sample files, BGZF inflate, index, "
-                                "VCF and writers included; both binaries read the files through the same single-threaded "
-                                "zlib shim" % (sub, " ".join(extra))}
+                        "outputs_identical": True, "ours_cuda_startup_s": t_start,
+                        "speedup_without_cuda_startup": t_ref / max(t_ours - (t_start or 0.0), 1e-3),
+                        "what": "wall time of `pomfret %s %s` on the un-replicated sample files, index, VCF and writers included. "
+                                "The reference inflates BGZF through the single-threaded zlib shim on %s threads; this "
+                                "front end ships the blocks to the device (inflate_kernel).  ours_s includes the CUDA "
+                                "driver/context start-up of the process (ours_cuda_startup_s), which a whole-genome "
+                                "run amortises and a sample of this size does not" % (sub, " ".join(extra), thr)}
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
@@ -613,6 +644,20 @@ def main():
                                     "resident, CUDA-event time"}
         line["roofline_haptag"] = {"kernel": "haptag_kernel", "bound": "hbm", "achieved": hap_gbs, "peak": peaks["hbm_gbs"],
                                    "unit": "GB/s", "frac": hap_gbs / peaks["hbm_gbs"], "algorithmic_bytes": int(untagged["bytes"])}
+    if ingest:
+        gbs_out = ingest["out"] / (ingest["inflate_ms"] * 1e-3) / 1e9
+        line["ingest"] = {"inflate_out_gbs": gbs_out, "inflate_in_gbs": ingest["in"] / (ingest["inflate_ms"] * 1e-3) / 1e9,
+                          "inflate_ms": ingest["inflate_ms"], "slice_ms": ingest["slice_ms"], "blocks": ingest["blocks"],
+                          "records": ingest["records"], "compressed_bytes": int(ingest["in"]), "inflated_bytes": int(ingest["out"]),
+                          "call_s": ingest["wall"],
+                          "what": "BGZF blocks of the sample's region queries from host memory: H2D, inflate_kernel (one warp per block, "
+                                  "ISIZE + CRC-32 checked), record walk and slicing; one launch per contig; call_s is the wall time of the "
+                                  "C-ABI calls incl. the D2H of the record headers"}
+        line["roofline_inflate"] = {"kernel": "inflate_kernel", "bound": "hbm", "achieved": gbs_out + ingest["in"] / (ingest["inflate_ms"] * 1e-3) / 1e9,
+                                    "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": (gbs_out + ingest["in"] / (ingest["inflate_ms"] * 1e-3) / 1e9) / peaks["hbm_gbs"],
+                                    "algorithmic_bytes": int(ingest["in"] + ingest["out"]),
+                                    "note": "bit-serial Huffman decoding: bound by the latency of one lane per block, not by HBM"}
     line.update(cli)
     if cpu:
         line["cpu_baseline"] = cpu

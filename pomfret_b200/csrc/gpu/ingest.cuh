@@ -36,24 +36,44 @@ struct InflateParams {
     int check_crc;
 };
 
-// ---- bit reader over the deflate payload of one block ----
-struct BitReader {
-    const uint8_t *p, *end;
+// ---- one warp per BGZF block ----
+// Lane 0 walks the Huffman codes (the bit-serial part of DEFLATE) over a window of the compressed bytes that the warp
+// keeps staged in shared memory, and turns them into tokens (literal byte / length + distance), 32 at a time; the 32
+// lanes then write the literals in one store and copy each match together (a match whose distance is shorter than
+// its length repeats a pattern that is already complete in front of it, so every byte of it is independent).
+// Code tables live in shared memory too.  The warp finally checks ISIZE and the CRC-32 of what it wrote: 32 segment
+// CRCs (slicing-by-4 tables) folded with the x^(8n) mod P operator.
+constexpr int INF_LIT_BITS = 9, INF_DIST_BITS = 6;
+constexpr int INF_WARPS = 8;             // warps (blocks in flight) per CTA
+constexpr uint32_t INF_WIN = 2048;       // staged window of the compressed payload
+constexpr uint32_t INF_TOKENS = 32;
+
+struct InflateWarpSmem {
+    __align__(16) uint8_t win[INF_WIN + 16];
+    uint16_t llut[1 << INF_LIT_BITS], dlut[1 << INF_DIST_BITS], clut[1 << 7];
+    uint16_t lcount[16], dcount[16], ccount[16];
+    uint16_t lsym[288], dsym[32], csym[19];
+    uint8_t lens[320];
+    uint32_t tokens[INF_TOKENS];
+    uint32_t crc[32];
+};
+
+struct BitReader {  // over the staged window; positions are offsets inside the window
+    const uint8_t *w;
+    uint32_t pos;   // next byte of the window to load
     uint64_t buf;
     int n;
     __device__ __forceinline__ void refill() {
-        while (n <= 56 && p < end) { buf |= (uint64_t)(*p++) << n; n += 8; }
+        while (n <= 56) { buf |= (uint64_t)w[pos++] << n; n += 8; }  // (the window is refilled long before pos reaches its end)
     }
     __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)buf & ((1u << k) - 1u); }
     __device__ __forceinline__ void drop(int k) { buf >>= k; n -= k; }
     __device__ __forceinline__ uint32_t take(int k) { uint32_t v = peek(k); drop(k); return v; }
 };
 
-constexpr int INF_LIT_BITS = 9, INF_DIST_BITS = 6;
-
 // Canonical Huffman code of `n` symbols with the given lengths: counts per length, symbols in code order, and a
 // first-level table of `bits` bits (entry: symbol | length << 12; 0: longer code or unused).  Returns false for an
-// over-subscribed set of lengths.
+// over-subscribed set of lengths.  (one lane)
 __device__ bool build_code(const uint8_t *lens, int n, uint16_t *count /*[16]*/, uint16_t *symbol, uint16_t *lut, int bits) {
     for (int i = 0; i < 16; i++) count[i] = 0;
     for (int i = 0; i < n; i++) count[lens[i]]++;
@@ -77,7 +97,7 @@ __device__ bool build_code(const uint8_t *lens, int n, uint16_t *count /*[16]*/,
     return true;
 }
 
-// one symbol: first-level table, else the canonical walk (RFC 1951 3.2.2) from the first length behind the table
+// one symbol: first-level table, else the canonical walk (RFC 1951 3.2.2)
 __device__ __forceinline__ int decode_symbol(BitReader &br, const uint16_t *count, const uint16_t *symbol, const uint16_t *lut, int bits) {
     const uint16_t e = lut[br.peek(bits)];
     if (e) { br.drop(e >> 12); return e & 0xfff; }
@@ -103,12 +123,37 @@ __device__ __forceinline__ uint32_t crc32_update(const uint32_t *tab, uint32_t c
     while (n--) crc = tab[(crc ^ *p++) & 0xffu] ^ (crc >> 8);
     return ~crc;
 }
+// a(x) * b(x) mod P over GF(2), reflected representation (x^0 is bit 31)
+__device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1u)) == 0) break; }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1;
+    }
+    return p;
+}
+// x^(8 n) mod P; x2n[i] = x^(2^i) mod P is tab[1024 + i]
+__device__ __forceinline__ uint32_t crc_x8nmodp(const uint32_t *tab, uint32_t n) {
+    uint32_t p = 1u << 31, k = 3;
+    while (n) { if (n & 1u) p = crc_multmodp(tab[1024 + (k & 31u)], p); n >>= 1; k++; }
+    return p;
+}
 
-constexpr int INFLATE_THREADS = 32;  // one warp per CTA: the blocks of a launch spread over all SMs
+__device__ __forceinline__ uint8_t ld_cg_u8(const uint8_t *p) {
+#ifdef POMFRET_CUDA_EMU
+    return *p;
+#else
+    return __ldcg(p);  // bytes this warp wrote a moment ago: read where the stores went (L2)
+#endif
+}
 
-__global__ void __launch_bounds__(INFLATE_THREADS) inflate_kernel(InflateParams P) {
-    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P) {
+    __shared__ InflateWarpSmem smem[INF_WARPS];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t bi = blockIdx.x * INF_WARPS + warp;
     if (bi >= P.n_blocks) return;
+    InflateWarpSmem &sm = smem[warp];
     const pomfret_gpu_bgzf_block B = P.blocks[bi];
     const uint8_t *blk = P.comp + B.comp_off;
     int err = 0;
@@ -121,105 +166,212 @@ __global__ void __launch_bounds__(INFLATE_THREADS) inflate_kernel(InflateParams 
     const uint32_t isize = B.isize;
     uint32_t o = 0;
     if (!err) {
+        const uint8_t *pay = blk + 12 + xlen;                 // deflate payload
+        const uint32_t pay_len = B.csize - 12 - xlen - 8;
+        uint32_t win_off = 0;                                 // payload offset of the window's first byte
+        // (re)stage the window at payload offset `at` (all lanes); bytes behind the payload read as zero
+        auto stage = [&](uint32_t at) {
+            for (uint32_t i = lane; i < INF_WIN + 16; i += 32) sm.win[i] = at + i < pay_len ? pay[at + i] : (uint8_t)0;
+            win_off = at;
+            __syncwarp();
+        };
+        stage(0);
         BitReader br;
-        br.p = blk + 12 + xlen;
-        br.end = blk + B.csize - 8;
-        br.buf = 0; br.n = 0;
-        uint16_t lcount[16], dcount[16], lsym[288], dsym[32], llut[1 << INF_LIT_BITS], dlut[1 << INF_DIST_BITS];
-        uint8_t lens[320];
+        br.w = sm.win; br.pos = 0; br.buf = 0; br.n = 0;
         bool last = false;
         while (!last && !err) {
-            br.refill();
-            last = br.take(1) != 0;
-            const uint32_t type = br.take(2);
-            if (type == 0) {  // stored
-                br.drop(br.n & 7);
-                br.refill();
-                const uint32_t len = br.take(16), nlen = br.take(16);
-                if ((len ^ 0xffffu) != nlen) { err = 2; break; }
-                // give the whole bytes of the bit buffer back
-                br.p -= br.n >> 3; br.buf = 0; br.n = 0;
-                if (br.p + len > br.end || o + len > isize) { err = 2; break; }
-                for (uint32_t i = 0; i < len; i++) out[o + i] = br.p[i];
-                o += len; br.p += len;
-                continue;
-            }
-            if (type == 3) { err = 2; break; }
-            if (type == 1) {  // fixed code
-                for (int i = 0; i < 144; i++) lens[i] = 8;
-                for (int i = 144; i < 256; i++) lens[i] = 9;
-                for (int i = 256; i < 280; i++) lens[i] = 7;
-                for (int i = 280; i < 288; i++) lens[i] = 8;
-                build_code(lens, 288, lcount, lsym, llut, INF_LIT_BITS);
-                for (int i = 0; i < 30; i++) lens[i] = 5;
-                build_code(lens, 30, dcount, dsym, dlut, INF_DIST_BITS);
-            } else {  // dynamic code
-                br.refill();
-                const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
-                if (nlen > 286 || ndist > 30) { err = 3; break; }
-                const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-                for (int i = 0; i < 19; i++) lens[i] = 0;
-                for (int i = 0; i < ncode; i++) { br.refill(); lens[order[i]] = (uint8_t)br.take(3); }
-                uint16_t ccount[16], csym[19], clut[1 << 7];
-                if (!build_code(lens, 19, ccount, csym, clut, 7)) { err = 3; break; }
-                int idx = 0;
-                while (idx < nlen + ndist) {
-                    br.refill();
-                    int sym = decode_symbol(br, ccount, csym, clut, 7);
-                    if (sym < 0) { err = 3; break; }
-                    if (sym < 16) lens[idx++] = (uint8_t)sym;
-                    else {
-                        int rep, val = 0;
-                        if (sym == 16) { if (idx == 0) { err = 3; break; } val = lens[idx - 1]; rep = 3 + (int)br.take(2); }
-                        else if (sym == 17) rep = 3 + (int)br.take(3);
-                        else rep = 11 + (int)br.take(7);
-                        if (idx + rep > nlen + ndist) { err = 3; break; }
-                        while (rep--) lens[idx++] = (uint8_t)val;
+            // ---- block header and code tables (lane 0), the window re-staged first so that 1 KB is ahead ----
+            {
+                const uint32_t consumed = __shfl_sync(FULL_MASK, br.pos - (uint32_t)(br.n >> 3), 0);  // whole bytes still in the bit buffer are re-read
+                const uint32_t bit_rem = __shfl_sync(FULL_MASK, (uint32_t)(br.n & 7), 0);
+                if (consumed >= INF_WIN / 2) {
+                    // keep the partial byte: restart the reader at the byte that holds the next bit
+                    const uint32_t at = win_off + consumed - (bit_rem ? 1u : 0u);
+                    stage(at);
+                    if (lane == 0) {
+                        br.pos = 0; br.buf = 0; br.n = 0;
+                        if (bit_rem) { br.refill(); br.drop(8 - (int)bit_rem); }
                     }
                 }
-                if (err) break;
-                if (lens[256] == 0) { err = 3; break; }
-                uint8_t dl[32];
-                for (int i = 0; i < ndist; i++) dl[i] = lens[nlen + i];
-                if (!build_code(lens, nlen, lcount, lsym, llut, INF_LIT_BITS)) { err = 3; break; }
-                if (!build_code(dl, ndist, dcount, dsym, dlut, INF_DIST_BITS)) { err = 3; break; }
             }
-            // ---- symbols ----
-            for (;;) {
+            int type = 0;
+            uint32_t stored_len = 0, stored_at = 0;
+            if (lane == 0) {
                 br.refill();
-                int sym = decode_symbol(br, lcount, lsym, llut, INF_LIT_BITS);
-                if (sym < 0) { err = 4; break; }
-                if (sym < 256) {
-                    if (o >= isize) { err = 5; break; }
-                    out[o++] = (uint8_t)sym;
-                    continue;
+                last = br.take(1) != 0;
+                type = (int)br.take(2);
+                if (type == 0) {  // stored
+                    br.drop(br.n & 7);
+                    br.refill();
+                    const uint32_t len = br.take(16), nlen = br.take(16);
+                    if ((len ^ 0xffffu) != nlen) err = 2;
+                    stored_len = len;
+                    stored_at = win_off + br.pos - (uint32_t)(br.n >> 3);  // payload offset of the first stored byte
+                } else if (type == 3) err = 2;
+                else if (type == 1) {  // fixed code
+                    for (int i = 0; i < 144; i++) sm.lens[i] = 8;
+                    for (int i = 144; i < 256; i++) sm.lens[i] = 9;
+                    for (int i = 256; i < 280; i++) sm.lens[i] = 7;
+                    for (int i = 280; i < 288; i++) sm.lens[i] = 8;
+                    build_code(sm.lens, 288, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS);
+                    for (int i = 0; i < 30; i++) sm.lens[i] = 5;
+                    build_code(sm.lens, 30, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS);
+                } else {  // dynamic code (at most 19*3 + 320*14 bits of header: inside the staged kilobyte)
+                    br.refill();
+                    const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+                    if (nlen > 286 || ndist > 30) err = 3;
+                    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                    for (int i = 0; i < 19; i++) sm.lens[i] = 0;
+                    for (int i = 0; i < ncode && !err; i++) { br.refill(); sm.lens[order[i]] = (uint8_t)br.take(3); }
+                    if (!err && !build_code(sm.lens, 19, sm.ccount, sm.csym, sm.clut, 7)) err = 3;
+                    int idx = 0;
+                    while (!err && idx < nlen + ndist) {
+                        br.refill();
+                        const int sym = decode_symbol(br, sm.ccount, sm.csym, sm.clut, 7);
+                        if (sym < 0) { err = 3; break; }
+                        if (sym < 16) sm.lens[idx++] = (uint8_t)sym;
+                        else {
+                            int rep, val = 0;
+                            if (sym == 16) { if (idx == 0) { err = 3; break; } val = sm.lens[idx - 1]; rep = 3 + (int)br.take(2); }
+                            else if (sym == 17) rep = 3 + (int)br.take(3);
+                            else rep = 11 + (int)br.take(7);
+                            if (idx + rep > nlen + ndist) { err = 3; break; }
+                            while (rep--) sm.lens[idx++] = (uint8_t)val;
+                        }
+                    }
+                    if (!err && sm.lens[256] == 0) err = 3;
+                    if (!err) {
+                        uint8_t dl[32];
+                        for (int i = 0; i < ndist; i++) dl[i] = sm.lens[nlen + i];
+                        if (!build_code(sm.lens, nlen, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS)) err = 3;
+                        else if (!build_code(dl, ndist, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS)) err = 3;
+                    }
                 }
-                if (sym == 256) break;
-                sym -= 257;
-                if (sym >= 29) { err = 4; break; }
-                // length / distance bases and extra bits (RFC 1951 3.2.5)
-                const uint32_t lext = sym < 8 ? 0u : (sym == 28 ? 0u : (uint32_t)(sym - 4) >> 2);
-                const uint32_t lbase = sym < 8 ? 3u + (uint32_t)sym : (sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext));
-                const uint32_t len = lbase + br.take((int)lext);
-                br.refill();
-                int ds = decode_symbol(br, dcount, dsym, dlut, INF_DIST_BITS);
-                if (ds < 0 || ds >= 30) { err = 4; break; }
-                const uint32_t dext = ds < 4 ? 0u : (uint32_t)(ds - 2) >> 1;
-                const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext);
-                const uint32_t dist = dbase + br.take((int)dext);
-                if (dist > o || o + len > isize) { err = 5; break; }
-                for (uint32_t i = 0; i < len; i++, o++) out[o] = out[o - dist];
+            }
+            err = __shfl_sync(FULL_MASK, err, 0);
+            last = __shfl_sync(FULL_MASK, (int)last, 0) != 0;
+            type = __shfl_sync(FULL_MASK, type, 0);
+            if (err) break;
+            if (type == 0) {
+                // ---- stored block: all lanes copy, then the reader restarts behind it ----
+                stored_len = __shfl_sync(FULL_MASK, stored_len, 0);
+                stored_at = __shfl_sync(FULL_MASK, stored_at, 0);
+                if (stored_at + stored_len > pay_len || o + stored_len > isize) { err = 2; break; }
+                for (uint32_t i = lane; i < stored_len; i += 32) out[o + i] = pay[stored_at + i];
+                o += stored_len;
+                stage(stored_at + stored_len);
+                if (lane == 0) { br.pos = 0; br.buf = 0; br.n = 0; }
+                continue;
+            }
+            // ---- symbols: bursts of up to 32 tokens by lane 0, executed by the warp ----
+            bool end_of_block = false;
+            while (!end_of_block && !err) {
+                {
+                    const uint32_t consumed = __shfl_sync(FULL_MASK, br.pos - (uint32_t)(br.n >> 3), 0);
+                    const uint32_t bit_rem = __shfl_sync(FULL_MASK, (uint32_t)(br.n & 7), 0);
+                    if (consumed >= INF_WIN / 2) {  // (a burst consumes at most 32 * 48 bits: the window never runs out)
+                        const uint32_t at = win_off + consumed - (bit_rem ? 1u : 0u);
+                        stage(at);
+                        if (lane == 0) {
+                            br.pos = 0; br.buf = 0; br.n = 0;
+                            if (bit_rem) { br.refill(); br.drop(8 - (int)bit_rem); }
+                        }
+                    }
+                }
+                uint32_t n_tok = 0;
+                if (lane == 0) {
+                    while (n_tok < INF_TOKENS) {
+                        br.refill();
+                        int sym = decode_symbol(br, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS);
+                        if (sym < 0) { err = 4; break; }
+                        if (sym < 256) { sm.tokens[n_tok++] = (uint32_t)sym; continue; }
+                        if (sym == 256) { end_of_block = true; break; }
+                        sym -= 257;
+                        if (sym >= 29) { err = 4; break; }
+                        // length / distance bases and extra bits (RFC 1951 3.2.5)
+                        const uint32_t lext = sym < 8 ? 0u : (sym == 28 ? 0u : (uint32_t)(sym - 4) >> 2);
+                        const uint32_t lbase = sym < 8 ? 3u + (uint32_t)sym : (sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext));
+                        const uint32_t len = lbase + br.take((int)lext);
+                        br.refill();
+                        const int ds = decode_symbol(br, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS);
+                        if (ds < 0 || ds >= 30) { err = 4; break; }
+                        const uint32_t dext = ds < 4 ? 0u : (uint32_t)(ds - 2) >> 1;
+                        const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext);
+                        const uint32_t dist = dbase + br.take((int)dext);
+                        sm.tokens[n_tok++] = 0x80000000u | (dist << 9) | len;
+                    }
+                    if (win_off + br.pos - (uint32_t)(br.n >> 3) > pay_len + 8) err = 4;  // ran past the payload
+                }
+                __syncwarp();
+                n_tok = __shfl_sync(FULL_MASK, n_tok, 0);
+                err = __shfl_sync(FULL_MASK, err, 0);
+                end_of_block = __shfl_sync(FULL_MASK, (int)end_of_block, 0) != 0;
+                if (err) break;
+                // ---- execute the tokens: output offsets by a scan, literals at once, matches one after the other ----
+                const uint32_t tok = lane < n_tok ? sm.tokens[lane] : 0u;
+                const bool is_match = lane < n_tok && (tok >> 31);
+                const uint32_t tlen = lane < n_tok ? (is_match ? tok & 0x1ffu : 1u) : 0u;
+                const uint32_t incl = warp_inclusive_sum(tlen);
+                const uint32_t at = o + incl - tlen;
+                const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+                if (o + total > isize) { err = 5; break; }
+                if (lane < n_tok && !is_match) out[at] = (uint8_t)tok;
+                unsigned mm = __ballot_sync(FULL_MASK, is_match);
+                const uint32_t tdist = (tok >> 9) & 0xffffu;
+                if (__any_sync(FULL_MASK, is_match && tdist > at)) { err = 5; break; }
+                while (mm) {
+                    const int src_lane = __ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    __syncwarp();  // what the batch has written so far is visible to the copy
+                    const uint32_t dst = __shfl_sync(FULL_MASK, at, src_lane), len = __shfl_sync(FULL_MASK, tlen, src_lane),
+                                   dist = __shfl_sync(FULL_MASK, tdist, src_lane);
+                    if (dist >= len || dist >= 32u) {
+                        // chunks of at most min(32, dist) bytes never read what they write themselves
+                        const uint32_t step = dist < 32u ? dist : 32u;
+                        for (uint32_t i0 = 0; i0 < len; i0 += step) {
+                            const uint32_t i = i0 + lane;
+                            uint8_t v = 0;
+                            if (lane < step && i < len) v = ld_cg_u8(out + dst + i - dist);
+                            if (lane < step && i < len) out[dst + i] = v;
+                            if (i0 + step < len && dist < len) __syncwarp();
+                        }
+                    } else {
+                        // a run: the `dist` bytes in front of the match repeat
+                        for (uint32_t i = lane; i < len; i += 32) out[dst + i] = ld_cg_u8(out + dst - dist + i % dist);
+                    }
+                }
+                o += total;
+                __syncwarp();
             }
         }
         if (!err && o != isize) err = 6;  // ISIZE of the footer
+        __syncwarp();
         if (!err && P.check_crc) {
+            // 32 segment CRCs, folded left to right: crc(A || B) = crc(A) * x^(8|B|) mod P  xor  crc(B)
             const uint8_t *f = blk + B.csize - 8;
             const uint32_t want = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
-            if (crc32_update(P.crc_tab, 0u, out, isize) != want) err = 7;
+            const uint32_t seg = ((isize + 31u) / 32u + 3u) & ~3u;
+            const uint32_t a = lane * seg < isize ? lane * seg : isize, z = a + seg < isize ? a + seg : isize;
+            sm.crc[lane] = crc32_update(P.crc_tab, 0u, out + a, z - a);
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t crc = 0;
+                const uint32_t shift_full = crc_x8nmodp(P.crc_tab, seg);
+                for (uint32_t l = 0; l < 32; l++) {
+                    const uint32_t la = l * seg < isize ? l * seg : isize, lz = la + seg < isize ? la + seg : isize;
+                    if (lz == la) break;
+                    const uint32_t sh = lz - la == seg ? shift_full : crc_x8nmodp(P.crc_tab, lz - la);
+                    crc = crc_multmodp(sh, crc) ^ sm.crc[l];
+                }
+                if (crc != want) err = 7;
+            }
+            err = __shfl_sync(FULL_MASK, err, 0);
         }
     }
-    P.status[bi] = err;
-    if (err) atomicAdd(P.n_bad, 1);
+    if (lane == 0) {
+        P.status[bi] = err;
+        if (err) atomicAdd(P.n_bad, 1);
+    }
 }
 
 // ---- record walk ----

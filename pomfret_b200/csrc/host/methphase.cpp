@@ -415,9 +415,101 @@ struct Worker {
         }
     }
 
+    // pre_haplotagging_read_in_one_ref through the compressed ingest: the contig is walked in slices of 2 Mb of
+    // reference; a slice's query returns every record that overlaps it, and a record belongs to the slice its start
+    // lies in, so every record is taken once, in BAM order.  The device inflates, slices and haplotags; the host sees
+    // one header per record.
+    void haptag_contig_device(const std::string &chrom, const KnownVariants &kv, TagMap *raw) {
+        const GpuApi &api = eng->api;
+        double t0 = now_s();
+        need_batch();
+        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
+        if (tid < 0) return;
+        if (fd < 0) {
+            fd = ::open(bam.fn.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "pre_haplotagging_read_in_one_ref", bam.fn.c_str()); exit(1); }
+            file_size = (uint64_t)st.st_size;
+        }
+        const int64_t contig_len = (int64_t)bam.hdr->target_len[tid], slice = 2000000;
+        uint32_t prev_i_left = 0;
+        int n_new[4] = {0, 0, 0, 0};
+        pomfret_gpu_ingest_filter flt;
+        memset(&flt, 0, sizeof(flt));  // primary records only (blockjoin.c:1862)
+        std::vector<pomfret_gpu_sliced_record> sl;
+        std::vector<pomfret_gpu_read_desc> descs;
+        std::vector<uint32_t> known_first, which;
+        for (int64_t beg = 0; beg < contig_len; beg += slice) {
+            const int64_t end = std::min(contig_len, beg + slice);
+            plan.clear();
+            if (!ingest_plan_region(bam.idx, tid, beg, end, 0, file_size, &plan)) { fprintf(stderr, "[E::%s] region query failed for %s\n", "pre_haplotagging_read_in_one_ref", chrom.c_str()); exit(1); }
+            if (plan.ranges.empty()) continue;
+            int rc;
+            if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+            void *comp = nullptr;
+            if ((rc = api.batch_ingest_buffer(batch, plan.comp_bytes + 64, &comp))) die_gpu(api, rc, "ingest_buffer");
+            std::string err;
+            if (!ingest_read(fd, &plan, (uint8_t *)comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
+            uint32_t n_rec = 0;
+            if ((rc = api.batch_ingest_bgzf(batch, comp, plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
+                                            (uint32_t)plan.streams.size(), &flt, &n_rec)))
+                die_gpu(api, rc, "ingest_bgzf");
+            sl.resize(n_rec ? n_rec : 1);
+            if ((rc = api.batch_ingest_records(batch, sl.data(), n_rec))) die_gpu(api, rc, "ingest_records");
+            stats.n_ingest_bytes += plan.comp_bytes;
+            descs.clear(); known_first.clear(); which.clear();
+            for (uint32_t i = 0; i < n_rec; i++) {
+                const pomfret_gpu_sliced_record &S = sl[i];
+                if (S.bad) { fprintf(stderr, "[E::%s] malformed alignment record in %s\n", "pomfret", bam.fn.c_str()); exit(1); }
+                if (!S.keep || (int64_t)S.pos < beg) continue;  // (a record that starts in an earlier slice was taken there)
+                if (!S.md) die_gpu(api, POMFRET_GPU_ERR_MISSING_MD, "haptag");
+                which.push_back(i);
+                stats.n_haptag_reads++;
+                stats.n_haptag_bases += S.l_qseq;
+                if (kv.vars.empty()) continue;
+                uint32_t k = prev_i_left;  // i_left cursor, blockjoin.c:1716-1720
+                while (k < kv.vars.size() && kv.vars[k].pos < S.pos) k++;
+                prev_i_left = k == 0 ? 0 : k - 1;
+                known_first.push_back(k);
+                pomfret_gpu_read_desc d;
+                memset(&d, 0, sizeof(d));
+                d.pos = S.pos; d.l_qseq = S.l_qseq; d.n_cigar = S.n_cigar; d.flag = S.flag; d.mapq = S.mapq;
+                d.hp = kHaptagUnphased; d.mn = -1; d.ml_len = -1;
+                d.cigar = (const uint32_t *)(uintptr_t)S.cigar; d.seq = (const uint8_t *)(uintptr_t)S.seq;
+                d.md = (const char *)(uintptr_t)S.md; d.md_len = S.md_len;
+                d.reserved = S.end_pos;
+                descs.push_back(d);
+            }
+            std::vector<uint8_t> tags(which.size() ? which.size() : 1, (uint8_t)kHaptagUnphased);
+            if (!kv.vars.empty() && !descs.empty()) {
+                if ((rc = api.batch_add_reads_device(batch, descs.data(), (uint32_t)descs.size(), nullptr))) die_gpu(api, rc, "batch_add_reads");
+                if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
+                if ((rc = api.haptag(batch, kv.vars.data(), (uint32_t)kv.vars.size(), kv.bases.data(), (uint32_t)kv.bases.size(), known_first.data())))
+                    die_gpu(api, rc, "haptag");
+                std::vector<int32_t> st(descs.size());
+                if ((rc = api.batch_collect_haptags(batch, tags.data(), st.data()))) die_gpu(api, rc, "collect_haptags");
+            }
+            for (size_t j = 0; j < which.size(); j++) {
+                const pomfret_gpu_sliced_record &S = sl[which[j]];
+                char buf[256];
+                const char *qn = S.qname;
+                if (S.l_qname > sizeof(S.qname)) {
+                    if ((rc = api.batch_ingest_qname(batch, which[j], buf, sizeof(buf)))) die_gpu(api, rc, "ingest_qname");
+                    qn = buf;
+                }
+                auto ins = raw->emplace(qn, (int)tags[j]);  // first alignment wins (blockjoin.c:1880-1889)
+                if (ins.second) n_new[tags[j] == 0 ? 0 : tags[j] == 1 ? 1 : 2]++; else n_new[3]++;
+            }
+        }
+        fprintf(stderr, "[dbg::%s] tagged: %d new hap0, %d new hap1, %d new unphased, %d dup\n", "pre_haplotagging_read_in_one_ref",
+                n_new[0], n_new[1], n_new[2], n_new[3]);
+        stats.t_haptag += now_s() - t0;
+    }
+
     // pre_haplotagging_read_in_one_ref (blockjoin.c:1841-1898): every primary record of the contig, in BAM order
     // into `raw` (first alignment of a name wins, :1880-1889)
     void haptag_contig(const std::string &chrom, const KnownVariants &kv, TagMap *raw) {
+        if (eng->gpu_ingest) { haptag_contig_device(chrom, kv, raw); return; }
         const GpuApi &api = eng->api;
         double t0 = now_s();
         need_batch();
@@ -527,7 +619,11 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
     size_t n_windows_total = 0;
     for (const Ranges &rg : ps.st.ranges) n_windows_total += rg.n;
     int per = opt.windows_per_batch > 0 ? opt.windows_per_batch : 8;
-    per = (int)std::max<size_t>(1, std::min<size_t>((size_t)per, n_windows_total / (2 * (size_t)std::max(1, opt.threads)) + 1));
+    {
+        size_t feeders = (size_t)std::max(1, opt.threads);
+        if (eng.gpu_ingest) feeders = std::min<size_t>(feeders, 3 * (size_t)std::max(1, eng.expected_devices(opt.gpus)));
+        per = (int)std::max<size_t>(1, std::min<size_t>((size_t)per, n_windows_total / (2 * feeders) + 1));
+    }
     results->assign(ps.st.ref_names.size(), {});
     uint64_t total_cost = 0;
     for (size_t r = 0; r < ps.st.ref_names.size(); r++) {
@@ -561,7 +657,12 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
     }
     std::vector<std::atomic<size_t>> cursor((size_t)n_dev);
     for (int d = 0; d < n_dev; d++) cursor[(size_t)d].store(set_begin[(size_t)d]);
-    const int n_workers = std::max(1, std::min<int>(opt.threads, (int)chunks.size()));
+    // With the compressed ingest a worker only reads file ranges and sorts record headers: three of them keep a device
+    // busy, and more only queue up behind the driver's allocation locks.  The host loader inflates on the workers
+    // themselves and takes every thread it is given.
+    int n_workers = std::max(1, std::min<int>(opt.threads, (int)chunks.size()));
+    if (eng.gpu_ingest) n_workers = std::min(n_workers, 3 * n_dev);
+    if (const char *e = getenv("POMFRET_WORKERS")) n_workers = std::max(1, atoi(e));
     std::mutex mu;
     auto body = [&](int wid) {
         Worker wk;
@@ -612,7 +713,8 @@ bool load_all_intervals(Engine &eng, const Options &opt, PhaseState *ps, RunStat
         std::condition_variable cv;
         size_t next_task = 0;
         bool done_reading = false;
-        const int n_workers = std::max(1, opt.threads);
+        int n_workers = std::max(1, opt.threads);
+        if (eng.gpu_ingest) n_workers = std::min(n_workers, 3 * std::max(1, eng.expected_devices(opt.gpus)));
         std::vector<std::thread> th;
         auto body = [&](int wid) {
             Worker wk;

@@ -115,6 +115,9 @@ def run_both(tmp, data, args, gpu_lib, outputs, sub="methphase"):
     env = dict(os.environ)
     if gpu_lib:
         env["POMFRET_GPU_LIB"] = gpu_lib
+        # (the emulator steps the inflate kernel far too slowly for whole files: the emulated runs use the host loader;
+        #  test_golden.py runs one small case through the compressed ingest, the GPU tests all of them)
+        env.setdefault("POMFRET_HOST_INFLATE", "1")
     res = {}
     for who, exe in (("ref", ob.REF_BIN), ("mine", MINE)):
         prefix = os.path.join(tmp, who)

@@ -162,9 +162,16 @@ def emu_gpu(built):
     return pb.load_gpu(build_emu.build())
 
 
+@pytest.fixture(scope="module")
+def synth_tiny(built, tmp_path_factory):
+    d = tmp_path_factory.mktemp("tiny")
+    return conftest.run_synth(str(d / "t"), ["-c", "34", "-s", "13", "-C", "chrT:200000:0-150000", "--readlen", "2500", "--block", "30000",
+                                              "--gap", "5000-6000"])
+
+
 @pytest.mark.emu
-def test_ingest_emulated(emu_gpu, synth_small):
-    assert check_ingest(emu_gpu, synth_small, 36, 2000, max_windows=1) > 500
+def test_ingest_emulated(emu_gpu, synth_tiny):
+    assert check_ingest(emu_gpu, synth_tiny, 34, 1200, max_windows=1) > 200
 
 
 @pytest.mark.emu
@@ -175,9 +182,9 @@ def test_inflate_handmade_members_emulated(emu_gpu):
 @pytest.mark.emu
 @pytest.mark.parametrize("level", [0, 6])
 def test_ingest_deflate_levels_emulated(emu_gpu, built, tmp_path, level):
-    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "30", "-s", "12", "-C", "chrT:300000:0-160000", "--readlen", "3000", "--block", "60000",
-                                                     "--gap", "8000-10000", "-l", str(level), "--qual"])
-    check_ingest(emu_gpu, data, 30, 1500, max_windows=1, full_pipeline=False)
+    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "12", "-s", "12", "-C", "chrT:200000:0-150000", "--readlen", "2500", "--block", "30000",
+                                                     "--gap", "5000-6000", "-l", str(level), "--qual"])
+    check_ingest(emu_gpu, data, 12, 1200, max_windows=1, full_pipeline=False)
 
 
 @pytest.mark.gpu

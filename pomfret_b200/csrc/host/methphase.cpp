@@ -68,6 +68,7 @@ struct Engine {
         ready = std::async(std::launch::async, [this, want_gpus, n_workers] { return start(want_gpus, n_workers); }).share();
     }
     bool wait() { return ready.valid() ? ready.get() : ctx != nullptr; }
+    bool is_ready() { return !ready.valid() || ready.wait_for(std::chrono::seconds(0)) == std::future_status::ready; }
     // devices the engine will report, without waiting for it: --gpus, else what CUDA_VISIBLE_DEVICES / the driver list
     int expected_devices(int want_gpus) {
         if (ready.valid() && ready.wait_for(std::chrono::seconds(0)) == std::future_status::ready) return ready.get() ? n_dev : 1;
@@ -244,8 +245,8 @@ struct Worker {
 
     // device loader (compressed ingest): the BGZF blocks of every run's index chunks go to the device as they lie in
     // the file; inflate, record walk, filters and tag lookup happen there; the host gets one header per record back
-    void load_chunk_device(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg, const RawTagMap *raw_tags) {
-        const GpuApi &api = eng->api;
+    // which blocks the chunk's region queries need (the index chunks of every run)
+    void plan_chunk(const std::string &chrom, const std::vector<WindowJob> &jobs, IngestPlan *pl) {
         const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
         if (fd < 0) {
             fd = ::open(bam.fn.c_str(), O_RDONLY);
@@ -253,20 +254,33 @@ struct Worker {
             if (fd < 0 || fstat(fd, &st) != 0) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "load_reads_given_interval", bam.fn.c_str()); exit(1); }
             file_size = (uint64_t)st.st_size;
         }
-        plan.clear();
+        pl->clear();
         const auto runs = runs_of(jobs);
         for (size_t r = 0; r < runs.size(); r++)
-            if (tid < 0 || !ingest_plan_region(bam.idx, tid, jobs[runs[r].first].beg0(), run_end0(jobs, runs[r]), (uint32_t)r, file_size, &plan)) {
+            if (tid < 0 || !ingest_plan_region(bam.idx, tid, jobs[runs[r].first].beg0(), run_end0(jobs, runs[r]), (uint32_t)r, file_size, pl)) {
                 fprintf(stderr, "[E::%s] region query failed for %s:%u-%u\n", "load_reads_given_interval", chrom.c_str(), jobs[runs[r].first].start, jobs[runs[r].first].end);
                 exit(1);
             }
+    }
+    void read_chunk(IngestPlan *pl, uint8_t *comp) {
+        std::string err;
+        if (!ingest_read(fd, pl, comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
+    }
+    // A chunk whose blocks were read ahead of time (while the CUDA start-up was still under way)
+    struct ReadAhead { size_t chunk; IngestPlan plan; std::vector<uint8_t> comp; };
+    const ReadAhead *ahead = nullptr;
+
+    void load_chunk_device(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg, const RawTagMap *raw_tags) {
+        const GpuApi &api = eng->api;
+        if (ahead) plan = ahead->plan; else plan_chunk(chrom, jobs, &plan);
+        const auto runs = runs_of(jobs);
         need_batch();
         int rc;
         if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
         void *comp = nullptr;
         if ((rc = api.batch_ingest_buffer(batch, plan.comp_bytes + 64, &comp))) die_gpu(api, rc, "ingest_buffer");
-        std::string err;
-        if (!ingest_read(fd, &plan, (uint8_t *)comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
+        if (ahead) memcpy(comp, ahead->comp.data(), plan.comp_bytes);
+        else read_chunk(&plan, (uint8_t *)comp);
         pomfret_gpu_ingest_filter flt;
         memset(&flt, 0, sizeof(flt));
         flt.min_mapq = (uint32_t)std::max(0, cfg.min_mapq);
@@ -670,19 +684,48 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
         const double tw0 = now_s();
         if (!wk.open(opt.fn_bam)) exit(1);
         const double tw1 = now_s();
-        size_t n_own = 0, n_helped = 0;
+        size_t n_own = 0, n_helped = 0, n_ahead = 0;
+        auto process = [&](size_t c, bool own) {
+            const Chunk &ch = chunks[c];
+            std::vector<WindowOut> outs;
+            wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
+            for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
+            (own ? n_own : n_helped)++;
+        };
+        // while the CUDA start-up is still under way: read the blocks of this worker's next chunks into plain memory
+        // (at most 768 MB per worker), so that the file reads are done by the time the device can take them
+        if (eng.gpu_ingest) {
+            std::deque<Worker::ReadAhead> queue;
+            size_t buffered = 0;
+            const size_t d = (size_t)wk.device;
+            while (!eng.is_ready() && buffered < ((size_t)768 << 20)) {
+                const size_t c = cursor[d].fetch_add(1);
+                if (c >= set_begin[d + 1]) break;
+                queue.emplace_back();
+                Worker::ReadAhead &ra = queue.back();
+                ra.chunk = c;
+                wk.plan_chunk(ps.st.ref_names[chunks[c].i_ref], chunks[c].jobs, &ra.plan);
+                ra.comp.resize(ra.plan.comp_bytes + 64);
+                wk.read_chunk(&ra.plan, ra.comp.data());
+                buffered += ra.comp.size();
+            }
+            n_ahead = queue.size();
+            for (Worker::ReadAhead &ra : queue) {
+                wk.ahead = &ra;
+                process(ra.chunk, true);
+                wk.ahead = nullptr;
+                std::vector<uint8_t>().swap(ra.comp);
+            }
+        }
         for (int k = 0; k < n_dev; k++) {
             const size_t d = (size_t)((wk.device + k) % n_dev);  // own region set first, then the others'
             for (;;) {
                 const size_t c = cursor[d].fetch_add(1);
                 if (c >= set_begin[d + 1]) break;
-                const Chunk &ch = chunks[c];
-                std::vector<WindowOut> outs;
-                wk.run_chunk(ps.st.ref_names[ch.i_ref], ch.jobs, cfg_per_ref[ch.i_ref], ps.stores_raw_tag ? &ps.qname2haptag_raw : nullptr, &outs);
-                for (size_t j = 0; j < ch.jobs.size(); j++) (*results)[ch.i_ref][ch.jobs[j].i_win] = std::move(outs[j]);
-                (k == 0 ? n_own : n_helped)++;
+                process(c, k == 0);
             }
         }
+        (void)n_ahead;
         const double tw2 = now_s();
         wk.close();
         fprintf(stderr, "[T::worker %d] device %d: %zu chunks of its region set, %zu of others; open %.2fs, chunks %.2fs (load %.2fs, gpu %.2fs), close %.2fs\n",

@@ -165,13 +165,13 @@ def emu_gpu(built):
 @pytest.fixture(scope="module")
 def synth_tiny(built, tmp_path_factory):
     d = tmp_path_factory.mktemp("tiny")
-    return conftest.run_synth(str(d / "t"), ["-c", "34", "-s", "13", "-C", "chrT:200000:0-150000", "--readlen", "2500", "--block", "30000",
-                                              "--gap", "5000-6000"])
+    return conftest.run_synth(str(d / "t"), ["-c", "14", "-s", "13", "-C", "chrT:120000:0-100000", "--readlen", "2500", "--block", "18000",
+                                              "--gap", "4000-5000"])
 
 
 @pytest.mark.emu
 def test_ingest_emulated(emu_gpu, synth_tiny):
-    assert check_ingest(emu_gpu, synth_tiny, 34, 1200, max_windows=1) > 200
+    assert check_ingest(emu_gpu, synth_tiny, 14, 1200, max_windows=1) > 100
 
 
 @pytest.mark.emu
@@ -182,9 +182,9 @@ def test_inflate_handmade_members_emulated(emu_gpu):
 @pytest.mark.emu
 @pytest.mark.parametrize("level", [0, 6])
 def test_ingest_deflate_levels_emulated(emu_gpu, built, tmp_path, level):
-    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "12", "-s", "12", "-C", "chrT:200000:0-150000", "--readlen", "2500", "--block", "30000",
-                                                     "--gap", "5000-6000", "-l", str(level), "--qual"])
-    check_ingest(emu_gpu, data, 12, 1200, max_windows=1, full_pipeline=False)
+    data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "6", "-s", "12", "-C", "chrT:120000:0-100000", "--readlen", "2500", "--block", "18000",
+                                                     "--gap", "4000-5000", "-l", str(level), "--qual"])
+    check_ingest(emu_gpu, data, 6, 1200, max_windows=1, full_pipeline=False)
 
 
 @pytest.mark.gpu

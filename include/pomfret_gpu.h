@@ -45,7 +45,9 @@ extern "C" {
 #define POMFRET_GPU_ERR_STATE -5
 #define POMFRET_GPU_ERR_FATAL_CIGAR -6  /* reference: "fatal: unknown cigar operation" blockjoin.c:777 */
 #define POMFRET_GPU_ERR_DUP_QNAME -7    /* reserved for the host loader, blockjoin.c:1149 */
-#define POMFRET_GPU_ERR_UNSUPPORTED -8  /* input outside the engine's compiled limits (e.g. k > 6) */
+#define POMFRET_GPU_ERR_UNSUPPORTED -8  /* input outside the engine's limits: methmer k > 8 (dense 3^k count tables), more than 1024
+                                           candidates per iteration, 60000 or more records in one window (16-bit read ids),
+                                           a read of 2^28 bases or more */
 #define POMFRET_GPU_ERR_MISSING_MD -9   /* reference: assert(tagd) blockjoin.c:1596 */
 #define POMFRET_GPU_ERR_BAD_MD -10      /* reference: "invalid MD" blockjoin.c:1622 */
 

@@ -60,7 +60,8 @@ struct DevArena {
             Chunk &c = chunks.back();
             if (c.used + bytes <= c.cap) { void *r = c.p + c.used; c.used += bytes; used_total += bytes; return r; }
         }
-        size_t want = std::max<size_t>(bytes, std::max<size_t>((size_t)64 << 20, chunks.empty() ? 0 : chunks.back().cap));
+        // (large steps: every cudaMalloc / cudaFree is a driver-wide lock, and the rewind below frees with a device-wide sync)
+        size_t want = std::max<size_t>(bytes, std::max<size_t>((size_t)256 << 20, chunks.empty() ? 0 : chunks.back().cap));
         void *p = nullptr;
         if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
         chunks.push_back({(uint8_t *)p, want, bytes});

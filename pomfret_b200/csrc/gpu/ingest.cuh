@@ -64,7 +64,26 @@ struct BitReader {  // over the staged window; positions are offsets inside the 
     uint64_t buf;
     int n;
     __device__ __forceinline__ void refill() {
-        while (n <= 56) { buf |= (uint64_t)w[pos++] << n; n += 8; }  // (the window is refilled long before pos reaches its end)
+        // at least 32 bits afterwards: four bytes at once (two aligned words of the window, funnel-shifted), then bytes
+        // (the window is re-staged long before pos reaches its end)
+        if (n <= 32) {
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);
+            const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
+            const uint32_t v = __funnelshift_r(w32[i], w32[i + 1], sh);
+            buf |= (uint64_t)v << n;
+            n += 32; pos += 4;
+        }
+        while (n <= 56) { buf |= (uint64_t)w[pos++] << n; n += 8; }
+    }
+    // enough for one code (15 bits) plus its extra bits (13): cheaper than a full refill between symbols
+    __device__ __forceinline__ void need32() {
+        if (n < 32) {
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);
+            const uint32_t i = pos >> 2, sh = (pos & 3u) * 8u;
+            const uint32_t v = __funnelshift_r(w32[i], w32[i + 1], sh);
+            buf |= (uint64_t)v << n;
+            n += 32; pos += 4;
+        }
     }
     __device__ __forceinline__ uint32_t peek(int k) const { return (uint32_t)buf & ((1u << k) - 1u); }
     __device__ __forceinline__ void drop(int k) { buf >>= k; n -= k; }
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                 uint32_t n_tok = 0;
                 if (lane == 0) {
                     while (n_tok < INF_TOKENS) {
-                        br.refill();
+                        br.need32();
                         int sym = decode_symbol(br, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS);
                         if (sym < 0) { err = 4; break; }
                         if (sym < 256) { sm.tokens[n_tok++] = (uint32_t)sym; continue; }
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                         const uint32_t lext = sym < 8 ? 0u : (sym == 28 ? 0u : (uint32_t)(sym - 4) >> 2);
                         const uint32_t lbase = sym < 8 ? 3u + (uint32_t)sym : (sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext));
                         const uint32_t len = lbase + br.take((int)lext);
-                        br.refill();
+                        br.need32();
                         const int ds = decode_symbol(br, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS);
                         if (ds < 0 || ds >= 30) { err = 4; break; }
                         const uint32_t dext = ds < 4 ? 0u : (uint32_t)(ds - 2) >> 1;

@@ -33,7 +33,7 @@ namespace pomfret_gpu {
 #endif
 constexpr int JOIN_THREADS = POMFRET_JOIN_THREADS;
 constexpr int JOIN_WARPS = JOIN_THREADS / 32;
-constexpr int JOIN_MAX_CAND = 128;
+constexpr int JOIN_MAX_CAND = 1024;       // candidate slots are sized at launch (dynamic shared memory); this only bounds the request
 constexpr int JOIN_U = 8;                 // methmer sub-chunks (32 each) whose loads are issued together
 constexpr int JOIN_CHUNK = JOIN_U * 32;   // methmers of a candidate whose keys are cached in shared memory
 constexpr int JOIN_STAGE = 128;           // score terms staged per warp between two runs of the ordered sum
@@ -65,8 +65,10 @@ struct JoinParams {
 // is odd so that consecutive sites fall into different shared-memory banks.
 __host__ __device__ __forceinline__ uint32_t join_n_keys(int k) { uint32_t v = 1; for (int i = 0; i < k; i++) v *= 3u; return v; }
 __host__ __device__ __forceinline__ uint32_t join_row_stride(int k) { return (join_n_keys(k) + 1u) | 1u; }
-__device__ __forceinline__ uint32_t compact_key(uint32_t key) {  // k <= 4
-    return ((key >> 6) & 3u) * 27u + ((key >> 4) & 3u) * 9u + ((key >> 2) & 3u) * 3u + (key & 3u);
+__device__ __forceinline__ uint32_t compact_key(uint32_t key) {  // k <= 8: the base-4 digits of the methmer key read in base 3
+    uint32_t v = ((key >> 6) & 3u) * 27u + ((key >> 4) & 3u) * 9u + ((key >> 2) & 3u) * 3u + (key & 3u);
+    if (key >> 8) v += (((key >> 14) & 3u) * 27u + ((key >> 12) & 3u) * 9u + ((key >> 10) & 3u) * 3u + ((key >> 8) & 3u)) * 81u;
+    return v;
 }
 // dynamic shared memory of join_kernel for the given capacities (bytes)
 // Score terms staged per candidate slot.  Measured on the 60x batch (profiles/r02_join_variants.txt): the kernel is
@@ -87,7 +89,7 @@ __host__ __device__ __forceinline__ size_t join_smem_bytes(uint32_t tab_entries,
     (void)n_warps;
     return (((size_t)tab_entries * entry_bytes + 7) & ~(size_t)7) + (size_t)(n_cand + 1) * (join_stage_cap(n_cand) + 1) * 8 +
            (size_t)meta_cap * 12 + (size_t)((meta_cap + 1) / 2) * 4 + (size_t)((meta_cap + 31) / 32) * 4 +
-           (size_t)(n_cand + 1) * JOIN_CHUNK + 64;
+           (size_t)(n_cand + 1) * JOIN_CHUNK + (size_t)(n_cand + 2) * 48 + 64;  // 48: the per-slot state arrays
 }
 
 // A table entry holds the counts of both haplotypes: 16 + 16 bits in a 32-bit word, or 8 + 8 bits in a 16-bit word for
@@ -149,12 +151,6 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     __shared__ uint32_t s_min, s_max, s_seq;
     // candidate slots, two copies: an iteration reads one and writes the other (no barrier between the warps that
     // still look for the best candidate and the one that already recycles its slot)
-    __shared__ uint32_t s_sid[2][JOIN_MAX_CAND + 1];    // read id
-    __shared__ uint32_t s_sseq[2][JOIN_MAX_CAND + 1];   // position in scan order (monotone counter), SLOT_FREE if empty
-    __shared__ int s_tag[JOIN_MAX_CAND + 1];
-    __shared__ uint32_t s_nz[JOIN_MAX_CAND + 1];      // score terms staged in the slot's row
-    __shared__ float2 s_pre[JOIN_MAX_CAND + 1];       // ordered sums of the terms that were folded before (rows that ran full)
-    __shared__ int2 s_ll[JOIN_MAX_CAND + 1];          // the two score_h_l counters of the slot
     __shared__ int s_best;
     __shared__ int s_tbl[4];
     POMFRET_DYN_SMEM(uint32_t, dyn);
@@ -189,6 +185,19 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
     uint32_t *s_tagged = reinterpret_cast<uint32_t *>(s_scan) + (P.meta_cap + 1) / 2;  // bit per read: tagged 0/1
     uint8_t *s_keys = reinterpret_cast<uint8_t *>(s_tagged + (P.meta_cap + 31) / 32);   // [n_cand + 1][JOIN_CHUNK]
+    // per-slot state, n_cand + 1 entries each (8-byte aligned: JOIN_CHUNK is a multiple of 8 and so is everything in front)
+    const uint32_t n_sl = (uint32_t)P.n_cand + 1u, n_sl2 = (n_sl + 1u) & ~1u;
+    float2 *s_pre = reinterpret_cast<float2 *>(s_keys + (((size_t)n_sl * JOIN_CHUNK + 7) & ~(size_t)7));  // ordered sums of the terms folded before (rows that ran full)
+    int2 *s_ll = reinterpret_cast<int2 *>(s_pre + n_sl);                      // the two score_h_l counters of the slot
+    uint32_t *s_sid_[2], *s_sseq_[2];
+    s_sid_[0] = reinterpret_cast<uint32_t *>(s_ll + n_sl);                   // read id
+    s_sid_[1] = s_sid_[0] + n_sl2;
+    s_sseq_[0] = s_sid_[1] + n_sl2;                                          // position in scan order (monotone counter), SLOT_FREE if empty
+    s_sseq_[1] = s_sseq_[0] + n_sl2;
+    int *s_tag = reinterpret_cast<int *>(s_sseq_[1] + n_sl2);
+    uint32_t *s_nz = reinterpret_cast<uint32_t *>(s_tag + n_sl2);            // score terms staged in the slot's row
+#define s_sid(b) s_sid_[b]
+#define s_sseq(b) s_sseq_[b]
     const bool tab_in_smem = kTabSmem || (size_t)n_sites * stride <= P.smem_tab_words;
     const bool meta_in_smem = n <= P.meta_cap;
     TabT *tab = kTabSmem ? s_tab : (tab_in_smem ? s_tab : reinterpret_cast<TabT *>(P.tab) + (size_t)S.tab_base[d] * stride);
@@ -292,7 +301,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     const int n_slots = n_cand + 1;
     auto scan_id = [&](int i0) -> uint32_t { return d == 0 ? (uint32_t)i0 : (meta_in_smem ? (uint32_t)s_scan[i0] : rev[i0]); };
     auto fill_keys = [&](int buf, int slot) {  // one warp: keys of the slot's read, global -> shared (compact u8)
-        const uint32_t id = s_sid[buf][slot];
+        const uint32_t id = s_sid(buf)[slot];
         const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
         if (nm <= JOIN_CHUNK) {  // longer reads are scored straight from the pool
             uint8_t *dk = s_keys + (size_t)slot * JOIN_CHUNK;
@@ -321,12 +330,12 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     auto rebuild_slots = [&](int buf) {
         int cursor = s_i_last, nocc = 0;
         uint32_t seq = 0;
-        for (int sl = lane; sl < n_slots; sl += 32) s_sseq[buf][sl] = SLOT_FREE;
+        for (int sl = lane; sl < n_slots; sl += 32) s_sseq(buf)[sl] = SLOT_FREE;
         __syncwarp();
         while (nocc < n_slots) {
             const int id = next_untagged(cursor);
             if (id < 0) break;
-            if (lane == 0) { s_sid[buf][nocc] = (uint32_t)id; s_sseq[buf][nocc] = seq; }
+            if (lane == 0) { s_sid(buf)[nocc] = (uint32_t)id; s_sseq(buf)[nocc] = seq; }
             __syncwarp();
             fill_keys(buf, nocc);
             nocc++; seq++;
@@ -373,8 +382,8 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
         // ---- score terms of the candidates, one warp per slot (use_mmr_count_predict_tag_for_one_read, :3594-3656):
         //      lookups and divisions in parallel, the non-zero terms compacted in methmer order into the slot's row ----
         for (int c = (int)warp; c < n_slots; c += (int)nwarps) {
-            if (s_sseq[cur][c] == SLOT_FREE || (full && c == newest)) { if (lane == 0) s_tag[c] = -2; continue; }  // empty / look-ahead
-            const uint32_t id = s_sid[cur][c];
+            if (s_sseq(cur)[c] == SLOT_FREE || (full && c == newest)) { if (lane == 0) s_tag[c] = -2; continue; }  // empty / look-ahead
+            const uint32_t id = s_sid(cur)[c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
             const bool cached = nm <= JOIN_CHUNK;
@@ -490,7 +499,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
                     const int2 ll = s_ll[c];
                     const float diff = sc0 > sc1 ? __fsub_rn(sc0, sc1) : __fsub_rn(sc1, sc0);
                     if (!(diff < 3.0f && (ll.x < 3 || ll.y < 3))) {
-                        const uint32_t sb = __float_as_uint(diff), sq = s_sseq[cur][c];
+                        const uint32_t sb = __float_as_uint(diff), sq = s_sseq(cur)[c];
                         s_tag[c] = sc0 > sc1 ? 0 : 1;
                         if (bc < 0 || sb > bs || (sb == bs && sq > bq)) { bs = sb; bq = sq; bc = c; }
                     } else s_tag[c] = -1;
@@ -506,7 +515,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
         }
         __syncthreads();
         const int best = s_best;
-        const uint32_t best_id = best >= 0 ? s_sid[cur][best] : 0u;
+        const uint32_t best_id = best >= 0 ? s_sid(cur)[best] : 0u;
         const int hap = best >= 0 ? s_tag[best] : -1;
         PF_MARK(3);  // best
         if (best >= 0) {
@@ -527,10 +536,10 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
                 const int nx = s_next_id;
                 const uint32_t seq_new = s_seq;
                 for (int c = (int)lane; c < n_slots; c += 32) {
-                    uint32_t sid = s_sid[cur][c], sq = s_sseq[cur][c];
+                    uint32_t sid = s_sid(cur)[c], sq = s_sseq(cur)[c];
                     if (c == best) { if (nx >= 0) { sid = (uint32_t)nx; sq = seq_new; } else sq = SLOT_FREE; }
-                    s_sid[cur ^ 1][c] = sid;
-                    s_sseq[cur ^ 1][c] = sq;
+                    s_sid(cur ^ 1)[c] = sid;
+                    s_sseq(cur ^ 1)[c] = sq;
                 }
                 __syncwarp();
                 if (lane == 31) {
@@ -583,6 +592,9 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
         }
     }
 }
+
+#undef s_sid
+#undef s_sseq
 
 }  // namespace pomfret_gpu
 #endif

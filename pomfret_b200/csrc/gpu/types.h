@@ -56,7 +56,7 @@ constexpr uint32_t RS_UNSORTED = 32u;  // calls are not strictly increasing (int
 constexpr uint32_t RS_OVERFLOW = 64u;  // call slots exhausted (internal: engine retries with more room)
 constexpr uint32_t RS_LEAN = 128u;     // decoded by the lean path (whole-record tables in shared memory)
 
-constexpr int kMaxK = 4;               // dense count tables cover methmer keys of up to kMaxK symbols
+constexpr int kMaxK = 8;               // dense count tables (3^k + 1 entries per site) cover methmer keys of up to kMaxK symbols
 
 }  // namespace pomfret_gpu
 #endif

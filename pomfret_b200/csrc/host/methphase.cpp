@@ -269,18 +269,29 @@ struct Worker {
     // A chunk whose blocks were read ahead of time (while the CUDA start-up was still under way)
     struct ReadAhead { size_t chunk; IngestPlan plan; std::vector<uint8_t> comp; };
     const ReadAhead *ahead = nullptr;
+    std::vector<uint8_t> comp_buf;  // the blocks of the chunk at hand
 
     void load_chunk_device(const std::string &chrom, const std::vector<WindowJob> &jobs, const pomfret_gpu_config &cfg, const RawTagMap *raw_tags) {
         const GpuApi &api = eng->api;
+        double tp = now_s();
+        auto lap = [&](int i) { const double t = now_s(); stats.t_phase[i] += t - tp; tp = t; };
         if (ahead) plan = ahead->plan; else plan_chunk(chrom, jobs, &plan);
         const auto runs = runs_of(jobs);
+        lap(0);
         need_batch();
+        lap(1);
         int rc;
         if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
-        void *comp = nullptr;
-        if ((rc = api.batch_ingest_buffer(batch, plan.comp_bytes + 64, &comp))) die_gpu(api, rc, "ingest_buffer");
-        if (ahead) memcpy(comp, ahead->comp.data(), plan.comp_bytes);
-        else read_chunk(&plan, (uint8_t *)comp);
+        lap(2);
+        // (plain memory: the blocks cross the bus once, pinning a buffer for them costs more than the driver's staging copy)
+        const void *comp = nullptr;
+        if (ahead) comp = ahead->comp.data();
+        else {
+            if (comp_buf.size() < plan.comp_bytes + 64) comp_buf.resize(plan.comp_bytes + plan.comp_bytes / 4 + 64);
+            read_chunk(&plan, comp_buf.data());
+            comp = comp_buf.data();
+        }
+        lap(3);
         pomfret_gpu_ingest_filter flt;
         memset(&flt, 0, sizeof(flt));
         flt.min_mapq = (uint32_t)std::max(0, cfg.min_mapq);
@@ -291,7 +302,9 @@ struct Worker {
                                         (uint32_t)plan.streams.size(), &flt, &n_rec)))
             die_gpu(api, rc, "ingest_bgzf");
         std::vector<pomfret_gpu_sliced_record> sl(n_rec ? n_rec : 1);
+        lap(4);
         if ((rc = api.batch_ingest_records(batch, sl.data(), n_rec))) die_gpu(api, rc, "ingest_records");
+        lap(5);
         stats.n_ingest_bytes += plan.comp_bytes;
         names.clear();
         names.reserve((size_t)n_rec * 40);
@@ -338,6 +351,7 @@ struct Worker {
             }
         }
         for (size_t i = 0; i < recs.size(); i++) recs[i].qname = names.data() + name_off[i];
+        lap(6);
     }
 
     // haplotag_region_given_bam for a chunk of windows of one contig.  Windows whose region queries overlap
@@ -396,7 +410,9 @@ struct Worker {
         stats.t_load += t1 - t0;
         if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
         if ((rc = api.decode(batch, (uint8_t)cfg.lo, (uint8_t)cfg.hi))) die_gpu(api, rc, "decode");
+        stats.t_phase[7] += now_s() - t1;
         if ((rc = api.pileup(batch, &cfg))) die_gpu(api, rc, "pileup");
+        stats.t_phase[8] += now_s() - t1;
         if ((rc = api.join(batch, &cfg))) die_gpu(api, rc, "join");
         const size_t n_slots = descs.size();
         std::vector<pomfret_gpu_window_result> res(jobs.size() ? jobs.size() : 1);
@@ -460,10 +476,10 @@ struct Worker {
             if (plan.ranges.empty()) continue;
             int rc;
             if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
-            void *comp = nullptr;
-            if ((rc = api.batch_ingest_buffer(batch, plan.comp_bytes + 64, &comp))) die_gpu(api, rc, "ingest_buffer");
+            if (comp_buf.size() < plan.comp_bytes + 64) comp_buf.resize(plan.comp_bytes + plan.comp_bytes / 4 + 64);
+            uint8_t *comp = comp_buf.data();
             std::string err;
-            if (!ingest_read(fd, &plan, (uint8_t *)comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
+            if (!ingest_read(fd, &plan, comp, &err)) { fprintf(stderr, "[E::%s] %s: %s\n", "pomfret", bam.fn.c_str(), err.c_str()); exit(1); }
             uint32_t n_rec = 0;
             if ((rc = api.batch_ingest_bgzf(batch, comp, plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
                                             (uint32_t)plan.streams.size(), &flt, &n_rec)))
@@ -613,8 +629,8 @@ bool files_exist(const Options &o) {  // sancheck_cliopt_t_files_exist, blockjoi
 }
 
 void check_limits(const pomfret_gpu_config &c) {
-    if (c.k > 4 || c.n_candidates_per_iter > 128) {
-        fprintf(stderr, "[E::%s] this build supports methmer k <= 4 and <= 128 candidates per iteration (got k=%d, n=%d)\n", "pomfret",
+    if (c.k > 8 || c.n_candidates_per_iter > 1024) {
+        fprintf(stderr, "[E::%s] this build supports methmer k <= 8 and <= 1024 candidates per iteration (got k=%d, n=%d)\n", "pomfret",
                 c.k, c.n_candidates_per_iter);
         exit(1);
     }
@@ -728,6 +744,9 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
         (void)n_ahead;
         const double tw2 = now_s();
         wk.close();
+        fprintf(stderr, "[T::worker %d] phases: plan+read %.3f, wait engine/batch %.3f, reset %.3f, (read) %.3f, ingest %.3f, records d2h %.3f, assign %.3f | submit+decode %.3f, ..pileup %.3f (cumulative)\n",
+                wid, wk.stats.t_phase[0], wk.stats.t_phase[1], wk.stats.t_phase[2], wk.stats.t_phase[3], wk.stats.t_phase[4], wk.stats.t_phase[5], wk.stats.t_phase[6],
+                wk.stats.t_phase[7], wk.stats.t_phase[8]);
         fprintf(stderr, "[T::worker %d] device %d: %zu chunks of its region set, %zu of others; open %.2fs, chunks %.2fs (load %.2fs, gpu %.2fs), close %.2fs\n",
                 wid, wk.device, n_own, n_helped, tw1 - tw0, tw2 - tw1, wk.stats.t_load, wk.stats.t_gpu, now_s() - tw2);
         std::lock_guard<std::mutex> lock(mu);

@@ -18,6 +18,7 @@ struct RunStats {
     uint64_t n_shared = 0;                                 // slots that reuse a record staged and decoded for an earlier window
     uint64_t n_haptag_reads = 0, n_haptag_bases = 0;       // records fed to the -u haplotagger
     double t_load = 0, t_gpu = 0, t_haptag = 0, t_total = 0;
+    double t_phase[12] = {};                               // per-phase wall times of the compressed-ingest loader (diagnostics)
 };
 
 int run_methphase(const Options &opt, RunStats *stats);

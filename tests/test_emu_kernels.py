@@ -74,6 +74,11 @@ def test_emulated_kernels_k2(emu_gpu, synth_small):
     _run(emu_gpu, synth_small, 24, 2000, k=2, k_span=900)
 
 
+def test_emulated_kernels_k5(emu_gpu, synth_small):
+    # methmers of five symbols: 3^5 + 1 entries per site (the round-1 engine stopped at k = 4)
+    _run(emu_gpu, synth_small, 24, 2000, k=5, k_span=2500)
+
+
 def test_emulated_kernels_call_slot_overflow(emu_gpu, synth_sparse_implicit):
     _run(emu_gpu, synth_sparse_implicit, 34, 1500)
 
@@ -98,7 +103,7 @@ def _run_cfg(emu_gpu, data, cov, readlen, tweak):
     host.bam_close(hb)
 
 
-@pytest.mark.parametrize("n_cand", [1, 40, 128])
+@pytest.mark.parametrize("n_cand", [1, 40, 200])
 def test_emulated_join_candidate_counts(emu_gpu, synth_small, n_cand):
     # fewer slots than warps, more slots than warps, more slots than lanes
     def tweak(cfg):

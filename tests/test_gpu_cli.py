@@ -106,3 +106,8 @@ def test_methphase_pinned_record_slabs(synth30, tmp_path, monkeypatch):
     monkeypatch.setenv("POMFRET_HOST_INFLATE", "1")
     monkeypatch.setenv("POMFRET_PIN_RECORDS", "1")
     run_both(str(tmp_path), synth30, ["-t", "3", "-c", "30"], None, [".mp.gtf", ".mp.vcf"])
+
+
+def test_methphase_hidden_options_k_and_n(synth30, tmp_path):
+    # the reference's hidden -k / -n options (cli.c:267-283) beyond what round 1 compiled in: k = 5, 200 candidates
+    run_both(str(tmp_path), synth30, ["-t", "3", "-c", "30", "-k", "5", "-n", "200"], None, [".mp.gtf", ".mp.vcf"])

@@ -96,7 +96,8 @@ def test_gpu_matches_oracle_call_slot_overflow(gpu, synth_sparse_implicit):
     _run(gpu, synth_sparse_implicit, 34, readlen=1500)
 
 
-@pytest.mark.parametrize("kw", [dict(k=2, k_span=800), dict(k=4, lo=80, hi=180), dict(k=1), dict(k_span=300)])
+@pytest.mark.parametrize("kw", [dict(k=2, k_span=800), dict(k=4, lo=80, hi=180), dict(k=1), dict(k_span=300), dict(k=5, k_span=3000),
+                                dict(k=6), dict(k=8, k_span=9000)])
 def test_gpu_matches_oracle_parameters(gpu, synth_small, kw):
     _run(gpu, synth_small, 30, readlen=2000, check_ref=False, **kw)
 
@@ -160,7 +161,7 @@ def _run_tweaked(gpu, data, cov, readlen, tweak, max_windows=None):
     host.bam_close(hb)
 
 
-@pytest.mark.parametrize("n_cand", [1, 3, 15, 40, 128])
+@pytest.mark.parametrize("n_cand", [1, 3, 15, 40, 128, 300])
 def test_gpu_join_candidate_counts(gpu, synth30, synth_small, n_cand):
     # fewer candidate slots than warps, more slots than warps, more slots than lanes
     def tweak(cfg):

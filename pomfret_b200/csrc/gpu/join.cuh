@@ -174,6 +174,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     const uint32_t *rev = P.rs_rev + first;
     const uint32_t n_ref = d == 0 ? S.n_left : S.n_right;
     const int n_cand = P.n_cand;
+    const bool key_fits_u8 = P.k <= 5;  // 3^5 = 243 compact keys: the candidates' key cache holds one byte per methmer
 
     // ---- shared-memory carve-up ----
     TabT *s_tab = reinterpret_cast<TabT *>(dyn);
@@ -185,9 +186,9 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     uint16_t *s_scan = reinterpret_cast<uint16_t *>(s_mst + P.meta_cap);  // scan order -> read id (direction 1)
     uint32_t *s_tagged = reinterpret_cast<uint32_t *>(s_scan) + (P.meta_cap + 1) / 2;  // bit per read: tagged 0/1
     uint8_t *s_keys = reinterpret_cast<uint8_t *>(s_tagged + (P.meta_cap + 31) / 32);   // [n_cand + 1][JOIN_CHUNK]
-    // per-slot state, n_cand + 1 entries each (8-byte aligned: JOIN_CHUNK is a multiple of 8 and so is everything in front)
+    // per-slot state, n_cand + 1 entries each (the first array holds 8-byte items: its address is rounded up)
     const uint32_t n_sl = (uint32_t)P.n_cand + 1u, n_sl2 = (n_sl + 1u) & ~1u;
-    float2 *s_pre = reinterpret_cast<float2 *>(s_keys + (((size_t)n_sl * JOIN_CHUNK + 7) & ~(size_t)7));  // ordered sums of the terms folded before (rows that ran full)
+    float2 *s_pre = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(s_keys + (size_t)n_sl * JOIN_CHUNK) + 7) & ~(uintptr_t)7);  // ordered sums of the terms folded before (rows that ran full)
     int2 *s_ll = reinterpret_cast<int2 *>(s_pre + n_sl);                      // the two score_h_l counters of the slot
     uint32_t *s_sid_[2], *s_sseq_[2];
     s_sid_[0] = reinterpret_cast<uint32_t *>(s_ll + n_sl);                   // read id
@@ -303,7 +304,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
     auto fill_keys = [&](int buf, int slot) {  // one warp: keys of the slot's read, global -> shared (compact u8)
         const uint32_t id = s_sid(buf)[slot];
         const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], off = meta_in_smem ? s_moff[id] : g_off[id];
-        if (nm <= JOIN_CHUNK) {  // longer reads are scored straight from the pool
+        if (nm <= JOIN_CHUNK && key_fits_u8) {  // longer reads (and keys of more than five symbols) are scored straight from the pool
             uint8_t *dk = s_keys + (size_t)slot * JOIN_CHUNK;
             for (uint32_t i = lane; i < nm; i += 32) dk[i] = (uint8_t)compact_key(pool[off + i]);
         }
@@ -386,7 +387,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
             const uint32_t id = s_sid(cur)[c];
             const uint32_t nm = meta_in_smem ? s_mn[id] : g_n[id], st = meta_in_smem ? s_mst[id] : g_start[id];
             const uint32_t off = meta_in_smem ? s_moff[id] : g_off[id];
-            const bool cached = nm <= JOIN_CHUNK;
+            const bool cached = nm <= JOIN_CHUNK && key_fits_u8;
             const uint8_t *ck = s_keys + (size_t)c * JOIN_CHUNK;
             float sc0 = 0.f, sc1 = 0.f;  // ordered sums of terms folded early (only when the row runs full)
             int l0 = 0, l1 = 0;
@@ -522,7 +523,7 @@ template <bool kTabSmem, typename TabT> __global__ void __launch_bounds__(JOIN_T
             // ---- insert_mmrs_to_counts (:3453-3486), all threads ----
             const uint32_t nm = meta_in_smem ? s_mn[best_id] : g_n[best_id], st = meta_in_smem ? s_mst[best_id] : g_start[best_id];
             const uint32_t off = meta_in_smem ? s_moff[best_id] : g_off[best_id];
-            const bool cached = nm <= JOIN_CHUNK;
+            const bool cached = nm <= JOIN_CHUNK && key_fits_u8;
             const uint8_t *ck = s_keys + (size_t)best * JOIN_CHUNK;
             const TabT inc = (TabT)(hap == 0 ? 1u : 1u << kShift);
             for (uint32_t i0 = tid; i0 < nm; i0 += nthreads) {

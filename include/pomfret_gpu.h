@@ -175,6 +175,7 @@ typedef struct pomfret_gpu_ingest_filter {  /* blockjoin.c:1081-1084; all zero =
     uint32_t min_len_floor;  /* 2: "len < 2" of the window loader */
     uint32_t check_de;
     float max_de;            /* MIN_ALN_DE 0.1 */
+    uint32_t keep_all_flags; /* 1: unmapped / secondary / supplementary records pass too (blockjoin.c:2512: no flag test) */
 } pomfret_gpu_ingest_filter;
 typedef struct pomfret_gpu_sliced_record {  /* one alignment record as the slicing kernel saw it; addresses are DEVICE addresses */
     uint32_t pos, end_pos, l_qseq, n_cigar;   /* n_cigar / cigar: the real operations, also for CG-tag records */
@@ -232,6 +233,13 @@ int pomfret_gpu_decode(pomfret_gpu_batch *b, uint8_t qual_lo, uint8_t qual_hi);
  * known_first[i] is the i_left cursor of read i (blockjoin.c:1716-1720), computed by the caller. */
 int pomfret_gpu_haptag(pomfret_gpu_batch *b, const pomfret_gpu_variant *known, uint32_t n_known,
                        const uint8_t *bases, uint32_t n_bases, const uint32_t *known_first);
+/* ---- (c') phase of unphased variants inside dropped intervals: recover_variant_phase_in_one_interval, blockjoin.c:2475-2600
+ * (SURVEY.md §8(f) row 3).  After haptag() — which parses the variants every record shows itself, with or without a
+ * known set — count, per known position (ascending), the records with read_hap 0 / 1 that show a variant there:
+ * votes[2*i + hap].  read_hap[i] = 255 leaves record i out.  votes[2*n_positions] = read variants at or behind the last
+ * known position (the reference never evaluates a known variant that ends its merged list, :2561). */
+int pomfret_gpu_variant_votes(pomfret_gpu_batch *b, const uint32_t *positions, uint32_t n_positions, const uint8_t *read_hap,
+                              int32_t *votes /* 2 * n_positions + 1 */);
 /* ---- (d) read set, CpG site pileup, methmer layout + extraction ---- */
 int pomfret_gpu_pileup(pomfret_gpu_batch *b, const pomfret_gpu_config *cfg);
 /* ---- (e) greedy propagation in both directions + join evaluation ---- */

@@ -57,7 +57,7 @@ class BgzfStream(C.Structure):
 class IngestFilter(C.Structure):
     """pomfret_gpu_ingest_filter"""
     _fields_ = [("min_mapq", C.c_uint32), ("min_len", C.c_uint32), ("min_len_floor", C.c_uint32), ("check_de", C.c_uint32),
-                ("max_de", C.c_float)]
+                ("max_de", C.c_float), ("keep_all_flags", C.c_uint32)]
 
 
 class SlicedRecord(C.Structure):

@@ -49,6 +49,7 @@ struct HaptagParams {
     uint8_t *out_tag;
     int32_t *out_status;
     int32_t *out_votes;  // 2 per read
+    uint32_t *out_counts; // 2 per read: insertions, MD variants left in the scratch lists (nullptr: not wanted)
 };
 
 struct HapWarpSmem {
@@ -345,6 +346,47 @@ __global__ void __launch_bounds__(HAP_WARPS * 32) haptag_kernel(HaptagParams P) 
         P.out_status[ri] = status;
         P.out_votes[2 * ri] = cnt[0];
         P.out_votes[2 * ri + 1] = cnt[1];
+        if (P.out_counts) { P.out_counts[2 * ri] = n_ins; P.out_counts[2 * ri + 1] = status == 0 ? n_mv : 0u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Votes for the phase of unphased variants inside a dropped interval (recover_variant_phase_in_one_interval,
+// reference blockjoin.c:2475-2600): every read that methylation phasing tagged contributes, at each known variant
+// position where the read itself shows a variant (an insertion from its CIGAR, a mismatch or deletion from its MD —
+// the lists parse_variants_for_one_read builds, left in the scratch arrays by haptag_kernel), one vote for its
+// haplotype.  One warp per read; positions are looked up in the sorted list of known positions.
+// votes: [2 * n_pos] counts per position and haplotype, then [2 * n_pos] = read variants at or behind the last
+// known position (the reference never evaluates a known variant that ends its merged list, :2561).
+// ---------------------------------------------------------------------------------------------
+struct VariantVoteParams {
+    uint32_t n_reads;
+    const uint32_t *ins_off, *mdv_off;
+    const uint32_t *ins_ref, *mv_pos;
+    const uint32_t *counts;     // 2 per read (haptag_kernel out_counts)
+    const uint8_t *read_hap;    // per read: haplotype from methylation phasing, 255 = the read does not take part
+    const uint32_t *poss;       // known positions, ascending
+    uint32_t n_pos;
+    int32_t *votes;
+};
+
+__global__ void __launch_bounds__(HAP_WARPS * 32) variant_vote_kernel(VariantVoteParams P) {
+    const uint32_t ri = blockIdx.x * HAP_WARPS + (threadIdx.x >> 5);
+    if (ri >= P.n_reads || P.n_pos == 0) return;
+    const uint32_t hap = P.read_hap[ri];
+    if (hap == 255u) return;
+    const unsigned lane = lane_id();
+    const uint32_t last = P.poss[P.n_pos - 1];
+    for (int list = 0; list < 2; list++) {
+        const uint32_t *v = list == 0 ? P.ins_ref + P.ins_off[ri] : P.mv_pos + P.mdv_off[ri];
+        const uint32_t n = P.counts[2 * ri + list];
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t p = v[i];
+            if (p >= last) atomicAdd(&P.votes[2 * P.n_pos], 1);
+            if (hap > 1u) continue;
+            // every known variant at this position (duplicates are adjacent)
+            for (uint32_t k = lower_bound_u32(P.poss, P.n_pos, p); k < P.n_pos && P.poss[k] == p; k++) atomicAdd(&P.votes[2 * k + hap], 1);
+        }
     }
 }
 

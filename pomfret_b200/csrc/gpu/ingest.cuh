@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) 
         else if (de[0] == 'd') { uint64_t u = (uint64_t)ld_u32(de + 1) | ((uint64_t)ld_u32(de + 5) << 32); de_v = (float)__longlong_as_double((long long)u); }
         else { const int64_t iv = aux2i(de, &ok); de_v = ok ? (float)iv : 0.f; }
     }
-    bool keep = !bad && !(flag & (4u | 256u | 2048u));
+    bool keep = !bad && (P.flt.keep_all_flags || !(flag & (4u | 256u | 2048u)));
     if (keep && mapq < P.flt.min_mapq) keep = false;
     if (keep && (l_qseq < P.flt.min_len_floor || l_qseq < P.flt.min_len)) keep = false;
     if (keep && P.flt.check_de && de_v > P.flt.max_de) keep = false;

@@ -445,6 +445,98 @@ struct Worker {
         }
     }
 
+    // recover_variant_phase_in_one_interval (blockjoin.c:2475-2600) on the device: the records of the interval are
+    // inflated and sliced there, the host looks their names up (which reads did methylation phasing tag, and how),
+    // haptag_kernel parses every record's own variants, variant_vote_kernel counts the votes per known position.
+    void recover_interval_device(const PhaseState &ps, const std::string &chrom, uint32_t start, uint32_t end, const std::vector<uint32_t> &poss,
+                                 std::unordered_map<uint32_t, uint32_t> *pos2hap) {
+        const GpuApi &api = eng->api;
+        if (poss.empty()) return;  // (the reference reads the interval anyway; nothing comes of it)
+        need_batch();
+        const int tid = sam_hdr_name2tid(bam.hdr, chrom.c_str());
+        if (tid < 0) return;
+        if (fd < 0) {
+            fd = ::open(bam.fn.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "recover_variant_phase_in_one_interval", bam.fn.c_str()); exit(1); }
+            file_size = (uint64_t)st.st_size;
+        }
+        plan.clear();
+        // "%s:%d-%d" of the reference: 1-based inclusive start
+        if (!ingest_plan_region(bam.idx, tid, start > 0 ? (int64_t)start - 1 : 0, (int64_t)end, 0, file_size, &plan)) return;
+        int rc;
+        if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+        if (plan.ranges.empty()) return;
+        if (comp_buf.size() < plan.comp_bytes + 64) comp_buf.resize(plan.comp_bytes + plan.comp_bytes / 4 + 64);
+        read_chunk(&plan, comp_buf.data());
+        pomfret_gpu_ingest_filter flt;
+        memset(&flt, 0, sizeof(flt));
+        flt.keep_all_flags = 1;  // blockjoin.c:2512-2518: every record the query returns is looked up by name
+        uint32_t n_rec = 0;
+        if ((rc = api.batch_ingest_bgzf(batch, comp_buf.data(), plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
+                                        (uint32_t)plan.streams.size(), &flt, &n_rec)))
+            die_gpu(api, rc, "ingest_bgzf");
+        std::vector<pomfret_gpu_sliced_record> sl(n_rec ? n_rec : 1);
+        if ((rc = api.batch_ingest_records(batch, sl.data(), n_rec))) die_gpu(api, rc, "ingest_records");
+        const int64_t beg0 = start > 0 ? (int64_t)start - 1 : 0;
+        std::vector<pomfret_gpu_read_desc> descs;
+        std::vector<uint8_t> read_hap;
+        for (uint32_t i = 0; i < n_rec; i++) {
+            const pomfret_gpu_sliced_record &S = sl[i];
+            if (S.bad) { fprintf(stderr, "[E::%s] malformed alignment record in %s\n", "pomfret", bam.fn.c_str()); exit(1); }
+            if (!S.keep || !((int64_t)S.pos < (int64_t)end && (int64_t)S.end_pos > beg0)) continue;
+            char buf[256];
+            const char *qn = S.qname;
+            if (S.l_qname > sizeof(S.qname)) {
+                if ((rc = api.batch_ingest_qname(batch, i, buf, sizeof(buf)))) die_gpu(api, rc, "ingest_qname");
+                qn = buf;
+            }
+            auto it = ps.qname2haptag.find(qn);
+            if (it == ps.qname2haptag.end()) continue;
+            int hap_raw;
+            if (ps.stores_raw_tag) {
+                auto ir = ps.qname2haptag_raw.find(qn);
+                if (ir == ps.qname2haptag_raw.end()) continue;
+                hap_raw = ir->second;
+            } else {
+                hap_raw = S.hp;
+                if (S.hp_irregular) fprintf(stderr, "[W::%s] irregular HP tag? qn=%s qs=%d\n", "get_hp_from_aln", qn, (int)S.pos);
+            }
+            if ((uint8_t)hap_raw == (uint8_t)kHaptagUnphased) continue;
+            if (!S.md) die_gpu(api, POMFRET_GPU_ERR_MISSING_MD, "recover");
+            pomfret_gpu_read_desc d;
+            memset(&d, 0, sizeof(d));
+            d.pos = S.pos; d.l_qseq = S.l_qseq; d.n_cigar = S.n_cigar; d.flag = S.flag; d.mapq = S.mapq;
+            d.hp = kHaptagUnphased; d.mn = -1; d.ml_len = -1;
+            d.cigar = (const uint32_t *)(uintptr_t)S.cigar; d.seq = (const uint8_t *)(uintptr_t)S.seq;
+            d.md = (const char *)(uintptr_t)S.md; d.md_len = S.md_len;
+            d.reserved = S.end_pos;
+            descs.push_back(d);
+            read_hap.push_back((uint8_t)it->second);
+        }
+        std::vector<int32_t> votes(2 * poss.size() + 1, 0);
+        if (!descs.empty()) {
+            if ((rc = api.batch_add_reads_device(batch, descs.data(), (uint32_t)descs.size(), nullptr))) die_gpu(api, rc, "batch_add_reads");
+            if ((rc = api.batch_submit(batch))) die_gpu(api, rc, "batch_submit");
+            if ((rc = api.haptag(batch, nullptr, 0, nullptr, 0, nullptr))) die_gpu(api, rc, "haptag");
+            std::vector<uint8_t> tags(descs.size());
+            std::vector<int32_t> st(descs.size());
+            if ((rc = api.batch_collect_haptags(batch, tags.data(), st.data()))) die_gpu(api, rc, "collect_haptags");  // (MD errors surface here)
+            if ((rc = api.variant_votes(batch, poss.data(), (uint32_t)poss.size(), read_hap.data(), votes.data()))) die_gpu(api, rc, "variant_votes");
+        }
+        // the reference's merged walk (blockjoin.c:2557-2600): known positions in order; of several known variants at
+        // one position only the last one sees the reads' variants; a known variant that ends the merged list (no read
+        // variant at or behind it) is never evaluated
+        const size_t n = poss.size();
+        for (size_t i = 0; i < n; i++) {
+            const bool is_last_entry = i + 1 == n && votes[2 * n] == 0;
+            if (is_last_entry) break;
+            int c0 = votes[2 * i], c1 = votes[2 * i + 1];
+            if (i + 1 < n && poss[i + 1] == poss[i]) c0 = c1 = 0;
+            (*pos2hap)[poss[i]] = c0 > c1 ? 1u : c1 > c0 ? 0u : (uint32_t)kHaptagUnphased;
+        }
+    }
+
     // pre_haplotagging_read_in_one_ref through the compressed ingest: the contig is walked in slices of 2 Mb of
     // reference; a slice's query returns every record that overlaps it, and a record belongs to the slice its start
     // lies in, so every record is taken once, in BAM order.  The device inflates, slices and haplotags; the host sees
@@ -942,7 +1034,16 @@ int run_methphase(const Options &opt, RunStats *stats) {
     if (opt.do_output_tsv) { output_tsv(ps, opt.output_prefix); fprintf(stderr, "[M::%s] tsv written.\n", "main_blockjoin"); }
     if (!opt.fn_vcf.empty()) {
         fprintf(stderr, "[M::%s] writing vcf...\n", "main_blockjoin");
-        recover_variant_phase_in_dropped_intervals(&ps, opt.fn_bam, opt.fn_vcf);
+        if (eng.gpu_ingest) {
+            Worker wk;
+            wk.eng = &eng; wk.id = 0; wk.device = 0;
+            if (!wk.open(opt.fn_bam)) exit(1);
+            recover_variant_phase_in_dropped_intervals(&ps, opt.fn_bam, opt.fn_vcf,
+                [&](const std::string &refname, uint32_t start, uint32_t end, const std::vector<uint32_t> &poss, std::unordered_map<uint32_t, uint32_t> *pos2hap) {
+                    wk.recover_interval_device(ps, refname, start, end, poss, pos2hap);
+                });
+            wk.close();
+        } else recover_variant_phase_in_dropped_intervals(&ps, opt.fn_bam, opt.fn_vcf);
         output_modify_vcf(opt.fn_vcf, ps, opt.output_prefix);
         fprintf(stderr, "[M::%s] vcf written.\n", "main_blockjoin");
     }

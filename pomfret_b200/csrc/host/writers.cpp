@@ -214,7 +214,8 @@ static void recover_one_interval(PhaseState *ps, BamReader &bam, const std::stri
     }
 }
 
-int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string &fn_bam, const std::string &fn_vcf) {
+int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string &fn_bam, const std::string &fn_vcf,
+                                               const RecoverIntervalFn &on_device) {
     const size_t n_ref = ps->st.ref_names.size();
     // known variants per contig: a second pass over the VCF keyed by contig name (blockjoin.c:2626-2640)
     std::vector<KnownVariants> vars(n_ref);
@@ -242,6 +243,7 @@ int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string
                 if (pos >= start && pos < end) poss.push_back(pos);
                 if (pos >= end) { prev_i = i; break; }
             }
+            if (on_device) { on_device(ps->st.ref_names[r], start, end, poss, &ps->varphase_in_dropped[r]); continue; }
             if (!opened) {
                 if (!bam.open(fn_bam)) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "recover_variant_phase_in_one_interval", fn_bam.c_str()); exit(1); }
                 opened = true;

@@ -4,6 +4,7 @@
 #ifndef POMFRET_HOST_WRITERS_H
 #define POMFRET_HOST_WRITERS_H
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -27,7 +28,12 @@ void output_tsv(const PhaseState &ps, const std::string &prefix);  // blockjoin.
 void output_debug_read2tag(const PhaseState &ps, const std::string &prefix);  // blockjoin.c:2223-2248 (hash order differs)
 
 // recover_variant_phase_in_dropped_intervals (blockjoin.c:2618-2692)
-int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string &fn_bam, const std::string &fn_vcf);
+// `on_device` (may be empty): evaluates one interval on the device instead of the host loop below it
+// (recover_variant_phase_in_one_interval, blockjoin.c:2475-2600)
+using RecoverIntervalFn = std::function<void(const std::string &refname, uint32_t start, uint32_t end, const std::vector<uint32_t> &poss,
+                                             std::unordered_map<uint32_t, uint32_t> *pos2hap)>;
+int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string &fn_bam, const std::string &fn_vcf,
+                                               const RecoverIntervalFn &on_device = RecoverIntervalFn());
 // output_modify_vcf (blockjoin.c:2909-2988); returns 0 or 1 on a fatal header problem
 int output_modify_vcf(const std::string &fn_vcf, const PhaseState &ps, const std::string &prefix);
 // output_modify_bam + sam_index_build3 (blockjoin.c:3022-3103, 4714-4731)

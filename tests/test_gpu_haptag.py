@@ -98,3 +98,87 @@ def test_haptag_gpu(untagged_small):
 def test_haptag_gpu_long_reads(built, tmp_path):
     data = conftest.run_synth(str(tmp_path / "untl"), ["-c", "30", "-s", "43", "-C", "chr20:64444167:7000000-8000000", "--untagged"])
     haptag_parity(pb.load_gpu(), data, "chr20")
+
+
+# ---- votes for the phase of unphased variants (recover_variant_phase_in_one_interval, blockjoin.c:2475-2600) ----
+def _read_variant_positions(d):
+    """positions of the variants a record shows itself (parse_variants_for_one_read, blockjoin.c:1545-1691):
+    insertions from the CIGAR, mismatches and deletions from MD — a plain re-derivation for the test"""
+    import re
+    out = []
+    ref = d.pos
+    cig = np.ctypeslib.as_array(C.cast(d.cigar, C.POINTER(C.c_uint32)), shape=(d.n_cigar,))
+    for c in cig:
+        op, ln = int(c) & 15, int(c) >> 4
+        if op in (0, 2, 3, 7, 8):
+            ref += ln
+        elif op == 1:
+            out.append(ref)
+    md = C.string_at(d.md, d.md_len).decode()
+    ref = d.pos
+    for num, dele, mis in re.findall(r"(\d+)|(\^[A-Za-z]+)|([A-Za-z])", md):
+        if num:
+            ref += int(num)
+        elif dele:
+            out.append(ref)
+            ref += len(dele) - 1
+        else:
+            out.append(ref)
+            ref += 1
+    return out
+
+
+def variant_votes_parity(gpu, data, chrom):
+    host = _setup_host()
+    hb = host.bam_open(data["bam"])
+    w = host.lib.pomfret_host_contig_load(hb, chrom.encode())
+    n = host.window_n(w)
+    cap = 1 << 17
+    vars_ = (pb.Variant * cap)()
+    bases = np.zeros(cap * 4, np.uint8)
+    nb = C.c_int()
+    nk = host.lib.pomfret_host_load_variants(data["vcf"].encode(), chrom.encode(), vars_, cap, bases.ctypes.data, cap * 4, C.byref(nb))
+    poss = np.array(sorted(vars_[i].pos for i in range(nk)), dtype=np.uint32)
+    poss = np.concatenate([poss[:50], poss[10:12], poss[50:]])  # a few duplicated positions
+    poss.sort()
+    rng = np.random.default_rng(5)
+    read_hap = rng.choice(np.array([0, 1, 2, 255], dtype=np.uint8), size=n, p=[0.4, 0.4, 0.1, 0.1])
+    descs = host.window_descs(w)
+    sz = C.sizeof(pb.ReadDesc)
+    want = np.zeros(2 * len(poss) + 1, np.int64)
+    last = int(poss[-1])
+    for i in range(n):
+        if read_hap[i] == 255:
+            continue
+        for p in _read_variant_positions(pb.ReadDesc.from_address(descs + i * sz)):
+            if p >= last:
+                want[2 * len(poss)] += 1
+            if read_hap[i] < 2:
+                for k in range(int(np.searchsorted(poss, p, "left")), int(np.searchsorted(poss, p, "right"))):
+                    want[2 * k + int(read_hap[i])] += 1
+    ctx = gpu.init([0])
+    b = gpu.batch_begin(ctx)
+    b.add_reads(descs, n)
+    b.submit()
+    b.haptag(np.zeros(1, np.uint8), 0, np.zeros(0, np.uint8), np.zeros(max(n, 1), np.uint32))
+    b.collect_haptags()
+    votes = np.zeros(2 * len(poss) + 1, np.int32)
+    gpu.lib.pomfret_gpu_variant_votes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    assert gpu.lib.pomfret_gpu_variant_votes(b.h, poss.ctypes.data, len(poss), read_hap.ctypes.data, votes.ctypes.data) == 0
+    assert np.array_equal(votes.astype(np.int64), want)
+    assert want[:-1].sum() > 100
+    b.end()
+    gpu.destroy(ctx)
+    host.window_free(w)
+    host.bam_close(hb)
+
+
+@pytest.mark.emu
+def test_variant_votes_emulated(untagged_small):
+    import build_emu
+    variant_votes_parity(pb.load_gpu(build_emu.build()), untagged_small, "chrU")
+
+
+@pytest.mark.gpu
+def test_variant_votes_gpu(untagged_small):
+    variant_votes_parity(pb.load_gpu(), untagged_small, "chrU")

@@ -12,9 +12,12 @@
  *                        vvar_t *known_vars, htstri_t *qname2haptag_raw)
  *                    reference blockjoin.c:1841-1898, called from :2075 and :2152
  *
- * BAM iteration and the record filters stay on the host (htslib side of the
- * seam); everything from "a record passed the filters" to "decision + one
- * haplotag per read" runs on the device.
+ * Two ways in.  (a) Records the caller has already read (htslib side of the seam:
+ * BAM iteration and the record filters on the host) are staged with add_reads().
+ * (a') Compressed ingest: the caller ships the BGZF blocks of its region queries as
+ * they lie in the file; inflate, record walk, filters and field slicing run on the
+ * device.  Either way everything from "a record passed the filters" to "decision +
+ * one haplotag per read" runs on the device.
  *
  * Conventions
  *   - every entry point returns 0 (POMFRET_GPU_OK) or a negative error code;
@@ -203,6 +206,11 @@ int pomfret_gpu_batch_ingest_bgzf(pomfret_gpu_batch *b, const void *comp, size_t
                                   uint32_t n_blocks, const pomfret_gpu_bgzf_stream *streams, uint32_t n_streams,
                                   const pomfret_gpu_ingest_filter *flt, uint32_t *n_records);
 int pomfret_gpu_batch_ingest_records(pomfret_gpu_batch *b, pomfret_gpu_sliced_record *out, uint32_t cap);
+/* Coverage estimate over the records of the ingest (estimate_read_coverage_dirtyfast, blockjoin.c:951-1040; SURVEY.md
+ * §8(f) row 4): with the filter set to {min_mapq 5, min_len 15000, check_de} the kept records that start at or behind
+ * min_pos each add one to bin i/bin_size for i = pos, pos+bin_size, ... < end_pos; *increments = how many of those
+ * fall on a bin below n_bins (the reference only uses the sum of a contig's bins: coverage = sum / n_bins). */
+int pomfret_gpu_batch_ingest_coverage(pomfret_gpu_batch *b, uint32_t min_pos, uint32_t bin_size, uint32_t n_bins, uint64_t *increments);
 /* add_reads_shared() for records of the ingest: the pointers of r[] are the device addresses of a sliced record and
  * r[i].reserved carries its end_pos; the payload is copied out of the inflated stream on the device. */
 int pomfret_gpu_batch_add_reads_device(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as);

@@ -131,6 +131,7 @@ class GpuLib:
         lib.pomfret_gpu_batch_ingest_records.argtypes = [vp, vp, C.c_uint32]
         lib.pomfret_gpu_debug_get_inflated.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.pomfret_gpu_batch_ingest_qname.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+        lib.pomfret_gpu_batch_ingest_coverage.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_add_windows.argtypes = [vp, vp, vp, vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
@@ -227,6 +228,12 @@ class Batch:
         if rc == 0:
             self.gpu.check(self.gpu.lib.pomfret_gpu_batch_ingest_records(self.h, recs, n.value), "ingest_records")
         return rc, recs, n.value
+
+    def ingest_coverage(self, min_pos, bin_size, n_bins):
+        """bin increments of the ingest's kept records (estimate_read_coverage_dirtyfast, blockjoin.c:1016-1021)"""
+        v = C.c_uint64()
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_ingest_coverage(self.h, min_pos, bin_size, n_bins, C.byref(v)), "ingest_coverage")
+        return v.value
 
     def inflated(self, stream, cap=1 << 28):
         n = C.c_size_t()

@@ -617,5 +617,25 @@ __global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) 
     P.rec[ri] = R;
 }
 
+// ---- coverage estimate (estimate_read_coverage_dirtyfast, blockjoin.c:951-1040) ----
+// The reference adds one to bin i/mod for i = start, start+mod, ... < end of every record that passes its filters and
+// then only ever uses the SUM of a contig's bins (tot / n_bins), so the bins are not materialised: every kept record
+// of the ingest that starts at or behind min_pos (records in front of it belong to the previous slice of the contig)
+// contributes the number of its increments that fall on a bin below n_bins.
+__global__ void coverage_kernel(const pomfret_gpu_sliced_record *rec, uint32_t n_records, uint32_t min_pos, uint32_t bin_size,
+                                uint32_t n_bins, unsigned long long *total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t inc = 0;
+    if (i < n_records && rec[i].keep && rec[i].pos >= min_pos && rec[i].end_pos > rec[i].pos) {
+        const uint32_t s = rec[i].pos, e = rec[i].end_pos;
+        inc = (e - s + bin_size - 1) / bin_size;                // i = s + j*mod < e
+        const uint32_t first_bin = s / bin_size;                // bin of step j: (s + j*mod)/mod = first_bin + j
+        const uint32_t room = first_bin < n_bins ? n_bins - first_bin : 0u;
+        if (inc > room) inc = room;
+    }
+    inc = warp_sum(inc);
+    if (lane_id() == 0 && inc) atomicAdd(total, (unsigned long long)inc);
+}
+
 }  // namespace pomfret_gpu
 #endif

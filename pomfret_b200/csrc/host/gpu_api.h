@@ -26,6 +26,7 @@ struct GpuApi {
                              uint32_t, const pomfret_gpu_ingest_filter *, uint32_t *) = nullptr;
     int (*batch_ingest_records)(pomfret_gpu_batch *, pomfret_gpu_sliced_record *, uint32_t) = nullptr;
     int (*batch_ingest_qname)(pomfret_gpu_batch *, uint32_t, char *, uint32_t) = nullptr;
+    int (*batch_ingest_coverage)(pomfret_gpu_batch *, uint32_t, uint32_t, uint32_t, uint64_t *) = nullptr;
     int (*variant_votes)(pomfret_gpu_batch *, const uint32_t *, uint32_t, const uint8_t *, int32_t *) = nullptr;
     int (*host_register)(pomfret_gpu_ctx *, void *, size_t) = nullptr;
     int (*host_unregister)(pomfret_gpu_ctx *, void *) = nullptr;

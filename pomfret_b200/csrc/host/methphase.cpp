@@ -537,6 +537,46 @@ struct Worker {
         }
     }
 
+    // estimate_read_coverage_dirtyfast (blockjoin.c:951-1040) for one contig through the compressed ingest: slices of
+    // 4 Mb of reference, a record belongs to the slice its start lies in; inflate, record walk, the estimator's own
+    // filters (:1000-1011) and the bin increments (:1016-1021) run on the device, the host only adds up one number per slice.
+    int coverage_contig_device(int tid) {
+        const GpuApi &api = eng->api;
+        need_batch();
+        if (fd < 0) {
+            fd = ::open(bam.fn.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) { fprintf(stderr, "[E::%s] failed to open input file: %s\n", "estimate_read_coverage_dirtyfast", bam.fn.c_str()); exit(1); }
+            file_size = (uint64_t)st.st_size;
+        }
+        const uint32_t mod = 5000;
+        const int64_t contig_len = (int64_t)bam.hdr->target_len[tid], slice = 4000000;
+        const uint32_t n_bins = (uint32_t)(contig_len / mod);
+        pomfret_gpu_ingest_filter flt;
+        memset(&flt, 0, sizeof(flt));
+        flt.min_mapq = 5; flt.min_len = 15000; flt.check_de = 1; flt.max_de = kMinAlnDe;
+        uint64_t tot = 0;
+        for (int64_t beg = 0; beg < contig_len; beg += slice) {
+            const int64_t end = std::min(contig_len, beg + slice);
+            plan.clear();
+            if (!ingest_plan_region(bam.idx, tid, beg, end, 0, file_size, &plan)) break;  // (no index data for this target)
+            if (plan.ranges.empty()) continue;
+            int rc;
+            if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+            if (comp_buf.size() < plan.comp_bytes + 64) comp_buf.resize(plan.comp_bytes + plan.comp_bytes / 4 + 64);
+            read_chunk(&plan, comp_buf.data());
+            uint32_t n_rec = 0;
+            if ((rc = api.batch_ingest_bgzf(batch, comp_buf.data(), plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
+                                            (uint32_t)plan.streams.size(), &flt, &n_rec)))
+                die_gpu(api, rc, "ingest_bgzf");
+            stats.n_ingest_bytes += plan.comp_bytes;
+            uint64_t inc = 0;
+            if ((rc = api.batch_ingest_coverage(batch, (uint32_t)beg, mod, n_bins, &inc))) die_gpu(api, rc, "ingest_coverage");
+            tot += inc;
+        }
+        return n_bins ? (int)(tot / n_bins) : 0;
+    }
+
     // pre_haplotagging_read_in_one_ref through the compressed ingest: the contig is walked in slices of 2 Mb of
     // reference; a slice's query returns every record that overlaps it, and a record belongs to the slice its start
     // lies in, so every record is taken once, in BAM order.  The device inflates, slices and haplotags; the host sees
@@ -970,6 +1010,40 @@ std::vector<int> estimate_read_coverage(const std::string &fn_bam) {
     return covs;
 }
 
+// The same on the device: contigs are handed to the feeder workers, see Worker::coverage_contig_device
+std::vector<int> estimate_read_coverage_device(Engine &eng, const Options &opt) {
+    const double T = now_s();
+    BamReader hdr;
+    std::vector<int> covs;
+    if (!hdr.open(opt.fn_bam)) return covs;
+    const int n_targets = hdr.hdr->n_targets;
+    covs.assign((size_t)n_targets, 0);
+    fprintf(stderr, "[M::%s] estimate read depths...\n", "estimate_read_coverage_dirtyfast");
+    std::atomic<int> next(0);
+    int n_workers = std::max(1, std::min(opt.threads, n_targets));
+    n_workers = std::min(n_workers, 3 * std::max(1, eng.expected_devices(opt.gpus)));
+    auto body = [&](int wid) {
+        Worker wk;
+        wk.eng = &eng; wk.id = wid; wk.device = wid;
+        bool opened = false;
+        for (;;) {
+            const int tid = next.fetch_add(1);
+            if (tid >= n_targets) break;
+            if (!opened) { if (!wk.open(opt.fn_bam)) exit(1); opened = true; }
+            covs[(size_t)tid] = wk.coverage_contig_device(tid);
+        }
+        if (opened) wk.close();
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_workers; t++) th.emplace_back(body, t);
+    body(0);
+    for (auto &t : th) t.join();
+    for (int i = 0; i < n_targets; i++)
+        fprintf(stderr, "[M::%s] %s est. coverage is %d\n", "estimate_read_coverage_dirtyfast", hdr.hdr->target_name[i], covs[(size_t)i]);
+    fprintf(stderr, "[T::%s] used %.1fs\n", "estimate_read_coverage_dirtyfast", now_s() - T);
+    return covs;
+}
+
 int run_methphase(const Options &opt, RunStats *stats) {
     const double T = now_s();
     if (!files_exist(opt)) return 1;
@@ -989,7 +1063,7 @@ int run_methphase(const Options &opt, RunStats *stats) {
     std::vector<int> covs;
     BamReader hdr_only;
     if (base.cov_for_selection <= 0) {
-        covs = estimate_read_coverage(opt.fn_bam);
+        covs = eng.gpu_ingest ? estimate_read_coverage_device(eng, opt) : estimate_read_coverage(opt.fn_bam);
         if (!hdr_only.open(opt.fn_bam)) return 1;
     }
     std::vector<pomfret_gpu_config> cfgs;
@@ -1100,7 +1174,7 @@ int run_report(const Options &opt, RunStats *stats) {
     BamReader hdr_only;
     if (read_coverage <= 0) {
         fprintf(stderr, "[M::%s] estimating read depths..\n", "main_methreport");
-        covs = estimate_read_coverage(opt.fn_bam);
+        covs = eng.gpu_ingest ? estimate_read_coverage_device(eng, opt) : estimate_read_coverage(opt.fn_bam);
         if (!hdr_only.open(opt.fn_bam)) return 1;
     }
     std::vector<pomfret_gpu_config> cfgs;

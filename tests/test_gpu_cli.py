@@ -111,3 +111,26 @@ def test_methphase_pinned_record_slabs(synth30, tmp_path, monkeypatch):
 def test_methphase_hidden_options_k_and_n(synth30, tmp_path):
     # the reference's hidden -k / -n options (cli.c:267-283) beyond what round 1 compiled in: k = 5, 200 candidates
     run_both(str(tmp_path), synth30, ["-t", "3", "-c", "30", "-k", "5", "-n", "200"], None, [".mp.gtf", ".mp.vcf"])
+
+
+def test_methphase_without_cov_uses_the_coverage_estimator(built, tmp_path):
+    # no -c: estimate_read_coverage_dirtyfast (blockjoin.c:951-1040) sets cov_for_selection / n_candidates per contig
+    # (:4381-4390); here the estimate comes from the compressed ingest + coverage_kernel
+    import re
+    import subprocess
+    from test_host_frontend import MINE
+    # two whole contigs at different depths (the second one behind two empty header targets), 20 kb reads: the estimator only
+    # counts reads of 15 kb and more
+    synth30 = conftest.run_synth(str(tmp_path / "cov"), ["-c", "34", "-s", "77", "-F", "2", "-C", "chrK:1400000:0-1400000",
+                                                         "-C", "chrM:900000:0-900000", "--block", "200000"])
+    est = {}
+    for who, exe in (("ref", ob.REF_BIN), ("mine", MINE)):
+        prefix = str(tmp_path / who)
+        p = subprocess.run([exe, "methphase", "-t", "2", "-o", prefix, "--vcf", synth30["vcf"], synth30["bam"]],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, (who, p.stderr[-2000:])
+        est[who] = re.findall(r"\] (\S+) est\. coverage is (\d+)", p.stderr)
+    assert est["ref"] == est["mine"] and any(int(c) > 0 for _, c in est["mine"]), est
+    import filecmp
+    for suffix in (".mp.gtf", ".mp.vcf"):
+        assert filecmp.cmp(str(tmp_path / "ref") + suffix, str(tmp_path / "mine") + suffix, shallow=False), suffix

@@ -62,6 +62,14 @@ def check_ingest(gpu, data, cov, readlen, max_windows=2, full_pipeline=True):
     for s, want in enumerate(zlib_inflate_blocks(plan)):
         got = bytes(b.inflated(s))
         assert got == want, "stream %d differs from zlib" % s
+    # (1b) coverage estimator sum over the sliced records (estimate_read_coverage_dirtyfast's bin loop, blockjoin.c:1016-1021)
+    for min_pos, bin_size, n_bins in ((0, 5000, 1 << 20), (regions[0][0] + 20000, 700, (regions[0][1] - 30000) // 700), (0, 1, 10)):
+        want = 0
+        for i in range(n):
+            R = recs[i]
+            if R.keep and R.pos >= min_pos:
+                want += sum(1 for p in range(R.pos, R.end_pos, bin_size) if p // bin_size < n_bins)
+        assert b.ingest_coverage(min_pos, bin_size, n_bins) == want, (min_pos, bin_size, n_bins)
     # (2) records of every query against the host loader (the shim's iterator + filters)
     wins = parity.load_windows(host, hb, gaps, cfg)
     dsz = C.sizeof(_ffi.ReadDesc)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Executed warp instructions and stall samples per CUDA source line of one kernel of an .ncu-rep
 (captured with --import-source on; read here, without a GPU, through ncu's own source page).
-usage: ncu_by_line.py report.ncu-rep [top_n]"""
+usage: ncu_by_line.py report.ncu-rep [top_n] [kernel name regex]"""
 import csv
 import os
 import subprocess
@@ -11,8 +11,10 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True,
-                         text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+    if len(sys.argv) > 3:
+        cmd += ["-k", "regex:" + sys.argv[3], "-c", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     cur_file, hdr, lines = None, None, []
     for r in rows:

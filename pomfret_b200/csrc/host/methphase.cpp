@@ -841,12 +841,16 @@ void run_windows(Engine &eng, const Options &opt, const PhaseState &ps, const st
             (own ? n_own : n_helped)++;
         };
         // while the CUDA start-up is still under way: read the blocks of this worker's next chunks into plain memory
-        // (at most 768 MB per worker), so that the file reads are done by the time the device can take them
+        // (POMFRET_READ_AHEAD_MB per worker, default 96: enough for the first chunks to be ready when the device is; a
+        //  page-fault storm over gigabytes of fresh buffers would hold up the driver's own start-up, which maps memory
+        //  in this same process), so that the file reads are done by the time the device can take them
         if (eng.gpu_ingest) {
             std::deque<Worker::ReadAhead> queue;
             size_t buffered = 0;
             const size_t d = (size_t)wk.device;
-            while (!eng.is_ready() && buffered < ((size_t)768 << 20)) {
+            size_t ahead_cap = (size_t)96 << 20;
+            if (const char *e = getenv("POMFRET_READ_AHEAD_MB")) ahead_cap = (size_t)std::max(0, atoi(e)) << 20;
+            while (!eng.is_ready() && buffered < ahead_cap) {
                 const size_t c = cursor[d].fetch_add(1);
                 if (c >= set_begin[d + 1]) break;
                 queue.emplace_back();

@@ -72,9 +72,21 @@ struct SegInfo {
 
 // Whole-record tables of the lean path (records of at most 65535 bases and LEAN_MI M/I operations: every position
 // fits 16 bits, so both tables of a record stay in shared memory and nothing goes through scratch arrays).
-constexpr int LEAN_CH = 2048;         // 16-byte SEQ chunks of a record: 65536 bases
-constexpr int LEAN_MI = 512;          // M/I operations in front of the first stopping operation
-constexpr int LEAN_MAXLEN = 65535;
+// (measured, profiles/r02e_decode_variants.txt: 9 / 10 / 12 CTAs per SM with 56 / 48 / 40 registers and smaller tables are
+//  slower than 8 CTAs with 64 registers — 0.590 / 0.649 / 0.845 against 0.576 ms on 50 k records)
+#ifndef POMFRET_DEC_LEAN_CH
+#define POMFRET_DEC_LEAN_CH 2048
+#endif
+#ifndef POMFRET_DEC_LEAN_MI
+#define POMFRET_DEC_LEAN_MI 512
+#endif
+#ifndef POMFRET_DEC_MIN_CTAS
+#define POMFRET_DEC_MIN_CTAS 8
+#endif
+constexpr int LEAN_CH = POMFRET_DEC_LEAN_CH;   // 16-byte SEQ chunks of a record (a multiple of 128): 2048 = 65536 bases
+constexpr int LEAN_MI = POMFRET_DEC_LEAN_MI;   // M/I operations in front of the first stopping operation (a multiple of 8)
+constexpr int LEAN_MAXLEN = LEAN_CH * 32 - 1 < 65535 ? LEAN_CH * 32 - 1 : 65535;
+static_assert(LEAN_CH % 128 == 0 && LEAN_CH <= 2048 && LEAN_MI % 8 == 0, "lean tables: whole super-tiles, 16-bit positions");
 constexpr int16_t LEAN_DROP = (int16_t)0x8000;
 
 struct DecodeWarpSmem {
@@ -1038,10 +1050,12 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             const uint32_t r = found ? rr : 0u;
             // chunk (scan order) that holds rank r: last c with l_first[c] <= r; unused entries are 0xffff
             // (the cursor is a pointer so that every step is load-with-immediate-offset, compare, predicated add)
+            // (the range shrinks by its probed half whether or not the step is taken — len - len/2 is at least the half
+            //  that stays — so the probe offsets are compile-time constants for any table size)
             const uint16_t *fq = sm.l_first;
 #pragma unroll
-            for (uint32_t st = LEAN_CH / 2; st >= 1; st >>= 1)
-                if (fq[st] <= r) fq += st;
+            for (uint32_t ln = LEAN_CH; ln > 1; ln -= ln >> 1)
+                if (fq[ln >> 1] <= r) fq += ln >> 1;
             const uint32_t c = (uint32_t)(fq - sm.l_first);
             const uint32_t f0 = fq[0], cnt = fq[1] - f0;
             const uint32_t chunk = rev ? n_ch - 1u - c : c;
@@ -1070,10 +1084,10 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             const uint32_t q = has_ml ? ml[ml_base + kk * stride + m_idx] : 255u;
             r_cat[row] = q < P.lo ? 1u : (q >= P.hi ? 0u : 2u);  // blockjoin.c:876-878
             // the operation whose inclusive trigger loop (blockjoin.c:663-665) handles the base: first one ending at or behind it
-            const uint16_t *eq = &sm.l_end[0] - 1;  // (eq[st] is l_end[j + st - 1])
+            const uint16_t *eq = &sm.l_end[0] - 1;  // (eq[h] is l_end[j + h - 1]; eq + 1 - l_end counts the entries < p)
 #pragma unroll
-            for (uint32_t st = LEAN_MI / 2; st >= 1; st >>= 1)
-                if (eq[st] < p) eq += st;
+            for (uint32_t ln = LEAN_MI; ln > 1; ln -= ln >> 1)
+                if (eq[ln >> 1] < p) eq += ln >> 1;
             const uint32_t j = (uint32_t)(eq + 1 - sm.l_end);
             const int32_t o = sm.l_off[j < (uint32_t)LEAN_MI ? j : 0u];
             const bool at_clip = j0 && p == clip;  // a base right at the clip edge (blockjoin.c:640-652)
@@ -1414,7 +1428,7 @@ static_assert(sizeof(DecodeWarpSmem) >= sizeof(GenSeg) * GEN_MAXSEG, "the genera
 
 // Persistent warps: every warp takes the next record off a queue (longest records first), so neither the
 // spread of record lengths inside a CTA nor the last wave of the grid leaves warp slots idle.
-__global__ void __launch_bounds__(DEC_WARPS * 32, 8) decode_kernel(DecodeParams P) {
+__global__ void __launch_bounds__(DEC_WARPS * 32, POMFRET_DEC_MIN_CTAS) decode_kernel(DecodeParams P) {
     __shared__ DecodeWarpSmem smem[DEC_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     DecodeWarpSmem &sm = smem[warp];

@@ -15,7 +15,9 @@ collect) over that batch.
                         PCIe, kernels, D2H of decisions and tags; region chunks pipelined
   cli_e2e               wall time of the drop-in CLI (`pomfret methphase`, BGZF inflate and writers included) next to the
                         unmodified reference CLI on the same files — the like-for-like number; cli_report: `report`
-  untagged              config 4: the -u read haplotagger over an untagged 30x sample (roofline_haptag)
+  untagged              config 4: the -u read haplotagger over an untagged 30x sample (roofline_haptag); cli_untagged, and
+                        cli_write_bam: the same run with --write-bam (output BAM re-tagged on the device, blocks compressed
+                        on the host threads, BAI from the block table; .mp.bam and .bai compared byte for byte)
   strong                N > 1: the same batch cut into one contiguous region set per rank (no data-path collective,
                         host gather of decisions, checked against rank 0's own full run)
   cpu_baseline          the compiled reference's per-window call sequence on a bounded sample, 1 thread (N = 1 only)
@@ -562,14 +564,15 @@ def main():
         env.pop("POMFRET_GPU_STAGE_THREADS", None)
         for key, sub, extra, d in (("cli_e2e", "methphase", ["-c", str(cov)], data),
                                    ("cli_report", "report", ["-c", str(cov), "--chunk-size", "50000", "--chunk-stride", "100000"], data),
-                                   ("cli_untagged", "methphase", ["-u", "-c", "30"], untagged["data"] if untagged else None)):
+                                   ("cli_untagged", "methphase", ["-u", "-c", "30"], untagged["data"] if untagged else None),
+                                   ("cli_write_bam", "methphase", ["-u", "-c", "30", "--write-bam"], untagged["data"] if untagged else None)):
             if d is None:
                 continue
             po, pr = os.path.join(tmp, key + "_ours"), os.path.join(tmp, key + "_ref")
             common = extra + ["--vcf", d["vcf"], d["bam"]]
             t_ours, t_start = min(wall([mine, sub, "-t", thr, "--gpus", str(world), "-o", po] + common, env, True) for _ in range(2))
             t_ref = wall([ob.REF_BIN, sub, "-t", thr, "-o", pr] + common)
-            suffixes = [".report.tsv"] if sub == "report" else [".mp.gtf", ".mp.vcf"]
+            suffixes = [".report.tsv"] if sub == "report" else [".mp.gtf", ".mp.vcf"] + ([".mp.bam", ".mp.bam.bai"] if "--write-bam" in extra else [])
             same = all(open(po + s_, "rb").read() == open(pr + s_, "rb").read() for s_ in suffixes)
             if not same:
                 raise RuntimeError("%s: output files differ from the reference's" % key)

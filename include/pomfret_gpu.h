@@ -193,11 +193,18 @@ typedef struct pomfret_gpu_sliced_record {  /* one alignment record as the slici
     uint8_t bad;                              /* malformed record (fields run past its end) */
     uint8_t has_mm, hp_irregular;             /* MM/Mm present; HP:0 ("irregular HP tag", blockjoin.c:916) */
     uint8_t l_qname;                          /* with the NUL */
-    uint8_t pad[3];
+    uint8_t hp_type;                          /* type byte of the first HP tag (0 if the record has none) */
+    uint8_t cg_cigar;                         /* 1: the CIGAR was taken from the CG tag */
+    uint8_t pad;
     uint64_t cigar, seq, mm, ml, md;          /* 0 if absent */
     uint64_t qname_dev;
+    uint32_t rec_bytes;                       /* the record in the file: 4 + block_size */
+    uint32_t hp_off;                          /* offset of the HP tag's type byte from the record's start (if hp_type) */
+    int32_t tid;
+    uint32_t reserved;
     char qname[48];                           /* NUL terminated prefix; the whole name if l_qname <= 48 */
 } pomfret_gpu_sliced_record;
+#define POMFRET_GPU_ANY_TID (-0x7fffffff - 1)  /* pomfret_gpu_bgzf_stream::tid: walk every record of the stream, whatever its target or position */
 /* pinned host buffer of the batch for the compressed blocks (valid until the next reset): the loader reads the file into it */
 int pomfret_gpu_batch_ingest_buffer(pomfret_gpu_batch *b, size_t bytes, void **out);
 /* H2D of the blocks, inflate (ISIZE + CRC-32 checked), record walk and slicing; *n_records = records found in the streams,
@@ -211,6 +218,14 @@ int pomfret_gpu_batch_ingest_records(pomfret_gpu_batch *b, pomfret_gpu_sliced_re
  * min_pos each add one to bin i/bin_size for i = pos, pos+bin_size, ... < end_pos; *increments = how many of those
  * fall on a bin below n_bins (the reference only uses the sum of a contig's bins: coverage = sum / n_bins). */
 int pomfret_gpu_batch_ingest_coverage(pomfret_gpu_batch *b, uint32_t min_pos, uint32_t bin_size, uint32_t n_bins, uint64_t *increments);
+/* Output-BAM re-tagging (output_modify_bam, blockjoin.c:3022-3103).  Every record of the ingest, in
+ * order, is copied into one contiguous uncompressed BAM stream with its HP tag set the way bam_aux_update_int(aln, "HP", v)
+ * does it (blockjoin.c:3092): hp_val[i] = v in 1..255 (values below 255 as type C, 255 as S); an integer HP tag of at least
+ * that size is overwritten in place (keeping its size, unsigned type), a smaller one grows, a record without the tag gets
+ * it appended; hp_val[i] = 0 copies the record unchanged.  dst_off[i] = offset of record i in the output stream (the caller
+ * derives the new sizes from rec_bytes / hp_type of the sliced records); the out_bytes bytes of the stream are written to
+ * host_out. */
+int pomfret_gpu_batch_ingest_retag(pomfret_gpu_batch *b, const uint64_t *dst_off, const uint8_t *hp_val, uint64_t out_bytes, void *host_out);
 /* add_reads_shared() for records of the ingest: the pointers of r[] are the device addresses of a sliced record and
  * r[i].reserved carries its end_pos; the payload is copied out of the inflated stream on the device. */
 int pomfret_gpu_batch_add_reads_device(pomfret_gpu_batch *b, const pomfret_gpu_read_desc *r, uint32_t n, const int64_t *same_as);

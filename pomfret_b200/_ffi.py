@@ -65,9 +65,10 @@ class SlicedRecord(C.Structure):
     _fields_ = [("pos", C.c_uint32), ("end_pos", C.c_uint32), ("l_qseq", C.c_uint32), ("n_cigar", C.c_uint32), ("flag", C.c_uint16),
                 ("mapq", C.c_uint8), ("tags_malformed", C.c_uint8), ("hp", C.c_int32), ("mn", C.c_int32), ("mm_len", C.c_uint32),
                 ("ml_len", C.c_int32), ("md_len", C.c_uint32), ("stream", C.c_uint32), ("keep", C.c_uint8), ("bad", C.c_uint8),
-                ("has_mm", C.c_uint8), ("hp_irregular", C.c_uint8), ("l_qname", C.c_uint8), ("pad", C.c_uint8 * 3),
+                ("has_mm", C.c_uint8), ("hp_irregular", C.c_uint8), ("l_qname", C.c_uint8), ("hp_type", C.c_uint8), ("cg_cigar", C.c_uint8), ("pad", C.c_uint8),
                 ("cigar", C.c_uint64), ("seq", C.c_uint64), ("mm", C.c_uint64), ("ml", C.c_uint64), ("md", C.c_uint64),
-                ("qname_dev", C.c_uint64), ("qname", C.c_char * 48)]
+                ("qname_dev", C.c_uint64), ("rec_bytes", C.c_uint32), ("hp_off", C.c_uint32), ("tid", C.c_int32),
+                ("reserved", C.c_uint32), ("qname", C.c_char * 48)]
 
 
 class Timing(C.Structure):
@@ -132,6 +133,7 @@ class GpuLib:
         lib.pomfret_gpu_debug_get_inflated.argtypes = [vp, C.c_uint32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.pomfret_gpu_batch_ingest_qname.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
         lib.pomfret_gpu_batch_ingest_coverage.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+        lib.pomfret_gpu_batch_ingest_retag.argtypes = [vp, vp, vp, C.c_uint64, vp]
         lib.pomfret_gpu_batch_add_window.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         lib.pomfret_gpu_batch_add_windows.argtypes = [vp, vp, vp, vp, vp, C.c_uint32]
         lib.pomfret_gpu_batch_submit.argtypes = [vp]
@@ -234,6 +236,13 @@ class Batch:
         v = C.c_uint64()
         self.gpu.check(self.gpu.lib.pomfret_gpu_batch_ingest_coverage(self.h, min_pos, bin_size, n_bins, C.byref(v)), "ingest_coverage")
         return v.value
+
+    def ingest_retag(self, dst_off, hp_val, out_bytes):
+        """re-tagged uncompressed BAM stream of the ingest's records (output_modify_bam, blockjoin.c:3022-3103)"""
+        out = np.zeros(max(int(out_bytes), 1), dtype=np.uint8)
+        self.gpu.check(self.gpu.lib.pomfret_gpu_batch_ingest_retag(self.h, dst_off.ctypes.data, hp_val.ctypes.data, int(out_bytes), out.ctypes.data),
+                       "ingest_retag")
+        return out[:int(out_bytes)]
 
     def inflated(self, stream, cap=1 << 28):
         n = C.c_size_t()

@@ -260,7 +260,7 @@ struct pomfret_gpu_batch {
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
     DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc, d_dup_of;
-    DevBuf d_comp, d_inflated, d_ing_tab, d_ing_small, d_rec_off, d_rec_stream, d_sliced, d_hap_counts, d_ing_cov;
+    DevBuf d_comp, d_inflated, d_ing_tab, d_ing_small, d_rec_off, d_rec_stream, d_sliced, d_hap_counts, d_ing_cov, d_retag_off, d_retag_val, d_retag_out;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -278,7 +278,7 @@ struct pomfret_gpu_batch {
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
                      &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_dup_of,
-                     &d_comp, &d_inflated, &d_ing_tab, &d_ing_small, &d_rec_off, &d_rec_stream, &d_sliced, &d_hap_counts, &d_ing_cov};
+                     &d_comp, &d_inflated, &d_ing_tab, &d_ing_small, &d_rec_off, &d_rec_stream, &d_sliced, &d_hap_counts, &d_ing_cov, &d_retag_off, &d_retag_val, &d_retag_out};
     }
 };
 

@@ -423,7 +423,7 @@ __global__ void walk_kernel(WalkParams P) {
         const uint32_t block_size = ld_u32(r);
         if (block_size < 32 || off + 4 + block_size > end) { atomicAdd(P.n_bad, 1); break; }  // the chunk does not hold whole records
         const int32_t tid = (int32_t)ld_u32(r + 4), pos = (int32_t)ld_u32(r + 8);
-        if (tid != S.tid || pos >= (int32_t)S.end0) break;  // sam_itr_next: the query is over (records are coordinate sorted)
+        if (S.tid != POMFRET_GPU_ANY_TID && (tid != S.tid || pos >= (int32_t)S.end0)) break;  // sam_itr_next: the query is over (records are coordinate sorted)
         if (P.fill) { P.rec_off[base + n] = off; P.rec_stream[base + n] = s; }
         n++;
         off += 4 + (uint64_t)block_size;
@@ -538,6 +538,7 @@ __global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) 
         else if (t0 == 'C' && t1 == 'G' && !cg) cg = val;
         p = q;
     }
+    bool cg_used = false;
     auto aux2i = [](const uint8_t *v, bool *ok) -> int64_t {  // bam_aux2i
         *ok = true;
         switch (v[0]) {
@@ -556,6 +557,7 @@ __global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) 
         if ((first & 15u) == 4u && (first >> 4) == l_qseq && n_real >= n_cigar && n_real < (1u << 29) && pos >= 0) {
             cigar = cg + 6;
             n_cigar = n_real;
+            cg_used = true;
         }
     }
     // ---- bam_endpos ----
@@ -612,6 +614,10 @@ __global__ void __launch_bounds__(SLICE_WARPS * 32) slice_kernel(SliceParams P) 
         const int64_t v = aux2i(hp, &ok);
         if (v == 0) R.hp_irregular = 1; else R.hp = (int32_t)(v - 1);
     }
+    R.rec_bytes = 4u + block_size;
+    R.tid = (int32_t)ld_u32(r + 4);
+    if (hp) { R.hp_type = hp[0]; R.hp_off = (uint32_t)(hp - r); }
+    R.cg_cigar = cg_used ? 1 : 0;
     R.keep = keep ? 1 : 0;
     R.bad = bad ? 1 : 0;
     P.rec[ri] = R;
@@ -635,6 +641,92 @@ __global__ void coverage_kernel(const pomfret_gpu_sliced_record *rec, uint32_t n
     }
     inc = warp_sum(inc);
     if (lane_id() == 0 && inc) atomicAdd(total, (unsigned long long)inc);
+}
+
+// ---- output-BAM re-tagging (output_modify_bam, blockjoin.c:3022-3103): one warp per record ----
+// The record is copied from the inflated stream to its place in the output stream with the HP tag set like
+// bam_aux_update_int(aln, "HP", v) (blockjoin.c:3092) sets it: v < 255 needs one byte (type C), 255 two (type S); an
+// integer HP tag that is large enough keeps its size and becomes unsigned, a smaller one grows (the tags behind it move
+// up), a record without the tag gets "HP" + type + value appended; block_size follows.
+struct RetagParams {
+    const uint8_t *in;            // inflated streams
+    const uint64_t *rec_off;
+    const pomfret_gpu_sliced_record *rec;
+    const uint64_t *dst_off;
+    const uint8_t *hp_val;
+    uint32_t n_records;
+    uint8_t *out;
+};
+
+// n bytes from src to dst, any alignment, whole warp: 32-bit stores built from two aligned source words
+__device__ __forceinline__ void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, unsigned lane) {
+    uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t words = n >> 2;
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3u) * 8u;
+    const uint32_t *s32 = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t w = lane; w < words; w += 32) {
+        const uint32_t lo = s32[w], hi = sh ? s32[w + 1] : 0u;
+        d32[w] = __funnelshift_r(lo, hi, sh);
+    }
+    const uint32_t done = words << 2;
+    if (done + lane < n) dst[done + lane] = src[done + lane];
+}
+
+__device__ __forceinline__ uint32_t aux_int_size(uint32_t type) {
+    return (type == 'c' || type == 'C') ? 1u : (type == 's' || type == 'S') ? 2u : (type == 'i' || type == 'I') ? 4u : 0u;
+}
+
+__global__ void __launch_bounds__(SLICE_WARPS * 32) retag_kernel(RetagParams P) {
+    const uint32_t ri = blockIdx.x * SLICE_WARPS + (threadIdx.x >> 5);
+    if (ri >= P.n_records) return;
+    const unsigned lane = lane_id();
+    const uint8_t *r = P.in + P.rec_off[ri];
+    uint8_t *o = P.out + P.dst_off[ri];
+    const uint32_t n = P.rec[ri].rec_bytes, hp_type = P.rec[ri].hp_type, hp_off = P.rec[ri].hp_off;
+    const uint32_t val = P.hp_val[ri];
+    const uint32_t old_sz = hp_type ? aux_int_size(hp_type) : 0u;
+    if (val == 0u || (hp_type && old_sz == 0u)) {  // left as it is (an HP tag that is not an integer: the update fails, the record is written unchanged)
+        warp_copy_bytes(o, r, n, lane);
+        return;
+    }
+    uint32_t sz = val < 255u ? 1u : 2u;
+    if (!hp_type) {
+        warp_copy_bytes(o, r, n, lane);
+        __syncwarp();
+        if (lane == 0) {
+            o[n] = 'H'; o[n + 1] = 'P'; o[n + 2] = sz == 1u ? 'C' : 'S';
+            o[n + 3] = (uint8_t)val;
+            if (sz == 2u) o[n + 4] = 0;
+            const uint32_t bs = n - 4u + 3u + sz;
+            o[0] = (uint8_t)bs; o[1] = (uint8_t)(bs >> 8); o[2] = (uint8_t)(bs >> 16); o[3] = (uint8_t)(bs >> 24);
+        }
+        return;
+    }
+    if (old_sz >= sz) {
+        warp_copy_bytes(o, r, n, lane);
+        __syncwarp();
+        if (lane == 0) {
+            o[hp_off] = old_sz == 1u ? 'C' : (old_sz == 2u ? 'S' : 'I');
+            for (uint32_t i = 0; i < old_sz; i++) o[hp_off + 1u + i] = (uint8_t)(val >> (8u * i));
+        }
+        return;
+    }
+    // grow: [0, hp_off) | type + value | the tags behind the old value
+    const uint32_t grow = sz - old_sz, tail_from = hp_off + 1u + old_sz;
+    warp_copy_bytes(o, r, hp_off, lane);
+    warp_copy_bytes(o + hp_off + 1u + sz, r + tail_from, n - tail_from, lane);
+    __syncwarp();
+    if (lane == 0) {
+        o[hp_off] = sz == 1u ? 'C' : 'S';
+        o[hp_off + 1u] = (uint8_t)val;
+        if (sz == 2u) o[hp_off + 2u] = 0;
+        const uint32_t bs = n - 4u + grow;
+        o[0] = (uint8_t)bs; o[1] = (uint8_t)(bs >> 8); o[2] = (uint8_t)(bs >> 16); o[3] = (uint8_t)(bs >> 24);
+    }
 }
 
 }  // namespace pomfret_gpu

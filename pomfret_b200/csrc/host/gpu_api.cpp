@@ -50,7 +50,7 @@ bool GpuApi::load(std::string *err) {
     BIND(host_unregister, "pomfret_gpu_host_unregister") BIND(batch_add_reads_device, "pomfret_gpu_batch_add_reads_device")
     BIND(batch_ingest_buffer, "pomfret_gpu_batch_ingest_buffer") BIND(batch_ingest_bgzf, "pomfret_gpu_batch_ingest_bgzf")
     BIND(batch_ingest_records, "pomfret_gpu_batch_ingest_records") BIND(batch_ingest_qname, "pomfret_gpu_batch_ingest_qname")
-    BIND(batch_ingest_coverage, "pomfret_gpu_batch_ingest_coverage")
+    BIND(batch_ingest_coverage, "pomfret_gpu_batch_ingest_coverage") BIND(batch_ingest_retag, "pomfret_gpu_batch_ingest_retag")
     BIND(variant_votes, "pomfret_gpu_variant_votes") BIND(batch_add_window, "pomfret_gpu_batch_add_window") BIND(batch_submit, "pomfret_gpu_batch_submit")
     BIND(decode, "pomfret_gpu_decode") BIND(haptag, "pomfret_gpu_haptag") BIND(pileup, "pomfret_gpu_pileup")
     BIND(join, "pomfret_gpu_join") BIND(batch_collect, "pomfret_gpu_batch_collect")

@@ -27,6 +27,7 @@ struct GpuApi {
     int (*batch_ingest_records)(pomfret_gpu_batch *, pomfret_gpu_sliced_record *, uint32_t) = nullptr;
     int (*batch_ingest_qname)(pomfret_gpu_batch *, uint32_t, char *, uint32_t) = nullptr;
     int (*batch_ingest_coverage)(pomfret_gpu_batch *, uint32_t, uint32_t, uint32_t, uint64_t *) = nullptr;
+    int (*batch_ingest_retag)(pomfret_gpu_batch *, const uint64_t *, const uint8_t *, uint64_t, void *) = nullptr;
     int (*variant_votes)(pomfret_gpu_batch *, const uint32_t *, uint32_t, const uint8_t *, int32_t *) = nullptr;
     int (*host_register)(pomfret_gpu_ctx *, void *, size_t) = nullptr;
     int (*host_unregister)(pomfret_gpu_ctx *, void *) = nullptr;

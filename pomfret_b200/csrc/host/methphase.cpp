@@ -577,6 +577,232 @@ struct Worker {
         return n_bins ? (int)(tot / n_bins) : 0;
     }
 
+    // output_modify_bam + sam_index_build3 (blockjoin.c:3022-3103, 4714-4731) with the device doing the read side: the
+    // file is walked in chunks cut at record starts (the linear index holds them); inflate, record walk and slicing run
+    // on the device, the host decides every record's tag from its name (retag_next), retag_kernel lays the records out
+    // as the uncompressed output stream with their HP tags set, the host cuts that stream into BGZF blocks exactly as
+    // bgzf_write / bgzf_flush_try would (a record that does not fit the open block starts a new one), compresses the
+    // blocks on `n_threads` threads with the shim's own block compressor (same bytes as the sequential writer) and
+    // builds the BAI from the records' positions and the blocks' addresses instead of reading the output back.
+    // Returns false — nothing written that matters, the caller runs the host writer — when the file holds something
+    // the raw-record path does not reproduce (CIGARs carried in the CG tag are re-encoded by bam_read1 / bam_write1,
+    // HP values outside 1..255).
+    bool rewrite_bam_device(const PhaseState &ps, const std::string &fn_out, const std::string &fn_bai, int n_threads) {
+        const GpuApi &api = eng->api;
+        need_batch();
+        if (fd < 0) {
+            fd = ::open(bam.fn.c_str(), O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) return false;
+            file_size = (uint64_t)st.st_size;
+        }
+        // ---- cut points: the first record, then record starts from the linear index, then the end of the file ----
+        const uint64_t first_voff = (uint64_t)bgzf_tell(bam.fp->fp.bgzf);
+        std::vector<uint64_t> cuts;
+        for (int t = 0; t < pomfret_idx_nref(bam.idx); t++) {
+            const uint64_t *lin = nullptr;
+            const int n = pomfret_idx_linear(bam.idx, t, &lin);
+            for (int i = 0; i < n; i++) if (lin[i] > first_voff) cuts.push_back(lin[i]);
+        }
+        std::sort(cuts.begin(), cuts.end());
+        cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        const uint64_t end_voff = file_size << 16;
+        size_t chunk_bytes = (size_t)48 << 20;
+        if (const char *e = getenv("POMFRET_REWRITE_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
+        std::vector<uint64_t> bounds{first_voff};
+        for (uint64_t c : cuts)
+            if ((c >> 16) - (bounds.back() >> 16) >= chunk_bytes && c < end_voff) bounds.push_back(c);
+        bounds.push_back(end_voff);
+
+        FILE *fo = fopen(fn_out.c_str(), "wb");
+        if (!fo) { fprintf(stderr, "[E::%s] failed to open output file: %s\n", "output_modify_bam", fn_out.c_str()); return false; }
+        setvbuf(fo, nullptr, _IOFBF, 4 << 20);
+        uint64_t file_addr = 0;
+        std::vector<uint8_t> cbuf;
+        std::vector<int> csize;
+        // compress blocks[i] = [ptr, len) in parallel, append them to the file in order; returns each block's address
+        auto emit_blocks = [&](const std::vector<std::pair<const uint8_t *, int>> &blocks, std::vector<uint64_t> *addrs) {
+            const size_t nb = blocks.size();
+            if (cbuf.size() < nb * (size_t)BGZF_MAX_BLOCK_SIZE) cbuf.resize(nb * (size_t)BGZF_MAX_BLOCK_SIZE);
+            csize.assign(nb, 0);
+            std::atomic<size_t> next(0);
+            auto work = [&] {
+                for (;;) {
+                    const size_t i = next.fetch_add(1);
+                    if (i >= nb) break;
+                    csize[i] = pomfret_bgzf_compress_block(cbuf.data() + i * (size_t)BGZF_MAX_BLOCK_SIZE, blocks[i].first, blocks[i].second, -1);
+                }
+            };
+            std::vector<std::thread> th;
+            const int nt = (int)std::min<size_t>((size_t)std::max(1, n_threads), nb);
+            for (int t = 1; t < nt; t++) th.emplace_back(work);
+            work();
+            for (auto &t : th) t.join();
+            for (size_t i = 0; i < nb; i++) {
+                if (csize[i] < 0 || fwrite(cbuf.data() + i * (size_t)BGZF_MAX_BLOCK_SIZE, 1, (size_t)csize[i], fo) != (size_t)csize[i]) {
+                    fprintf(stderr, "[E::%s] failed to write %s\n", "output_modify_bam", fn_out.c_str());
+                    exit(1);
+                }
+                if (addrs) addrs->push_back(file_addr);
+                file_addr += (uint64_t)csize[i];
+            }
+        };
+        // ---- header (bam_hdr_write: its own blocks, flushed) ----
+        {
+            std::vector<uint8_t> h;
+            auto p32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) h.push_back((uint8_t)(v >> (8 * i))); };
+            h.insert(h.end(), {'B', 'A', 'M', 1});
+            p32((uint32_t)bam.hdr->l_text);
+            h.insert(h.end(), bam.hdr->text, bam.hdr->text + bam.hdr->l_text);
+            p32((uint32_t)bam.hdr->n_targets);
+            for (int i = 0; i < bam.hdr->n_targets; i++) {
+                const uint32_t l = (uint32_t)strlen(bam.hdr->target_name[i]) + 1;
+                p32(l);
+                h.insert(h.end(), bam.hdr->target_name[i], bam.hdr->target_name[i] + l);
+                p32(bam.hdr->target_len[i]);
+            }
+            std::vector<std::pair<const uint8_t *, int>> blocks;
+            for (size_t o = 0; o < h.size(); o += BGZF_BLOCK_SIZE) blocks.emplace_back(h.data() + o, (int)std::min<size_t>(BGZF_BLOCK_SIZE, h.size() - o));
+            emit_blocks(blocks, nullptr);
+        }
+        // ---- records ----
+        struct RecMeta { int32_t tid; uint32_t pos, end; uint8_t unmapped; uint64_t p0, p1; };
+        std::vector<RecMeta> metas;                      // for the index
+        std::vector<std::pair<uint64_t, uint64_t>> blk;  // (stream offset of the block's first byte, file address)
+        std::vector<uint8_t> ustream;                    // pending bytes of the open block + the chunk's stream
+        size_t pending = 0;                              // bytes of the open block carried from the previous chunk
+        uint64_t stream_pos = 0;                         // stream offset of ustream[pending]
+        RetagCursor cur;
+        std::vector<pomfret_gpu_sliced_record> sl;
+        std::vector<uint64_t> dst_off;
+        std::vector<uint8_t> hp_val;
+        bool ok = true;
+        pomfret_gpu_ingest_filter flt;
+        memset(&flt, 0, sizeof(flt));
+        flt.keep_all_flags = 1;
+        for (size_t c = 0; ok && c + 1 < bounds.size(); c++) {
+            const uint64_t vbeg = bounds[c], vend = bounds[c + 1];
+            plan.clear();
+            IngestPlan::Range r;
+            r.file_off = vbeg >> 16;
+            uint64_t stop = (vend >> 16) + ((vend & 0xffff) ? 65536 : 0);
+            if (stop > file_size) stop = file_size;
+            if (stop <= r.file_off) continue;
+            r.bytes = stop - r.file_off; r.comp_off = 0; r.vbeg = vbeg; r.vend = vend; r.run = 0; r.tid = POMFRET_GPU_ANY_TID; r.end0 = 0;
+            plan.comp_bytes = r.bytes;
+            plan.ranges.push_back(r);
+            int rc;
+            if ((rc = api.batch_reset(batch))) die_gpu(api, rc, "batch_reset");
+            if (comp_buf.size() < plan.comp_bytes + 64) comp_buf.resize(plan.comp_bytes + plan.comp_bytes / 4 + 64);
+            read_chunk(&plan, comp_buf.data());
+            uint32_t n_rec = 0;
+            if ((rc = api.batch_ingest_bgzf(batch, comp_buf.data(), plan.comp_bytes, plan.blocks.data(), (uint32_t)plan.blocks.size(), plan.streams.data(),
+                                            (uint32_t)plan.streams.size(), &flt, &n_rec)))
+                die_gpu(api, rc, "ingest_bgzf");
+            stats.n_ingest_bytes += plan.comp_bytes;
+            if (n_rec == 0) continue;
+            sl.resize(n_rec);
+            if ((rc = api.batch_ingest_records(batch, sl.data(), n_rec))) die_gpu(api, rc, "ingest_records");
+            dst_off.resize(n_rec); hp_val.resize(n_rec);
+            uint64_t out_bytes = 0;
+            const size_t meta0 = metas.size();
+            for (uint32_t i = 0; i < n_rec && ok; i++) {
+                const pomfret_gpu_sliced_record &S = sl[i];
+                if (S.bad) { fprintf(stderr, "[E::%s] malformed alignment record in %s\n", "pomfret", bam.fn.c_str()); exit(1); }
+                if (S.cg_cigar) { ok = false; break; }
+                char buf[256];
+                const char *qn = S.qname;
+                if (S.l_qname > sizeof(S.qname)) {
+                    if ((rc = api.batch_ingest_qname(batch, i, buf, sizeof(buf)))) die_gpu(api, rc, "ingest_qname");
+                    qn = buf;
+                }
+                const int tid = S.tid;
+                const char *refname = tid >= 0 && tid < bam.hdr->n_targets ? bam.hdr->target_name[tid] : "";
+                if (!ps.stores_raw_tag && S.hp_irregular) fprintf(stderr, "[W::%s] irregular HP tag? qn=%s qs=%d\n", "get_hp_from_aln", qn, (int)S.pos);
+                const int hp = retag_next(ps, &cur, tid, refname, qn, (int)S.pos, S.hp);
+                const int val = hp + 1;
+                if (val < 1 || val > 255) { ok = false; break; }
+                hp_val[i] = (uint8_t)val;
+                // the record's size behind bam_aux_update_int (kernel: retag_kernel)
+                const uint32_t sz = val < 255 ? 1u : 2u;
+                const uint32_t t = S.hp_type;
+                const uint32_t old_sz = !t ? 0u : (t == 'c' || t == 'C') ? 1u : (t == 's' || t == 'S') ? 2u : (t == 'i' || t == 'I') ? 4u : 0u;
+                uint32_t grow = 0;
+                if (!t) grow = 3u + sz;
+                else if (old_sz == 0u) grow = 0;          // not an integer tag: the update fails, the record stays as it is
+                else if (old_sz < sz) grow = sz - old_sz;
+                dst_off[i] = out_bytes;
+                const uint64_t nbytes = (uint64_t)S.rec_bytes + grow;
+                metas.push_back({tid, S.pos, S.end_pos, (uint8_t)((S.flag & 4u) != 0), stream_pos + out_bytes, stream_pos + out_bytes + nbytes});
+                out_bytes += nbytes;
+            }
+            if (!ok) break;
+            if (ustream.size() < pending + out_bytes + 64) ustream.resize(pending + out_bytes + out_bytes / 8 + 64);
+            if ((rc = api.batch_ingest_retag(batch, dst_off.data(), hp_val.data(), out_bytes, ustream.data() + pending))) die_gpu(api, rc, "ingest_retag");
+            // ---- cut into blocks (bgzf_flush_try before a record, bgzf_write's flush when a block is full) ----
+            std::vector<std::pair<const uint8_t *, int>> blocks;
+            std::vector<uint64_t> starts;
+            size_t open_at = 0;              // offset in ustream of the open block's first byte
+            const uint64_t base_pos = stream_pos - pending;  // stream offset of ustream[0]
+            auto cut = [&](size_t at) {
+                if (at > open_at) { blocks.emplace_back(ustream.data() + open_at, (int)(at - open_at)); starts.push_back(base_pos + open_at); }
+                open_at = at;
+            };
+            size_t at = pending;
+            for (size_t i = meta0; i < metas.size(); i++) {
+                size_t rem = (size_t)(metas[i].p1 - metas[i].p0);
+                if ((at - open_at) + rem > (size_t)BGZF_BLOCK_SIZE) cut(at);
+                while (rem) {
+                    const size_t room = (size_t)BGZF_BLOCK_SIZE - (at - open_at);
+                    const size_t n = std::min(rem, room);
+                    at += n; rem -= n;
+                    if (at - open_at == (size_t)BGZF_BLOCK_SIZE) cut(at);
+                }
+            }
+            std::vector<uint64_t> addrs;
+            emit_blocks(blocks, &addrs);
+            for (size_t i = 0; i < addrs.size(); i++) blk.emplace_back(starts[i], addrs[i]);
+            // the open block's bytes stay for the next chunk
+            const size_t tail = at - open_at;
+            memmove(ustream.data(), ustream.data() + open_at, tail);
+            pending = tail;
+            stream_pos += out_bytes;
+        }
+        if (!ok) { fclose(fo); return false; }
+        if (pending) {
+            std::vector<std::pair<const uint8_t *, int>> blocks{{ustream.data(), (int)pending}};
+            std::vector<uint64_t> addrs;
+            emit_blocks(blocks, &addrs);
+            blk.emplace_back(stream_pos - pending, addrs[0]);
+        }
+        const uint64_t eof_addr = file_addr;
+        {
+            const uint8_t *e = nullptr;
+            const int n = pomfret_bgzf_eof_block(&e);
+            if (fwrite(e, 1, (size_t)n, fo) != (size_t)n) { fprintf(stderr, "[E::%s] failed to write %s\n", "output_modify_bam", fn_out.c_str()); exit(1); }
+        }
+        if (fclose(fo) != 0) { fprintf(stderr, "[E::%s] failed to write %s\n", "output_modify_bam", fn_out.c_str()); exit(1); }
+        fprintf(stderr, "[M::%s] bam written. now indexing...\n", "main_blockjoin");
+        // ---- index (sam_index_build3): virtual offsets from the block table ----
+        blk.emplace_back(stream_pos, eof_addr);  // a position at the end of the stream names the block behind the last one
+        pomfret_bai_builder *B = pomfret_bai_new(bam.hdr->n_targets);
+        size_t k = 0;
+        auto voff = [&](uint64_t p) {
+            while (k + 1 < blk.size() && blk[k + 1].first <= p) k++;
+            return (blk[k].second << 16) | (p - blk[k].first);
+        };
+        int stat = 0;
+        for (const RecMeta &m : metas) {
+            const uint64_t off0 = voff(m.p0), off1 = voff(m.p1);
+            if (pomfret_bai_add(B, m.tid, (hts_pos_t)(int32_t)m.pos, (hts_pos_t)m.end, m.unmapped, off0, off1) != 0) { stat = -1; break; }
+        }
+        const int rs = pomfret_bai_finish(B, stat == 0 ? fn_bai.c_str() : nullptr);
+        if (stat == 0) stat = rs;
+        if (stat != 0) fprintf(stderr, "[W::%s] failed to build index for output bam (status code=%d)\n", "main_blockjoin", stat);
+        fprintf(stderr, "[M::%s] bam index written.\n", "main_blockjoin");
+        return true;
+    }
+
     // pre_haplotagging_read_in_one_ref through the compressed ingest: the contig is walked in slices of 2 Mb of
     // reference; a slice's query returns every record that overlaps it, and a record belongs to the slice its start
     // lies in, so every record is taken once, in BAM order.  The device inflates, slices and haplotags; the host sees
@@ -1128,11 +1354,22 @@ int run_methphase(const Options &opt, RunStats *stats) {
     fprintf(stderr, "[T::%s] gtf/vcf written at %.2fs\n", "run_methphase", now_s() - T);
     if (opt.do_output_bam) {
         const std::string fn_bam_out = opt.output_prefix + ".mp.bam", fn_bai_out = opt.output_prefix + ".mp.bam.bai";
-        output_modify_bam(opt.fn_bam, ps, fn_bam_out);
-        fprintf(stderr, "[M::%s] bam written. now indexing...\n", "main_blockjoin");
-        int stat = sam_index_build3(fn_bam_out.c_str(), fn_bai_out.c_str(), 0, opt.threads_bam);
-        if (stat != 0) fprintf(stderr, "[W::%s] failed to build index for output bam (status code=%d)\n", "main_blockjoin", stat);
-        fprintf(stderr, "[M::%s] bam index written.\n", "main_blockjoin");
+        bool done = false;
+        if (eng.gpu_ingest && !getenv("POMFRET_HOST_BAM_REWRITE")) {
+            Worker wk;
+            wk.eng = &eng; wk.id = 0; wk.device = 0;
+            if (!wk.open(opt.fn_bam)) exit(1);
+            done = wk.rewrite_bam_device(ps, fn_bam_out, fn_bai_out, std::max(opt.threads, opt.threads_bam));
+            wk.close();
+            if (!done) fprintf(stderr, "[M::%s] records the device re-tagger does not copy verbatim (CG-tag CIGARs): host writer\n", "output_modify_bam");
+        }
+        if (!done) {
+            output_modify_bam(opt.fn_bam, ps, fn_bam_out);
+            fprintf(stderr, "[M::%s] bam written. now indexing...\n", "main_blockjoin");
+            int stat = sam_index_build3(fn_bam_out.c_str(), fn_bai_out.c_str(), 0, opt.threads_bam);
+            if (stat != 0) fprintf(stderr, "[W::%s] failed to build index for output bam (status code=%d)\n", "main_blockjoin", stat);
+            fprintf(stderr, "[M::%s] bam index written.\n", "main_blockjoin");
+        }
     }
     stats->t_total = now_s() - T;
     return 0;

@@ -387,6 +387,41 @@ int output_modify_vcf(const std::string &fn_vcf, const PhaseState &ps, const std
 
 // ---------------- BAM ----------------
 
+// The tag a record gets in the output BAM (blockjoin.c:3056-3092): stateful over the records in file order
+// (check_if_in_phased_intervals keeps a cursor per contig, the flip status changes when the cursor moves).
+int retag_next(const PhaseState &ps, RetagCursor *c, int tid, const char *refname, const char *qn, int start_pos, int hp_of_record) {
+    if (tid != c->prev_tid) { c->prev_unphased_idx = 1; c->prev_tid = tid; }
+    int hp_raw;
+    if (ps.stores_raw_tag) {
+        auto it = ps.qname2haptag_raw.find(qn);
+        hp_raw = it == ps.qname2haptag_raw.end() ? kHaptagUnphased : it->second;
+    } else hp_raw = hp_of_record;
+    // check_if_in_phased_intervals, blockjoin.c:2406-2426 (merged gap arrays, cursor starts at 1)
+    const int i_ref = ref_index(ps.st, refname);
+    bool updated = false;
+    if (i_ref >= 0) {
+        const Ranges &r = ps.st.ranges[i_ref];
+        const int prev = c->prev_unphased_idx;
+        for (int j = c->prev_unphased_idx; j < (int)r.n; j++) {
+            if (j < 1) continue;
+            if ((uint32_t)start_pos >= r.ends[j - 1] && (uint32_t)start_pos <= r.starts[j]) {
+                if (j != prev) { updated = true; c->prev_unphased_idx = j; }
+                break;
+            }
+        }
+        if (updated) {
+            const int idx = c->prev_unphased_idx - 1;
+            c->need_flip = idx >= 0 && idx < (int)r.flips_onraw.size() ? r.flips_onraw[idx] : 0;
+        }
+    }
+    // get_read_new_haplotag, blockjoin.c:2990-3020
+    int hp;
+    auto it = ps.qname2haptag.find(qn);
+    if (it != ps.qname2haptag.end()) { hp = it->second; if (c->need_flip) hp ^= 1; }
+    else { hp = hp_raw; if ((hp == 0 || hp == 1) && c->need_flip) hp ^= 1; }
+    return hp;
+}
+
 int output_modify_bam(const std::string &fn_bam, const PhaseState &ps, const std::string &fn_out) {
     BamReader in;
     if (!in.open(fn_bam)) { fprintf(stderr, "[E::%s] failed to open input bam: %s\n", "output_modify_bam", fn_bam.c_str()); return 1; }
@@ -394,42 +429,14 @@ int output_modify_bam(const std::string &fn_bam, const PhaseState &ps, const std
     BGZF *out = bgzf_open(fn_out.c_str(), "w");
     if (!out) { fprintf(stderr, "[E::%s] failed to open output file: %s\n", "output_modify_bam", fn_out.c_str()); return 1; }
     if (bam_hdr_write(out, in.hdr) != 0) { fprintf(stderr, "[E::%s] failed to write bam header\n", "output_modify_bam"); exit(1); }
-    int prev_unphased_idx = 1, prev_tid = 0, need_flip = 0;
+    RetagCursor cur;
     bam1_t *b = in.rec;
     while (sam_itr_next(in.fp, itr, b) >= 0) {
         const int tid = b->core.tid;
-        if (tid != prev_tid) { prev_unphased_idx = 1; prev_tid = tid; }
         const char *refname = tid >= 0 && tid < in.hdr->n_targets ? in.hdr->target_name[tid] : "";
         const char *qn = bam_get_qname(b);
         const int start_pos = (int)b->core.pos;
-        int hp_raw;
-        if (ps.stores_raw_tag) {
-            auto it = ps.qname2haptag_raw.find(qn);
-            hp_raw = it == ps.qname2haptag_raw.end() ? kHaptagUnphased : it->second;
-        } else hp_raw = hp_from_record(b);
-        // check_if_in_phased_intervals, blockjoin.c:2406-2426 (merged gap arrays, cursor starts at 1)
-        const int i_ref = ref_index(ps.st, refname);
-        bool updated = false;
-        if (i_ref >= 0) {
-            const Ranges &r = ps.st.ranges[i_ref];
-            const int prev = prev_unphased_idx;
-            for (int j = prev_unphased_idx; j < (int)r.n; j++) {
-                if (j < 1) continue;
-                if ((uint32_t)start_pos >= r.ends[j - 1] && (uint32_t)start_pos <= r.starts[j]) {
-                    if (j != prev) { updated = true; prev_unphased_idx = j; }
-                    break;
-                }
-            }
-            if (updated) {
-                const int idx = prev_unphased_idx - 1;
-                need_flip = idx >= 0 && idx < (int)r.flips_onraw.size() ? r.flips_onraw[idx] : 0;
-            }
-        }
-        // get_read_new_haplotag, blockjoin.c:2990-3020
-        int hp;
-        auto it = ps.qname2haptag.find(qn);
-        if (it != ps.qname2haptag.end()) { hp = it->second; if (need_flip) hp ^= 1; }
-        else { hp = hp_raw; if ((hp == 0 || hp == 1) && need_flip) hp ^= 1; }
+        const int hp = retag_next(ps, &cur, tid, refname, qn, start_pos, ps.stores_raw_tag ? kHaptagUnphased : hp_from_record(b));
         bam_aux_update_int(b, "HP", hp + 1);
         if (bam_write1(out, b) < 0) fprintf(stderr, "[E::%s] failed to write bam entry (ref=%s pos=%d qn=%s)\n", "output_modify_bam", refname, start_pos, qn);
     }

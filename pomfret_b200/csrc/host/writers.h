@@ -38,6 +38,10 @@ int recover_variant_phase_in_dropped_intervals(PhaseState *ps, const std::string
 int output_modify_vcf(const std::string &fn_vcf, const PhaseState &ps, const std::string &prefix);
 // output_modify_bam + sam_index_build3 (blockjoin.c:3022-3103, 4714-4731)
 int output_modify_bam(const std::string &fn_bam, const PhaseState &ps, const std::string &fn_out);
+// the tag a record gets there (blockjoin.c:3056-3092), stateful over the records in file order; hp_of_record is
+// get_hp_from_aln of the record (used unless the run stores raw tags)
+struct RetagCursor { int prev_unphased_idx = 1, prev_tid = 0, need_flip = 0; };
+int retag_next(const PhaseState &ps, RetagCursor *c, int tid, const char *refname, const char *qn, int start_pos, int hp_of_record);
 
 // parse_variants_for_one_read on the host (only the dropped-interval rescue needs it here;
 // the -u path runs the CUDA kernel).  Returns 0 or a POMFRET_GPU_ERR_* code.

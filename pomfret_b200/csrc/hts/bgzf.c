@@ -158,15 +158,17 @@ int64_t bgzf_seek(BGZF *fp, int64_t pos, int whence) {
 
 /* ---------- writing ---------- */
 
-static int deflate_block(BGZF *fp, int ulen) {
-    uint8_t *dst = fp->cblock;
+/* one BGZF block around `ulen` bytes of `src`: header with BSIZE, raw deflate, CRC-32, ISIZE; dst holds
+ * BGZF_MAX_BLOCK_SIZE bytes.  Returns the block's size or -1.  (Also what a caller that compresses blocks on its own
+ * threads uses, so that its blocks are the bytes bgzf_write would have produced.) */
+int pomfret_bgzf_compress_block(uint8_t *dst, const uint8_t *src, int ulen, int compress_level) {
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
-    zs.next_in = fp->ublock;
+    zs.next_in = (Bytef *)src;
     zs.avail_in = ulen;
     zs.next_out = dst + BLOCK_HEADER_LENGTH;
     zs.avail_out = BGZF_MAX_BLOCK_SIZE - BLOCK_HEADER_LENGTH - BLOCK_FOOTER_LENGTH;
-    int level = fp->compress_level < 0 ? Z_DEFAULT_COMPRESSION : fp->compress_level;
+    int level = compress_level < 0 ? Z_DEFAULT_COMPRESSION : compress_level;
     if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
     int rc = deflate(&zs, Z_FINISH);
     deflateEnd(&zs);
@@ -175,10 +177,19 @@ static int deflate_block(BGZF *fp, int ulen) {
     int total = clen + BLOCK_HEADER_LENGTH + BLOCK_FOOTER_LENGTH;
     memcpy(dst, k_eof_block, BLOCK_HEADER_LENGTH);
     st16(dst + 16, (uint16_t)(total - 1));
-    uint32_t crc = (uint32_t)crc32(crc32(0L, NULL, 0), fp->ublock, ulen);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, NULL, 0), src, ulen);
     st32(dst + BLOCK_HEADER_LENGTH + clen, crc);
     st32(dst + BLOCK_HEADER_LENGTH + clen + 4, (uint32_t)ulen);
     return total;
+}
+
+int pomfret_bgzf_eof_block(const uint8_t **p) {
+    *p = k_eof_block;
+    return (int)sizeof(k_eof_block);
+}
+
+static int deflate_block(BGZF *fp, int ulen) {
+    return pomfret_bgzf_compress_block(fp->cblock, fp->ublock, ulen, fp->compress_level);
 }
 
 int bgzf_flush(BGZF *fp) {

@@ -37,6 +37,9 @@ int64_t bgzf_seek(BGZF *fp, int64_t pos, int whence);
 int bgzf_flush(BGZF *fp);
 int bgzf_flush_try(BGZF *fp, ssize_t size);
 int bgzf_mt(BGZF *fp, int n_threads, int n_sub_blks);
+/* shim extras: a whole BGZF block from ulen bytes (what bgzf_write emits), the EOF marker block */
+int pomfret_bgzf_compress_block(uint8_t *dst, const uint8_t *src, int ulen, int compress_level);
+int pomfret_bgzf_eof_block(const uint8_t **p);
 
 #ifdef __cplusplus
 }

@@ -44,6 +44,8 @@ void hts_idx_destroy(hts_idx_t *idx);
 void hts_itr_destroy(hts_itr_t *itr);
 /* shim extension (not htslib API): the (begin, end) virtual-offset pairs of the file chunks of a region iterator */
 int pomfret_itr_chunks(const hts_itr_t *itr, const uint64_t **pairs);
+int pomfret_idx_linear(const hts_idx_t *idx, int tid, const uint64_t **lin);
+int pomfret_idx_nref(const hts_idx_t *idx);
 
 /* shim extension: number of records / uncompressed bytes pulled through
  * iterators by this process (used by the throughput harness). */

@@ -229,6 +229,14 @@ hts_itr_t *sam_itr_querys(const hts_idx_t *idx, sam_hdr_t *hdr, const char *regi
 
 /* shim extension: the file chunks an iterator would walk, as (begin, end) virtual offsets in file order
  * (a loader that ships the BGZF blocks to the device instead of inflating them here) */
+/* linear index of one target: virtual offsets of the first record that overlaps each 16 kb window (record starts) */
+int pomfret_idx_linear(const hts_idx_t *idx, int tid, const uint64_t **lin) {
+    if (!idx || tid < 0 || tid >= idx->n_ref) return 0;
+    *lin = idx->refs[tid].lin;
+    return idx->refs[tid].n_lin;
+}
+int pomfret_idx_nref(const hts_idx_t *idx) { return idx ? idx->n_ref : 0; }
+
 int pomfret_itr_chunks(const hts_itr_t *itr, const uint64_t **pairs) {
     if (!itr || itr->whole_file) return -1;
     *pairs = (const uint64_t *)itr->chunks;

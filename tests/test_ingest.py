@@ -222,3 +222,50 @@ def test_ingest_deflate_levels_gpu(built, tmp_path, level):
     data = conftest.run_synth(str(tmp_path / "lv"), ["-c", "30", "-s", "12", "-C", "chr20:64444167:3000000-3600000", "--block", "200000",
                                                      "--gap", "20000-40000", "-l", str(level), "--qual"])
     check_ingest(pb.load_gpu(), data, 30, 15000, max_windows=2)
+
+
+def _rewrite_case(tmp_path, data, args, gpu_lib, extra_env=None):
+    """`methphase --write-bam` through the compressed ingest: the output BAM comes from retag_kernel + host block cutting +
+    parallel block compression and the BAI from the block table (Worker::rewrite_bam_device); both must be the bytes the
+    reference writes through bam_write1 / sam_index_build3 (blockjoin.c:3022-3103, 4714-4731)."""
+    import filecmp
+    import os
+    import subprocess
+    from test_host_frontend import MINE
+    env = dict(os.environ)
+    if gpu_lib:
+        env["POMFRET_GPU_LIB"] = gpu_lib
+    env.update(extra_env or {})
+    out = {}
+    for who, exe in (("ref", ob.REF_BIN), ("mine", MINE)):
+        prefix = str(tmp_path / who)
+        p = subprocess.run([exe, "methphase"] + args + ["--write-bam", "-o", prefix, "--vcf", data["vcf"], data["bam"]], env=env,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, (who, p.stderr[-2000:])
+        out[who] = p.stderr
+    assert "host writer" not in out["mine"]
+    for suffix in (".mp.gtf", ".mp.vcf", ".mp.bam", ".mp.bam.bai"):
+        assert filecmp.cmp(str(tmp_path / "ref") + suffix, str(tmp_path / "mine") + suffix, shallow=False), suffix
+
+
+@pytest.mark.emu
+@pytest.mark.skipif(not __import__("os").path.exists(ob.REF_BIN), reason="oracle/_ref/pomfret not built")
+def test_write_bam_device_rewrite_emulated(built, synth_tiny, tmp_path):
+    import build_emu
+    # two chunks (the cut points come from the linear index), open block carried from one to the next
+    _rewrite_case(tmp_path, synth_tiny, ["-c", "14", "-L", "1200", "-t", "3"], build_emu.build(), {"POMFRET_REWRITE_CHUNK_MB": "1"})
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not __import__("os").path.exists(ob.REF_BIN), reason="oracle/_ref/pomfret not built")
+@pytest.mark.parametrize("chunk_mb", ["1", "48"])
+def test_write_bam_device_rewrite_gpu(built, synth30, tmp_path, chunk_mb):
+    _rewrite_case(tmp_path, synth30, ["-c", "30", "-t", "6"], None, {"POMFRET_REWRITE_CHUNK_MB": chunk_mb})
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not __import__("os").path.exists(ob.REF_BIN), reason="oracle/_ref/pomfret not built")
+def test_write_bam_device_rewrite_untagged_gpu(built, tmp_path):
+    # -u: the raw tags come from the read haplotagger, most records have no HP tag (appended), unphased ones get 255 (type S)
+    data = conftest.run_synth(str(tmp_path / "unt"), ["-c", "30", "-s", "35", "-C", "chr20:64444167:5000000-6000000", "-F", "2", "--untagged"])
+    _rewrite_case(tmp_path, data, ["-u", "-c", "30", "-t", "4"], None, {"POMFRET_REWRITE_CHUNK_MB": "4"})

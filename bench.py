@@ -264,8 +264,17 @@ def main():
     # the records of the sample in ONE host buffer registered with the engine (pinned + mapped), the way a loader keeps
     # the buffers it inflates BGZF blocks into; every replica's descriptors point into it
     sizes = [host.window_arena(w)[1] for w, _, _, _, _ in wins]
-    big = np.empty(sum((x + 63) & ~63 for x in sizes) + 8192, dtype=np.uint8)
-    big_base = (big.ctypes.data + 4095) & ~4095
+    big_bytes = sum((x + 63) & ~63 for x in sizes) + 8192
+    # pinned by the allocator (cudaHostAlloc through torch: what a loader that owns its inflate buffers would use; the
+    # engine takes such memory as it is) unless POMFRET_BENCH_PINNED=0: then plain memory, pinned by host_register()
+    pinned_alloc = os.environ.get("POMFRET_BENCH_PINNED", "1") != "0"
+    if pinned_alloc:
+        big = torch.empty(big_bytes, dtype=torch.uint8, pin_memory=True)
+        big_ptr = big.data_ptr()
+    else:
+        big = np.empty(big_bytes, dtype=np.uint8)
+        big_ptr = big.ctypes.data
+    big_base = (big_ptr + 4095) & ~4095
     win_descs = []
     o = 0
     dsz = C.sizeof(_ffi.ReadDesc)
@@ -619,6 +628,7 @@ def main():
             "e2e": {"value": tot_reads / e2e_mean, "unit": "reads/s", "ms_per_step": e2e_mean * 1e3,
                     "bases_per_s": tot_bases / e2e_mean, "h2d_bytes_per_step": int(h2d_e2e),
                     "d2h_bytes_per_step": int(d2h_e2e), "batches_per_step": nb, "steps": n_e2e,
+                    "host_memory": "cudaHostAlloc (torch pinned tensor)" if pinned_alloc else "malloc + cudaHostRegister",
                     "host_buffers": "C ABI from one registered (pinned, mapped) host buffer per rank holding already inflated "
                                     "BAM records; payloads gathered by the device over PCIe; BGZF inflate is NOT in this number "
                                     "(cli_e2e has it)",

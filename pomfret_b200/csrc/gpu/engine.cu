@@ -203,7 +203,7 @@ enum Stage { ST_EMPTY = 0, ST_SUBMITTED = 1, ST_DECODED = 2, ST_PILED = 3, ST_JO
 
 }  // namespace
 
-struct HostRegion { uintptr_t begin, end; uint64_t dev; };  // registered caller memory and its device-visible address
+struct HostRegion { uintptr_t begin, end; uint64_t dev; bool ours = true; };  // registered caller memory and its device-visible address (ours: registered here, unregistered here)
 
 struct pomfret_gpu_ctx {
     std::vector<int> devices;
@@ -341,11 +341,16 @@ void pomfret_gpu_destroy(pomfret_gpu_ctx *ctx) { delete ctx; }
 int pomfret_gpu_host_register(pomfret_gpu_ctx *ctx, void *ptr, size_t bytes) {
     if (!ctx || !ptr || !bytes) return POMFRET_GPU_ERR_ARG;
     CK(cudaSetDevice(ctx->devices[0]));
-    CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    // memory that is pinned already (cudaHostAlloc / cudaMallocHost, e.g. a torch pinned tensor) is taken as it is:
+    // it is device-visible under unified addressing and stays the caller's to free
+    bool ours = true;
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); ours = false; }
+    else if (e != cudaSuccess) { cudaGetLastError(); return POMFRET_GPU_ERR_CUDA; }
     void *dev = nullptr;
-    if (cudaHostGetDevicePointer(&dev, ptr, 0) != cudaSuccess || !dev) { cudaHostUnregister(ptr); return POMFRET_GPU_ERR_CUDA; }
+    if (cudaHostGetDevicePointer(&dev, ptr, 0) != cudaSuccess || !dev) { cudaGetLastError(); if (ours) cudaHostUnregister(ptr); return POMFRET_GPU_ERR_CUDA; }
     std::lock_guard<std::mutex> g(ctx->mu);
-    HostRegion r{(uintptr_t)ptr, (uintptr_t)ptr + bytes, (uint64_t)(uintptr_t)dev};
+    HostRegion r{(uintptr_t)ptr, (uintptr_t)ptr + bytes, (uint64_t)(uintptr_t)dev, ours};
     ctx->regions.insert(std::upper_bound(ctx->regions.begin(), ctx->regions.end(), r,
                                          [](const HostRegion &a, const HostRegion &c) { return a.begin < c.begin; }), r);
     return POMFRET_GPU_OK;
@@ -357,7 +362,9 @@ int pomfret_gpu_host_unregister(pomfret_gpu_ctx *ctx, void *ptr) {
         std::lock_guard<std::mutex> g(ctx->mu);
         auto it = std::find_if(ctx->regions.begin(), ctx->regions.end(), [&](const HostRegion &r) { return r.begin == (uintptr_t)ptr; });
         if (it == ctx->regions.end()) return POMFRET_GPU_ERR_ARG;
+        const bool ours = it->ours;
         ctx->regions.erase(it);
+        if (!ours) return POMFRET_GPU_OK;
     }
     CK(cudaHostUnregister(ptr));
     return POMFRET_GPU_OK;

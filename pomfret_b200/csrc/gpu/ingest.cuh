@@ -132,6 +132,36 @@ __device__ __forceinline__ int decode_symbol(BitReader &br, const uint16_t *coun
     return -1;
 }
 
+// Length / distance bases and extra-bit counts (RFC 1951 3.2.5), symbols 257..285 and 0..29
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_ext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_ext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+// the 32 bits of the staged window that start at bit `bitpos` (two aligned words, funnel-shifted): enough for one code
+// (15 bits) with its extra bits (13), so the symbol loop keeps nothing but the bit position between symbols
+__device__ __forceinline__ uint32_t win_bits(const uint8_t *win, uint32_t bitpos) {
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(win);
+    const uint32_t i = bitpos >> 5;
+    return __funnelshift_r(w32[i], w32[i + 1], bitpos & 31u);
+}
+
+// one symbol out of the bits `v`: first-level table, else the canonical walk (RFC 1951 3.2.2); *len = its code length
+__device__ __forceinline__ int decode_symbol_bits(uint32_t v, const uint16_t *count, const uint16_t *symbol, const uint16_t *lut, int bits, uint32_t *len) {
+    const uint16_t e = lut[v & ((1u << bits) - 1u)];
+    if (e) { *len = e >> 12; return e & 0xfff; }
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)(v & 1u);
+        v >>= 1;
+        const int c = count[l];
+        if (code - c < first) { *len = (uint32_t)l; return symbol[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    *len = 0;
+    return -1;
+}
+
 __device__ __forceinline__ uint32_t crc32_update(const uint32_t *tab, uint32_t crc, const uint8_t *p, uint32_t n) {
     crc = ~crc;
     while (n && ((uintptr_t)p & 3u)) { crc = tab[(crc ^ *p++) & 0xffu] ^ (crc >> 8); n--; }
@@ -283,43 +313,41 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                 continue;
             }
             // ---- symbols: bursts of up to 32 tokens by lane 0, executed by the warp ----
+            // (inside the loop lane 0 keeps only the bit position in the staged window; the byte-wise reader takes over
+            //  again at the end of the block)
             bool end_of_block = false;
+            uint32_t bitpos = 0;
+            if (lane == 0) bitpos = br.pos * 8u - (uint32_t)br.n;
             while (!end_of_block && !err) {
                 {
-                    const uint32_t consumed = __shfl_sync(FULL_MASK, br.pos - (uint32_t)(br.n >> 3), 0);
-                    const uint32_t bit_rem = __shfl_sync(FULL_MASK, (uint32_t)(br.n & 7), 0);
+                    const uint32_t consumed = __shfl_sync(FULL_MASK, bitpos >> 3, 0);
                     if (consumed >= INF_WIN / 2) {  // (a burst consumes at most 32 * 48 bits: the window never runs out)
-                        const uint32_t at = win_off + consumed - (bit_rem ? 1u : 0u);
-                        stage(at);
-                        if (lane == 0) {
-                            br.pos = 0; br.buf = 0; br.n = 0;
-                            if (bit_rem) { br.refill(); br.drop(8 - (int)bit_rem); }
-                        }
+                        stage(win_off + consumed);
+                        bitpos &= 7u;
                     }
                 }
                 uint32_t n_tok = 0;
                 if (lane == 0) {
                     while (n_tok < INF_TOKENS) {
-                        br.need32();
-                        int sym = decode_symbol(br, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS);
+                        uint32_t v = win_bits(sm.win, bitpos), cl;
+                        int sym = decode_symbol_bits(v, sm.lcount, sm.lsym, sm.llut, INF_LIT_BITS, &cl);
                         if (sym < 0) { err = 4; break; }
-                        if (sym < 256) { sm.tokens[n_tok++] = (uint32_t)sym; continue; }
-                        if (sym == 256) { end_of_block = true; break; }
+                        if (sym < 256) { sm.tokens[n_tok++] = (uint32_t)sym; bitpos += cl; continue; }
+                        if (sym == 256) { end_of_block = true; bitpos += cl; break; }
                         sym -= 257;
                         if (sym >= 29) { err = 4; break; }
-                        // length / distance bases and extra bits (RFC 1951 3.2.5)
-                        const uint32_t lext = sym < 8 ? 0u : (sym == 28 ? 0u : (uint32_t)(sym - 4) >> 2);
-                        const uint32_t lbase = sym < 8 ? 3u + (uint32_t)sym : (sym == 28 ? 258u : 3u + ((4u + ((uint32_t)sym & 3u)) << lext));
-                        const uint32_t len = lbase + br.take((int)lext);
-                        br.need32();
-                        const int ds = decode_symbol(br, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS);
+                        const uint32_t lext = c_len_ext[sym];
+                        const uint32_t len = (uint32_t)c_len_base[sym] + ((v >> cl) & ((1u << lext) - 1u));
+                        bitpos += cl + lext;
+                        v = win_bits(sm.win, bitpos);
+                        const int ds = decode_symbol_bits(v, sm.dcount, sm.dsym, sm.dlut, INF_DIST_BITS, &cl);
                         if (ds < 0 || ds >= 30) { err = 4; break; }
-                        const uint32_t dext = ds < 4 ? 0u : (uint32_t)(ds - 2) >> 1;
-                        const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + ((uint32_t)ds & 1u)) << dext);
-                        const uint32_t dist = dbase + br.take((int)dext);
+                        const uint32_t dext = c_dist_ext[ds];
+                        const uint32_t dist = (uint32_t)c_dist_base[ds] + ((v >> cl) & ((1u << dext) - 1u));
+                        bitpos += cl + dext;
                         sm.tokens[n_tok++] = 0x80000000u | (dist << 9) | len;
                     }
-                    if (win_off + br.pos - (uint32_t)(br.n >> 3) > pay_len + 8) err = 4;  // ran past the payload
+                    if (win_off + (bitpos >> 3) > pay_len + 8) err = 4;  // ran past the payload
                 }
                 __syncwarp();
                 n_tok = __shfl_sync(FULL_MASK, n_tok, 0);
@@ -361,6 +389,10 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                 }
                 o += total;
                 __syncwarp();
+            }
+            if (lane == 0) {  // back to the byte-wise reader: restart it at the byte that holds the next bit
+                br.pos = bitpos >> 3; br.buf = 0; br.n = 0;
+                if (bitpos & 7u) { br.refill(); br.drop((int)(bitpos & 7u)); }
             }
         }
         if (!err && o != isize) err = 6;  // ISIZE of the footer

@@ -269,3 +269,108 @@ def test_write_bam_device_rewrite_untagged_gpu(built, tmp_path):
     # -u: the raw tags come from the read haplotagger, most records have no HP tag (appended), unphased ones get 255 (type S)
     data = conftest.run_synth(str(tmp_path / "unt"), ["-c", "30", "-s", "35", "-C", "chr20:64444167:5000000-6000000", "-F", "2", "--untagged"])
     _rewrite_case(tmp_path, data, ["-u", "-c", "30", "-t", "4"], None, {"POMFRET_REWRITE_CHUNK_MB": "4"})
+
+
+# ---- retag_kernel alone: hand-made records with every kind of HP tag against a plain restatement of bam_aux_update_int ----
+def _aux_update_int(rec, val):
+    """bam_aux_update_int(aln, "HP", val) on the bytes of one BAM record (block_size included); htslib semantics as the
+    reference uses them at blockjoin.c:3092"""
+    sz, ty = (1, b"C") if val < 255 else (2, b"S")
+    l_qname, n_cigar, l_seq = rec[12], struct.unpack_from("<H", rec, 16)[0], struct.unpack_from("<I", rec, 20)[0]
+    p = 36 + l_qname + 4 * n_cigar + (l_seq + 1) // 2 + l_seq
+    found = None
+    while p + 3 <= len(rec):
+        tag, t = rec[p:p + 2], chr(rec[p + 2])
+        q = p + 3
+        if t in "AcC":
+            q += 1
+        elif t in "sS":
+            q += 2
+        elif t in "iIf":
+            q += 4
+        elif t in "ZH":
+            q = rec.index(b"\0", q) + 1
+        elif t == "B":
+            es = {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[chr(rec[q])]
+            q += 5 + es * struct.unpack_from("<I", rec, q + 1)[0]
+        if tag == b"HP" and found is None:
+            found = (p + 2, t)
+        p = q
+    if found is None:
+        out = bytearray(rec) + b"HP" + ty + val.to_bytes(sz, "little")
+    else:
+        at, t = found
+        old = {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4}.get(t)
+        if old is None:
+            return bytes(rec)                     # not an integer tag: the update fails, the record is written as it is
+        if old >= sz:
+            out = bytearray(rec)
+            out[at:at + 1 + old] = {1: b"C", 2: b"S", 4: b"I"}[old] + val.to_bytes(old, "little")
+        else:
+            out = bytearray(rec[:at]) + ty + val.to_bytes(sz, "little") + rec[at + 1 + old:]
+    struct.pack_into("<I", out, 0, len(out) - 4)
+    return bytes(out)
+
+
+def _handmade_record(rng, i, hp_tag):
+    name = ("read%d" % i).encode() + b"x" * int(rng.integers(0, 60)) + b"\0"   # some names longer than the inline prefix
+    l_seq = int(rng.integers(1, 400))
+    cigar = struct.pack("<I", (l_seq << 4) | 0)
+    seq = bytes(rng.integers(0, 256, size=(l_seq + 1) // 2, dtype=np.uint8))
+    qual = bytes(rng.integers(0, 60, size=l_seq, dtype=np.uint8))
+    aux = b"NMC" + bytes([i & 0xff]) + b"MDZ" + str(l_seq).encode() + b"\0"
+    aux += hp_tag
+    aux += b"deffff\x80\x3c" if i % 3 == 0 else b"XYBc" + struct.pack("<I", 3) + b"\x01\x02\x03"
+    body = struct.pack("<iiBBHHHIiii", 0, 100 + 7 * i, len(name), 60, 4680, 1, 0, l_seq, -1, -1, 0) + name + cigar + seq + qual + aux
+    return struct.pack("<I", len(body)) + body
+
+
+def check_retag(gpu):
+    rng = np.random.default_rng(11)
+    tags = [b"", b"HPC\x01", b"HPc\x02", b"HPS\x01\x00", b"HPs\x02\x00", b"HPI\x01\0\0\0", b"HPi\x02\0\0\0", b"HPZab\0", b"HPA1"]
+    recs = [_handmade_record(rng, i, tags[i % len(tags)]) for i in range(120)]
+    payload = b"".join(recs)
+    # BGZF blocks of at most 20000 bytes: records straddle them
+    members, blocks_py = [], []
+    for o in range(0, len(payload), 20000):
+        piece = payload[o:o + 20000]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        members.append(bgzf_member(piece, co.compress(piece) + co.flush()))
+    comp = np.frombuffer(b"".join(members), dtype=np.uint8).copy()
+    blocks = (_ffi.BgzfBlock * len(members))()
+    co_, oo = 0, 0
+    for i, m in enumerate(members):
+        n = min(20000, len(payload) - 20000 * i)
+        blocks[i] = _ffi.BgzfBlock(co_, len(m), n, oo)
+        co_ += len(m)
+        oo += n
+    streams = (_ffi.BgzfStream * 1)()
+    streams[0] = _ffi.BgzfStream(0, len(payload), 0, -0x80000000, 0, 0, len(members), 0)   # POMFRET_GPU_ANY_TID
+    ctx = gpu.init()
+    b = gpu.batch_begin(ctx)
+    flt = _ffi.IngestFilter(0, 0, 0, 0, 0.0, 1)
+    rc, sl, n = b.ingest_bgzf(comp.ctypes.data, len(comp), blocks, len(members), streams, 1, flt)
+    assert rc == 0 and n == len(recs)
+    vals = np.array([[1, 2, 255, 0][int(v)] for v in rng.integers(0, 4, size=n)], dtype=np.uint8)
+    want = [r if v == 0 else _aux_update_int(r, int(v)) for r, v in zip(recs, vals)]
+    for i in range(n):
+        assert sl[i].rec_bytes == len(recs[i]) and sl[i].tid == 0 and not sl[i].bad
+        assert (sl[i].hp_type != 0) == (tags[i % len(tags)] != b"")
+    dst = np.zeros(n, np.uint64)
+    dst[1:] = np.cumsum([len(w) for w in want])[:-1]
+    got = bytes(b.ingest_retag(dst, vals, sum(len(w) for w in want)))
+    for i, w in enumerate(want):
+        o = int(dst[i])
+        assert got[o:o + len(w)] == w, (i, tags[i % len(tags)], int(vals[i]))
+    b.end()
+    gpu.destroy(ctx)
+
+
+@pytest.mark.emu
+def test_retag_kernel_emulated(emu_gpu):
+    check_retag(emu_gpu)
+
+
+@pytest.mark.gpu
+def test_retag_kernel_gpu(built):
+    check_retag(pb.load_gpu())

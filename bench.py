@@ -269,9 +269,16 @@ def main():
     # engine takes such memory as it is) unless POMFRET_BENCH_PINNED=0: then plain memory, pinned by host_register()
     pinned_alloc = os.environ.get("POMFRET_BENCH_PINNED", "1") != "0"
     if pinned_alloc:
-        big = torch.empty(big_bytes, dtype=torch.uint8, pin_memory=True)
-        big_ptr = big.data_ptr()
-    else:
+        try:
+            big = torch.empty(big_bytes, dtype=torch.uint8, pin_memory=True)
+            big_ptr = big.data_ptr()
+            probe = (big_ptr + 4095) & ~4095
+            gpu.host_register(ctx, probe, 4096)      # does the engine take this memory?
+            gpu.host_unregister(ctx, probe)
+        except Exception as exc:  # fall back to plain memory pinned by host_register()
+            sys.stderr.write("[bench] pinned allocation not usable (%s): malloc + cudaHostRegister\n" % exc)
+            pinned_alloc = False
+    if not pinned_alloc:
         big = np.empty(big_bytes, dtype=np.uint8)
         big_ptr = big.ctypes.data
     big_base = (big_ptr + 4095) & ~4095

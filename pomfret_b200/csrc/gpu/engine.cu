@@ -344,11 +344,16 @@ int pomfret_gpu_host_register(pomfret_gpu_ctx *ctx, void *ptr, size_t bytes) {
     // memory that is pinned already (cudaHostAlloc / cudaMallocHost, e.g. a torch pinned tensor) is taken as it is:
     // it is device-visible under unified addressing and stays the caller's to free
     bool ours = true;
-    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); ours = false; }
-    else if (e != cudaSuccess) { cudaGetLastError(); return POMFRET_GPU_ERR_CUDA; }
     void *dev = nullptr;
-    if (cudaHostGetDevicePointer(&dev, ptr, 0) != cudaSuccess || !dev) { cudaGetLastError(); if (ours) cudaHostUnregister(ptr); return POMFRET_GPU_ERR_CUDA; }
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+        ours = false;
+        dev = at.devicePointer;
+    } else {
+        cudaGetLastError();
+        CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+        if (cudaHostGetDevicePointer(&dev, ptr, 0) != cudaSuccess || !dev) { cudaGetLastError(); cudaHostUnregister(ptr); return POMFRET_GPU_ERR_CUDA; }
+    }
     std::lock_guard<std::mutex> g(ctx->mu);
     HostRegion r{(uintptr_t)ptr, (uintptr_t)ptr + bytes, (uint64_t)(uintptr_t)dev, ours};
     ctx->regions.insert(std::upper_bound(ctx->regions.begin(), ctx->regions.end(), r,

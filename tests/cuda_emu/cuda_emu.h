@@ -223,6 +223,9 @@ cudaError_t cudaMallocHost(void **p, size_t n);
 cudaError_t cudaHostAlloc(void **p, size_t n, unsigned flags);
 cudaError_t cudaFreeHost(void *p);
 enum { cudaHostRegisterPortable = 1, cudaHostRegisterMapped = 2 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned) { *d = h; return cudaSuccess; }

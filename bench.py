@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=env_int("POMFRET_BENCH_REPLICAS", 6),
                     help="times the sample's windows are staged (as distinct records) to form one WGS-scale batch")
     ap.add_argument("--cpu-sample-windows", type=int, default=24)
-    ap.add_argument("--e2e-batches", type=int, default=4, help="region chunks per step on the end-to-end path")
+    ap.add_argument("--e2e-batches", type=int, default=8, help="region chunks per step on the end-to-end path")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight when measuring device-resident throughput")
     ap.add_argument("--skip-cli", action="store_true", help="leave out the CLI wall-time comparisons (profiling runs)")
     ap.add_argument("--skip-untagged", action="store_true")

@@ -39,8 +39,8 @@ struct InflateParams {
 // ---- one warp per BGZF block ----
 // Lane 0 walks the Huffman codes (the bit-serial part of DEFLATE) over a window of the compressed bytes that the warp
 // keeps staged in shared memory, and turns them into tokens (literal byte / length + distance), 32 at a time; the 32
-// lanes then produce the burst's output one byte per lane: every byte finds its token and follows match references
-// back to a literal of the burst or to a byte an earlier burst wrote.
+// lanes then write the literals in one store and copy each match together (a match whose distance is shorter than
+// its length repeats a pattern that is already complete in front of it, so every byte of it is independent).
 // Code tables live in shared memory too.  The warp finally checks ISIZE and the CRC-32 of what it wrote: 32 segment
 // CRCs (slicing-by-4 tables) folded with the x^(8n) mod P operator.
 constexpr int INF_LIT_BITS = 9, INF_DIST_BITS = 6;
@@ -55,7 +55,6 @@ struct InflateWarpSmem {
     uint16_t lsym[288], dsym[32], csym[19];
     uint8_t lens[320];
     uint32_t tokens[INF_TOKENS];
-    uint32_t tat[INF_TOKENS];   // output offset of every token of the burst, relative to the burst's first byte
     uint32_t crc[32];
 };
 
@@ -356,6 +355,8 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                 end_of_block = __shfl_sync(FULL_MASK, (int)end_of_block, 0) != 0;
                 if (err) break;
                 // ---- execute the tokens: output offsets by a scan, literals at once, matches one after the other ----
+                // (measured and rejected, profiles/r02_inflate_variants.txt: producing the burst one output byte per lane —
+                //  token search + reference chasing instead of per-match copies — runs at 20 GB/s against 29 GB/s)
                 const uint32_t tok = lane < n_tok ? sm.tokens[lane] : 0u;
                 const bool is_match = lane < n_tok && (tok >> 31);
                 const uint32_t tlen = lane < n_tok ? (is_match ? tok & 0x1ffu : 1u) : 0u;
@@ -363,39 +364,30 @@ __global__ void __launch_bounds__(INF_WARPS * 32) inflate_kernel(InflateParams P
                 const uint32_t at = o + incl - tlen;
                 const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
                 if (o + total > isize) { err = 5; break; }
+                if (lane < n_tok && !is_match) out[at] = (uint8_t)tok;
+                unsigned mm = __ballot_sync(FULL_MASK, is_match);
                 const uint32_t tdist = (tok >> 9) & 0xffffu;
                 if (__any_sync(FULL_MASK, is_match && tdist > at)) { err = 5; break; }
-                // One output byte per lane, 32 at a time: the token that produces byte p is found by a search over the
-                // burst's token starts; a match byte is followed back to its source (p - dist, folded into the pattern if
-                // the match overlaps itself) until it lands on a literal of this burst or on a byte an earlier burst
-                // wrote.  No byte of the burst is read back from memory, so nothing is serialised between its matches.
-                sm.tat[lane] = lane < n_tok ? at - o : total;  // (unused entries: never found)
-                __syncwarp();
-                for (uint32_t j0 = 0; j0 < total; j0 += 32) {
-                    const uint32_t j = j0 + lane;
-                    bool pending = j < total;
-                    uint32_t p = j;
-                    uint8_t byte = 0;
-                    while (__any_sync(FULL_MASK, pending)) {
-                        if (pending) {
-                            uint32_t t = sm.tat[16] <= p ? 16u : 0u;
-                            if (sm.tat[t + 8] <= p) t += 8;
-                            if (sm.tat[t + 4] <= p) t += 4;
-                            if (sm.tat[t + 2] <= p) t += 2;
-                            if (sm.tat[t + 1] <= p) t += 1;
-                            const uint32_t tk = sm.tokens[t];
-                            if (!(tk >> 31)) { byte = (uint8_t)tk; pending = false; }
-                            else {
-                                const uint32_t dist = (tk >> 9) & 0xffffu, start = sm.tat[t];
-                                uint32_t off = p - start;
-                                if (off >= dist) off %= dist;  // a run: the `dist` bytes in front of the match repeat
-                                const int32_t src = (int32_t)(start + off) - (int32_t)dist;  // relative to the burst's first byte
-                                if (src < 0) { byte = ld_cg_u8(out + o - (uint32_t)(-src)); pending = false; }
-                                else p = (uint32_t)src;
-                            }
+                while (mm) {
+                    const int src_lane = __ffs((int)mm) - 1;
+                    mm &= mm - 1;
+                    __syncwarp();  // what the batch has written so far is visible to the copy
+                    const uint32_t dst = __shfl_sync(FULL_MASK, at, src_lane), len = __shfl_sync(FULL_MASK, tlen, src_lane),
+                                   dist = __shfl_sync(FULL_MASK, tdist, src_lane);
+                    if (dist >= len || dist >= 32u) {
+                        // chunks of at most min(32, dist) bytes never read what they write themselves
+                        const uint32_t step = dist < 32u ? dist : 32u;
+                        for (uint32_t i0 = 0; i0 < len; i0 += step) {
+                            const uint32_t i = i0 + lane;
+                            uint8_t v = 0;
+                            if (lane < step && i < len) v = ld_cg_u8(out + dst + i - dist);
+                            if (lane < step && i < len) out[dst + i] = v;
+                            if (i0 + step < len && dist < len) __syncwarp();
                         }
+                    } else {
+                        // a run: the `dist` bytes in front of the match repeat
+                        for (uint32_t i = lane; i < len; i += 32) out[dst + i] = ld_cg_u8(out + dst - dist + i % dist);
                     }
-                    if (j < total) out[o + j] = byte;
                 }
                 o += total;
                 __syncwarp();

@@ -1,5 +1,5 @@
 """Decode kernel probe (GPU box): share of records on the lean path, decode time with and without it.
-usage: python profiles/decode_probe.py [contigs] [contig_mb]"""
+usage: python profiles/decode_probe.py [contigs] [contig_mb] [extra pomfret-synth arguments, e.g. --implicit 0.05]"""
 import os, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,8 @@ import tempfile
 nc = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 mb = float(sys.argv[2]) if len(sys.argv) > 2 else 2.5
 tmp = tempfile.mkdtemp()
-data = conftest.run_synth(os.path.join(tmp, "s"), bench.synth_args(nc, mb, 60, 100))
+extra = sys.argv[3:]   # e.g. --implicit 0.05: non-CpG C+m entries => implicit canonical calls => the general (lane 0) path
+data = conftest.run_synth(os.path.join(tmp, "s"), bench.synth_args(nc, mb, 60, 100) + extra)
 host = pb.load_host(); gpu = pb.load_gpu()
 cfg = pb.make_config(60)
 hb = host.bam_open(data["bam"])

@@ -39,7 +39,7 @@ void print_help_methphase(const Options &o) {
                     "               supplied. Ignores any haptags present in the bam.\n"
                     "               All variants supplies by the vcf will be used as evidences.\n");
     fprintf(stderr, "  -t     [opt] Number of threads to use. [%d]\n", o.threads);
-    fprintf(stderr, "  --gpus [opt] Number of B200 devices to shard contigs over. [all visible]\n");
+    fprintf(stderr, "  --gpus [opt] Number of B200 devices to shard contigs over. [of the visible ones, one per 4 GiB of BAM]\n");
     fprintf(stderr, "Note: Inputs may need to be opened or read for more than once.\n");
 }
 
@@ -85,7 +85,7 @@ bool parse_cli(int argc, char **argv, Options *o) {
         case 313: case 'U': o->write_bam_input_haplotagging = true; break;
         case 314: o->chunk_size = atoi(arg); break;
         case 315: o->chunk_stride = atoi(arg); break;
-        case 501: o->gpus = atoi(arg); break;
+        case 501: o->gpus = strcmp(arg, "all") == 0 ? 1024 : atoi(arg); break;  // (absent: chosen from the size of the input)
         case 502: o->windows_per_batch = atoi(arg); break;
         default: break;
         }

@@ -20,7 +20,7 @@ struct Options {
     int chunk_size = 50000, chunk_stride = 1000000;
     int verbose = 0;
     // additions of this implementation (do not change results)
-    int gpus = 0;                // 0 = all visible devices
+    int gpus = 0;                // 0 = not given: one device per 4 GiB of BAM; "all" = every visible device
     int windows_per_batch = 8;
 };
 

@@ -1274,7 +1274,20 @@ std::vector<int> estimate_read_coverage_device(Engine &eng, const Options &opt) 
     return covs;
 }
 
-int run_methphase(const Options &opt, RunStats *stats) {
+// --gpus absent: as many of the visible devices as the input can keep busy — one per 4 GiB of BAM file.  Every device
+// costs a CUDA context (0.3 s and more of start-up each) and its feeder workers their arenas; a small input is done
+// on one device before a second one would be ready.  An explicit --gpus N is taken as it is.
+Options resolve_gpus(const Options &in) {
+    Options o = in;
+    if (o.gpus <= 0) {
+        struct stat st;
+        if (stat(o.fn_bam.c_str(), &st) == 0) o.gpus = (int)std::min<uint64_t>(1024, std::max<uint64_t>(1, ((uint64_t)st.st_size + ((uint64_t)4 << 30) - 1) / ((uint64_t)4 << 30)));
+    }
+    return o;
+}
+
+int run_methphase(const Options &opt_in, RunStats *stats) {
+    const Options opt = resolve_gpus(opt_in);
     const double T = now_s();
     if (!files_exist(opt)) return 1;
     Engine eng;
@@ -1375,7 +1388,8 @@ int run_methphase(const Options &opt, RunStats *stats) {
     return 0;
 }
 
-int run_report(const Options &opt, RunStats *stats) {
+int run_report(const Options &opt_in, RunStats *stats) {
+    const Options opt = resolve_gpus(opt_in);
     const double T = now_s();
     if (opt.fn_bam.empty()) { fprintf(stderr, "[E::%s] input bam file name missing\n", "main_methreport"); exit(1); }
     if (opt.fn_vcf.empty()) { fprintf(stderr, "[E::%s] input vcf file name missing\n", "main_methreport"); exit(1); }

@@ -55,6 +55,8 @@ struct DecodeParams {
     const uint32_t *order; // queue order: record indices, longest first (nullptr: batch order)
     uint32_t lo, hi;
     uint32_t no_lean;      // test / measurement hook: every record takes the streaming path
+    uint32_t *generic_list;  // records that need the general sequential path, handed to decode_generic_kernel (nullptr: lane 0 runs them in place)
+    uint32_t *n_generic;
 };
 
 struct SegInfo {
@@ -1460,6 +1462,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, POMFRET_DEC_MIN_CTAS) decode_k
             need_generic = __any_sync(FULL_MASK, need_generic);
             if (need_generic) {
                 __syncwarp();
+                if (P.generic_list) {
+                    // The general path is sequential: instead of idling 31 lanes on it, the record goes on a list that
+                    // decode_generic_kernel works through with one record per THREAD (32 records per warp).
+                    if (lane == 0) {
+                        P.generic_list[atomicAdd(P.n_generic, 1u)] = ri;
+                        P.r_end[ri] = R.pos + rlen;
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 if (lane == 0) status = decode_generic(P, R, reinterpret_cast<GenSeg *>(&sm), &n_calls);
                 status = __shfl_sync(FULL_MASK, status, 0);
                 n_calls = __shfl_sync(FULL_MASK, n_calls, 0);
@@ -1473,6 +1485,23 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, POMFRET_DEC_MIN_CTAS) decode_k
         }
         __syncwarp();
     }
+}
+
+// The records decode_kernel put aside for the general sequential path (several C+m streams, more than N_MODS streams,
+// implicit canonical calls, blockjoin.c:666-700): one record per thread, segment tables in local memory.  An all-context
+// 5mC data set sends every record here; one record per warp (lane 0) left 31 of 32 lanes of every warp slot idle.
+constexpr int GEN_THREADS = 64;
+__global__ void __launch_bounds__(GEN_THREADS) decode_generic_kernel(DecodeParams P) {
+    const uint32_t i = blockIdx.x * GEN_THREADS + threadIdx.x;
+    if (i >= *P.n_generic) return;
+    const uint32_t ri = P.generic_list[i];
+    const ReadRec &R = P.reads[ri];
+    GenSeg segs[GEN_MAXSEG];
+    uint32_t n_calls = 0;
+    const uint32_t status = decode_generic(P, R, segs, &n_calls);
+    if (status & RS_OVERFLOW) atomicAdd(P.n_overflow, 1u);
+    P.r_ncalls[ri] = (status & RS_KEPT) || (status & RS_OVERFLOW) ? n_calls : 0;
+    P.r_status[ri] = status;
 }
 
 // A record that lies in two windows occupies two slots of the batch but is decoded once: the later slot takes

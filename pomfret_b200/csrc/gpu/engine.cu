@@ -260,7 +260,7 @@ struct pomfret_gpu_batch {
     DevBuf d_mm_xl[2], d_mm_xr[2], d_mm_off[2], d_mm_n[2], d_mm_start[2], d_pool_total, d_mmr_pool, d_ent_pool, d_tab;
     DevBuf d_tags[2], d_order[2];
     DevBuf d_known, d_bases, d_known_first, d_hap_tag, d_hap_status, d_flags, d_cta, d_order_len, d_gsrc, d_dup_of;
-    DevBuf d_comp, d_inflated, d_ing_tab, d_ing_small, d_rec_off, d_rec_stream, d_sliced, d_hap_counts, d_ing_cov, d_retag_off, d_retag_val, d_retag_out;
+    DevBuf d_comp, d_inflated, d_ing_tab, d_ing_small, d_rec_off, d_rec_stream, d_sliced, d_hap_counts, d_ing_cov, d_retag_off, d_retag_val, d_retag_out, d_generic;
     uint32_t pool_cap = 0, tab_sites = 0, site_total = 0, max_sites = 0, max_win_reads = 0;
     pomfret_gpu_config cfg = {};
     uint32_t lo = 0, hi = 0;
@@ -278,7 +278,7 @@ struct pomfret_gpu_batch {
                      &d_mm_n[1], &d_mm_start[0], &d_mm_start[1], &d_pool_total, &d_mmr_pool, &d_ent_pool,
                      &d_tab, &d_tags[0], &d_tags[1], &d_order[0], &d_order[1], &d_known, &d_bases,
                      &d_known_first, &d_hap_tag, &d_hap_status, &d_flags, &d_cta, &d_order_len, &d_gsrc, &d_dup_of,
-                     &d_comp, &d_inflated, &d_ing_tab, &d_ing_small, &d_rec_off, &d_rec_stream, &d_sliced, &d_hap_counts, &d_ing_cov, &d_retag_off, &d_retag_val, &d_retag_out};
+                     &d_comp, &d_inflated, &d_ing_tab, &d_ing_small, &d_rec_off, &d_rec_stream, &d_sliced, &d_hap_counts, &d_ing_cov, &d_retag_off, &d_retag_val, &d_retag_out, &d_generic};
     }
 };
 
@@ -865,6 +865,17 @@ static int launch_decode(pomfret_gpu_batch *b) {
     P.lo = b->lo; P.hi = b->hi;
     P.no_lean = 0;
     if (const char *e = getenv("POMFRET_GPU_DECODE_LEAN")) P.no_lean = !strcmp(e, "0");  // test hook: streaming path for every record
+    // records for the general sequential path are collected and run one per thread by decode_generic_kernel
+    // (POMFRET_GPU_DECODE_GENERIC=inplace: lane 0 of the record's warp runs them, the round-1 form; measurement hook)
+    P.generic_list = nullptr;
+    P.n_generic = b->d_flags.as<uint32_t>() + 2;
+    {
+        const char *e = getenv("POMFRET_GPU_DECODE_GENERIC");
+        if (!(e && !strcmp(e, "inplace")) && nr) {
+            if ((rc = b->d_generic.ensure(nr * 4 + 16))) return rc;
+            P.generic_list = b->d_generic.as<uint32_t>();
+        }
+    }
     const size_t nq = nr - b->n_dups;  // the queue holds every distinct record once
     P.n_queue = (uint32_t)nq;
     if (nq) {
@@ -875,6 +886,10 @@ static int launch_decode(pomfret_gpu_batch *b) {
         }
         POMFRET_LAUNCH(decode_kernel, grid, DEC_WARPS * 32, 0, b->stream, P);
         b->tm.launches++;
+        if (P.generic_list) {  // (the count stays on the device: threads beyond it leave at once)
+            POMFRET_LAUNCH(decode_generic_kernel, (unsigned)((nq + GEN_THREADS - 1) / GEN_THREADS), GEN_THREADS, 0, b->stream, P);
+            b->tm.launches++;
+        }
     }
     if (b->n_dups) {
         POMFRET_LAUNCH(share_decoded_kernel, (unsigned)((nr + 255) / 256), 256, 0, b->stream, b->d_dup_of.as<uint32_t>(), (uint32_t)nr,

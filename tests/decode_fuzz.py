@@ -269,7 +269,7 @@ def check_against_port(gpu, R, lo=100, hi=156, register=None):
     b.submit()
     b.decode(lo, hi)
     if register:
-        assert b.timing().launches == 2, "the records were expected to be gathered by the device"
+        assert b.timing().launches == 3, "the records were expected to be gathered by the device"  # gather, decode, generic decode
     port = ob.port_lib()
     bad = []
     n_overflow = 0

@@ -882,6 +882,8 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
     uint32_t *rank = P.tmp_rank + R.calls_off;
     uint32_t *opos = P.calls_pos + R.calls_off;
     uint8_t *ocat = P.calls_cat + R.calls_off;
+    uint32_t *trig_p = P.tmp_mpos + R.calls_off;
+    uint8_t *trig_cat = P.tmp_mcat + R.calls_off;
     const uint32_t cap = R.calls_cap;
 
     // ---- MM structure and delta lists (ranks of the C+m list -> rank[]) ----
@@ -1106,6 +1108,13 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             const bool emit = r_emit[row];
             const uint32_t pos = r_pos[row], cat = r_cat[row];
             const unsigned okm = __ballot_sync(FULL_MASK, r_ok[row]);
+            // the kept mods themselves (read offset, category), in list order: what get_mod_poss_on_ref is handed; the
+            // implicit-call walk below reads them back
+            if (r_ok[row]) {
+                const uint32_t ti = n_mods + (uint32_t)__popc(okm & ((1u << lane) - 1u));
+                trig_p[ti] = r_p[row];
+                trig_cat[ti] = (uint8_t)cat;
+            }
             n_mods += (uint32_t)__popc(okm);
             n_behind_clip += (uint32_t)__popc(__ballot_sync(FULL_MASK, r_ok[row] && r_p[row] > clip));
             // ordered, de-duplicated store (blockjoin.c:704-709: of the bases that land on one position the one latest in
@@ -1140,10 +1149,96 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
         }
         if (done) break;
     }
-    if (__any_sync(FULL_MASK, implicit)) return false;            // implicit canonical calls: general path
-    if (n_mods == 0) { *status_out = RS_LEAN; *n_calls_out = 0; return true; }  // get_mod_poss_on_ref returns 0: record dropped
+    const bool has_implicit = __any_sync(FULL_MASK, implicit);
+    if (n_mods == 0) { *status_out = RS_LEAN | (has_implicit ? RS_HAS_IMPLICIT : 0u); *n_calls_out = 0; return true; }  // get_mod_poss_on_ref returns 0: record dropped
     if (j0 && n_behind_clip == 0) return false;                     // every listed base inside the clip: lingering-trigger quirk, streaming path
     __syncwarp();
+    if (has_implicit) {
+        // ---- implicit canonical calls (blockjoin.c:666-700, 727-761): a listed cytosine outside a CpG makes
+        // get_mod_poss_on_ref fill in every unlisted CpG of the aligned stretches as unmethylated.  The walk over
+        // CIGAR operations and kept mods stays sequential (executed by the whole warp, uniformly), as in the reference;
+        // the CpG scan of the stretch between two mods is done by the 32 lanes.  The explicit calls stored above are
+        // overwritten: the merged sequence is rebuilt from the kept mods.
+        uint32_t n = 0, last = 0;
+        bool uns = false;
+        auto trig = [&](uint32_t k, uint32_t *tp, uint32_t *tc) {
+            const uint32_t ti = rev ? n_mods - 1u - k : k;  // ascending read offsets
+            *tp = trig_p[ti]; *tc = trig_cat[ti];
+        };
+        auto push = [&](uint32_t pp, uint32_t c) {  // CallSink::push
+            if (n > 0 && n <= cap && pp <= last) uns = true;
+            if (n < cap) { if (lane == 0) { opos[n] = pp; ocat[n] = (uint8_t)c; } last = pp; }
+            n++;
+        };
+        auto fill = [&](uint32_t from, uint32_t until, uint32_t i_ref_, int32_t offset_) {  // gen_implicit_fill, 32 positions per step
+            for (uint32_t b0 = from; b0 < until; b0 += 32) {
+                const uint32_t t = b0 + lane;
+                const bool hit = t < until && t < len - 1u && seq_nib(seq, t) == 2u && seq_nib(seq, t + 1u) == 4u;
+                unsigned hm = __ballot_sync(FULL_MASK, hit);
+                if (!hm) continue;
+                // positions ascend inside a stretch: only its first CpG can sit on the call pushed last ("implicit but not pushing")
+                const uint32_t p_first = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
+                if (n > 0 && n <= cap && last == p_first) hm &= hm - 1u;
+                if (!hm) continue;
+                const uint32_t p_lo = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
+                if (n > 0 && n <= cap && p_lo <= last) uns = true;
+                if ((hm >> lane) & 1u) {
+                    const uint32_t idx = n + (uint32_t)__popc(hm & ((1u << lane) - 1u));
+                    if (idx < cap) { opos[idx] = i_ref_ + t + (uint32_t)offset_; ocat[idx] = 1; }
+                }
+                const uint32_t cnt = (uint32_t)__popc(hm);
+                if (n + cnt - 1u < cap) last = i_ref_ + b0 + (31u - (uint32_t)__clz((int)hm)) + (uint32_t)offset_;
+                n += cnt;
+                __syncwarp();
+            }
+        };
+        uint32_t i_read2 = 0, i_ref2 = qs, it = 0, next, nq;
+        trig(0, &next, &nq);
+        uint32_t ic = 0;
+        if ((cigar[0] & 15u) == 4u) {
+            i_read2 = cigar[0] >> 4;
+            while (next < i_read2) {
+                it++;
+                if (it < n_mods) trig(it, &next, &nq); else break;
+            }
+            if (next == i_read2) {
+                push(i_ref2 + (uint32_t)cg, nq);
+                it++;
+                if (it < n_mods) trig(it, &next, &nq);
+            }
+            i_ref2 -= cigar[0] >> 4;
+            ic = 1;
+        }
+        int32_t off2 = 0;
+        for (; ic < n_cigar; ic++) {
+            const uint32_t op = cigar[ic] & 15u, L = cigar[ic] >> 4;
+            if (op <= 1u) {
+                uint32_t pos_canonical = i_read2;
+                while (i_read2 + L >= next) {
+                    if (op == 0u && next != 0xffffffffu) {
+                        const uint32_t until = next - 1u < i_read2 + L ? next - 1u : i_read2 + L;
+                        fill(pos_canonical, until, i_ref2, off2);
+                        const uint32_t pt = i_ref2 + next + (uint32_t)cg + (uint32_t)off2;
+                        if (n > 0 && n <= cap && last == pt) { if (lane == 0) ocat[n - 1u] = (uint8_t)nq; }  // CallSink::last_is / set_last_cat
+                        else push(pt, nq);
+                        pos_canonical = cg == 0 ? next + 1u : next + 2u;
+                    }
+                    it++;
+                    if (it >= n_mods) { next = 0xffffffffu; break; }
+                    trig(it, &next, &nq);
+                }
+                if (op == 0u) {
+                    fill(pos_canonical, i_read2 + L, i_ref2, off2);
+                    i_read2 += L;
+                } else { i_read2 += L; off2 -= (int32_t)L; }
+            } else if (op == 2u) off2 += (int32_t)L;
+            else break;  // (3, 4: the walk ends; anything else was ruled out by the CIGAR pass above)
+        }
+        __syncwarp();
+        *n_calls_out = n;
+        *status_out = RS_KEPT | RS_LEAN | RS_HAS_IMPLICIT | (n > cap ? RS_OVERFLOW : 0u) | (uns ? RS_UNSORTED : 0u);
+        return true;
+    }
     if (rev && n_out && cap - n_out) {  // slide the calls down to the front of the record's slots
         const uint32_t shift = cap - n_out;
         for (uint32_t i0 = 0; i0 < n_out; i0 += 32) {

@@ -489,6 +489,102 @@ __device__ bool mm_parse_list_lean(const uint8_t *mm, SegInfo &g, DecodeWarpSmem
 }
 
 // ---------------------------------------------------------------------------------------------
+// get_mod_poss_on_ref with implicit canonical calls (blockjoin.c:605-792 with seqi given: 666-700, 727-761): a listed
+// cytosine outside a CpG makes the reference fill in every unlisted CpG of the aligned stretches as unmethylated.  The
+// walk over CIGAR operations and kept mods (read offset, category; trig_p / trig_cat, n_mods of them, in ascending or
+// descending read order) stays sequential, executed by the whole warp uniformly, statement by statement as in
+// decode_generic(); the CpG scan of the stretch between two mods is done by the 32 lanes.  Writes the calls to
+// opos / ocat (cap slots), *n_out = calls produced; returns RS_KEPT | RS_OVERFLOW | RS_UNSORTED | RS_FATAL_CIGAR bits.
+// ---------------------------------------------------------------------------------------------
+__device__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n_cigar, const uint8_t *seq, uint32_t len, uint32_t qs, bool rev,
+                                  const uint32_t *trig_p, const uint8_t *trig_cat, uint32_t n_mods, bool descending, uint32_t *opos,
+                                  uint8_t *ocat, uint32_t cap, uint32_t *n_out) {
+    const unsigned lane = lane_id();
+    const int cg = rev ? -1 : 0;
+    bool fatal = false;
+    uint32_t n = 0, last = 0;
+    bool uns = false;
+    auto trig = [&](uint32_t k, uint32_t *tp, uint32_t *tc) {
+        const uint32_t ti = descending ? n_mods - 1u - k : k;  // ascending read offsets
+        *tp = trig_p[ti]; *tc = trig_cat[ti];
+    };
+    auto push = [&](uint32_t pp, uint32_t c) {  // CallSink::push
+        if (n > 0 && n <= cap && pp <= last) uns = true;
+        if (n < cap) { if (lane == 0) { opos[n] = pp; ocat[n] = (uint8_t)c; } last = pp; }
+        n++;
+    };
+    auto fill = [&](uint32_t from, uint32_t until, uint32_t i_ref_, int32_t offset_) {  // gen_implicit_fill, 32 positions per step
+        for (uint32_t b0 = from; b0 < until; b0 += 32) {
+            const uint32_t t = b0 + lane;
+            const bool hit = t < until && t < len - 1u && seq_nib(seq, t) == 2u && seq_nib(seq, t + 1u) == 4u;
+            unsigned hm = __ballot_sync(FULL_MASK, hit);
+            if (!hm) continue;
+            // positions ascend inside a stretch: only its first CpG can sit on the call pushed last ("implicit but not pushing")
+            const uint32_t p_first = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
+            if (n > 0 && n <= cap && last == p_first) hm &= hm - 1u;
+            if (!hm) continue;
+            const uint32_t p_lo = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
+            if (n > 0 && n <= cap && p_lo <= last) uns = true;
+            if ((hm >> lane) & 1u) {
+                const uint32_t idx = n + (uint32_t)__popc(hm & ((1u << lane) - 1u));
+                if (idx < cap) { opos[idx] = i_ref_ + t + (uint32_t)offset_; ocat[idx] = 1; }
+            }
+            const uint32_t cnt = (uint32_t)__popc(hm);
+            if (n + cnt - 1u < cap) last = i_ref_ + b0 + (31u - (uint32_t)__clz((int)hm)) + (uint32_t)offset_;
+            n += cnt;
+            __syncwarp();
+        }
+    };
+    uint32_t i_read2 = 0, i_ref2 = qs, it = 0, next, nq;
+    trig(0, &next, &nq);
+    uint32_t ic = 0;
+    if ((cigar[0] & 15u) == 4u) {
+        i_read2 = cigar[0] >> 4;
+        while (next < i_read2) {
+            it++;
+            if (it < n_mods) trig(it, &next, &nq); else break;
+        }
+        if (next == i_read2) {
+            push(i_ref2 + (uint32_t)cg, nq);
+            it++;
+            if (it < n_mods) trig(it, &next, &nq);
+        }
+        i_ref2 -= cigar[0] >> 4;
+        ic = 1;
+    }
+    int32_t off2 = 0;
+    for (; ic < n_cigar; ic++) {
+        const uint32_t op = cigar[ic] & 15u, L = cigar[ic] >> 4;
+        if (op <= 1u) {
+            uint32_t pos_canonical = i_read2;
+            while (i_read2 + L >= next) {
+                if (op == 0u && next != 0xffffffffu) {
+                    const uint32_t until = next - 1u < i_read2 + L ? next - 1u : i_read2 + L;
+                    fill(pos_canonical, until, i_ref2, off2);
+                    const uint32_t pt = i_ref2 + next + (uint32_t)cg + (uint32_t)off2;
+                    if (n > 0 && n <= cap && last == pt) { if (lane == 0) ocat[n - 1u] = (uint8_t)nq; }  // CallSink::last_is / set_last_cat
+                    else push(pt, nq);
+                    pos_canonical = cg == 0 ? next + 1u : next + 2u;
+                }
+                it++;
+                if (it >= n_mods) { next = 0xffffffffu; break; }
+                trig(it, &next, &nq);
+            }
+            if (op == 0u) {
+                fill(pos_canonical, i_read2 + L, i_ref2, off2);
+                i_read2 += L;
+            } else { i_read2 += L; off2 -= (int32_t)L; }
+        } else if (op == 2u) off2 += (int32_t)L;
+        else if (op == 3u || op == 4u) break;
+        else { fatal = true; break; }
+    }
+    __syncwarp();
+    *n_out = n;
+    if (fatal) return RS_FATAL_CIGAR;
+    return RS_KEPT | (n > cap ? RS_OVERFLOW : 0u) | (uns ? RS_UNSORTED : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // The warp-parallel fast path.  Returns status bits; n_calls_out receives the number of calls.
 // ---------------------------------------------------------------------------------------------
 __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeWarpSmem &sm, uint32_t *n_calls_out,
@@ -558,7 +654,7 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
     // category; ML reads and the stores are coalesced in list order.  Reverse-strand records are scanned
     // from the right end of SEQ so ranks count from the read's own 5' end (htslib walks the delta list
     // backwards instead).
-    uint32_t n_mods = 0, mbase = 0;
+    uint32_t n_mods = 0, mbase = 0, n_listed = 0;
     bool has_implicit = false;
     const bool do_select = !mm_error && rel >= 0 && sm.seg[rel].n_delta > 0;
     // reverse strand: "MM tag refers to bases beyond sequence length" iff count(complement base) < sum(delta+1)
@@ -667,16 +763,18 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
                     }
                     const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
                     // blockjoin.c:846-858: C must be followed by G; on reverse alignments SEQ shows the G, preceded by C
+                    const uint32_t slot = rev ? cap - 1u - k : k;
                     if (p > 0 && p < len - 1) {
                         const bool ok = rev ? seq_nib(seq, p - 1) == 2u : seq_nib(seq, p + 1) == 4u;
                         if (ok) {
                             const uint32_t q = has_ml ? ml[ml_base + k * stride + m_idx] : 255u;
-                            const uint32_t slot = rev ? cap - 1u - k : k;
                             mpos[slot] = p;
                             mcat[slot] = (uint8_t)(q < P.lo ? 1 : (q >= P.hi ? 0 : 2));  // blockjoin.c:876-878
-                        } else implicit = true;
-                    } else if (k == 0) drop_first = true;
-                    else drop_last = true;
+                        } else { implicit = true; mpos[slot] = 0xffffffffu; }  // (a hole: squeezed out below if the record has implicit calls)
+                    } else {
+                        mpos[slot] = 0xffffffffu;
+                        if (k == 0) drop_first = true; else drop_last = true;
+                    }
                 }
                 tcur += (uint32_t)__popc(act);
                 if (act != FULL_MASK) break;
@@ -690,10 +788,37 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
         const uint32_t d0 = __any_sync(FULL_MASK, drop_first) ? 1u : 0u, d1 = __any_sync(FULL_MASK, drop_last) ? 1u : 0u;
         n_mods = tcur - d0 - d1;
         mbase = rev ? cap - tcur + d1 : d0;  // mods occupy tmp[mbase, mbase+n_mods), ascending SEQ position
+        n_listed = tcur;
     }
     if (mm_error) { status |= RS_MM_ERROR; n_mods = 0; has_implicit = false; }
-    if (has_implicit) { *need_generic = true; return 0; }
     __syncwarp();
+    if (has_implicit) {
+        // Implicit canonical calls: the listed bases that are not CpGs left holes among the kept mods; squeeze them out
+        // (ascending SEQ position either way: slot k on forward, cap-1-k on reversed alignments), then the sequential
+        // walk with the lanes scanning the stretches (implicit_walk).
+        const uint32_t lbase = rev ? cap - n_listed : 0u;
+        uint32_t nk = 0;
+        for (uint32_t i0 = 0; i0 < n_listed; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t pp = 0xffffffffu;
+            uint8_t cc = 0;
+            if (i < n_listed) { pp = mpos[lbase + i]; cc = mcat[lbase + i]; }
+            const unsigned vm = __ballot_sync(FULL_MASK, pp != 0xffffffffu);
+            __syncwarp();
+            if (pp != 0xffffffffu) {
+                const uint32_t d = nk + (uint32_t)__popc(vm & ((1u << lane) - 1u));
+                mpos[lbase + d] = pp; mcat[lbase + d] = cc;
+            }
+            nk += (uint32_t)__popc(vm);
+            __syncwarp();
+        }
+        status |= RS_HAS_IMPLICIT;
+        if (R.n_cigar == 0 || nk == 0) return status;  // get_mod_poss_on_ref returns 0: record dropped
+        uint32_t n = 0;
+        const uint32_t wst = implicit_walk(cigar, R.n_cigar, seq, len, R.pos, rev, mpos + lbase, mcat + lbase, nk, false, opos, ocat, cap, &n);
+        *n_calls_out = n;
+        return status | wst;
+    }
 
     // ---- CIGAR walk ----
     const uint32_t n_cigar = R.n_cigar;
@@ -1159,84 +1284,10 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
         // CIGAR operations and kept mods stays sequential (executed by the whole warp, uniformly), as in the reference;
         // the CpG scan of the stretch between two mods is done by the 32 lanes.  The explicit calls stored above are
         // overwritten: the merged sequence is rebuilt from the kept mods.
-        uint32_t n = 0, last = 0;
-        bool uns = false;
-        auto trig = [&](uint32_t k, uint32_t *tp, uint32_t *tc) {
-            const uint32_t ti = rev ? n_mods - 1u - k : k;  // ascending read offsets
-            *tp = trig_p[ti]; *tc = trig_cat[ti];
-        };
-        auto push = [&](uint32_t pp, uint32_t c) {  // CallSink::push
-            if (n > 0 && n <= cap && pp <= last) uns = true;
-            if (n < cap) { if (lane == 0) { opos[n] = pp; ocat[n] = (uint8_t)c; } last = pp; }
-            n++;
-        };
-        auto fill = [&](uint32_t from, uint32_t until, uint32_t i_ref_, int32_t offset_) {  // gen_implicit_fill, 32 positions per step
-            for (uint32_t b0 = from; b0 < until; b0 += 32) {
-                const uint32_t t = b0 + lane;
-                const bool hit = t < until && t < len - 1u && seq_nib(seq, t) == 2u && seq_nib(seq, t + 1u) == 4u;
-                unsigned hm = __ballot_sync(FULL_MASK, hit);
-                if (!hm) continue;
-                // positions ascend inside a stretch: only its first CpG can sit on the call pushed last ("implicit but not pushing")
-                const uint32_t p_first = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
-                if (n > 0 && n <= cap && last == p_first) hm &= hm - 1u;
-                if (!hm) continue;
-                const uint32_t p_lo = i_ref_ + b0 + (uint32_t)__ffs((int)hm) - 1u + (uint32_t)offset_;
-                if (n > 0 && n <= cap && p_lo <= last) uns = true;
-                if ((hm >> lane) & 1u) {
-                    const uint32_t idx = n + (uint32_t)__popc(hm & ((1u << lane) - 1u));
-                    if (idx < cap) { opos[idx] = i_ref_ + t + (uint32_t)offset_; ocat[idx] = 1; }
-                }
-                const uint32_t cnt = (uint32_t)__popc(hm);
-                if (n + cnt - 1u < cap) last = i_ref_ + b0 + (31u - (uint32_t)__clz((int)hm)) + (uint32_t)offset_;
-                n += cnt;
-                __syncwarp();
-            }
-        };
-        uint32_t i_read2 = 0, i_ref2 = qs, it = 0, next, nq;
-        trig(0, &next, &nq);
-        uint32_t ic = 0;
-        if ((cigar[0] & 15u) == 4u) {
-            i_read2 = cigar[0] >> 4;
-            while (next < i_read2) {
-                it++;
-                if (it < n_mods) trig(it, &next, &nq); else break;
-            }
-            if (next == i_read2) {
-                push(i_ref2 + (uint32_t)cg, nq);
-                it++;
-                if (it < n_mods) trig(it, &next, &nq);
-            }
-            i_ref2 -= cigar[0] >> 4;
-            ic = 1;
-        }
-        int32_t off2 = 0;
-        for (; ic < n_cigar; ic++) {
-            const uint32_t op = cigar[ic] & 15u, L = cigar[ic] >> 4;
-            if (op <= 1u) {
-                uint32_t pos_canonical = i_read2;
-                while (i_read2 + L >= next) {
-                    if (op == 0u && next != 0xffffffffu) {
-                        const uint32_t until = next - 1u < i_read2 + L ? next - 1u : i_read2 + L;
-                        fill(pos_canonical, until, i_ref2, off2);
-                        const uint32_t pt = i_ref2 + next + (uint32_t)cg + (uint32_t)off2;
-                        if (n > 0 && n <= cap && last == pt) { if (lane == 0) ocat[n - 1u] = (uint8_t)nq; }  // CallSink::last_is / set_last_cat
-                        else push(pt, nq);
-                        pos_canonical = cg == 0 ? next + 1u : next + 2u;
-                    }
-                    it++;
-                    if (it >= n_mods) { next = 0xffffffffu; break; }
-                    trig(it, &next, &nq);
-                }
-                if (op == 0u) {
-                    fill(pos_canonical, i_read2 + L, i_ref2, off2);
-                    i_read2 += L;
-                } else { i_read2 += L; off2 -= (int32_t)L; }
-            } else if (op == 2u) off2 += (int32_t)L;
-            else break;  // (3, 4: the walk ends; anything else was ruled out by the CIGAR pass above)
-        }
-        __syncwarp();
+        uint32_t n = 0;
+        const uint32_t wst = implicit_walk(cigar, n_cigar, seq, len, qs, rev, trig_p, trig_cat, n_mods, rev, opos, ocat, cap, &n);
         *n_calls_out = n;
-        *status_out = RS_KEPT | RS_LEAN | RS_HAS_IMPLICIT | (n > cap ? RS_OVERFLOW : 0u) | (uns ? RS_UNSORTED : 0u);
+        *status_out = RS_LEAN | RS_HAS_IMPLICIT | wst;
         return true;
     }
     if (rev && n_out && cap - n_out) {  // slide the calls down to the front of the record's slots

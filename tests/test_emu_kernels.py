@@ -83,6 +83,14 @@ def test_emulated_kernels_call_slot_overflow(emu_gpu, synth_sparse_implicit):
     _run(emu_gpu, synth_sparse_implicit, 34, 1500)
 
 
+@pytest.mark.emu
+def test_emulated_kernels_implicit_mode_streaming_path(emu_gpu, synth_sparse_implicit, monkeypatch):
+    # the same with the lean path switched off: the streaming path squeezes the non-CpG holes out of its kept mods and
+    # runs the implicit-call walk (what records over 65 535 bases take)
+    monkeypatch.setenv("POMFRET_GPU_DECODE_LEAN", "0")
+    _run(emu_gpu, synth_sparse_implicit, 34, 1500)
+
+
 def _run_cfg(emu_gpu, data, cov, readlen, tweak):
     """like _run, with the engine / oracle configurations adjusted by tweak(cfg)"""
     host = pb.load_host()

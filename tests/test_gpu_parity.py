@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import conftest
 import oracle_bindings as ob
 import parity
 import pomfret_b200 as pb
@@ -94,6 +95,20 @@ def test_gpu_matches_oracle_implicit(gpu, synth_implicit):
 
 def test_gpu_matches_oracle_call_slot_overflow(gpu, synth_sparse_implicit):
     _run(gpu, synth_sparse_implicit, 34, readlen=1500)
+
+
+@pytest.mark.parametrize("which", ["implicit", "sparse"])
+def test_gpu_matches_oracle_implicit_streaming_path(gpu, synth_implicit, synth_sparse_implicit, which, monkeypatch):
+    # implicit canonical calls through the streaming path (lean path off): what records over 65 535 bases take
+    monkeypatch.setenv("POMFRET_GPU_DECODE_LEAN", "0")
+    _run(gpu, synth_implicit if which == "implicit" else synth_sparse_implicit, 34, readlen=1500)
+
+
+def test_gpu_implicit_long_reads(gpu, built, tmp_path):
+    # 20 kb reads (some beyond the lean path's limits) with non-CpG entries: lean + streaming implicit walks on real sizes
+    data = conftest.run_synth(str(tmp_path / "impl"), ["-c", "30", "-s", "47", "-C", "chr20:64444167:9000000-9400000", "--implicit", "0.05",
+                                                        "--listed", "0.7"])
+    _run(gpu, data, 30)
 
 
 @pytest.mark.parametrize("kw", [dict(k=2, k_span=800), dict(k=4, lo=80, hi=180), dict(k=1), dict(k_span=300), dict(k=5, k_span=3000),

@@ -22,8 +22,10 @@
 //   5. CIGAR walk: M/I ops compacted (read-end, offset) into shared memory in chunks; each kept mod
 //      binary-searches the op that the reference's inclusive trigger loop would handle it under;
 //      positions de-duplicated with the reference's overwrite rule and written out.
-// Records that need the general sequential semantics (several C+m segments, >10 mod streams,
-// implicit canonical calls, more segments than the table holds) take decode_generic() on lane 0.
+// Records with implicit canonical calls (a listed cytosine outside a CpG, blockjoin.c:666-700) stay on these paths: the
+// walk over CIGAR operations and kept mods is then run sequentially by the warp with the lanes scanning the stretches
+// for CpGs (implicit_walk).  Records that need the general sequential semantics (several C+m segments, >10 mod streams,
+// more segments than the table holds) are collected and run one per thread (decode_generic_kernel).
 #ifndef POMFRET_GPU_DECODE_CUH
 #define POMFRET_GPU_DECODE_CUH
 #include "gpu_rt.h"

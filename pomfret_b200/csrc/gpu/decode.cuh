@@ -1235,13 +1235,6 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             const bool emit = r_emit[row];
             const uint32_t pos = r_pos[row], cat = r_cat[row];
             const unsigned okm = __ballot_sync(FULL_MASK, r_ok[row]);
-            // the kept mods themselves (read offset, category), in list order: what get_mod_poss_on_ref is handed; the
-            // implicit-call walk below reads them back
-            if (r_ok[row]) {
-                const uint32_t ti = n_mods + (uint32_t)__popc(okm & ((1u << lane) - 1u));
-                trig_p[ti] = r_p[row];
-                trig_cat[ti] = (uint8_t)cat;
-            }
             n_mods += (uint32_t)__popc(okm);
             n_behind_clip += (uint32_t)__popc(__ballot_sync(FULL_MASK, r_ok[row] && r_p[row] > clip));
             // ordered, de-duplicated store (blockjoin.c:704-709: of the bases that land on one position the one latest in
@@ -1286,6 +1279,61 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
         // CIGAR operations and kept mods stays sequential (executed by the whole warp, uniformly), as in the reference;
         // the CpG scan of the stretch between two mods is done by the 32 lanes.  The explicit calls stored above are
         // overwritten: the merged sequence is rebuilt from the kept mods.
+        // the kept mods themselves (read offset, category), in list order — what get_mod_poss_on_ref is handed: the listed
+        // bases are resolved once more, one row at a time (only records with implicit calls pay for this)
+        {
+            uint32_t nt = 0;
+            for (uint32_t k0 = 0; k0 < n_targets; k0 += 32) {
+                const uint32_t k = k0 + lane;
+                const uint32_t kk = k < n_targets ? k : n_targets - 1u;
+                const uint32_t rr = rank[kk];
+                const bool found = k < n_targets && rr < total;  // ranks ascend: the bases that lie beyond SEQ form the tail of the list
+                const uint32_t r = found ? rr : 0u;
+                // chunk (scan order) that holds rank r: last c with l_first[c] <= r; unused entries are 0xffff
+                // (the cursor is a pointer so that every step is load-with-immediate-offset, compare, predicated add)
+                // (the range shrinks by its probed half whether or not the step is taken — len - len/2 is at least the half
+                //  that stays — so the probe offsets are compile-time constants for any table size)
+                const uint16_t *fq = sm.l_first;
+#pragma unroll
+                for (uint32_t ln = LEAN_CH; ln > 1; ln -= ln >> 1)
+                    if (fq[ln >> 1] <= r) fq += ln >> 1;
+                const uint32_t c = (uint32_t)(fq - sm.l_first);
+                const uint32_t f0 = fq[0], cnt = fq[1] - f0;
+                const uint32_t chunk = rev ? n_ch - 1u - c : c;
+                uint32_t n = rev ? cnt - 1u - (r - f0) : r - f0;  // index in base order inside the chunk
+                const uint32_t coff = chunk * 16u < last_chunk_off ? chunk * 16u : last_chunk_off;
+                const uint4 v = *reinterpret_cast<const uint4 *>(seq + coff);
+                const uint32_t g0 = nib_eq_flags(v.x, pat), g1 = nib_eq_flags(v.y, pat), g2 = nib_eq_flags(v.z, pat),
+                               g3 = nib_eq_flags(v.w, pat);
+                const uint32_t c0 = (uint32_t)__popc(g0), c1 = c0 + (uint32_t)__popc(g1), c2 = c1 + (uint32_t)__popc(g2);
+                const uint32_t wj = (n >= c0 ? 1u : 0u) + (n >= c1 ? 1u : 0u) + (n >= c2 ? 1u : 0u);
+                const uint32_t f = wj == 0u ? g0 : (wj == 1u ? g1 : (wj == 2u ? g2 : g3));
+                n -= wj == 0u ? 0u : (wj == 1u ? c0 : (wj == 2u ? c1 : c2));
+                const uint32_t p = chunk * 32u + wj * 8u + select_base_in_word(f, n);
+                // blockjoin.c:846-858: C must be followed by G; on reversed alignments SEQ shows the G, preceded by C
+                const bool inner = found && p > 0 && p < len - 1;
+                // the neighbouring base: inside the 16-byte chunk at hand (nibble i of a word holds base i ^ 1) unless the base
+                // is the chunk's first / last one
+                const uint32_t b = (p & 31u) + (rev ? 0xffffffffu : 1u);  // neighbour's index inside the chunk: -1 .. 32
+                uint32_t nb;
+                if (b < 32u) {
+                    const uint32_t w = b < 16u ? (b < 8u ? v.x : v.y) : (b < 24u ? v.z : v.w);
+                    nb = (w >> ((((b & 7u) ^ 1u)) << 2)) & 0xfu;
+                } else nb = inner ? seq_nib(seq, rev ? p - 1u : p + 1u) : 0u;
+                const bool ok = inner && nb == want_nb;
+                const uint32_t q = has_ml ? ml[ml_base + kk * stride + m_idx] : 255u;
+                const uint32_t cat = q < P.lo ? 1u : (q >= P.hi ? 0u : 2u);
+                const unsigned okm = __ballot_sync(FULL_MASK, ok);
+                if (ok) {
+                    const uint32_t ti = nt + (uint32_t)__popc(okm & ((1u << lane) - 1u));
+                    trig_p[ti] = p;
+                    trig_cat[ti] = (uint8_t)cat;
+                }
+                nt += (uint32_t)__popc(okm);
+                if (__ballot_sync(FULL_MASK, found) != FULL_MASK) break;
+            }
+            __syncwarp();
+        }
         uint32_t n = 0;
         const uint32_t wst = implicit_walk(cigar, n_cigar, seq, len, qs, rev, trig_p, trig_cat, n_mods, rev, opos, ocat, cap, &n);
         *n_calls_out = n;

@@ -501,7 +501,7 @@ __device__ bool mm_parse_list_lean(const uint8_t *mm, SegInfo &g, DecodeWarpSmem
 // The walk's critical path is a chain of dependent loads, so what it reads sits close: SEQ in a window of the warp's
 // shared memory (swin, swin_bytes: a multiple of 16; re-staged as the walk moves right), the kept mods and the CIGAR
 // operations in registers, 32 at a time, handed out by shuffles.
-__device__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n_cigar, const uint8_t *seq, uint32_t len, uint32_t qs, bool rev,
+__device__ __noinline__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n_cigar, const uint8_t *seq, uint32_t len, uint32_t qs, bool rev,
                                   const uint32_t *trig_p, const uint8_t *trig_cat, uint32_t n_mods, bool descending, uint32_t *opos,
                                   uint8_t *ocat, uint32_t cap, uint32_t *n_out, uint8_t *swin, uint32_t swin_bytes) {
     const unsigned lane = lane_id();

@@ -498,59 +498,17 @@ __device__ bool mm_parse_list_lean(const uint8_t *mm, SegInfo &g, DecodeWarpSmem
 // decode_generic(); the CpG scan of the stretch between two mods is done by the 32 lanes.  Writes the calls to
 // opos / ocat (cap slots), *n_out = calls produced; returns RS_KEPT | RS_OVERFLOW | RS_UNSORTED | RS_FATAL_CIGAR bits.
 // ---------------------------------------------------------------------------------------------
-// The walk's critical path is a chain of dependent loads, so what it reads sits close: SEQ in a window of the warp's
-// shared memory (swin, swin_bytes: a multiple of 16; re-staged as the walk moves right), the kept mods and the CIGAR
-// operations in registers, 32 at a time, handed out by shuffles.
-__device__ __noinline__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n_cigar, const uint8_t *seq, uint32_t len, uint32_t qs, bool rev,
+__device__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n_cigar, const uint8_t *seq, uint32_t len, uint32_t qs, bool rev,
                                   const uint32_t *trig_p, const uint8_t *trig_cat, uint32_t n_mods, bool descending, uint32_t *opos,
-                                  uint8_t *ocat, uint32_t cap, uint32_t *n_out, uint8_t *swin, uint32_t swin_bytes) {
+                                  uint8_t *ocat, uint32_t cap, uint32_t *n_out) {
     const unsigned lane = lane_id();
     const int cg = rev ? -1 : 0;
     bool fatal = false;
     uint32_t n = 0, last = 0;
     bool uns = false;
-    uint32_t tblk = 0xffffffffu, tp_r = 0, tc_r = 0;  // kept mods [32 * tblk, 32 * tblk + 32), one per lane
     auto trig = [&](uint32_t k, uint32_t *tp, uint32_t *tc) {
-        if ((k >> 5) != tblk) {
-            tblk = k >> 5;
-            const uint32_t kk = tblk * 32u + lane;
-            if (kk < n_mods) {
-                const uint32_t ti = descending ? n_mods - 1u - kk : kk;  // ascending read offsets
-                tp_r = trig_p[ti]; tc_r = trig_cat[ti];
-            }
-        }
-        *tp = __shfl_sync(FULL_MASK, tp_r, (int)(k & 31u));
-        *tc = __shfl_sync(FULL_MASK, tc_r, (int)(k & 31u));
-    };
-    uint32_t cblk = 0xffffffffu, c_r = 0;             // CIGAR operations, likewise
-    auto cig = [&](uint32_t i) {
-        if ((i >> 5) != cblk) {
-            cblk = i >> 5;
-            const uint32_t ii = cblk * 32u + lane;
-            c_r = ii < n_cigar ? cigar[ii] : 0u;
-        }
-        return __shfl_sync(FULL_MASK, c_r, (int)(i & 31u));
-    };
-    const uint32_t n_bytes = (len + 1u) >> 1;
-    uint32_t wb = 0, wn = 0;                           // window: SEQ bytes [wb, wb + wn)
-    // nibble t of SEQ, with the window covering the bytes of positions [b0, b0 + 33] (b0 uniform)
-    auto cover = [&](uint32_t b0) {
-        const uint32_t lo = b0 >> 1, hi = (b0 + 33u) >> 1;  // bytes needed: [lo, hi]
-        if (swin_bytes == 0 || (lo >= wb && hi < wb + wn)) return;
-        __syncwarp();
-        wb = lo & ~15u;
-        wn = swin_bytes;
-        for (uint32_t o = lane * 16u; o < swin_bytes; o += 512u) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (wb + o < n_bytes) v = *reinterpret_cast<const uint4 *>(seq + wb + o);  // (the field is zero padded to 16 bytes)
-            *reinterpret_cast<uint4 *>(swin + o) = v;
-        }
-        __syncwarp();
-    };
-    auto nib = [&](uint32_t t) -> uint32_t {
-        const uint32_t by = t >> 1;
-        const uint32_t b = swin_bytes ? swin[by - wb] : seq[by];
-        return (b >> ((~t & 1u) << 2)) & 0xfu;
+        const uint32_t ti = descending ? n_mods - 1u - k : k;  // ascending read offsets
+        *tp = trig_p[ti]; *tc = trig_cat[ti];
     };
     auto push = [&](uint32_t pp, uint32_t c) {  // CallSink::push
         if (n > 0 && n <= cap && pp <= last) uns = true;
@@ -560,8 +518,7 @@ __device__ __noinline__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n
     auto fill = [&](uint32_t from, uint32_t until, uint32_t i_ref_, int32_t offset_) {  // gen_implicit_fill, 32 positions per step
         for (uint32_t b0 = from; b0 < until; b0 += 32) {
             const uint32_t t = b0 + lane;
-            cover(b0);
-            const bool hit = t < until && t < len - 1u && nib(t) == 2u && nib(t + 1u) == 4u;
+            const bool hit = t < until && t < len - 1u && seq_nib(seq, t) == 2u && seq_nib(seq, t + 1u) == 4u;
             unsigned hm = __ballot_sync(FULL_MASK, hit);
             if (!hm) continue;
             // positions ascend inside a stretch: only its first CpG can sit on the call pushed last ("implicit but not pushing")
@@ -583,9 +540,8 @@ __device__ __noinline__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n
     uint32_t i_read2 = 0, i_ref2 = qs, it = 0, next, nq;
     trig(0, &next, &nq);
     uint32_t ic = 0;
-    const uint32_t cig0 = cig(0);
-    if ((cig0 & 15u) == 4u) {
-        i_read2 = cig0 >> 4;
+    if ((cigar[0] & 15u) == 4u) {
+        i_read2 = cigar[0] >> 4;
         while (next < i_read2) {
             it++;
             if (it < n_mods) trig(it, &next, &nq); else break;
@@ -595,13 +551,12 @@ __device__ __noinline__ uint32_t implicit_walk(const uint32_t *cigar, uint32_t n
             it++;
             if (it < n_mods) trig(it, &next, &nq);
         }
-        i_ref2 -= cig0 >> 4;
+        i_ref2 -= cigar[0] >> 4;
         ic = 1;
     }
     int32_t off2 = 0;
     for (; ic < n_cigar; ic++) {
-        const uint32_t cgo = cig(ic);
-        const uint32_t op = cgo & 15u, L = cgo >> 4;
+        const uint32_t op = cigar[ic] & 15u, L = cigar[ic] >> 4;
         if (op <= 1u) {
             uint32_t pos_canonical = i_read2;
             while (i_read2 + L >= next) {
@@ -862,8 +817,7 @@ __device__ uint32_t decode_fast(const DecodeParams &P, const ReadRec &R, DecodeW
         status |= RS_HAS_IMPLICIT;
         if (R.n_cigar == 0 || nk == 0) return status;  // get_mod_poss_on_ref returns 0: record dropped
         uint32_t n = 0;
-        const uint32_t wst = implicit_walk(cigar, R.n_cigar, seq, len, R.pos, rev, mpos + lbase, mcat + lbase, nk, false, opos, ocat, cap, &n,
-                                           reinterpret_cast<uint8_t *>(sm.first), (uint32_t)(DEC_FC * 4) & ~15u);  // (the section tables are done with)
+        const uint32_t wst = implicit_walk(cigar, R.n_cigar, seq, len, R.pos, rev, mpos + lbase, mcat + lbase, nk, false, opos, ocat, cap, &n);
         *n_calls_out = n;
         return status | wst;
     }
@@ -1381,8 +1335,7 @@ __device__ bool decode_lean(const DecodeParams &P, const ReadRec &R, DecodeWarpS
             __syncwarp();
         }
         uint32_t n = 0;
-        const uint32_t wst = implicit_walk(cigar, n_cigar, seq, len, qs, rev, trig_p, trig_cat, n_mods, rev, opos, ocat, cap, &n,
-                                           reinterpret_cast<uint8_t *>(sm.l_first), (uint32_t)(LEAN_CH * 2) & ~15u);  // (the rank table is done with)
+        const uint32_t wst = implicit_walk(cigar, n_cigar, seq, len, qs, rev, trig_p, trig_cat, n_mods, rev, opos, ocat, cap, &n);
         *n_calls_out = n;
         *status_out = RS_LEAN | RS_HAS_IMPLICIT | wst;
         return true;

@@ -121,8 +121,9 @@ __device__ __forceinline__ uint32_t md_class_word(const uint32_t (&w)[4], uint32
 #pragma unroll
     for (uint32_t i = 0; i < 16; i++) {
         const uint32_t c = (w[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-        const uint32_t lc = c | 0x20u;  // letters: case folded
-        const uint32_t cl = (c - '0') <= 9u ? 0u : (c == '^' ? 1u : ((lc == 'a' || lc == 'c' || lc == 'g' || lc == 't' || lc == 'u' || lc == 'n') ? 2u : 3u));
+        const uint32_t li = (c | 0x20u) - 'a';  // letters: case folded, index in the alphabet
+        const bool letter = li < 26u && ((0x00182045u >> li) & 1u);  // a c g n t u
+        const uint32_t cl = (c - '0') <= 9u ? 0u : (c == '^' ? 1u : (letter ? 2u : 3u));
         cw |= (i < nv ? cl : 0u) << (2 * i);
     }
     return cw;
